@@ -1,0 +1,430 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the batched c64 FFT hot path (BASELINE.json config 2).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--workload c64|f128] [--n N] [--batch B]
+
+Step   = one pass of the hot path over one batch: unordered fwd THEN inv of `batch`
+         polynomials of size n, in place (2 * batch transforms).
+value  = transforms/s, whole job (all ranks), inputs resident in HBM, CUDA-event timed,
+         max over ranks.  Inputs (2 GiB per GPU at the default size) are far larger than the
+         126 MB L2, so no flush is needed between iterations.
+e2e    = the same step through the public host-memory call (Plan.fwd_inv_host ->
+         cfft_c64_fwd_inv_host): pinned host buffers, H2D + fwd + inv + D2H inside the timed
+         region.
+roofline    = achieved HBM GB/s of the dominant kernel (algorithmic bytes 2 * 16 * n per
+              transform per launch / average launch time from CUDA events on the launch
+              stream) against MEASURED_PEAKS.json.
+cpu_baseline= the oracle port of the reference algorithm (-O3 build, bit-identical results) on
+              the host cores, bounded sample of the same workload.
+--impl reference times that CPU port with all host threads on the same metric/config (the
+Rust reference itself cannot be built in this image: no cargo/rustc).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c64", choices=["c64", "f128"])
+    ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--base-n", type=int, default=0)
+    ap.add_argument("--algo", default="")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)", d
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)", {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); power.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def workload_defaults(args):
+    if args.workload == "c64":
+        n = args.n or 2048
+        batch = args.batch or 65536
+        base_n = args.base_n or min(n, 256)
+        algo = args.algo or "Dif16"
+    else:
+        n = args.n or 2048
+        batch = args.batch or 16384
+        base_n, algo = n, ""
+    return n, batch, base_n, algo
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_port_rate(workload, n, base_n, algo, threads, seconds):
+    """transforms/s of the oracle port (fast build) on `threads` host threads: fwd+inv steps over
+    a bounded sample until ~`seconds` of wall time."""
+    import numpy as np
+    import oracle_lib as O
+
+    rng = np.random.default_rng(0)
+    rows = max(threads * 8, 256)
+    if workload == "c64":
+        plan = O.UnorderedPlan(n, O.ALGO_NAMES.index(algo), base_n, fast=True)
+        buf = rng.random((rows, n)) + 1j * rng.random((rows, n))
+
+        def step():
+            plan.fwd_inplace(buf, threads)
+            plan.inv_inplace(buf, threads)
+            np.multiply(buf, 1.0 / n, out=buf)
+    else:
+        rows = max(threads * 2, 32)
+        plan = O.F128Plan(n, fast=True)
+        planes = [rng.random((rows, n)), np.zeros((rows, n)), rng.random((rows, n)), np.zeros((rows, n))]
+
+        def step():
+            plan.fwd_inplace(planes, O.F128_FMA, threads)
+            plan.inv_inplace(planes, O.F128_FMA, threads)
+            for p in planes:
+                p *= 1.0 / n
+    step()
+    t0 = time.perf_counter()
+    steps = 0
+    while True:
+        step()
+        steps += 1
+        el = time.perf_counter() - t0
+        if el >= seconds or steps >= 100000:
+            break
+    return 2.0 * rows * steps / el, rows, steps, el
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, batch, base_n, algo = workload_defaults(args)
+    threads = host_threads()
+    import numpy as np
+    import oracle_lib as O
+
+    O.build()
+    rng = np.random.default_rng(0)
+    # each step = fwd+inv over a bounded sample of the workload's batch
+    rows = min(batch, max(threads * 16, 512)) if args.workload == "c64" else min(batch, max(threads * 4, 64))
+    if args.workload == "c64":
+        plan = O.UnorderedPlan(n, O.ALGO_NAMES.index(algo), base_n, fast=True)
+        buf = rng.random((rows, n)) + 1j * rng.random((rows, n))
+
+        def step():
+            plan.fwd_inplace(buf, threads)
+            plan.inv_inplace(buf, threads)
+            np.multiply(buf, 1.0 / n, out=buf)
+    else:
+        plan = O.F128Plan(n, fast=True)
+        planes = [rng.random((rows, n)), np.zeros((rows, n)), rng.random((rows, n)), np.zeros((rows, n))]
+
+        def step():
+            plan.fwd_inplace(planes, O.F128_FMA, threads)
+            plan.inv_inplace(planes, O.F128_FMA, threads)
+            for p in planes:
+                p *= 1.0 / n
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    el = time.perf_counter() - t0
+    value = 2.0 * rows * args.steps / el
+    sample = "%d of %d polynomials per step, fwd+inv, %d host threads" % (rows, batch, threads)
+    line = {
+        "impl": "reference",
+        "metric": "batched %s FFT transforms/s (fwd+inv)" % ("c64" if args.workload == "c64" else "fft128"),
+        "value": value, "unit": "transforms/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64" if args.workload == "c64" else "f64x2 (double-double)", "data": "synthetic",
+        "config": config_dict(args.workload, n, batch, base_n, algo, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "transforms/s", "cores": threads, "kind": "port", "sample": sample,
+                         "note": "C restatement of the reference algorithm (oracle/, -O3 build, bit-identical "
+                                 "to the reference's golden vector); the Rust crate cannot be built here"},
+        "e2e": {"value": value, "unit": "transforms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(workload, n, batch, base_n, algo, gpus):
+    if workload == "c64":
+        return {"workload": "unordered c64 fwd+inv N=%d batch %d per GPU (BASELINE.json configs[1], TFHE bootstrapping shape)" % (n, batch),
+                "n": n, "batch_per_gpu": batch, "plan": "UserProvided{base_algo: %s, base_n: %d}" % (algo, base_n),
+                "sharding": "batch split across %d GPU(s), no collective" % gpus,
+                "l2": "inputs (%.2f GiB per GPU) larger than L2, no flush" % (batch * n * 16 / 2**30)}
+    return {"workload": "fft128 negacyclic fwd+inv n=%d batch %d per GPU (BASELINE.json configs[3])" % (n, batch),
+            "n": n, "batch_per_gpu": batch, "sharding": "batch split across %d GPU(s), no collective" % gpus,
+            "l2": "inputs (%.2f GiB per GPU) larger than L2, no flush" % (batch * n * 32 / 2**30)}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+
+    import concrete_fft_b200 as C
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        sys.exit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    n, batch, base_n, algo = workload_defaults(args)
+    dev = torch.device("cuda", local)
+    g = torch.Generator(device=dev).manual_seed(0x5EED0000 + rank)
+    A = C.ordered.FftAlgo
+
+    if args.workload == "c64":
+        plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(A[algo], base_n), device=local)
+        data = torch.view_as_complex(torch.rand(batch, n, 2, dtype=torch.float64, device=dev, generator=g)).contiguous()
+        bytes_per_launch = 2 * 16 * n * batch
+        inv_scale = 1.0 / n
+
+        def fwd():
+            plan.fwd(data)
+
+        def inv():
+            plan.inv(data)
+
+        def renorm():
+            data.mul_(inv_scale)
+    else:
+        plan = C.fft128.Plan(n, device=local)
+        planes = [torch.rand(batch, n, dtype=torch.float64, device=dev, generator=g), torch.zeros(batch, n, dtype=torch.float64, device=dev),
+                  torch.rand(batch, n, dtype=torch.float64, device=dev, generator=g), torch.zeros(batch, n, dtype=torch.float64, device=dev)]
+        bytes_per_launch = 2 * 32 * n * batch
+        inv_scale = 1.0 / n
+
+        def fwd():
+            plan.fwd(*planes)
+
+        def inv():
+            plan.inv(*planes)
+
+        def renorm():
+            for p in planes:
+                p.mul_(inv_scale)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident timing ------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        fwd(); inv()
+    renorm_all = lambda: [renorm() for _ in range(max(args.warmup, 3))]
+    renorm_all()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    K = args.steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    launches0 = C.launch_count()
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_begin.record()
+    for i in range(K):
+        ev[i][0].record()
+        fwd()
+        ev[i][1].record()
+        inv()
+        ev[i][2].record()
+        if (i + 1) % 64 == 0:  # fwd+inv multiplies by n: rescale (exact, power of two) before f64 overflows
+            for _ in range(64):
+                renorm()
+    t_end.record()
+    barrier()
+    launches = C.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = t_begin.elapsed_time(t_end)
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
+    inv_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = 2.0 * batch * world * K / (total_ms * 1e-3)
+
+    # ---- end to end through the host-memory API ----------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        if args.workload == "c64":
+            host = torch.view_as_complex(torch.rand(batch, n, 2, dtype=torch.float64)).contiguous().pin_memory()
+            hnp = host.numpy()
+            h2d = d2h = batch * n * 16
+
+            def e2e_step():
+                plan.fwd_inv_host(hnp)
+                return float(hnp[0, 0].real)
+        else:
+            hp = [torch.rand(batch, n, dtype=torch.float64).pin_memory() for _ in range(4)]
+            hn = [p.numpy() for p in hp]
+            h2d = d2h = 2 * batch * n * 32  # fwd call + inv call, each uploads and downloads
+
+            def e2e_step():
+                plan.fwd(*hn)
+                plan.inv(*hn)
+                return float(hn[0][0, 0])
+        e2e_step()
+        if args.workload == "c64":
+            np.multiply(hnp, inv_scale, out=hnp)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+            if args.workload == "c64":
+                np.multiply(hnp[:1], inv_scale, out=hnp[:1])
+        barrier()
+        el = time.perf_counter() - t0
+        te = torch.tensor([el], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        el = float(te.item())
+        e2e = {"value": 2.0 * batch * world * args.e2e_steps / el, "unit": "transforms/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
+               "ms_per_step": 1e3 * el / args.e2e_steps,
+               "api": "Plan.fwd_inv_host -> cfft_c64_fwd_inv_host (pinned host buffers)" if args.workload == "c64"
+                      else "fft128.Plan.fwd + inv on pinned host planes -> cfft_f128_{fwd,inv}_host"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src, _ = measured_peaks()
+    dom_ms = min(fwd_ms, inv_ms) if False else fwd_ms
+    achieved = bytes_per_launch / (dom_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": plan.kernel_name() + " (fwd launch)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_per_launch,
+                "fwd_ms": fwd_ms, "inv_ms": inv_ms,
+                "inv_achieved": bytes_per_launch / (inv_ms * 1e-3) / 1e9,
+                "gflops_5nlog2n": 5.0 * n * (n.bit_length() - 1) * value / 1e9}
+    if args.workload == "f128":
+        instr = 94.0 * (n // 2) * (n.bit_length() - 1)  # FP64 instructions per transform
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        fp64_peak = 64 * 148 * sm_mhz * 1e6
+        rate = instr * batch / (fwd_ms * 1e-3)
+        roofline.update({"bound": "fp64-pipe", "fp64_instr_per_transform": instr, "fp64_instr_per_s": rate,
+                         "fp64_pipe_frac_at_sampled_clock": rate / fp64_peak,
+                         "fp64_pipe_frac_at_max_clock": rate / (64 * 148 * 1965e6)})
+
+    cpu = None
+    if not args.no_cpu:
+        import oracle_lib as O
+
+        O.build()
+        threads = host_threads()
+        rate, rows, steps, el = cpu_port_rate(args.workload, n, base_n, algo, threads, args.cpu_seconds)
+        cpu = {"value": rate, "unit": "transforms/s", "cores": threads, "kind": "port",
+               "sample": "%d polynomials x %d fwd+inv steps in %.1f s (same n / plan as the GPU run)" % (rows, steps, el)}
+
+    line = {
+        "metric": "batched %s FFT transforms/s (fwd+inv)" % ("c64" if args.workload == "c64" else "fft128"),
+        "value": value, "unit": "transforms/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64" if args.workload == "c64" else "f64x2 (double-double)", "data": "synthetic",
+        "config": config_dict(args.workload, n, batch, base_n, algo, world),
+        "hbm_gbs_whole_step": 2 * bytes_per_launch * world * K / (total_ms * 1e-3) / 1e9,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

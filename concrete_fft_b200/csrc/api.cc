@@ -1,0 +1,448 @@
+// api.cc -- the extern "C" surface declared in include/cfft_b200.h: plan construction
+// (tables + stage schedule), argument checking with the reference's preconditions, and the
+// host-buffer pipelines.  No CPU fallback: every compute entry needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/cfft_b200.h"
+#include "plan.h"
+
+using namespace cfft;
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launches{0};
+
+cfft_status fail(cfft_status st, const std::string &msg)
+{
+    g_last_error = msg;
+    return st;
+}
+cfft_status cuda_fail(cudaError_t e, const char *what)
+{
+    return fail(CFFT_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                                        \
+    do {                                                                \
+        cudaError_t e__ = (call);                                       \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);           \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        ok = (prev == dev) || cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard()
+    {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+// ---- stage schedules ------------------------------------------------------------------------
+
+// Stockham stages of the ordered base FFT of size base_n (type-level recursion of e.g.
+// src/dif4.rs:246-303 / src/dit4.rs:223-280 flattened): appended in execution order.
+void append_base_stages(StageProgram &pg, int algo, uint64_t base_n, uint32_t tw_off)
+{
+    if (base_n <= 1) return;
+    const int R = algo_radix(algo);
+    const unsigned rho = ilog2(uint64_t(R));
+    unsigned bits = ilog2(base_n);
+    std::vector<uint32_t> strides;
+    uint32_t s = 1;
+    while (bits > rho) {
+        strides.push_back(s);
+        s *= uint32_t(R);
+        bits -= rho;
+    }
+    const Stage end = {ST_END, 1 << bits, 0, tw_off};
+    if (!algo_is_dit(algo)) {
+        for (uint32_t st : strides) pg.st[pg.count++] = Stage{ST_CORE_DIF, R, st, tw_off};
+        pg.st[pg.count++] = end;
+    } else {
+        pg.st[pg.count++] = end;
+        for (auto it = strides.rbegin(); it != strides.rend(); ++it) pg.st[pg.count++] = Stage{ST_CORE_DIT, R, *it, tw_off};
+    }
+}
+
+void build_c64_programs(cfft_plan *p)
+{
+    const uint64_t n = p->n, base_n = p->base_n;
+    StageProgram &f = p->prog[0], &v = p->prog[1];
+    f.count = v.count = 0;
+
+    // forward: unordered levels top-down (src/unordered.rs:392-439), then the base FFT
+    struct Lvl { int r; uint64_t span; uint32_t off_f, off_i; };
+    std::vector<Lvl> lv;
+    uint64_t cur = n;
+    uint32_t head = 0, tail = uint32_t(n + base_n);
+    while (cur > base_n) {
+        const int r = top_radix(cur, base_n);
+        const uint32_t sz = uint32_t((r - 1) * (cur / r));
+        tail -= sz;
+        lv.push_back(Lvl{r, cur, head, tail});
+        head += sz;
+        cur /= r;
+    }
+    for (const Lvl &l : lv) f.st[f.count++] = Stage{ST_TOP, l.r, uint32_t(l.span), l.off_f};
+    append_base_stages(f, p->algo, base_n, head + uint32_t(base_n));
+
+    // inverse: base FFT first, then the levels bottom-up (src/unordered.rs:442-489)
+    append_base_stages(v, p->algo, base_n, uint32_t(base_n));
+    for (auto it = lv.rbegin(); it != lv.rend(); ++it) v.st[v.count++] = Stage{ST_TOP, it->r, uint32_t(it->span), it->off_i};
+}
+
+cfft_status upload_c64(cfft_plan *p)
+{
+    for (int d = 0; d < 2; d++) {
+        const size_t bytes = p->h_tw[d].size() * sizeof(cplx);
+        if (bytes == 0) continue;
+        CU(cudaMalloc(reinterpret_cast<void **>(&p->d_tw[d]), bytes));
+        CU(cudaMemcpy(p->d_tw[d], p->h_tw[d].data(), bytes, cudaMemcpyHostToDevice));
+    }
+    if (p->kind == KIND_UNORDERED) {
+        // src/unordered.rs:714-720
+        std::vector<cplx> mono(p->n);
+        const double theta = -2.0 / double(p->n);
+        for (uint64_t i = 0; i < p->n; i++) {
+            double s, c;
+            sincospi64(theta * double(i), s, c);
+            mono[i] = cplx{c, s};
+        }
+        CU(cudaMalloc(reinterpret_cast<void **>(&p->d_monomial_tw), p->n * sizeof(cplx)));
+        CU(cudaMemcpy(p->d_monomial_tw, mono.data(), p->n * sizeof(cplx), cudaMemcpyHostToDevice));
+    }
+    return CFFT_OK;
+}
+
+cfft_status check_device(int device)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(CFFT_ECUDA, std::string("no CUDA device available (this library has no CPU fallback): ") +
+                                    cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(CFFT_EINVAL, "device index out of range");
+    return CFFT_OK;
+}
+
+// Method::Measure replacement: deterministic per-size choice (see DESIGN.md "plan selection").
+void measure_choice(uint64_t n, int *algo, uint64_t *base_n)
+{
+    // the reference keeps base_n = n for n <= 256 (src/unordered.rs:561-564) and otherwise
+    // picks base_n in {512, 1024}; radix-16 stages minimise the number of shared-memory
+    // exchanges on the device.
+    *algo = CFFT_DIF16;
+    if (n <= 256) *base_n = n;
+    else *base_n = (n >= 1024) ? 1024 : 512;
+}
+
+} // namespace
+
+namespace cfft {
+void count_launch(uint64_t k) { g_launches.fetch_add(k, std::memory_order_relaxed); }
+cfft_status set_last_error(cfft_status st, const std::string &msg) { return fail(st, msg); }
+} // namespace cfft
+
+extern "C" {
+
+const char *cfft_status_string(cfft_status st)
+{
+    switch (st) {
+    case CFFT_OK: return "ok";
+    case CFFT_EINVAL: return "invalid argument";
+    case CFFT_ECUDA: return "CUDA error";
+    case CFFT_ENOMEM: return "out of memory";
+    case CFFT_EUNSUPPORTED: return "unsupported";
+    case CFFT_ELENGTH: return "buffer length does not match the plan";
+    default: return "unknown status";
+    }
+}
+const char *cfft_last_error(void) { return g_last_error.c_str(); }
+uint64_t cfft_launch_count(void) { return g_launches.load(); }
+const char *cfft_version(void) { return "cfft_b200 0.1.0 sm_100a"; }
+
+cfft_status cfft_ordered_plan_create(cfft_plan **out, int device, uint64_t n, int method, int algo, int allow_large)
+{
+    if (!out) return fail(CFFT_EINVAL, "out is null");
+    *out = nullptr;
+    if (!is_pow2(n)) return fail(CFFT_EINVAL, "n must be a power of two (src/ordered.rs:243)");
+    if (ilog2(n) >= 11 && !allow_large) return fail(CFFT_EINVAL, "ordered plans need n <= 2^10 (src/ordered.rs:244)");
+    if (ilog2(n) >= 11) return fail(CFFT_EUNSUPPORTED, "ordered plans above 2^10 are not implemented yet");
+    if (method == CFFT_METHOD_MEASURE) algo = CFFT_DIF16;
+    else if (method != CFFT_METHOD_USER) return fail(CFFT_EINVAL, "unknown method");
+    if (algo < CFFT_DIF2 || algo > CFFT_DIT16) return fail(CFFT_EINVAL, "unknown FftAlgo");
+    cfft_status st = check_device(device);
+    if (st != CFFT_OK) return st;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
+
+    cfft_plan *p = new (std::nothrow) cfft_plan;
+    if (!p) return fail(CFFT_ENOMEM, "plan allocation failed");
+    p->kind = KIND_ORDERED;
+    p->device = device;
+    p->n = n;
+    p->algo = algo;
+    p->base_n = n;
+    p->method = method;
+    p->kernel_name = "exact-tile";
+    // src/ordered.rs:259-270: zero-initialised 2n tables, filled by init_wt
+    p->h_tw[0].assign(2 * n, cplx{0.0, 0.0});
+    p->h_tw[1].assign(2 * n, cplx{0.0, 0.0});
+    init_wt(size_t(algo_radix(algo)), n, p->h_tw[0].data(), p->h_tw[1].data());
+    // the ordered table is the unordered layout with zero levels: [base table (2n)]
+    StageProgram &f = p->prog[0], &v = p->prog[1];
+    f.count = v.count = 0;
+    append_base_stages(f, algo, n, uint32_t(n));
+    append_base_stages(v, algo, n, uint32_t(n));
+    st = upload_c64(p);
+    if (st != CFFT_OK) { cfft_plan_destroy(p); return st; }
+    *out = p;
+    return CFFT_OK;
+}
+
+cfft_status cfft_unordered_plan_create(cfft_plan **out, int device, uint64_t n, int method, int base_algo,
+                                       uint64_t base_n)
+{
+    if (!out) return fail(CFFT_EINVAL, "out is null");
+    *out = nullptr;
+    if (!is_pow2(n)) return fail(CFFT_EINVAL, "n must be a power of two (src/unordered.rs:660)");
+    if (n > (uint64_t{1} << 26)) return fail(CFFT_EINVAL, "n above 2^26 is not supported");
+    if (method == CFFT_METHOD_MEASURE) measure_choice(n, &base_algo, &base_n);
+    else if (method != CFFT_METHOD_USER) return fail(CFFT_EINVAL, "unknown method");
+    if (base_algo < CFFT_DIF2 || base_algo > CFFT_DIT16) return fail(CFFT_EINVAL, "unknown FftAlgo");
+    // src/unordered.rs:664-669
+    if (!is_pow2(base_n)) return fail(CFFT_EINVAL, "base_n must be a power of two");
+    if (base_n > n) return fail(CFFT_EINVAL, "base_n must be <= n");
+    if (base_n != n && base_n < 32) return fail(CFFT_EINVAL, "base_n must be >= 32 unless it equals n");
+    if (ilog2(base_n) > 10) return fail(CFFT_EINVAL, "base_n must be <= 1024");
+    cfft_status st = check_device(device);
+    if (st != CFFT_OK) return st;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
+
+    cfft_plan *p = new (std::nothrow) cfft_plan;
+    if (!p) return fail(CFFT_ENOMEM, "plan allocation failed");
+    p->kind = KIND_UNORDERED;
+    p->device = device;
+    p->n = n;
+    p->algo = base_algo;
+    p->base_n = base_n;
+    p->method = method;
+    p->kernel_name = "exact-tile";
+    init_unordered_twiddles(n, base_n, size_t(algo_radix(base_algo)), p->h_tw[0], p->h_tw[1]);
+    build_c64_programs(p);
+    st = upload_c64(p);
+    if (st != CFFT_OK) { cfft_plan_destroy(p); return st; }
+    *out = p;
+    return CFFT_OK;
+}
+
+cfft_status cfft_f128_plan_create(cfft_plan **out, int device, uint64_t n)
+{
+    if (!out) return fail(CFFT_EINVAL, "out is null");
+    *out = nullptr;
+    if (!is_pow2(n)) return fail(CFFT_EINVAL, "n must be a power of two (src/fft128/mod.rs:1865)");
+    if (n < 32) return fail(CFFT_EINVAL, "n must be >= 32 (src/fft128/mod.rs:1866)");
+    if (n > (uint64_t{1} << 26)) return fail(CFFT_EINVAL, "n above 2^26 is not supported");
+    cfft_status st = check_device(device);
+    if (st != CFFT_OK) return st;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
+
+    cfft_plan *p = new (std::nothrow) cfft_plan;
+    if (!p) return fail(CFFT_ENOMEM, "plan allocation failed");
+    p->kind = KIND_F128;
+    p->device = device;
+    p->n = n;
+    p->base_n = n;
+    p->kernel_name = "f128-radix8-tile";
+    for (int i = 0; i < 4; i++) p->h_f128_tw[i].assign(n, 0.0);
+    init_negacyclic_twiddles(n, p->h_f128_tw[0].data(), p->h_f128_tw[1].data(), p->h_f128_tw[2].data(),
+                             p->h_f128_tw[3].data());
+    for (int i = 0; i < 4; i++) {
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p->d_f128_tw[i]), n * sizeof(double));
+        if (e == cudaSuccess)
+            e = cudaMemcpy(p->d_f128_tw[i], p->h_f128_tw[i].data(), n * sizeof(double), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cfft_plan_destroy(p); return cuda_fail(e, "f128 twiddle upload"); }
+    }
+    *out = p;
+    return CFFT_OK;
+}
+
+void cfft_plan_destroy(cfft_plan *p)
+{
+    if (!p) return;
+    DeviceGuard guard(p->device);
+    for (int d = 0; d < 2; d++) if (p->d_tw[d]) cudaFree(p->d_tw[d]);
+    if (p->d_monomial_tw) cudaFree(p->d_monomial_tw);
+    for (int i = 0; i < 4; i++) if (p->d_f128_tw[i]) cudaFree(p->d_f128_tw[i]);
+    delete p;
+}
+
+cfft_status cfft_plan_clone(const cfft_plan *p, cfft_plan **out)
+{
+    if (!p || !out) return fail(CFFT_EINVAL, "null argument");
+    switch (p->kind) {
+    case KIND_ORDERED: return cfft_ordered_plan_create(out, p->device, p->n, CFFT_METHOD_USER, p->algo, p->allow_large);
+    case KIND_UNORDERED: return cfft_unordered_plan_create(out, p->device, p->n, CFFT_METHOD_USER, p->algo, p->base_n);
+    default: return cfft_f128_plan_create(out, p->device, p->n);
+    }
+}
+
+uint64_t cfft_plan_fft_size(const cfft_plan *p) { return p ? p->n : 0; }
+int cfft_plan_kind(const cfft_plan *p) { return p ? p->kind : -1; }
+int cfft_plan_device(const cfft_plan *p) { return p ? p->device : -1; }
+const char *cfft_plan_kernel_name(const cfft_plan *p) { return p ? p->kernel_name.c_str() : ""; }
+
+cfft_status cfft_plan_algo(const cfft_plan *p, int *algo, uint64_t *base_n)
+{
+    if (!p || p->kind == KIND_F128) return fail(CFFT_EINVAL, "not a c64 plan");
+    if (algo) *algo = p->algo;
+    if (base_n) *base_n = p->base_n;
+    return CFFT_OK;
+}
+
+cfft_status cfft_plan_scratch_req(const cfft_plan *p, uint64_t *bytes, uint64_t *align)
+{
+    if (!p) return fail(CFFT_EINVAL, "null plan");
+    // ordered: n c64 (src/ordered.rs:320-322); unordered: base_n c64 (src/unordered.rs:798-800);
+    // fft128 needs none.  CACHELINE_ALIGN of aligned-vec 0.5 is 128 on x86-64.
+    if (bytes) *bytes = (p->kind == KIND_F128) ? 0 : p->base_n * sizeof(cplx);
+    if (align) *align = 128;
+    return CFFT_OK;
+}
+
+cfft_status cfft_plan_copy_twiddles(const cfft_plan *p, int which, void *host_out, uint64_t bytes)
+{
+    if (!p || !host_out) return fail(CFFT_EINVAL, "null argument");
+    DeviceGuard guard(p->device);
+    if (p->kind == KIND_F128) {
+        if (which < 0 || which > 3 || bytes != p->n * sizeof(double)) return fail(CFFT_EINVAL, "bad table / size");
+        CU(cudaMemcpy(host_out, p->d_f128_tw[which], bytes, cudaMemcpyDeviceToHost));
+        return CFFT_OK;
+    }
+    if (which < 0 || which > 1 || bytes != p->h_tw[which].size() * sizeof(cplx)) return fail(CFFT_EINVAL, "bad table / size");
+    CU(cudaMemcpy(host_out, p->d_tw[which], bytes, cudaMemcpyDeviceToHost));
+    return CFFT_OK;
+}
+
+// ---- device entry points -----------------------------------------------------------------
+
+static cfft_status run_c64(const cfft_plan *p, bool inverse, void *dev_buf, uint64_t batch, void *stream)
+{
+    if (!p || p->kind == KIND_F128) return fail(CFFT_EINVAL, "not a c64 plan");
+    if (!dev_buf && batch) return fail(CFFT_EINVAL, "null buffer");
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
+    cudaError_t e = launch_c64_exact(p, inverse, static_cast<double2 *>(dev_buf), batch, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, inverse ? "c64 inv launch" : "c64 fwd launch");
+    return CFFT_OK;
+}
+
+cfft_status cfft_c64_fwd(const cfft_plan *p, void *dev_buf, uint64_t batch, void *stream)
+{
+    return run_c64(p, false, dev_buf, batch, stream);
+}
+cfft_status cfft_c64_inv(const cfft_plan *p, void *dev_buf, uint64_t batch, void *stream)
+{
+    return run_c64(p, true, dev_buf, batch, stream);
+}
+
+static cfft_status run_f128(const cfft_plan *p, bool inverse, double *re0, double *re1, double *im0, double *im1,
+                            uint64_t batch, void *stream)
+{
+    if (!p || p->kind != KIND_F128) return fail(CFFT_EINVAL, "not an fft128 plan");
+    if (batch && (!re0 || !re1 || !im0 || !im1)) return fail(CFFT_EINVAL, "null buffer");
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
+    cudaError_t e = launch_f128(p, inverse, re0, re1, im0, im1, batch, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, inverse ? "f128 inv launch" : "f128 fwd launch");
+    return CFFT_OK;
+}
+
+cfft_status cfft_f128_fwd(const cfft_plan *p, double *re0, double *re1, double *im0, double *im1, uint64_t batch,
+                          void *stream)
+{
+    return run_f128(p, false, re0, re1, im0, im1, batch, stream);
+}
+cfft_status cfft_f128_inv(const cfft_plan *p, double *re0, double *re1, double *im0, double *im1, uint64_t batch,
+                          void *stream)
+{
+    return run_f128(p, true, re0, re1, im0, im1, batch, stream);
+}
+
+cfft_status cfft_unordered_fwd_monomial(const cfft_plan *p, uint64_t degree, void *dev_buf, void *stream)
+{
+    if (!p || p->kind != KIND_UNORDERED) return fail(CFFT_EINVAL, "not an unordered plan");
+    if (degree >= p->n) return fail(CFFT_EINVAL, "degree must be < n (src/unordered.rs:859)");
+    if (!dev_buf) return fail(CFFT_EINVAL, "null buffer");
+    DeviceGuard guard(p->device);
+    cudaError_t e = launch_monomial(p, degree, static_cast<double2 *>(dev_buf), static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "fwd_monomial launch");
+    return CFFT_OK;
+}
+
+cfft_status cfft_unordered_permutation(const cfft_plan *p, uint64_t *out)
+{
+    if (!p || p->kind == KIND_F128 || !out) return fail(CFFT_EINVAL, "not a c64 plan / null out");
+    const unsigned nb = ilog2(p->n), bb = ilog2(p->base_n);
+    for (uint64_t i = 0; i < p->n; i++) out[i] = bit_rev_twice(nb, bb, i);
+    return CFFT_OK;
+}
+
+static cfft_status run_permute(const cfft_plan *p, bool to_std, const void *src, void *dst, uint64_t batch, void *stream)
+{
+    if (!p || p->kind == KIND_F128) return fail(CFFT_EINVAL, "not a c64 plan");
+    if (batch && (!src || !dst)) return fail(CFFT_EINVAL, "null buffer");
+    if (src == dst) return fail(CFFT_EINVAL, "src and dst must not overlap");
+    DeviceGuard guard(p->device);
+    cudaError_t e = launch_permute(p, to_std, static_cast<const double2 *>(src), static_cast<double2 *>(dst), batch,
+                                   static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "permute launch");
+    return CFFT_OK;
+}
+cfft_status cfft_unordered_to_standard(const cfft_plan *p, const void *src, void *dst, uint64_t batch, void *stream)
+{
+    return run_permute(p, true, src, dst, batch, stream);
+}
+cfft_status cfft_unordered_from_standard(const cfft_plan *p, const void *src, void *dst, uint64_t batch, void *stream)
+{
+    return run_permute(p, false, src, dst, batch, stream);
+}
+
+cfft_status cfft_unordered_to_standard_host(const cfft_plan *p, const void *src, void *dst)
+{
+    if (!p || p->kind == KIND_F128 || !src || !dst) return fail(CFFT_EINVAL, "bad argument");
+    const unsigned nb = ilog2(p->n), bb = ilog2(p->base_n);
+    const cplx *s = static_cast<const cplx *>(src);
+    cplx *d = static_cast<cplx *>(dst);
+    for (uint64_t i = 0; i < p->n; i++) d[i] = s[bit_rev_twice(nb, bb, i)]; // src/unordered.rs:967-969
+    return CFFT_OK;
+}
+cfft_status cfft_unordered_from_standard_host(const cfft_plan *p, const void *src, uint64_t count, void *dst)
+{
+    if (!p || p->kind == KIND_F128 || !src || !dst) return fail(CFFT_EINVAL, "bad argument");
+    const unsigned nb = ilog2(p->n), bb = ilog2(p->base_n);
+    const cplx *s = static_cast<const cplx *>(src);
+    cplx *d = static_cast<cplx *>(dst);
+    for (uint64_t i = 0; i < count && i < p->n; i++) d[bit_rev_twice(nb, bb, i)] = s[i]; // :1019-1022
+    if (count != p->n) return fail(CFFT_ELENGTH, "invalid length (src/unordered.rs:1027-1028)");
+    return CFFT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,341 @@
+// c64_tile.cu -- the "exact" c64 kernels: execute the reference's stage schedule for ANY
+// (base_algo, base_n) plan, butterfly for butterfly, so the output is bit-identical to
+// concrete-fft's for the same plan (and lands in the same permuted order).
+//
+//   c64_tile_kernel   one CTA owns a tile of <= 4096 contiguous c64 held in shared memory
+//                     (two ping-pong buffers) and runs every stage whose span fits the tile:
+//                     unordered levels  src/unordered.rs:222-293 (fwd_process_x*, inv_process_x*)
+//                     Stockham stages   src/dif{2,4,8,16}.rs / src/dit{2,4,8,16}.rs (_generic + _end)
+//   c64_global_stage  unordered levels whose span exceeds a tile (N >= 8192), one in-place pass
+//                     over HBM per level -- the reference recursion's top levels.
+//   monomial / permute kernels: src/unordered.rs:844-900 and :942-1036.
+//
+// HBM traffic of the tile kernel is the algorithmic minimum (read N, write N c64 per transform);
+// twiddles come from the plan's tables through L1/L2.
+#include "c64_math.cuh"
+#include "plan.h"
+
+namespace cfft {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ uint32_t brev_small(uint32_t k, int bits)
+{
+    return __brev(k) >> (32 - bits);
+}
+
+// ---- in-tile stages -------------------------------------------------------------------------
+
+// unordered level on blocks of n_cur elements, in place.
+// fwd: v = DFT_r(z[p + m k]); z[p + m bitrev(k)] = w_k v_k          src/unordered.rs:244-278
+// inv: v_k = w_k z[p + m bitrev(k)]; z[p + m k] = DFT_r^-1(v)_k     src/unordered.rs:254-293
+template <int R, bool FWD>
+__device__ __forceinline__ void stage_top(c64 *buf, uint32_t valid, uint32_t n_cur, const c64 *__restrict__ w)
+{
+    constexpr int RB = (R == 2) ? 1 : (R == 4 ? 2 : 3);
+    const uint32_t m = n_cur / R;
+    for (uint32_t b = threadIdx.x; b < valid / R; b += kThreads) {
+        const uint32_t blk = b / m, p = b - blk * m;
+        c64 *z = buf + blk * n_cur + p;
+        const c64 *wp = w + (R - 1) * p;
+        c64 v[R];
+        if (FWD) {
+#pragma unroll
+            for (int k = 0; k < R; k++) v[k] = z[m * k];
+            bfR<R, true>(v);
+            z[0] = v[0];
+#pragma unroll
+            for (int k = 1; k < R; k++) z[m * brev_small(k, RB)] = cmul(wp[k - 1], v[k]);
+        } else {
+            v[0] = z[0];
+#pragma unroll
+            for (int k = 1; k < R; k++) v[k] = cmul(wp[k - 1], z[m * brev_small(k, RB)]);
+            bfR<R, false>(v);
+#pragma unroll
+            for (int k = 0; k < R; k++) z[m * k] = v[k];
+        }
+    }
+}
+
+// Stockham DIF stage on blocks of base_n: x -> y.
+// y[q + s(R p + k)] = w[R p s + k] * DFT_R(x[q + s(p + m k)])_k
+template <int R, bool FWD>
+__device__ __forceinline__ void stage_core_dif(const c64 *x, c64 *y, uint32_t valid, uint32_t base_n, uint32_t s,
+                                               const c64 *__restrict__ w)
+{
+    const uint32_t per_blk = base_n / R, m = per_blk / s;
+    for (uint32_t b = threadIdx.x; b < valid / R; b += kThreads) {
+        const uint32_t blk = b / per_blk, rem = b - blk * per_blk;
+        const uint32_t p = rem / s, q = rem - p * s;
+        const c64 *xi = x + blk * base_n + q + s * p;
+        c64 *yo = y + blk * base_n + q + s * R * p;
+        const c64 *wp = w + R * p * s;
+        c64 v[R];
+#pragma unroll
+        for (int k = 0; k < R; k++) v[k] = xi[s * m * k];
+        bfR<R, FWD>(v);
+        yo[0] = v[0];
+#pragma unroll
+        for (int k = 1; k < R; k++) yo[s * k] = cmul(wp[k], v[k]);
+    }
+}
+
+// Stockham DIT stage on blocks of base_n: y -> x.
+// x[q + s(p + m k)] = DFT_R(w[R p s + k] * y[q + s(R p + k)])_k
+template <int R, bool FWD>
+__device__ __forceinline__ void stage_core_dit(const c64 *y, c64 *x, uint32_t valid, uint32_t base_n, uint32_t s,
+                                               const c64 *__restrict__ w)
+{
+    const uint32_t per_blk = base_n / R, m = per_blk / s;
+    for (uint32_t b = threadIdx.x; b < valid / R; b += kThreads) {
+        const uint32_t blk = b / per_blk, rem = b - blk * per_blk;
+        const uint32_t p = rem / s, q = rem - p * s;
+        const c64 *yi = y + blk * base_n + q + s * R * p;
+        c64 *xo = x + blk * base_n + q + s * p;
+        const c64 *wp = w + R * p * s;
+        c64 v[R];
+        v[0] = yi[0];
+#pragma unroll
+        for (int k = 1; k < R; k++) v[k] = cmul(wp[k], yi[s * k]);
+        bfR<R, FWD>(v);
+#pragma unroll
+        for (int k = 0; k < R; k++) xo[s * m * k] = v[k];
+    }
+}
+
+// terminal twiddle-free pass, in place
+template <int R, bool FWD>
+__device__ __forceinline__ void stage_end(c64 *buf, uint32_t valid, uint32_t base_n)
+{
+    const uint32_t part = base_n / R;
+    for (uint32_t b = threadIdx.x; b < valid / R; b += kThreads) {
+        const uint32_t blk = b / part, j = b - blk * part;
+        c64 *z = buf + blk * base_n + j;
+        c64 v[R];
+#pragma unroll
+        for (int k = 0; k < R; k++) v[k] = z[part * k];
+        bfR<R, FWD>(v);
+#pragma unroll
+        for (int k = 0; k < R; k++) z[part * k] = v[k];
+    }
+}
+
+template <bool FWD>
+__global__ void __launch_bounds__(kThreads)
+c64_tile_kernel(c64 *__restrict__ data, uint64_t total, uint32_t tile, uint32_t base_n, StageProgram prog,
+                const c64 *__restrict__ tw)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c64 *cur = reinterpret_cast<c64 *>(smem_raw);
+    c64 *oth = cur + tile;
+
+    const uint64_t start = uint64_t(blockIdx.x) * tile;
+    const uint32_t valid = (total - start < tile) ? uint32_t(total - start) : tile;
+    c64 *g = data + start;
+
+    for (uint32_t i = threadIdx.x; i < valid; i += kThreads) cur[i] = g[i];
+    __syncthreads();
+
+    for (int si = 0; si < prog.count; si++) {
+        const Stage st = prog.st[si];
+        const c64 *w = tw + st.tw_off;
+        if (st.kind == ST_TOP) {
+            if (st.radix == 8) stage_top<8, FWD>(cur, valid, st.span, w);
+            else if (st.radix == 4) stage_top<4, FWD>(cur, valid, st.span, w);
+            else stage_top<2, FWD>(cur, valid, st.span, w);
+        } else if (st.kind == ST_END) {
+            if (st.radix == 16) stage_end<16, FWD>(cur, valid, base_n);
+            else if (st.radix == 8) stage_end<8, FWD>(cur, valid, base_n);
+            else if (st.radix == 4) stage_end<4, FWD>(cur, valid, base_n);
+            else stage_end<2, FWD>(cur, valid, base_n);
+        } else {
+            if (st.kind == ST_CORE_DIF) {
+                if (st.radix == 16) stage_core_dif<16, FWD>(cur, oth, valid, base_n, st.span, w);
+                else if (st.radix == 8) stage_core_dif<8, FWD>(cur, oth, valid, base_n, st.span, w);
+                else if (st.radix == 4) stage_core_dif<4, FWD>(cur, oth, valid, base_n, st.span, w);
+                else stage_core_dif<2, FWD>(cur, oth, valid, base_n, st.span, w);
+            } else {
+                if (st.radix == 16) stage_core_dit<16, FWD>(cur, oth, valid, base_n, st.span, w);
+                else if (st.radix == 8) stage_core_dit<8, FWD>(cur, oth, valid, base_n, st.span, w);
+                else if (st.radix == 4) stage_core_dit<4, FWD>(cur, oth, valid, base_n, st.span, w);
+                else stage_core_dit<2, FWD>(cur, oth, valid, base_n, st.span, w);
+            }
+            c64 *t = cur; cur = oth; oth = t;
+        }
+        __syncthreads();
+    }
+
+    for (uint32_t i = threadIdx.x; i < valid; i += kThreads) g[i] = cur[i];
+}
+
+// ---- unordered level through HBM (span > tile) ----------------------------------------------
+template <int R, bool FWD>
+__global__ void __launch_bounds__(kThreads)
+c64_global_stage(c64 *__restrict__ data, uint64_t total, uint32_t n_cur, const c64 *__restrict__ w)
+{
+    constexpr int RB = (R == 2) ? 1 : (R == 4 ? 2 : 3);
+    const uint32_t m = n_cur / R;
+    const uint64_t nb = total / R;
+    for (uint64_t b = uint64_t(blockIdx.x) * kThreads + threadIdx.x; b < nb; b += uint64_t(gridDim.x) * kThreads) {
+        const uint64_t blk = b / m;
+        const uint32_t p = uint32_t(b - blk * m);
+        c64 *z = data + blk * n_cur + p;
+        const c64 *wp = w + (R - 1) * p;
+        c64 v[R];
+        if (FWD) {
+#pragma unroll
+            for (int k = 0; k < R; k++) v[k] = z[size_t(m) * k];
+            bfR<R, true>(v);
+            z[0] = v[0];
+#pragma unroll
+            for (int k = 1; k < R; k++) z[size_t(m) * brev_small(k, RB)] = cmul(wp[k - 1], v[k]);
+        } else {
+            v[0] = z[0];
+#pragma unroll
+            for (int k = 1; k < R; k++) v[k] = cmul(wp[k - 1], z[size_t(m) * brev_small(k, RB)]);
+            bfR<R, false>(v);
+#pragma unroll
+            for (int k = 0; k < R; k++) z[size_t(m) * k] = v[k];
+        }
+    }
+}
+
+// ---- fwd_monomial: buf[i] = tw[(idx(i) * degree) & (n - 1)]   src/unordered.rs:871-891 ---------
+__global__ void monomial_kernel(c64 *__restrict__ buf, const c64 *__restrict__ tw, uint32_t n, uint32_t nbits,
+                                uint32_t base_nbits, uint32_t degree)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // idx(i) = bit_rev_twice_inv(i) (src/unordered.rs:1054-1059); the n == base_n and
+    // n == 2 base_n special cases of :872-885 are this same map written out.
+    const uint32_t mask = (1u << base_nbits) - 1;
+    const uint32_t low = base_nbits ? (__brev(i & mask) >> (32 - base_nbits)) : 0;
+    const uint32_t t = (i & ~mask) | low;
+    const uint32_t idx = nbits ? (__brev(t) >> (32 - nbits)) : 0;
+    buf[i] = tw[(uint64_t(idx) * degree) & (n - 1)];
+}
+
+// ---- standard-order gather / scatter   src/unordered.rs:967-969, 1019-1022 --------------------
+template <bool TO_STANDARD>
+__global__ void permute_kernel(const c64 *__restrict__ src, c64 *__restrict__ dst, uint64_t total, uint32_t n,
+                               uint32_t nbits, uint32_t base_nbits)
+{
+    for (uint64_t e = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += uint64_t(gridDim.x) * blockDim.x) {
+        const uint64_t row = e / n;
+        const uint32_t i = uint32_t(e - row * n);
+        // bit_rev_twice(i), src/unordered.rs:1046-1051
+        const uint32_t irev = nbits ? (__brev(i) >> (32 - nbits)) : 0;
+        const uint32_t mask = (1u << base_nbits) - 1;
+        const uint32_t low = base_nbits ? (__brev(irev & mask) >> (32 - base_nbits)) : 0;
+        const uint32_t pos = (irev & ~mask) | low;
+        if (TO_STANDARD) dst[e] = src[row * n + pos];
+        else dst[row * n + pos] = src[e];
+    }
+}
+
+template <bool FWD>
+cudaError_t launch_global_stage(const Stage &st, c64 *data, uint64_t total, const c64 *tw, cudaStream_t stream)
+{
+    const uint64_t nb = total / st.radix;
+    uint64_t blocks = (nb + kThreads - 1) / kThreads;
+    if (blocks > 148ull * 16) blocks = 148ull * 16;
+    const dim3 grid(static_cast<unsigned>(blocks));
+    const c64 *w = tw + st.tw_off;
+    if (st.radix == 8) c64_global_stage<8, FWD><<<grid, kThreads, 0, stream>>>(data, total, st.span, w);
+    else if (st.radix == 4) c64_global_stage<4, FWD><<<grid, kThreads, 0, stream>>>(data, total, st.span, w);
+    else c64_global_stage<2, FWD><<<grid, kThreads, 0, stream>>>(data, total, st.span, w);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <bool FWD>
+cudaError_t launch_tile(const StageProgram &prog, c64 *data, uint64_t total, uint32_t tile, uint32_t base_n,
+                        const c64 *tw, cudaStream_t stream)
+{
+    const size_t smem = size_t(tile) * sizeof(c64) * 2;
+    static thread_local int configured_device = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured_device != dev) {
+        cudaError_t e = cudaFuncSetAttribute(c64_tile_kernel<FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             int(kTileMax * sizeof(c64) * 2));
+        if (e != cudaSuccess) return e;
+        configured_device = dev;
+    }
+    const uint64_t tiles = (total + tile - 1) / tile;
+    c64_tile_kernel<FWD><<<dim3(static_cast<unsigned>(tiles)), kThreads, smem, stream>>>(data, total, tile, base_n,
+                                                                                         prog, tw);
+    count_launch();
+    return cudaGetLastError();
+}
+
+} // namespace
+
+cudaError_t launch_c64_exact(const cfft_plan *plan, bool inverse, double2 *data, uint64_t batch, cudaStream_t stream)
+{
+    const uint64_t n = plan->n;
+    if (n <= 1 || batch == 0) return cudaSuccess; // src/ordered.rs:210-212: n == 1 is a no-op
+    const uint64_t total = n * batch;
+    const StageProgram &full = plan->prog[inverse ? 1 : 0];
+    const c64 *tw = plan->d_tw[inverse ? 1 : 0];
+
+    // tile = whole transforms when they fit, else a 4096-element sub-block of one transform
+    uint32_t tile;
+    if (n >= kTileMax) tile = kTileMax;
+    else {
+        uint64_t rows = 2048 / n;
+        if (rows < 1) rows = 1;
+        if (rows > batch) rows = batch;
+        tile = uint32_t(rows * n);
+    }
+
+    StageProgram in_tile;
+    in_tile.count = 0;
+    for (int i = 0; i < full.count; i++)
+        if (!(full.st[i].kind == ST_TOP && full.st[i].span > tile)) in_tile.st[in_tile.count++] = full.st[i];
+
+    cudaError_t e;
+    if (!inverse) {
+        for (int i = 0; i < full.count; i++)
+            if (full.st[i].kind == ST_TOP && full.st[i].span > tile)
+                if ((e = launch_global_stage<true>(full.st[i], data, total, tw, stream)) != cudaSuccess) return e;
+        return launch_tile<true>(in_tile, data, total, tile, uint32_t(plan->base_n), tw, stream);
+    }
+    if ((e = launch_tile<false>(in_tile, data, total, tile, uint32_t(plan->base_n), tw, stream)) != cudaSuccess)
+        return e;
+    for (int i = 0; i < full.count; i++)
+        if (full.st[i].kind == ST_TOP && full.st[i].span > tile)
+            if ((e = launch_global_stage<false>(full.st[i], data, total, tw, stream)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+cudaError_t launch_monomial(const cfft_plan *plan, uint64_t degree, double2 *data, cudaStream_t stream)
+{
+    const uint32_t n = uint32_t(plan->n);
+    const unsigned threads = 256, blocks = (n + threads - 1) / threads;
+    monomial_kernel<<<blocks, threads, 0, stream>>>(data, plan->d_monomial_tw, n, ilog2(n), ilog2(plan->base_n),
+                                                    uint32_t(degree));
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_permute(const cfft_plan *plan, bool to_standard, const double2 *src, double2 *dst, uint64_t batch,
+                           cudaStream_t stream)
+{
+    const uint64_t total = plan->n * batch;
+    if (total == 0) return cudaSuccess;
+    uint64_t blocks = (total + 255) / 256;
+    if (blocks > 148ull * 32) blocks = 148ull * 32;
+    const uint32_t nbits = ilog2(plan->n), bbits = ilog2(plan->base_n);
+    if (to_standard)
+        permute_kernel<true><<<unsigned(blocks), 256, 0, stream>>>(src, dst, total, uint32_t(plan->n), nbits, bbits);
+    else
+        permute_kernel<false><<<unsigned(blocks), 256, 0, stream>>>(src, dst, total, uint32_t(plan->n), nbits, bbits);
+    count_launch();
+    return cudaGetLastError();
+}
+
+} // namespace cfft

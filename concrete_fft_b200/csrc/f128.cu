@@ -1,0 +1,326 @@
+// f128.cu -- fft128: negacyclic radix-2 transform on double-double ("f128") complex data,
+// four planar f64 arrays (re hi, re lo, im hi, im lo), in place, bit-reversed Fourier order.
+//
+// Reference: src/fft128/mod.rs:352-402 (forward), :1105-1155 (inverse), complex multiply
+// :310-346, double-double ops src/fft128/f128_ops.rs:6-40, 302-307, 350-356 and the FMA
+// multiply :837-841 (the form the reference's AVX2 / AVX-512 paths execute on x86).
+// Every double op is an explicitly rounded intrinsic, in the reference's order, so the output
+// is bit-identical to the reference's AVX path.
+//
+// Work split: a thread owns G = 2^S elements (S <= 3 consecutive stages) at stride u and runs
+// those stages in registers: 94 FP64 instructions per butterfly, no memory traffic in between.
+// Passes exchange data through shared memory (one tile = <= 4096 elements = 128 KiB); the
+// first pass reads HBM and the last writes HBM, so a transform moves 2 x 32 B x n and is bound
+// by the FP64 pipe.  Stages whose span exceeds a tile (n > 4096) run as separate HBM passes.
+#include <cuda_runtime.h>
+
+#include "plan.h"
+
+namespace cfft {
+namespace {
+
+#define F128_DEV __device__ __forceinline__
+
+struct dd { double hi, lo; };
+
+F128_DEV dd quick_two_sum(double a, double b)
+{
+    double s = __dadd_rn(a, b);
+    return {s, __dsub_rn(b, __dsub_rn(s, a))};
+}
+F128_DEV dd two_sum(double a, double b)
+{
+    double s = __dadd_rn(a, b);
+    double bb = __dsub_rn(s, a);
+    return {s, __dadd_rn(__dsub_rn(a, __dsub_rn(s, bb)), __dsub_rn(b, bb))};
+}
+F128_DEV dd two_diff(double a, double b)
+{
+    double s = __dsub_rn(a, b);
+    double bb = __dsub_rn(s, a);
+    return {s, __dsub_rn(__dsub_rn(a, __dsub_rn(s, bb)), __dadd_rn(b, bb))};
+}
+// add_estimate_f128_f128, f128_ops.rs:302-307
+F128_DEV dd dd_add(dd a, dd b)
+{
+    dd s = two_sum(a.hi, b.hi);
+    double e = __dadd_rn(s.lo, __dadd_rn(a.lo, b.lo));
+    return quick_two_sum(s.hi, e);
+}
+// sub_estimate_f128_f128, f128_ops.rs:350-356
+F128_DEV dd dd_sub(dd a, dd b)
+{
+    dd s = two_diff(a.hi, b.hi);
+    double e = __dadd_rn(s.lo, a.lo);
+    e = __dsub_rn(e, b.lo);
+    return quick_two_sum(s.hi, e);
+}
+// mul_f128x4, f128_ops.rs:837-841
+F128_DEV dd dd_mul(dd a, dd b)
+{
+    double p = __dmul_rn(a.hi, b.hi);
+    double e = __fma_rn(a.hi, b.hi, -p);
+    e = __fma_rn(a.hi, b.lo, __fma_rn(a.lo, b.hi, e));
+    return quick_two_sum(p, e);
+}
+
+struct ddc { dd re, im; };
+
+// forward butterfly: z1w = z1 * w; (z0 + z1w, z0 - z1w)            mod.rs:386-395, 310-326
+F128_DEV void bfly_fwd(ddc &z0, ddc &z1, ddc w)
+{
+    dd rr = dd_mul(z1.re, w.re), ri = dd_mul(z1.re, w.im);
+    dd ir = dd_mul(z1.im, w.re), ii = dd_mul(z1.im, w.im);
+    dd zr = dd_sub(rr, ii), zi = dd_add(ir, ri);
+    ddc a = {dd_add(z0.re, zr), dd_add(z0.im, zi)};
+    ddc b = {dd_sub(z0.re, zr), dd_sub(z0.im, zi)};
+    z0 = a;
+    z1 = b;
+}
+// inverse butterfly: (z0 + z1, (z0 - z1) * conj(w))                mod.rs:1139-1148, 330-346
+F128_DEV void bfly_inv(ddc &z0, ddc &z1, ddc w)
+{
+    dd dr = dd_sub(z0.re, z1.re), di = dd_sub(z0.im, z1.im);
+    ddc a = {dd_add(z0.re, z1.re), dd_add(z0.im, z1.im)};
+    dd rr = dd_mul(dr, w.re), ri = dd_mul(dr, w.im);
+    dd ir = dd_mul(di, w.re), ii = dd_mul(di, w.im);
+    z0 = a;
+    z1 = {dd_add(rr, ii), dd_sub(ir, ri)};
+}
+
+struct Planes { double *p[4]; };
+struct CPlanes { const double *p[4]; };
+
+F128_DEV ddc load_tw(const CPlanes &tw, uint32_t i)
+{
+    return {{__ldg(tw.p[0] + i), __ldg(tw.p[1] + i)}, {__ldg(tw.p[2] + i), __ldg(tw.p[3] + i)}};
+}
+
+// Stages d0 .. d0+S-1 (t_d = n >> (d+1), m_d = 1 << d) on the G = 2^S elements
+// base + e*u, u = n >> (d0+S).  `row_pos` = position of element 0 inside its transform.
+template <int S, bool FWD>
+F128_DEV void run_group(ddc (&z)[1 << S], const CPlanes &tw, uint32_t row_pos, uint32_t logn, int d0)
+{
+    constexpr int G = 1 << S;
+    const uint32_t B = row_pos >> (logn - d0); // block index at stage d0
+    if (FWD) {
+#pragma unroll
+        for (int k = 0; k < S; k++) {
+            const int h = G >> (k + 1);
+            const uint32_t m = 1u << (d0 + k);
+#pragma unroll
+            for (int blk = 0; blk < (1 << k); blk++) {
+                const ddc w = load_tw(tw, m + (B << k) + blk);
+#pragma unroll
+                for (int j = 0; j < h; j++) bfly_fwd(z[blk * 2 * h + j], z[blk * 2 * h + j + h], w);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = S - 1; k >= 0; k--) {
+            const int h = G >> (k + 1);
+            const uint32_t m = 1u << (d0 + k);
+#pragma unroll
+            for (int blk = 0; blk < (1 << k); blk++) {
+                const ddc w = load_tw(tw, m + (B << k) + blk);
+#pragma unroll
+                for (int j = 0; j < h; j++) bfly_inv(z[blk * 2 * h + j], z[blk * 2 * h + j + h], w);
+            }
+        }
+    }
+}
+
+constexpr int kThreads = 256;
+
+// one pass over a tile; src / dst are either the HBM tile or the shared-memory tile
+template <int S, bool FWD>
+F128_DEV void tile_pass(const Planes &src, const Planes &dst, uint32_t tile, uint32_t tile_row_off, uint32_t n,
+                        uint32_t logn, int d0, const CPlanes &tw)
+{
+    constexpr int G = 1 << S;
+    const uint32_t u = n >> (d0 + S);
+    for (uint32_t g = threadIdx.x; g < tile / G; g += kThreads) {
+        const uint32_t hi = g / u, lo = g - hi * u;
+        const uint32_t base = hi * (G * u) + lo;
+        ddc z[G];
+#pragma unroll
+        for (int e = 0; e < G; e++) {
+            const uint32_t i = base + e * u;
+            z[e] = {{src.p[0][i], src.p[1][i]}, {src.p[2][i], src.p[3][i]}};
+        }
+        run_group<S, FWD>(z, tw, (tile_row_off + base) & (n - 1), logn, d0);
+#pragma unroll
+        for (int e = 0; e < G; e++) {
+            const uint32_t i = base + e * u;
+            dst.p[0][i] = z[e].re.hi;
+            dst.p[1][i] = z[e].re.lo;
+            dst.p[2][i] = z[e].im.hi;
+            dst.p[3][i] = z[e].im.lo;
+        }
+    }
+}
+
+struct PassList {
+    int count;
+    int d0[8];
+    int s[8];
+};
+
+template <bool FWD>
+__global__ void __launch_bounds__(kThreads, 2)
+f128_tile_kernel(Planes data, uint64_t total, uint32_t tile, uint32_t n, uint32_t logn, PassList passes, CPlanes tw)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sm = reinterpret_cast<double *>(smem_raw);
+    const uint64_t start = uint64_t(blockIdx.x) * tile;
+    const uint32_t valid = (total - start < tile) ? uint32_t(total - start) : tile;
+    const uint32_t row_off = uint32_t(start & (n - 1));
+
+    Planes g, s;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        g.p[i] = data.p[i] + start;
+        s.p[i] = sm + size_t(i) * tile;
+    }
+    for (int pi = 0; pi < passes.count; pi++) {
+        const Planes &src = (pi == 0) ? g : s;
+        const Planes &dst = (pi == passes.count - 1) ? g : s;
+        const int d0 = passes.d0[pi];
+        switch (passes.s[pi]) {
+        case 3: tile_pass<3, FWD>(src, dst, valid, row_off, n, logn, d0, tw); break;
+        case 2: tile_pass<2, FWD>(src, dst, valid, row_off, n, logn, d0, tw); break;
+        default: tile_pass<1, FWD>(src, dst, valid, row_off, n, logn, d0, tw); break;
+        }
+        __syncthreads();
+    }
+}
+
+// stages whose span exceeds a tile: one in-place pass through HBM
+template <int S, bool FWD>
+__global__ void __launch_bounds__(kThreads, 2)
+f128_global_pass(Planes data, uint64_t total, uint32_t n, uint32_t logn, int d0, CPlanes tw)
+{
+    constexpr int G = 1 << S;
+    const uint32_t u = n >> (d0 + S);
+    const uint64_t groups = total / G;
+    for (uint64_t g = uint64_t(blockIdx.x) * kThreads + threadIdx.x; g < groups; g += uint64_t(gridDim.x) * kThreads) {
+        const uint64_t hi = g / u;
+        const uint32_t lo = uint32_t(g - hi * u);
+        const uint64_t base = hi * (uint64_t(G) * u) + lo;
+        ddc z[G];
+#pragma unroll
+        for (int e = 0; e < G; e++) {
+            const uint64_t i = base + uint64_t(e) * u;
+            z[e] = {{data.p[0][i], data.p[1][i]}, {data.p[2][i], data.p[3][i]}};
+        }
+        run_group<S, FWD>(z, tw, uint32_t(base & (n - 1)), logn, d0);
+#pragma unroll
+        for (int e = 0; e < G; e++) {
+            const uint64_t i = base + uint64_t(e) * u;
+            data.p[0][i] = z[e].re.hi;
+            data.p[1][i] = z[e].re.lo;
+            data.p[2][i] = z[e].im.hi;
+            data.p[3][i] = z[e].im.lo;
+        }
+    }
+}
+
+template <bool FWD>
+cudaError_t launch_global(int S, Planes data, uint64_t total, uint32_t n, uint32_t logn, int d0, CPlanes tw,
+                          cudaStream_t stream)
+{
+    uint64_t blocks = (total / (1u << S) + kThreads - 1) / kThreads;
+    if (blocks > 148ull * 8) blocks = 148ull * 8;
+    const unsigned gsz = unsigned(blocks);
+    if (S == 3) f128_global_pass<3, FWD><<<gsz, kThreads, 0, stream>>>(data, total, n, logn, d0, tw);
+    else if (S == 2) f128_global_pass<2, FWD><<<gsz, kThreads, 0, stream>>>(data, total, n, logn, d0, tw);
+    else f128_global_pass<1, FWD><<<gsz, kThreads, 0, stream>>>(data, total, n, logn, d0, tw);
+    count_launch();
+    return cudaGetLastError();
+}
+
+constexpr uint32_t kF128TileMax = 4096; // 4 planes x 8 B x 4096 = 128 KiB of shared memory
+
+template <bool FWD>
+cudaError_t configure_tile_kernel()
+{
+    static thread_local int configured_device = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured_device == dev) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(f128_tile_kernel<FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         int(kF128TileMax * 4 * sizeof(double)));
+    if (e == cudaSuccess) configured_device = dev;
+    return e;
+}
+
+} // namespace
+
+cudaError_t launch_f128(const cfft_plan *plan, bool inverse, double *re0, double *re1, double *im0, double *im1,
+                        uint64_t batch, cudaStream_t stream)
+{
+    const uint32_t n = uint32_t(plan->n), logn = ilog2(plan->n);
+    if (batch == 0) return cudaSuccess;
+    const uint64_t total = uint64_t(n) * batch;
+    Planes data = {{re0, re1, im0, im1}};
+    CPlanes tw = {{plan->d_f128_tw[0], plan->d_f128_tw[1], plan->d_f128_tw[2], plan->d_f128_tw[3]}};
+
+    // tile: whole transforms (up to 2048 elements) or a 4096-element sub-block of one transform
+    uint32_t tile;
+    int D0 = 0; // stages d < D0 span more than a tile
+    if (n > kF128TileMax) {
+        tile = kF128TileMax;
+        D0 = int(logn - ilog2(kF128TileMax));
+    } else if (n >= 2048) {
+        tile = n;
+    } else {
+        uint64_t rows = 2048 / n;
+        if (rows > batch) rows = batch;
+        tile = uint32_t(rows * n);
+    }
+
+    // global passes for d in [0, D0), at most 3 stages each; tile passes for d in [D0, logn)
+    int gd0[8], gs[8], gcount = 0;
+    for (int d = 0; d < D0;) {
+        const int s = (D0 - d >= 3) ? 3 : (D0 - d);
+        gd0[gcount] = d;
+        gs[gcount++] = s;
+        d += s;
+    }
+    PassList passes;
+    passes.count = 0;
+    for (int d = D0; d < int(logn);) {
+        const int s = (int(logn) - d >= 3) ? 3 : (int(logn) - d);
+        passes.d0[passes.count] = d;
+        passes.s[passes.count++] = s;
+        d += s;
+    }
+    const size_t smem = size_t(tile) * 4 * sizeof(double);
+    const unsigned tiles = unsigned((total + tile - 1) / tile);
+    cudaError_t e;
+
+    if (!inverse) {
+        for (int i = 0; i < gcount; i++)
+            if ((e = launch_global<true>(gs[i], data, total, n, logn, gd0[i], tw, stream)) != cudaSuccess) return e;
+        if ((e = configure_tile_kernel<true>()) != cudaSuccess) return e;
+        f128_tile_kernel<true><<<tiles, kThreads, smem, stream>>>(data, total, tile, n, logn, passes, tw);
+        count_launch();
+        return cudaGetLastError();
+    }
+    // inverse: same passes in reverse order
+    PassList rev;
+    rev.count = passes.count;
+    for (int i = 0; i < passes.count; i++) {
+        rev.d0[i] = passes.d0[passes.count - 1 - i];
+        rev.s[i] = passes.s[passes.count - 1 - i];
+    }
+    if ((e = configure_tile_kernel<false>()) != cudaSuccess) return e;
+    f128_tile_kernel<false><<<tiles, kThreads, smem, stream>>>(data, total, tile, n, logn, rev, tw);
+    count_launch();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    for (int i = gcount - 1; i >= 0; i--)
+        if ((e = launch_global<false>(gs[i], data, total, n, logn, gd0[i], tw, stream)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+} // namespace cfft

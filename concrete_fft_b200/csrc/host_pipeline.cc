@@ -1,0 +1,280 @@
+// host_pipeline.cc -- the *_host entry points: host memory in, host memory out.
+//
+// This is the literal stand-in for the reference's Plan::fwd(&mut [c64], stack) /
+// Plan::inv / fft128 Plan::fwd / inv (one synchronous call on host slices), extended with a
+// batch count.  The batch is cut into chunks that flow through three slots, each with its own
+// stream and device buffer:  H2D(chunk i+1)  ||  kernels(chunk i)  ||  D2H(chunk i-1).
+// Pinned (or cudaHostRegister'ed) caller memory is DMA'd directly; pageable memory is staged
+// through internal pinned buffers.
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/cfft_b200.h"
+#include "plan.h"
+
+using namespace cfft;
+
+namespace {
+
+constexpr int kSlots = 3;
+constexpr size_t kChunkBytes = size_t(32) << 20;
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    void *dev = nullptr;
+    void *pinned = nullptr;
+    size_t dev_bytes = 0, pinned_bytes = 0;
+    // pending copy-out from the pinned staging buffer (pageable callers only)
+    bool pending = false;
+    size_t pend_row0 = 0, pend_rows = 0;
+};
+
+struct PipeCtx {
+    int device = -1;
+    Slot slot[kSlots];
+};
+
+std::mutex g_pool_mu;
+std::vector<PipeCtx *> g_pool;
+
+PipeCtx *acquire_ctx(int device)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        for (size_t i = 0; i < g_pool.size(); i++)
+            if (g_pool[i]->device == device) {
+                PipeCtx *c = g_pool[i];
+                g_pool.erase(g_pool.begin() + long(i));
+                return c;
+            }
+    }
+    PipeCtx *c = new PipeCtx;
+    c->device = device;
+    return c;
+}
+void release_ctx(PipeCtx *c)
+{
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_pool.push_back(c);
+}
+
+cudaError_t ensure_slot(Slot &s, size_t dev_bytes, size_t pinned_bytes)
+{
+    cudaError_t e;
+    if (!s.stream) {
+        if ((e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    if (s.dev_bytes < dev_bytes) {
+        if (s.dev) cudaFree(s.dev);
+        s.dev = nullptr;
+        s.dev_bytes = 0;
+        if ((e = cudaMalloc(&s.dev, dev_bytes)) != cudaSuccess) return e;
+        s.dev_bytes = dev_bytes;
+    }
+    if (s.pinned_bytes < pinned_bytes) {
+        if (s.pinned) cudaFreeHost(s.pinned);
+        s.pinned = nullptr;
+        s.pinned_bytes = 0;
+        if ((e = cudaHostAlloc(&s.pinned, pinned_bytes, cudaHostAllocDefault)) != cudaSuccess) return e;
+        s.pinned_bytes = pinned_bytes;
+    }
+    return cudaSuccess;
+}
+
+bool is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+thread_local std::string g_err;
+
+// planes: host base pointers; each plane holds batch rows of row_bytes.
+// op: 0 fwd, 1 inv, 2 fwd then inv
+cfft_status run_pipeline(const cfft_plan *plan, void *const *planes, int nplanes, size_t row_bytes, uint64_t batch,
+                         int op, std::string &err)
+{
+    if (batch == 0) return CFFT_OK;
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
+    if (prev_dev != plan->device && cudaSetDevice(plan->device) != cudaSuccess) {
+        err = "cudaSetDevice failed";
+        return CFFT_ECUDA;
+    }
+    bool pinned = true;
+    for (int i = 0; i < nplanes; i++) pinned = pinned && is_pinned(planes[i]);
+
+    size_t rows_per_chunk = kChunkBytes / (row_bytes * size_t(nplanes));
+    if (rows_per_chunk < 1) rows_per_chunk = 1;
+    if (rows_per_chunk > batch) rows_per_chunk = size_t(batch);
+    const size_t chunk_plane_bytes = rows_per_chunk * row_bytes;
+    const size_t chunk_bytes = chunk_plane_bytes * size_t(nplanes);
+
+    PipeCtx *ctx = acquire_ctx(plan->device);
+    cudaError_t e = cudaSuccess;
+    const char *what = "";
+    auto flush_pending = [&](Slot &s) {
+        if (!s.pending) return;
+        for (int pl = 0; pl < nplanes; pl++)
+            std::memcpy(static_cast<char *>(planes[pl]) + s.pend_row0 * row_bytes,
+                        static_cast<char *>(s.pinned) + size_t(pl) * chunk_plane_bytes, s.pend_rows * row_bytes);
+        s.pending = false;
+    };
+
+    const size_t nchunks = (size_t(batch) + rows_per_chunk - 1) / rows_per_chunk;
+    for (size_t c = 0; c < nchunks && e == cudaSuccess; c++) {
+        Slot &s = ctx->slot[c % kSlots];
+        what = "pipeline slot setup";
+        if ((e = ensure_slot(s, chunk_bytes, pinned ? 0 : chunk_bytes)) != cudaSuccess) break;
+        const size_t row0 = c * rows_per_chunk;
+        const size_t rows = (row0 + rows_per_chunk <= batch) ? rows_per_chunk : size_t(batch) - row0;
+        if (!pinned) {
+            // the slot's previous D2H must have landed before its staging buffer is reused
+            what = "pipeline event sync";
+            if (c >= kSlots && (e = cudaEventSynchronize(s.done)) != cudaSuccess) break;
+            flush_pending(s);
+            for (int pl = 0; pl < nplanes; pl++)
+                std::memcpy(static_cast<char *>(s.pinned) + size_t(pl) * chunk_plane_bytes,
+                            static_cast<char *>(planes[pl]) + row0 * row_bytes, rows * row_bytes);
+        }
+        what = "pipeline H2D";
+        for (int pl = 0; pl < nplanes && e == cudaSuccess; pl++) {
+            const void *src = pinned ? static_cast<char *>(planes[pl]) + row0 * row_bytes
+                                     : static_cast<char *>(s.pinned) + size_t(pl) * chunk_plane_bytes;
+            e = cudaMemcpyAsync(static_cast<char *>(s.dev) + size_t(pl) * chunk_plane_bytes, src, rows * row_bytes,
+                                cudaMemcpyHostToDevice, s.stream);
+        }
+        if (e != cudaSuccess) break;
+        what = "pipeline kernel launch";
+        char *d = static_cast<char *>(s.dev);
+        for (int pass = 0; pass < (op == 2 ? 2 : 1) && e == cudaSuccess; pass++) {
+            const bool inverse = (op == 1) || (op == 2 && pass == 1);
+            if (plan->kind == KIND_F128)
+                e = launch_f128(plan, inverse, reinterpret_cast<double *>(d),
+                                reinterpret_cast<double *>(d + chunk_plane_bytes),
+                                reinterpret_cast<double *>(d + 2 * chunk_plane_bytes),
+                                reinterpret_cast<double *>(d + 3 * chunk_plane_bytes), rows, s.stream);
+            else
+                e = launch_c64_exact(plan, inverse, reinterpret_cast<double2 *>(d), rows, s.stream);
+        }
+        if (e != cudaSuccess) break;
+        what = "pipeline D2H";
+        for (int pl = 0; pl < nplanes && e == cudaSuccess; pl++) {
+            void *dst = pinned ? static_cast<char *>(planes[pl]) + row0 * row_bytes
+                               : static_cast<char *>(s.pinned) + size_t(pl) * chunk_plane_bytes;
+            e = cudaMemcpyAsync(dst, d + size_t(pl) * chunk_plane_bytes, rows * row_bytes, cudaMemcpyDeviceToHost,
+                                s.stream);
+        }
+        if (e != cudaSuccess) break;
+        if (!pinned) {
+            s.pending = true;
+            s.pend_row0 = row0;
+            s.pend_rows = rows;
+        }
+        e = cudaEventRecord(s.done, s.stream);
+    }
+    // drain
+    for (int i = 0; i < kSlots; i++) {
+        Slot &s = ctx->slot[i];
+        if (!s.stream) continue;
+        cudaError_t e2 = cudaStreamSynchronize(s.stream);
+        if (e == cudaSuccess && e2 != cudaSuccess) {
+            e = e2;
+            what = "pipeline drain";
+        }
+        if (e == cudaSuccess) flush_pending(s);
+        s.pending = false;
+    }
+    release_ctx(ctx);
+    if (prev_dev >= 0 && prev_dev != plan->device) cudaSetDevice(prev_dev);
+    if (e != cudaSuccess) {
+        err = std::string(what) + ": " + cudaGetErrorString(e);
+        return CFFT_ECUDA;
+    }
+    return CFFT_OK;
+}
+
+} // namespace
+
+// defined in api.cc
+extern "C" const char *cfft_last_error(void);
+namespace cfft { cfft_status set_last_error(cfft_status st, const std::string &msg); }
+
+extern "C" {
+
+static cfft_status c64_host(const cfft_plan *p, void *host_buf, uint64_t len, uint64_t batch, int op)
+{
+    if (!p || p->kind == KIND_F128) return set_last_error(CFFT_EINVAL, "not a c64 plan");
+    if (len != batch * p->n) return set_last_error(CFFT_ELENGTH, "buffer length != batch * fft size (src/unordered.rs:827)");
+    if (!host_buf && len) return set_last_error(CFFT_EINVAL, "null buffer");
+    std::string err;
+    void *planes[1] = {host_buf};
+    cfft_status st = run_pipeline(p, planes, 1, size_t(p->n) * sizeof(cplx), batch, op, err);
+    return st == CFFT_OK ? st : set_last_error(st, err);
+}
+
+cfft_status cfft_c64_fwd_host(const cfft_plan *p, void *host_buf, uint64_t len, uint64_t batch)
+{
+    return c64_host(p, host_buf, len, batch, 0);
+}
+cfft_status cfft_c64_inv_host(const cfft_plan *p, void *host_buf, uint64_t len, uint64_t batch)
+{
+    return c64_host(p, host_buf, len, batch, 1);
+}
+cfft_status cfft_c64_fwd_inv_host(const cfft_plan *p, void *host_buf, uint64_t len, uint64_t batch)
+{
+    return c64_host(p, host_buf, len, batch, 2);
+}
+
+static cfft_status f128_host(const cfft_plan *p, double *re0, double *re1, double *im0, double *im1, uint64_t len,
+                             uint64_t batch, int op)
+{
+    if (!p || p->kind != KIND_F128) return set_last_error(CFFT_EINVAL, "not an fft128 plan");
+    if (len != batch * p->n) return set_last_error(CFFT_ELENGTH, "buffer length != batch * fft size (src/fft128/mod.rs:1912-1915)");
+    if (len && (!re0 || !re1 || !im0 || !im1)) return set_last_error(CFFT_EINVAL, "null buffer");
+    std::string err;
+    void *planes[4] = {re0, re1, im0, im1};
+    cfft_status st = run_pipeline(p, planes, 4, size_t(p->n) * sizeof(double), batch, op, err);
+    return st == CFFT_OK ? st : set_last_error(st, err);
+}
+
+cfft_status cfft_f128_fwd_host(const cfft_plan *p, double *re0, double *re1, double *im0, double *im1, uint64_t len,
+                               uint64_t batch)
+{
+    return f128_host(p, re0, re1, im0, im1, len, batch, 0);
+}
+cfft_status cfft_f128_inv_host(const cfft_plan *p, double *re0, double *re1, double *im0, double *im1, uint64_t len,
+                               uint64_t batch)
+{
+    return f128_host(p, re0, re1, im0, im1, len, batch, 1);
+}
+
+cfft_status cfft_unordered_fwd_monomial_host(const cfft_plan *p, uint64_t degree, void *host_buf, uint64_t len)
+{
+    if (!p || p->kind != KIND_UNORDERED) return set_last_error(CFFT_EINVAL, "not an unordered plan");
+    if (len != p->n) return set_last_error(CFFT_ELENGTH, "buffer length != fft size (src/unordered.rs:858)");
+    if (degree >= p->n) return set_last_error(CFFT_EINVAL, "degree must be < n (src/unordered.rs:859)");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != p->device) cudaSetDevice(p->device);
+    void *d = nullptr;
+    cudaError_t e = cudaMalloc(&d, p->n * sizeof(cplx));
+    if (e == cudaSuccess) e = launch_monomial(p, degree, static_cast<double2 *>(d), nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(host_buf, d, p->n * sizeof(cplx), cudaMemcpyDeviceToHost);
+    if (d) cudaFree(d);
+    if (prev >= 0 && prev != p->device) cudaSetDevice(prev);
+    if (e != cudaSuccess) return set_last_error(CFFT_ECUDA, std::string("fwd_monomial: ") + cudaGetErrorString(e));
+    return CFFT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,76 @@
+// plan.h -- the plan object behind the C ABI (include/cfft_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "tables.h"
+
+namespace cfft {
+
+enum PlanKind { KIND_ORDERED = 0, KIND_UNORDERED = 1, KIND_F128 = 2 };
+
+// One butterfly stage of the reference's schedule, in execution order.
+enum StageKind : int {
+    ST_TOP = 0,      // unordered in-place radix-2/4/8 level (src/unordered.rs:222-293); span = n_cur
+    ST_CORE_DIF = 1, // Stockham DIF stage, twiddles on outputs (e.g. src/dif4.rs:118-168); span = s
+    ST_CORE_DIT = 2, // Stockham DIT stage, twiddles on inputs  (e.g. src/dit4.rs:96-145);  span = s
+    ST_END = 3       // terminal twiddle-free pass (e.g. src/dif4.rs:217-244)
+};
+
+struct Stage {
+    int kind;
+    int radix;
+    uint32_t span;   // ST_TOP: n_cur; cores: stride s; END: unused
+    uint32_t tw_off; // offset (in c64) of this stage's twiddles inside the direction's table
+};
+
+constexpr int kMaxStages = 24;
+struct StageProgram {
+    int count;
+    Stage st[kMaxStages];
+};
+
+constexpr uint32_t kTileMax = 4096; // c64 per CTA tile in the exact kernel (2 x 64 KiB of smem)
+
+} // namespace cfft
+
+// Opaque to C callers.
+struct cfft_plan {
+    int kind = 0;
+    int device = 0;
+    uint64_t n = 0;
+    int algo = 0;        // ordered: algo; unordered: base_algo
+    uint64_t base_n = 0; // ordered: n
+    int method = 0;
+    bool allow_large = false;
+    std::string kernel_name;
+
+    // c64
+    std::vector<cfft::cplx> h_tw[2]; // [0] fwd, [1] inv (host copies, kept for clone / tests)
+    double2 *d_tw[2] = {nullptr, nullptr};
+    double2 *d_monomial_tw = nullptr; // n entries, e^{-2 pi i k / n} (src/unordered.rs:714-720)
+    cfft::StageProgram prog[2];       // [0] fwd, [1] inv: every stage in execution order
+    int fast_variant = 0;             // 0 = exact tile kernel only, else id of a specialised kernel
+
+    // fft128
+    std::vector<double> h_f128_tw[4];
+    double *d_f128_tw[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+namespace cfft {
+
+// kernels (c64_tile.cu)
+cudaError_t launch_c64_exact(const cfft_plan *plan, bool inverse, double2 *data, uint64_t batch, cudaStream_t st);
+cudaError_t launch_monomial(const cfft_plan *plan, uint64_t degree, double2 *data, cudaStream_t st);
+cudaError_t launch_permute(const cfft_plan *plan, bool to_standard, const double2 *src, double2 *dst,
+                           uint64_t batch, cudaStream_t st);
+// kernels (f128.cu)
+cudaError_t launch_f128(const cfft_plan *plan, bool inverse, double *re0, double *re1, double *im0, double *im1,
+                        uint64_t batch, cudaStream_t st);
+
+void count_launch(uint64_t k = 1);
+
+} // namespace cfft

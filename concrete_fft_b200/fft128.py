@@ -1,0 +1,83 @@
+"""Mirror of concrete_fft::fft128 (src/fft128/mod.rs): negacyclic transform on double-double
+complex data held in four planar f64 arrays (re hi, re lo, im hi, im lo)."""
+import ctypes
+
+from . import _native as N
+from ._buffers import current_stream_ptr, f64_view
+
+
+class f128:
+    """src/fft128/mod.rs:3-7: value = hi + lo."""
+
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, hi=0.0, lo=0.0):
+        self.hi, self.lo = float(hi), float(lo)
+
+    def __repr__(self):
+        return "f128(%r, %r)" % (self.hi, self.lo)
+
+
+class Plan:
+    """fft128::Plan, src/fft128/mod.rs:1832-1961."""
+
+    def __init__(self, n, device=0):
+        h = ctypes.c_void_p()
+        N.check(N.lib.cfft_f128_plan_create(ctypes.byref(h), device, n))
+        self._h = h
+
+    new = classmethod(lambda cls, n, **kw: cls(n, **kw))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            N.lib.cfft_plan_destroy(self._h)
+            self._h = None
+
+    def fft_size(self):
+        return int(N.lib.cfft_plan_fft_size(self._h))
+
+    def device(self):
+        return int(N.lib.cfft_plan_device(self._h))
+
+    def kernel_name(self):
+        return N.lib.cfft_plan_kernel_name(self._h).decode()
+
+    def __repr__(self):
+        return "Plan { fft_size: %d }" % self.fft_size()
+
+    def _run(self, planes, inverse):
+        n = self.fft_size()
+        views = [f64_view(p) for p in planes]
+        kinds = {v[0] for v in views}
+        if len(kinds) != 1:
+            raise TypeError("all four planes must live in the same memory space")
+        for v in views:  # four assert_eq!, src/fft128/mod.rs:1912-1915
+            if v[2] == 0 or v[2] % n or v[2] != views[0][2]:
+                raise N.PanicError("assertion failed: buf.len() == fft_size")
+        length, batch = views[0][2], views[0][2] // n
+        ptrs = [v[1] for v in views]
+        if "host" in kinds:
+            fn = N.lib.cfft_f128_inv_host if inverse else N.lib.cfft_f128_fwd_host
+            N.check(fn(self._h, *ptrs, length, batch))
+        else:
+            dev = views[0][3]
+            fn = N.lib.cfft_f128_inv if inverse else N.lib.cfft_f128_fwd
+            N.check(fn(self._h, *ptrs, batch, current_stream_ptr(dev)))
+
+    def fwd(self, buf_re0, buf_re1, buf_im0, buf_im1):
+        """src/fft128/mod.rs:1905-1928: standard order in, bit-reversed order out."""
+        self._run((buf_re0, buf_re1, buf_im0, buf_im1), False)
+
+    def inv(self, buf_re0, buf_re1, buf_im0, buf_im1):
+        """src/fft128/mod.rs:1938-1960: bit-reversed order in, standard order out, unnormalised."""
+        self._run((buf_re0, buf_re1, buf_im0, buf_im1), True)
+
+    def twiddles(self):
+        import numpy as np
+
+        out = []
+        for w in range(4):
+            a = np.empty(self.fft_size(), np.float64)
+            N.check(N.lib.cfft_plan_copy_twiddles(self._h, w, a.ctypes.data, a.nbytes))
+            out.append(a)
+        return out

@@ -1,0 +1,153 @@
+"""Mirror of concrete_fft::ordered (src/ordered.rs): standard-order forward / inverse FFT.
+
+    plan = Plan(n, Method.UserProvided(FftAlgo.Dif4))     # Plan::new, src/ordered.rs:242
+    plan.fwd(buf)                                          # Plan::fwd, src/ordered.rs:342
+
+`buf` is a numpy complex128 array (host memory, synchronous, like the Rust call) or a torch
+complex128 CUDA tensor (device memory, stream ordered).  A buffer of batch * n elements is
+treated as `batch` independent transforms.  Neither direction is normalised.
+"""
+import ctypes
+import enum
+
+from . import _native as N
+from ._buffers import c64_view, current_stream_ptr
+
+
+class FftAlgo(enum.IntEnum):
+    """src/ordered.rs:28-45"""
+    Dif2 = 0
+    Dit2 = 1
+    Dif4 = 2
+    Dit4 = 3
+    Dif8 = 4
+    Dit8 = 5
+    Dif16 = 6
+    Dit16 = 7
+
+
+class Method:
+    """src/ordered.rs:50-59"""
+
+    def __init__(self, kind, algo=None, duration=None):
+        self.kind, self.algo, self.duration = kind, algo, duration
+
+    @staticmethod
+    def UserProvided(algo):
+        return Method(N.METHOD_USER, FftAlgo(algo))
+
+    @staticmethod
+    def Measure(duration=None):
+        """The duration is accepted for source compatibility; selection happens on the device."""
+        return Method(N.METHOD_MEASURE, None, duration)
+
+    def __eq__(self, other):
+        return isinstance(other, Method) and (self.kind, self.algo) == (other.kind, other.algo)
+
+    def __repr__(self):
+        return "UserProvided(%s)" % self.algo.name if self.kind == N.METHOD_USER else "Measure(%r)" % (self.duration,)
+
+
+class StackReq:
+    """What Plan::fft_scratch returns in the reference (dyn_stack::StackReq): size + alignment."""
+
+    def __init__(self, size_bytes, align_bytes):
+        self.size_bytes, self.align_bytes = size_bytes, align_bytes
+
+    def __repr__(self):
+        return "StackReq(size_bytes=%d, align_bytes=%d)" % (self.size_bytes, self.align_bytes)
+
+
+class _PlanBase:
+    _h = None
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            N.lib.cfft_plan_destroy(self._h)
+            self._h = None
+
+    def fft_size(self):
+        return int(N.lib.cfft_plan_fft_size(self._h))
+
+    def kernel_name(self):
+        return N.lib.cfft_plan_kernel_name(self._h).decode()
+
+    def device(self):
+        return int(N.lib.cfft_plan_device(self._h))
+
+    def _algo(self):
+        a, b = ctypes.c_int(), ctypes.c_uint64()
+        N.check(N.lib.cfft_plan_algo(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return FftAlgo(a.value), int(b.value)
+
+    def fft_scratch(self):
+        size, align = ctypes.c_uint64(), ctypes.c_uint64()
+        N.check(N.lib.cfft_plan_scratch_req(self._h, ctypes.byref(size), ctypes.byref(align)))
+        return StackReq(int(size.value), int(align.value))
+
+    def _c64(self, buf, inverse):
+        n = self.fft_size()
+        kind, ptr, length, batch, dev = c64_view(buf, n)
+        if length == 0 or length % n != 0:
+            raise N.PanicError("assertion failed: buf.len() == fft_size (got %d, fft size %d)" % (length, n))
+        if kind == "host":
+            fn = N.lib.cfft_c64_inv_host if inverse else N.lib.cfft_c64_fwd_host
+            N.check(fn(self._h, ptr, length, batch))
+        else:
+            if dev != self.device():
+                raise ValueError("buffer is on cuda:%d but the plan lives on cuda:%d" % (dev, self.device()))
+            fn = N.lib.cfft_c64_inv if inverse else N.lib.cfft_c64_fwd
+            N.check(fn(self._h, ptr, batch, current_stream_ptr(dev)))
+
+    def fwd(self, buf, stack=None):
+        """In-place forward transform.  `stack` (the reference's PodStack scratch) is accepted and ignored."""
+        self._c64(buf, False)
+
+    def inv(self, buf, stack=None):
+        """In-place unnormalised inverse transform."""
+        self._c64(buf, True)
+
+    def fwd_inv_host(self, buf):
+        """fwd then inv on the device between one upload and one download (bench `e2e` step)."""
+        n = self.fft_size()
+        kind, ptr, length, batch, _ = c64_view(buf, n)
+        if kind != "host" or length % n:
+            raise N.PanicError("fwd_inv_host needs a host buffer of batch * n elements")
+        N.check(N.lib.cfft_c64_fwd_inv_host(self._h, ptr, length, batch))
+
+    def twiddles(self, inverse=False):
+        """Device twiddle table copied back to the host (tests)."""
+        import numpy as np
+
+        n = self.fft_size()
+        count = 2 * n if isinstance(self, Plan) else n + self._algo()[1]
+        out = np.empty(count, np.complex128)
+        N.check(N.lib.cfft_plan_copy_twiddles(self._h, int(inverse), out.ctypes.data, out.nbytes))
+        return out
+
+
+class Plan(_PlanBase):
+    """ordered::Plan, src/ordered.rs:187-374."""
+
+    def __init__(self, n, method, device=0, allow_large=False):
+        if not isinstance(method, Method):
+            raise TypeError("method must be an ordered.Method")
+        h = ctypes.c_void_p()
+        algo = int(method.algo) if method.algo is not None else 0
+        N.check(N.lib.cfft_ordered_plan_create(ctypes.byref(h), device, n, method.kind, algo, int(allow_large)))
+        self._h = h
+
+    new = classmethod(lambda cls, n, method, **kw: cls(n, method, **kw))
+
+    def algo(self):
+        return self._algo()[0]
+
+    def clone(self):
+        h = ctypes.c_void_p()
+        N.check(N.lib.cfft_plan_clone(self._h, ctypes.byref(h)))
+        p = object.__new__(Plan)
+        p._h = h
+        return p
+
+    def __repr__(self):
+        return "Plan { algo: %s, fft_size: %d }" % (self.algo().name, self.fft_size())

@@ -1,0 +1,181 @@
+/*
+ * cfft_b200.h -- C ABI of the B200-native batched FFT that replaces concrete-fft's
+ * transform hot path (zama-ai/concrete-fft v0.5.1).
+ *
+ * The reference has no FFI layer: its boundary is the Rust public API
+ * (ordered::Plan, unordered::Plan, fft128::Plan).  Each entry point below names the Rust
+ * item it stands in for (file:line under the reference tree); a thin Rust crate
+ * (rust/concrete-fft-b200) keeps those Rust signatures and forwards
+ * to these symbols.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only; `stream` is a cudaStream_t passed as void* (NULL =
+ *    the legacy default stream).
+ *  - Every function returns a cfft_status (0 = ok, < 0 = error) and never aborts; the Rust
+ *    shim turns a non-zero status into the panic the reference would raise.
+ *  - Plans are immutable after creation: fwd/inv may be called concurrently from many host
+ *    threads on one plan (the guarantee `&self` gives in the reference).
+ *  - Batched: `batch` independent transforms stored back to back (row stride = fft size).
+ *    The reference API is one polynomial per call, i.e. batch = 1.
+ *  - Transforms are unnormalised: inv(fwd(x)) = n * x (src/ordered.rs:7-11).
+ *  - c64 = { double re, im }, 16 bytes (src/lib.rs:84).
+ *  - There is no CPU fallback: every compute entry point needs a CUDA device and fails with
+ *    CFFT_ECUDA otherwise.
+ */
+#ifndef CFFT_B200_H
+#define CFFT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t cfft_status;
+enum {
+    CFFT_OK = 0,
+    CFFT_EINVAL = -1,       /* a precondition the reference asserts on was violated */
+    CFFT_ECUDA = -2,        /* CUDA runtime error, see cfft_last_error() */
+    CFFT_ENOMEM = -3,
+    CFFT_EUNSUPPORTED = -4, /* valid in the reference, not implemented here (none at present) */
+    CFFT_ELENGTH = -5       /* buffer length != fft size (assert_eq! at src/unordered.rs:827) */
+};
+
+/* ordered::FftAlgo, src/ordered.rs:28-45 (same discriminant order) */
+enum {
+    CFFT_DIF2 = 0, CFFT_DIT2, CFFT_DIF4, CFFT_DIT4, CFFT_DIF8, CFFT_DIT8, CFFT_DIF16, CFFT_DIT16
+};
+
+/* ordered::Method / unordered::Method, src/ordered.rs:50-59, src/unordered.rs:526-537 */
+enum {
+    CFFT_METHOD_USER = 0,   /* Method::UserProvided */
+    CFFT_METHOD_MEASURE = 1 /* Method::Measure(_): on-device autotune instead of CPU timing */
+};
+
+typedef struct cfft_plan cfft_plan;
+
+/* ---- plan lifetime ---------------------------------------------------------------- */
+
+/* ordered::Plan::new(n, method), src/ordered.rs:242-278.
+ * n must be a power of two.  The reference also asserts n <= 2^10 (src/ordered.rs:244);
+ * `allow_large` != 0 lifts that cap up to 2^20 (an extension: BASELINE.json config 3 asks
+ * for a standard-order N = 2^16 transform the reference cannot build). */
+cfft_status cfft_ordered_plan_create(cfft_plan **out, int device, uint64_t n, int method,
+                                     int algo, int allow_large);
+
+/* unordered::Plan::new(n, method), src/unordered.rs:659-747.
+ * USER: base_n power of two, <= n, <= 1024, >= 32 unless == n (src/unordered.rs:664-669).
+ * MEASURE: base_algo / base_n are ignored; the choice is made on the device and is a pure
+ * function of (n, device kind), never of a timing race across runs. */
+cfft_status cfft_unordered_plan_create(cfft_plan **out, int device, uint64_t n, int method,
+                                       int base_algo, uint64_t base_n);
+
+/* fft128::Plan::new(n), src/fft128/mod.rs:1864-1881: n power of two, >= 32. */
+cfft_status cfft_f128_plan_create(cfft_plan **out, int device, uint64_t n);
+
+/* Drop for the three Plan types. */
+void cfft_plan_destroy(cfft_plan *plan);
+
+/* Clone for the three Plan types (#[derive(Clone)], src/unordered.rs:495). */
+cfft_status cfft_plan_clone(const cfft_plan *plan, cfft_plan **out);
+
+/* ---- plan queries ----------------------------------------------------------------- */
+
+/* Plan::fft_size, src/ordered.rs:291-293, src/unordered.rs:760-762, src/fft128/mod.rs:1891-1893 */
+uint64_t cfft_plan_fft_size(const cfft_plan *plan);
+
+/* ordered::Plan::algo (src/ordered.rs:305-307) / unordered::Plan::algo (src/unordered.rs:783-785).
+ * For an ordered plan *base_n = n.  CFFT_EINVAL for an fft128 plan. */
+cfft_status cfft_plan_algo(const cfft_plan *plan, int *algo, uint64_t *base_n);
+
+/* Plan::fft_scratch, src/ordered.rs:320-322 (n c64), src/unordered.rs:798-800 (base_n c64).
+ * Size in bytes / alignment the reference's StackReq would carry.  The device path needs no
+ * caller scratch; the Rust shim reports this so that callers sizing a PodStack keep working. */
+cfft_status cfft_plan_scratch_req(const cfft_plan *plan, uint64_t *bytes, uint64_t *align);
+
+/* 0 = ordered, 1 = unordered, 2 = fft128 */
+int cfft_plan_kind(const cfft_plan *plan);
+int cfft_plan_device(const cfft_plan *plan);
+
+/* Which kernel family serves this plan: "exact-tile", "fast-..." (see DESIGN.md). */
+const char *cfft_plan_kernel_name(const cfft_plan *plan);
+
+/* ---- c64 transforms --------------------------------------------------------------- */
+
+/* {ordered,unordered}::Plan::fwd / inv on device memory, in place, stream ordered.
+ * src/ordered.rs:342-373, src/unordered.rs:826-839, 927-940.
+ * dev_buf: batch * n c64 on the plan's device.  Unordered: fwd output / inv input are in the
+ * plan's permuted order, index for index as the reference (src/unordered.rs:1046-1051). */
+cfft_status cfft_c64_fwd(const cfft_plan *plan, void *dev_buf, uint64_t batch, void *stream);
+cfft_status cfft_c64_inv(const cfft_plan *plan, void *dev_buf, uint64_t batch, void *stream);
+
+/* Same on HOST memory, synchronous: H2D, transform, D2H through an internal pinned, chunked,
+ * double-buffered pipeline.  This is the literal drop-in for Plan::fwd(&mut [c64], stack)
+ * (batch = 1) and the entry bench.py times as `e2e`.  `len` = number of c64 in host_buf and
+ * must equal batch * n (CFFT_ELENGTH otherwise: the assert_eq! of src/unordered.rs:827). */
+cfft_status cfft_c64_fwd_host(const cfft_plan *plan, void *host_buf, uint64_t len, uint64_t batch);
+cfft_status cfft_c64_inv_host(const cfft_plan *plan, void *host_buf, uint64_t len, uint64_t batch);
+/* fwd immediately followed by inv on the device between one H2D and one D2H (the
+ * BASELINE.json "fwd+inv" step); result = n * input. */
+cfft_status cfft_c64_fwd_inv_host(const cfft_plan *plan, void *host_buf, uint64_t len, uint64_t batch);
+
+/* unordered::Plan::fwd_monomial(degree, buf), src/unordered.rs:844-900: writes the permuted
+ * forward transform of X^degree.  degree < n (CFFT_EINVAL otherwise). */
+cfft_status cfft_unordered_fwd_monomial(const cfft_plan *plan, uint64_t degree, void *dev_buf,
+                                        void *stream);
+cfft_status cfft_unordered_fwd_monomial_host(const cfft_plan *plan, uint64_t degree,
+                                             void *host_buf, uint64_t len);
+
+/* ---- standard-order mapping (serde) ------------------------------------------------ */
+
+/* bit_rev_twice table: out[i] = position of Fourier coefficient i in the plan's buffer,
+ * src/unordered.rs:1046-1051.  `out` has n entries (host).  Identity for ordered plans. */
+cfft_status cfft_unordered_permutation(const cfft_plan *plan, uint64_t *out);
+
+/* Device gather / scatter behind serialize_fourier_buffer / deserialize_fourier_buffer,
+ * src/unordered.rs:951-1036: dst[b][i] = src[b][perm[i]]  /  dst[b][perm[i]] = src[b][i].
+ * src and dst must not overlap. */
+cfft_status cfft_unordered_to_standard(const cfft_plan *plan, const void *dev_src, void *dev_dst,
+                                       uint64_t batch, void *stream);
+cfft_status cfft_unordered_from_standard(const cfft_plan *plan, const void *dev_src, void *dev_dst,
+                                         uint64_t batch, void *stream);
+/* Host versions (the exact loops of src/unordered.rs:967-969 and :1019-1025 on host memory).
+ * from_standard returns CFFT_ELENGTH when count != n (serde invalid_length, :1027-1028). */
+cfft_status cfft_unordered_to_standard_host(const cfft_plan *plan, const void *src, void *dst);
+cfft_status cfft_unordered_from_standard_host(const cfft_plan *plan, const void *src,
+                                              uint64_t count, void *dst);
+
+/* ---- fft128 ------------------------------------------------------------------------ */
+
+/* fft128::Plan::fwd / inv, src/fft128/mod.rs:1905-1960.  Four planar arrays of batch * n
+ * doubles (re hi, re lo, im hi, im lo), in place.  Output of fwd / input of inv is in
+ * bit-reversed order exactly as the reference. */
+cfft_status cfft_f128_fwd(const cfft_plan *plan, double *re0, double *re1, double *im0,
+                          double *im1, uint64_t batch, void *stream);
+cfft_status cfft_f128_inv(const cfft_plan *plan, double *re0, double *re1, double *im0,
+                          double *im1, uint64_t batch, void *stream);
+/* host-memory versions; `len` = doubles per array, must equal batch * n */
+cfft_status cfft_f128_fwd_host(const cfft_plan *plan, double *re0, double *re1, double *im0,
+                               double *im1, uint64_t len, uint64_t batch);
+cfft_status cfft_f128_inv_host(const cfft_plan *plan, double *re0, double *re1, double *im0,
+                               double *im1, uint64_t len, uint64_t batch);
+
+/* ---- diagnostics ------------------------------------------------------------------- */
+
+const char *cfft_status_string(cfft_status st);
+/* thread-local text of the last failure on this thread ("" if none) */
+const char *cfft_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+uint64_t cfft_launch_count(void);
+/* "cfft_b200 <version> sm_100a" */
+const char *cfft_version(void);
+/* copy of a plan's device twiddle table to host (tests: table parity with the reference's
+ * init_wt / init_twiddles / init_negacyclic_twiddles).  which: c64 0 = fwd, 1 = inv table
+ * (n + base_n c64 each; 2n for ordered); fft128 0..3 = re0, re1, im0, im1 (n doubles). */
+cfft_status cfft_plan_copy_twiddles(const cfft_plan *plan, int which, void *host_out, uint64_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFFT_B200_H */

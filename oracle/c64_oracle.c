@@ -167,7 +167,7 @@ static inline void bf16(int fwd, oc64 *v)
     v[15] = cadd(E[7], u7);
 }
 
-static inline void bfR(int R, int fwd, oc64 *v)
+static inline __attribute__((always_inline)) void bfR(const int R, const int fwd, oc64 *v)
 {
     switch (R) {
     case 2: bf2(v); break;
@@ -253,7 +253,7 @@ void orc_init_wt(size_t r, size_t n, oc64 *w, oc64 *w_inv)
 
 /* DIF core, radix R, stride s: e.g. src/dif4.rs:118-168, src/dif16.rs:449-623.
  * reads x[q + s(p + m k)], writes y[q + s(R p + k)] = w[R p s + k] * DFT_R(x)_k */
-static void dif_core(int R, int fwd, size_t n, size_t s, const oc64 *x, oc64 *y, const oc64 *w)
+static inline __attribute__((always_inline)) void dif_core_impl(const int R, const int fwd, size_t n, size_t s, const oc64 *x, oc64 *y, const oc64 *w)
 {
     size_t m = n / ((size_t)R * s);
     for (size_t p = 0; p < m; p++) {
@@ -270,9 +270,17 @@ static void dif_core(int R, int fwd, size_t n, size_t s, const oc64 *x, oc64 *y,
     }
 }
 
+/* radix / direction become compile-time constants in each arm (speed only; same arithmetic) */
+static void dif_core(int R, int fwd, size_t n, size_t s, const oc64 *x, oc64 *y, const oc64 *w)
+{
+#define ARM(r) case r: if (fwd) dif_core_impl(r, 1, n, s, x, y, w); else dif_core_impl(r, 0, n, s, x, y, w); break
+    switch (R) { ARM(2); ARM(4); ARM(8); default: if (fwd) dif_core_impl(16, 1, n, s, x, y, w); else dif_core_impl(16, 0, n, s, x, y, w); break; }
+#undef ARM
+}
+
 /* DIT core, radix R, stride s: e.g. src/dit4.rs:96-145, src/dit16.rs:366-548.
  * reads y[q + s(R p + k)] * w[R p s + k], writes x[q + s(p + m k)] = DFT_R(.)_k */
-static void dit_core(int R, int fwd, size_t n, size_t s, oc64 *x, const oc64 *y, const oc64 *w)
+static inline __attribute__((always_inline)) void dit_core_impl(const int R, const int fwd, size_t n, size_t s, oc64 *x, const oc64 *y, const oc64 *w)
 {
     size_t m = n / ((size_t)R * s);
     for (size_t p = 0; p < m; p++) {
@@ -289,8 +297,16 @@ static void dit_core(int R, int fwd, size_t n, size_t s, oc64 *x, const oc64 *y,
     }
 }
 
+/* radix / direction become compile-time constants in each arm (speed only; same arithmetic) */
+static void dit_core(int R, int fwd, size_t n, size_t s, oc64 *x, const oc64 *y, const oc64 *w)
+{
+#define ARM(r) case r: if (fwd) dit_core_impl(r, 1, n, s, x, y, w); else dit_core_impl(r, 0, n, s, x, y, w); break
+    switch (R) { ARM(2); ARM(4); ARM(8); default: if (fwd) dit_core_impl(16, 1, n, s, x, y, w); else dit_core_impl(16, 0, n, s, x, y, w); break; }
+#undef ARM
+}
+
 /* terminal twiddle-free pass: e.g. src/dif4.rs:217-244; dst may alias src */
-static void end_stage(int R, int fwd, size_t n, const oc64 *src, oc64 *dst)
+static inline __attribute__((always_inline)) void end_stage_impl(const int R, const int fwd, size_t n, const oc64 *src, oc64 *dst)
 {
     size_t part = n / (size_t)R;
     for (size_t j = 0; j < part; j++) {
@@ -301,6 +317,14 @@ static void end_stage(int R, int fwd, size_t n, const oc64 *src, oc64 *dst)
         for (int k = 0; k < R; k++)
             dst[(size_t)k * part + j] = v[k];
     }
+}
+
+/* radix / direction become compile-time constants in each arm (speed only; same arithmetic) */
+static void end_stage(int R, int fwd, size_t n, const oc64 *src, oc64 *dst)
+{
+#define ARM(r) case r: if (fwd) end_stage_impl(r, 1, n, src, dst); else end_stage_impl(r, 0, n, src, dst); break
+    switch (R) { ARM(2); ARM(4); ARM(8); default: if (fwd) end_stage_impl(16, 1, n, src, dst); else end_stage_impl(16, 0, n, src, dst); break; }
+#undef ARM
 }
 
 static int algo_radix(int algo)
@@ -439,7 +463,7 @@ static size_t brev(unsigned nbits, size_t i)
 }
 
 /* src/unordered.rs:222-293 (fwd_process_x{2,4,8}) */
-static void fwd_top_stage(int r, size_t n, oc64 *z, const oc64 *w)
+static inline __attribute__((always_inline)) void fwd_top_stage_impl(const int r, size_t n, oc64 *z, const oc64 *w)
 {
     size_t m = n / (size_t)r;
     unsigned rb = ilog2((size_t)r);
@@ -455,8 +479,17 @@ static void fwd_top_stage(int r, size_t n, oc64 *z, const oc64 *w)
     }
 }
 
+static void fwd_top_stage(int r, size_t n, oc64 *z, const oc64 *w)
+{
+    switch (r) {
+    case 2: fwd_top_stage_impl(2, n, z, w); break;
+    case 4: fwd_top_stage_impl(4, n, z, w); break;
+    default: fwd_top_stage_impl(8, n, z, w); break;
+    }
+}
+
 /* src/unordered.rs:232-293 (inv_process_x{2,4,8}) */
-static void inv_top_stage(int r, size_t n, oc64 *z, const oc64 *w)
+static inline __attribute__((always_inline)) void inv_top_stage_impl(const int r, size_t n, oc64 *z, const oc64 *w)
 {
     size_t m = n / (size_t)r;
     unsigned rb = ilog2((size_t)r);
@@ -469,6 +502,15 @@ static void inv_top_stage(int r, size_t n, oc64 *z, const oc64 *w)
         bfR(r, 0, v);
         for (int k = 0; k < r; k++)
             z[p + m * (size_t)k] = v[k];
+    }
+}
+
+static void inv_top_stage(int r, size_t n, oc64 *z, const oc64 *w)
+{
+    switch (r) {
+    case 2: inv_top_stage_impl(2, n, z, w); break;
+    case 4: inv_top_stage_impl(4, n, z, w); break;
+    default: inv_top_stage_impl(8, n, z, w); break;
     }
 }
 

@@ -1,0 +1,82 @@
+"""CPU checks of the boundary: the shared library loads, exports every symbol the public header
+declares, and rejects what the reference panics on before touching CUDA."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "cfft_b200.h")
+
+
+@pytest.fixture(scope="module")
+def C():
+    lib = os.path.join(ROOT, "concrete_fft_b200", "libcfft_b200.so")
+    if not os.path.exists(lib):
+        import __graft_entry__ as g
+
+        g.build()
+    import concrete_fft_b200
+
+    return concrete_fft_b200
+
+
+def header_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cfft_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(C):
+    names = header_functions()
+    assert len(names) >= 30
+    lib = ctypes.CDLL(os.path.join(ROOT, "concrete_fft_b200", "libcfft_b200.so"))
+    for name in names:
+        assert hasattr(lib, name), "libcfft_b200.so does not export " + name
+    # and the Python binding covers the same set
+    assert sorted(C._native.EXPORTED_SYMBOLS) == names
+
+
+def test_no_oracle_in_product():
+    """The product must not include, link or call anything under oracle/."""
+    for base, _, files in os.walk(os.path.join(ROOT, "concrete_fft_b200")):
+        for f in files:
+            if f.endswith((".py", ".cc", ".cu", ".cuh", ".h", ".sh")):
+                text = open(os.path.join(base, f)).read()
+                assert "oracle" not in text.lower(), os.path.join(base, f)
+
+
+def test_argument_checks_match_reference_panics(C):
+    U, Od, F = C.unordered, C.ordered, C.fft128
+    A = Od.FftAlgo
+    with pytest.raises(C.PanicError):
+        Od.Plan(48, Od.Method.UserProvided(A.Dif4))  # not a power of two, src/ordered.rs:243
+    with pytest.raises(C.PanicError):
+        Od.Plan(2048, Od.Method.UserProvided(A.Dif4))  # > 2^10, src/ordered.rs:244
+    for n, algo, base_n in [(2048, A.Dif4, 16), (2048, A.Dif4, 2048), (64, A.Dif4, 128), (100, A.Dif4, 32), (64, A.Dif4, 48)]:
+        with pytest.raises(C.PanicError):
+            U.Plan(n, U.Method.UserProvided(algo, base_n))  # src/unordered.rs:660-669
+    for n in [16, 48, 0]:
+        with pytest.raises(C.PanicError):
+            F.Plan(n)  # src/fft128/mod.rs:1865-1866
+
+
+def test_no_cpu_fallback(C):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    with pytest.raises(C.CfftError) as e:
+        C.unordered.Plan(1024, C.unordered.Method.UserProvided(C.ordered.FftAlgo.Dif4, 32))
+    assert e.value.status == C._native.ECUDA
+
+
+def test_method_and_enum_surface(C):
+    A = C.ordered.FftAlgo
+    assert [a.name for a in A] == ["Dif2", "Dit2", "Dif4", "Dit4", "Dif8", "Dit8", "Dif16", "Dit16"]
+    assert C.ordered.Method.UserProvided(A.Dif4) == C.ordered.Method.UserProvided(A.Dif4)
+    assert C.ordered.Method.UserProvided(A.Dif4) != C.ordered.Method.UserProvided(A.Dit4)
+    m = C.unordered.Method.UserProvided(A.Dif16, 256)
+    assert (m.base_algo, m.base_n) == (A.Dif16, 256)
+    assert "cfft_b200" in C.version()

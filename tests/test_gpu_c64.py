@@ -1,0 +1,294 @@
+"""GPU parity tests for the c64 path, through the C ABI (via the Python mirror of the Rust API).
+
+Bar: BIT-EXACT against the oracle (= the reference's result for the same plan), which is far
+inside the stated tolerance (relative L2 <= 1e-13 * log2 N); the tolerance is asserted as well
+against an independent FFT (numpy / pocketfft) so both statements are on record.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def C():
+    import concrete_fft_b200
+
+    return concrete_fft_b200
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+
+    return torch
+
+
+def rand_c(rng, *shape):
+    return rng.random(shape) + 1j * rng.random(shape)
+
+
+def bits_equal(a, b):
+    return np.array_equal(np.ascontiguousarray(a).view(np.uint64), np.ascontiguousarray(b).view(np.uint64))
+
+
+def dev_run(torch, fn, x):
+    d = torch.from_numpy(np.ascontiguousarray(x).copy()).cuda()
+    fn(d)
+    torch.cuda.synchronize()
+    return d.cpu().numpy()
+
+
+def test_golden_vector_bit_exact_on_gpu(C, torch):
+    """src/unordered.rs:1176-9396 (test_equivalency) executed by the CUDA path."""
+    x = np.fromfile(os.path.join(GOLD, "unordered_n2048_dif4_b32_input.f64"), dtype=np.complex128)
+    t = np.fromfile(os.path.join(GOLD, "unordered_n2048_dif4_b32_target.f64"), dtype=np.complex128)
+    plan = C.unordered.Plan(2048, C.unordered.Method.UserProvided(C.ordered.FftAlgo.Dif4, 32))
+    assert plan.algo() == (C.ordered.FftAlgo.Dif4, 32)
+    assert bits_equal(dev_run(torch, plan.fwd, x), t)
+    h = x.copy()
+    plan.fwd(h)  # host-memory entry point (the literal Plan::fwd(&mut [c64]) drop-in)
+    assert bits_equal(h, t)
+    plan.inv(h)
+    assert np.abs(h / 2048 - x).max() < 1e-12
+
+
+@pytest.mark.parametrize("algo", range(8))
+def test_ordered_all_algos_bit_exact(C, torch, algo):
+    """src/ordered.rs:389-467: all 8 algorithms, n = 2 .. 1024, fwd and inv."""
+    rng = np.random.default_rng(200 + algo)
+    for k in range(0, 11):
+        n = 1 << k
+        x = rand_c(rng, 3, n)
+        plan = C.ordered.Plan(n, C.ordered.Method.UserProvided(C.ordered.FftAlgo(algo)))
+        assert plan.fft_size() == n and plan.algo() == C.ordered.FftAlgo(algo)
+        assert plan.fft_scratch().size_bytes == 16 * n
+        if n == 1:
+            assert bits_equal(dev_run(torch, plan.fwd, x), x)
+            continue
+        ref = O.OrderedPlan(n, algo)
+        y = dev_run(torch, plan.fwd, x)
+        assert bits_equal(y, ref.fwd(x)), (algo, n)
+        assert np.abs(y - np.fft.fft(x, axis=1)).max() < 1e-12
+        assert bits_equal(dev_run(torch, plan.inv, y), ref.inv(y)), (algo, n)
+        # twiddle tables are the reference's init_wt tables, bit for bit (NaN slots included)
+        tw = np.zeros((2, 2 * n), np.complex128)
+        if n >= (2 << (algo >> 1)):
+            O.lib().orc_init_wt(2 << (algo >> 1), n, tw[0].ctypes.data, tw[1].ctypes.data)
+        assert bits_equal(plan.twiddles(False), tw[0]) and bits_equal(plan.twiddles(True), tw[1])
+
+
+@pytest.mark.parametrize("algo", range(8))
+def test_unordered_plans_bit_exact(C, torch, algo):
+    """Every (base_algo, base_n) the reference accepts, n = 32 .. 2^14: same bits, same order."""
+    rng = np.random.default_rng(300 + algo)
+    A = C.ordered.FftAlgo
+    for k in range(5, 15):
+        n = 1 << k
+        for bk in sorted({5, 6, 8, 9, 10, k} & set(range(5, min(k, 10) + 1))):
+            base_n = 1 << bk
+            x = rand_c(rng, 2, n)
+            plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(A(algo), base_n))
+            ref = O.UnorderedPlan(n, algo, base_n)
+            y = dev_run(torch, plan.fwd, x)
+            want = ref.fwd(x)
+            assert bits_equal(y, want), (algo, n, base_n)
+            z = dev_run(torch, plan.inv, y)
+            assert bits_equal(z, ref.inv(want)), (algo, n, base_n)
+            # stated tolerance vs an independent FFT through the permutation
+            pi = plan.permutation().astype(np.int64)
+            assert np.array_equal(pi, O.permutation(n, base_n))
+            f = np.fft.fft(x, axis=1)
+            rel = np.linalg.norm(y[:, pi] - f, axis=1) / np.linalg.norm(f, axis=1)
+            assert rel.max() <= 1e-13 * k
+            assert plan.fft_scratch().size_bytes == 16 * base_n
+            if k in (5, 11) and bk == 5:
+                assert bits_equal(plan.twiddles(False), ref.twiddles(False))
+                assert bits_equal(plan.twiddles(True), ref.twiddles(True))
+
+
+def test_unordered_small_sizes_base_equals_n(C, torch):
+    rng = np.random.default_rng(4)
+    for n in [1, 2, 4, 8, 16]:
+        x = rand_c(rng, 5, n)
+        plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(C.ordered.FftAlgo.Dif4, n))
+        y = dev_run(torch, plan.fwd, x)
+        if n > 1:
+            assert bits_equal(y, O.UnorderedPlan(n, O.DIF4, n).fwd(x))
+        assert np.abs(y - np.fft.fft(x, axis=1)).max() < 1e-13
+
+
+def test_large_n_multi_pass(C, torch):
+    """N = 2^16 and 2^17 (levels above one tile run as HBM passes): bit-exact, correct order."""
+    rng = np.random.default_rng(5)
+    for n, base_n, algo in [(1 << 16, 1024, O.DIF16), (1 << 16, 512, O.DIT8), (1 << 17, 32, O.DIF4)]:
+        x = rand_c(rng, 2, n)
+        plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(C.ordered.FftAlgo(algo), base_n))
+        ref = O.UnorderedPlan(n, algo, base_n)
+        y = dev_run(torch, plan.fwd, x)
+        want = ref.fwd(x)
+        assert bits_equal(y, want)
+        assert bits_equal(dev_run(torch, plan.inv, y), ref.inv(want))
+
+
+def test_measure_method_is_deterministic_and_valid(C, torch):
+    rng = np.random.default_rng(6)
+    for n in [64, 256, 512, 2048, 8192]:
+        p1 = C.unordered.Plan(n, C.unordered.Method.Measure())
+        p2 = C.unordered.Plan(n, C.unordered.Method.Measure())
+        assert p1.algo() == p2.algo()
+        algo, base_n = p1.algo()
+        if n <= 256:
+            assert base_n == n  # src/unordered.rs:561-564
+        else:
+            assert base_n in (512, 1024) and base_n <= n  # src/unordered.rs:568
+        x = rand_c(rng, 2, n)
+        assert bits_equal(dev_run(torch, p1.fwd, x), O.UnorderedPlan(n, int(algo), base_n).fwd(x))
+
+
+def test_fwd_monomial(C, torch):
+    """src/unordered.rs:1108-1137, plus bit-exactness against the oracle's table lookup."""
+    rng = np.random.default_rng(7)
+    for n in [256, 512, 1024]:
+        for base_n in [32, n, n // 2, n // 4, n // 8]:
+            plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(C.ordered.FftAlgo.Dif4, base_n))
+            ref = O.UnorderedPlan(n, O.DIF4, base_n)
+            for _ in range(3):
+                d = int(rng.integers(0, n))
+                buf = torch.zeros(n, dtype=torch.complex128, device="cuda")
+                plan.fwd_monomial(d, buf)
+                torch.cuda.synchronize()
+                got = buf.cpu().numpy()
+                assert bits_equal(got, ref.fwd_monomial(d))
+                z = np.zeros(n, np.complex128)
+                z[d] = 1.0
+                plan.fwd(z)
+                assert np.abs(got - z).max() < 1e-12
+                h = np.zeros(n, np.complex128)
+                plan.fwd_monomial(d, h)
+                assert bits_equal(h, got)
+    with pytest.raises(C.PanicError):
+        plan.fwd_monomial(n, np.zeros(n, np.complex128))  # degree < n, src/unordered.rs:859
+
+
+def test_serde_standard_order_mapping(C, torch):
+    """src/unordered.rs:9399-9467: plan1 (base 32) -> standard order -> plan2 (base 64) -> inv."""
+    rng = np.random.default_rng(8)
+    A = C.ordered.FftAlgo
+    for n in [64, 128, 256, 512, 1024]:
+        x = rand_c(rng, n)
+        p1 = C.unordered.Plan(n, C.unordered.Method.UserProvided(A.Dif4, 32))
+        p2 = C.unordered.Plan(n, C.unordered.Method.UserProvided(A.Dif4, 64))
+        f = x.copy()
+        p1.fwd(f)
+        blob = p1.serialize_bincode(f)
+        assert len(blob) == 8 + 16 * n
+        g = np.zeros(n, np.complex128)
+        p2.deserialize_bincode(blob, g)
+        p2.inv(g)
+        assert np.abs(g / n - x).max() < 1e-12
+        # device gather / scatter agree with the host loops
+        fd = torch.from_numpy(f).cuda()
+        std = p1.serialize_fourier_buffer(fd)
+        assert bits_equal(std.cpu().numpy(), p1.serialize_fourier_buffer(f))
+        back = torch.zeros_like(fd)
+        p1.deserialize_fourier_buffer(std, back)
+        torch.cuda.synchronize()
+        assert bits_equal(back.cpu().numpy(), f)
+        with pytest.raises(C.InvalidLength):
+            p2.deserialize_fourier_buffer(np.zeros(n - 1, np.complex128), g)
+        with pytest.raises(C.InvalidLength):
+            p2.deserialize_fourier_buffer(np.zeros(n + 1, np.complex128), g)
+
+
+def test_length_mismatch_panics(C, torch):
+    plan = C.unordered.Plan(256, C.unordered.Method.UserProvided(C.ordered.FftAlgo.Dif4, 32))
+    with pytest.raises(C.PanicError):
+        plan.fwd(np.zeros(255, np.complex128))  # assert_eq!, src/unordered.rs:827
+    with pytest.raises(C.PanicError):
+        plan.inv(torch.zeros(300, dtype=torch.complex128, device="cuda"))
+    with pytest.raises(C.PanicError):
+        plan.fwd(np.zeros(0, np.complex128))
+
+
+def test_host_pipeline_pinned_and_pageable_ragged_batches(C, torch):
+    """The host entry chunks the batch through three slots; sizes that do not divide a chunk,
+    pageable and pinned memory must all give the oracle's bits."""
+    rng = np.random.default_rng(9)
+    n = 2048
+    plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(C.ordered.FftAlgo.Dif16, 256))
+    ref = O.UnorderedPlan(n, O.DIF16, 256)
+    for batch in [1, 3, 1024 + 7, 3 * 1024 + 1]:
+        x = rand_c(rng, batch, n)
+        want = ref.fwd(x, threads=8)
+        pageable = x.copy()
+        plan.fwd(pageable)
+        assert bits_equal(pageable, want)
+        pinned = torch.from_numpy(x.copy()).pin_memory()
+        plan.fwd(pinned.numpy())
+        assert bits_equal(pinned.numpy(), want)
+        plan.inv(pinned.numpy())
+        assert bits_equal(pinned.numpy(), ref.inv(want, threads=8))
+        both = x.copy()
+        plan.fwd_inv_host(both)
+        assert bits_equal(both, pinned.numpy())
+
+
+def test_clone_and_concurrent_streams(C, torch):
+    rng = np.random.default_rng(10)
+    n = 1024
+    plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(C.ordered.FftAlgo.Dit4, 64))
+    twin = plan.clone()
+    assert twin.algo() == plan.algo() and twin.fft_size() == n
+    x = rand_c(rng, 64, n)
+    want = O.UnorderedPlan(n, O.DIT4, 64).fwd(x)
+    streams = [torch.cuda.Stream() for _ in range(4)]
+    bufs = [torch.from_numpy(x.copy()).cuda() for _ in streams]
+    torch.cuda.synchronize()
+    for s, b in zip(streams, bufs):
+        with torch.cuda.stream(s):
+            (plan if s is streams[0] else twin).fwd(b)
+    torch.cuda.synchronize()
+    for b in bufs:
+        assert bits_equal(b.cpu().numpy(), want)
+
+
+def test_full_size_properties_n2048_batch65536(C, torch):
+    """BASELINE config 2 at full size (2 GiB on the device): size-independent properties --
+    round trip, linearity, Parseval -- plus bit-exactness of sampled rows against the oracle."""
+    n, batch = 2048, 65536
+    plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(C.ordered.FftAlgo.Dif16, 256))
+    g = torch.Generator(device="cuda").manual_seed(0x5EED0000)
+    x = torch.rand(batch, n, 2, dtype=torch.float64, device="cuda", generator=g)
+    x = torch.view_as_complex(x).contiguous()
+    # row 0 = the reference's golden-vector input
+    gold = np.fromfile(os.path.join(GOLD, "unordered_n2048_dif4_b32_input.f64"), dtype=np.complex128)
+    x[0] = torch.from_numpy(gold).cuda()
+    y = x.clone()
+    plan.fwd(y)
+    rows = [0, 1, 777, 32768, 65535]
+    ref = O.UnorderedPlan(n, O.DIF16, 256)
+    xs = x[rows].cpu().numpy()
+    assert bits_equal(y[rows].cpu().numpy(), ref.fwd(xs))
+    # Parseval: sum |X|^2 = n sum |x|^2, per row
+    ex = (x.real ** 2 + x.imag ** 2).sum(1)
+    ey = (y.real ** 2 + y.imag ** 2).sum(1)
+    assert float(((ey - n * ex).abs() / (n * ex)).max()) < 1e-13
+    # linearity on a slice: F(a x0 + x1) = a F(x0) + F(x1)
+    a = 0.75
+    lin = (a * x[:1024] + x[1024:2048]).contiguous()
+    plan.fwd(lin)
+    want = a * y[:1024] + y[1024:2048]
+    rel = (lin - want).abs().pow(2).sum(1).sqrt() / want.abs().pow(2).sum(1).sqrt()
+    assert float(rel.max()) < 1e-13 * 11
+    # round trip
+    plan.inv(y)
+    torch.cuda.synchronize()
+    err = float((y / n - x).abs().max())
+    assert err < 1e-12

@@ -1,0 +1,137 @@
+"""GPU parity tests for fft128, through the C ABI.
+
+Bar: bit-exact against the oracle's FMA variant (the arithmetic the reference's AVX2/AVX-512
+paths execute on x86, src/fft128/f128_ops.rs:837-841).  Stated tolerance against the scalar
+variant and in absolute terms: |gpu - scalar_ref| <= 32 * log2(n) * 2^-106 * rms|X|, and the
+reference's own property bound 1e-30 * N for the negacyclic product (src/fft128/mod.rs:2062).
+"""
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from f128_util import dd_mul_pointwise, dd_to_fraction, negacyclic_schoolbook_exact
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def C():
+    import concrete_fft_b200
+
+    return concrete_fft_b200
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+
+    return torch
+
+
+def planes_random(rng, batch, n, full_width=True):
+    re0, im0 = rng.random((batch, n)), rng.random((batch, n))
+    if full_width:
+        re1 = (rng.random((batch, n)) - 0.5) * np.spacing(re0)
+        im1 = (rng.random((batch, n)) - 0.5) * np.spacing(im0)
+    else:
+        re1, im1 = np.zeros((batch, n)), np.zeros((batch, n))
+    return [re0, re1, im0, im1]
+
+
+def dev_run(torch, fn, planes):
+    d = [torch.from_numpy(np.ascontiguousarray(p).copy()).cuda() for p in planes]
+    fn(*d)
+    torch.cuda.synchronize()
+    return [t.cpu().numpy() for t in d]
+
+
+def bits_equal(a, b):
+    return all(np.array_equal(x.view(np.uint64), y.view(np.uint64)) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("logn", range(5, 15))
+def test_fwd_inv_bit_exact(C, torch, logn):
+    """n = 32 .. 16384 (the reference bench's range, benches/fft.rs:213)."""
+    n = 1 << logn
+    rng = np.random.default_rng(logn)
+    batch = 3 if n <= 4096 else 2
+    planes = planes_random(rng, batch, n)
+    plan = C.fft128.Plan(n)
+    assert plan.fft_size() == n
+    ref = O.F128Plan(n)
+    y = dev_run(torch, plan.fwd, planes)
+    want = ref.fwd(*planes, variant=O.F128_FMA)
+    assert bits_equal(y, want)
+    z = dev_run(torch, plan.inv, y)
+    assert bits_equal(z, ref.inv(*want, variant=O.F128_FMA))
+    tw = plan.twiddles()
+    assert bits_equal(tw, ref.twiddles())
+    # stated ulp bound against the reference's scalar multiply variant
+    sc = ref.fwd(*planes, variant=O.F128_SCALAR)
+    rms = np.sqrt(np.mean(want[0] ** 2 + want[2] ** 2))
+    bound = 32 * logn * 2.0 ** -106 * rms
+    for hi, lo, shi, slo in [(y[0], y[1], sc[0], sc[1]), (y[2], y[3], sc[2], sc[3])]:
+        diff = (hi - shi) + (lo - slo)
+        assert np.abs(diff).max() <= bound
+
+
+def test_many_small_transforms_per_tile(C, torch):
+    rng = np.random.default_rng(20)
+    for n, batch in [(32, 129), (64, 70), (512, 9), (2048, 5)]:
+        planes = planes_random(rng, batch, n)
+        plan = C.fft128.Plan(n)
+        assert bits_equal(dev_run(torch, plan.fwd, planes), O.F128Plan(n).fwd(*planes, variant=O.F128_FMA))
+
+
+@pytest.mark.parametrize("npoly", [64, 512, 4096])
+def test_negacyclic_product_property(C, torch, npoly):
+    """src/fft128/mod.rs:1972-2065 through the CUDA path (host-memory entry points)."""
+    rng = np.random.default_rng(npoly)
+    n = npoly // 2
+    lhs, rhs = rng.random(npoly), rng.random(npoly)
+    exact = negacyclic_schoolbook_exact(lhs, rhs)
+    plan = C.fft128.Plan(n)
+    L = [lhs[:n].copy(), np.zeros(n), lhs[n:].copy(), np.zeros(n)]
+    R = [rhs[:n].copy(), np.zeros(n), rhs[n:].copy(), np.zeros(n)]
+    plan.fwd(*L)
+    plan.fwd(*R)
+    P = [np.ascontiguousarray(p) for p in dd_mul_pointwise(L, R, 2.0 / npoly)]
+    plan.inv(*P)
+    got_hi = np.concatenate([P[0], P[2]])
+    got_lo = np.concatenate([P[1], P[3]])
+    err = max(abs(dd_to_fraction(h, l) - e) for h, l, e in zip(got_hi, got_lo, exact))
+    assert float(err) < 1e-30 * npoly
+
+
+def test_length_mismatch_panics(C, torch):
+    plan = C.fft128.Plan(64)
+    a = np.zeros(64)
+    with pytest.raises(C.PanicError):
+        plan.fwd(a, a.copy(), a.copy(), np.zeros(63))  # src/fft128/mod.rs:1912-1915
+    with pytest.raises(C.PanicError):
+        plan.fwd(np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0))
+
+
+def test_full_size_n2048_batch16384_roundtrip(C, torch):
+    """BASELINE config 4 at full size (1 GiB): round trip to double-double accuracy and sampled
+    rows bit-exact against the oracle."""
+    n, batch = 2048, 16384
+    plan = C.fft128.Plan(n)
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    re0 = torch.rand(batch, n, dtype=torch.float64, device="cuda", generator=g)
+    im0 = torch.rand(batch, n, dtype=torch.float64, device="cuda", generator=g)
+    re1, im1 = torch.zeros_like(re0), torch.zeros_like(im0)
+    w = [re0.clone(), re1.clone(), im0.clone(), im1.clone()]
+    plan.fwd(*w)
+    rows = [0, 5000, 16383]
+    src = [t[rows].cpu().numpy() for t in (re0, re1, im0, im1)]
+    want = O.F128Plan(n).fwd(*src, variant=O.F128_FMA)
+    assert bits_equal([t[rows].cpu().numpy() for t in w], want)
+    plan.inv(*w)
+    torch.cuda.synchronize()
+    # (hi + lo) / n - x, evaluated in double-double: hi/n is exact (n is a power of two)
+    err_re = ((w[0] / n - re0) + w[1] / n).abs().max()
+    err_im = ((w[2] / n - im0) + w[3] / n).abs().max()
+    assert float(err_re) < 1e-28 and float(err_im) < 1e-28
