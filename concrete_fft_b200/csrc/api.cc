@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -129,6 +130,43 @@ cfft_status upload_c64(cfft_plan *p)
     return CFFT_OK;
 }
 
+// Planar copies of the plan's twiddles for c64_fast.cu: per unordered level w_k[p] (k-major,
+// (r-1) x m), then the planar half of the base init_wt table.  Same values, different layout
+// (the reference itself lays the level tables out per SIMD width, src/unordered.rs:373-385).
+cfft_status build_fast_tables(cfft_plan *p)
+{
+    if (getenv("CFFT_B200_FORCE_EXACT")) return CFFT_OK;
+    if (p->kind != KIND_UNORDERED || !fast_b256_supported(p->n, p->algo, p->base_n)) return CFFT_OK;
+    for (int d = 0; d < 2; d++) {
+        std::vector<cplx> out;
+        uint32_t off[3] = {0, 0, 0};
+        const StageProgram &pg = p->prog[0]; // level list top-down with forward offsets
+        int lvl = 0;
+        // inverse offsets of the same levels live in prog[1] in reverse order
+        std::vector<Stage> tops_f, tops_i;
+        for (int i = 0; i < pg.count; i++) if (pg.st[i].kind == ST_TOP) tops_f.push_back(pg.st[i]);
+        for (int i = p->prog[1].count - 1; i >= 0; i--) if (p->prog[1].st[i].kind == ST_TOP) tops_i.push_back(p->prog[1].st[i]);
+        for (size_t i = 0; i < tops_f.size() && lvl < 2; i++, lvl++) {
+            const Stage &st = d == 0 ? tops_f[i] : tops_i[i];
+            const uint32_t r = uint32_t(st.radix), m = st.span / r;
+            off[lvl] = uint32_t(out.size());
+            const cplx *src = p->h_tw[d].data() + st.tw_off;
+            for (uint32_t k = 1; k < r; k++)
+                for (uint32_t q = 0; q < m; q++) out.push_back(src[(r - 1) * q + (k - 1)]);
+        }
+        off[2] = uint32_t(out.size());
+        // base table: forward at the end of the level tables, inverse at offset 0; planar half first
+        const size_t base_off = d == 0 ? p->h_tw[0].size() - 2 * p->base_n : 0;
+        for (uint64_t i = 0; i < p->base_n; i++) out.push_back(p->h_tw[d][base_off + i]);
+        CU(cudaMalloc(reinterpret_cast<void **>(&p->d_fast_tw[d]), out.size() * sizeof(cplx)));
+        CU(cudaMemcpy(p->d_fast_tw[d], out.data(), out.size() * sizeof(cplx), cudaMemcpyHostToDevice));
+        for (int i = 0; i < 3; i++) p->fast_off[i] = off[i];
+    }
+    p->fast_variant = 1;
+    p->kernel_name = "fast-b256-regs";
+    return CFFT_OK;
+}
+
 cfft_status check_device(int device)
 {
     int count = 0;
@@ -154,6 +192,11 @@ void measure_choice(uint64_t n, int *algo, uint64_t *base_n)
 } // namespace
 
 namespace cfft {
+cudaError_t launch_c64(const cfft_plan *plan, bool inverse, double2 *data, uint64_t batch, cudaStream_t st)
+{
+    if (plan->fast_variant == 1) return launch_c64_fast_b256(plan, inverse, data, batch, st);
+    return launch_c64_exact(plan, inverse, data, batch, st);
+}
 void count_launch(uint64_t k) { g_launches.fetch_add(k, std::memory_order_relaxed); }
 cfft_status set_last_error(cfft_status st, const std::string &msg) { return fail(st, msg); }
 } // namespace cfft
@@ -247,6 +290,7 @@ cfft_status cfft_unordered_plan_create(cfft_plan **out, int device, uint64_t n, 
     init_unordered_twiddles(n, base_n, size_t(algo_radix(base_algo)), p->h_tw[0], p->h_tw[1]);
     build_c64_programs(p);
     st = upload_c64(p);
+    if (st == CFFT_OK) st = build_fast_tables(p);
     if (st != CFFT_OK) { cfft_plan_destroy(p); return st; }
     *out = p;
     return CFFT_OK;
@@ -289,6 +333,7 @@ void cfft_plan_destroy(cfft_plan *p)
     if (!p) return;
     DeviceGuard guard(p->device);
     for (int d = 0; d < 2; d++) if (p->d_tw[d]) cudaFree(p->d_tw[d]);
+    for (int d = 0; d < 2; d++) if (p->d_fast_tw[d]) cudaFree(p->d_fast_tw[d]);
     if (p->d_monomial_tw) cudaFree(p->d_monomial_tw);
     for (int i = 0; i < 4; i++) if (p->d_f128_tw[i]) cudaFree(p->d_f128_tw[i]);
     delete p;
@@ -349,7 +394,7 @@ static cfft_status run_c64(const cfft_plan *p, bool inverse, void *dev_buf, uint
     if (!dev_buf && batch) return fail(CFFT_EINVAL, "null buffer");
     DeviceGuard guard(p->device);
     if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
-    cudaError_t e = launch_c64_exact(p, inverse, static_cast<double2 *>(dev_buf), batch, static_cast<cudaStream_t>(stream));
+    cudaError_t e = launch_c64(p, inverse, static_cast<double2 *>(dev_buf), batch, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, inverse ? "c64 inv launch" : "c64 fwd launch");
     return CFFT_OK;
 }

@@ -1,0 +1,232 @@
+// c64_fast.cu -- register-resident c64 kernels for unordered plans with base (Dif16, 256):
+//   n = 256 * R1 * R2,  R1, R2 in {1, 2, 4, 8}  ->  n = 256 .. 8192   (TFHE polynomial sizes)
+//
+// Same butterflies, same twiddle values and same permuted output order as the reference for
+// Method::UserProvided { base_algo: Dif16, base_n: 256 }, so the result is bit-identical to
+// concrete-fft's (checked against the oracle in tests/test_gpu_c64.py):
+//   unordered levels  fwd_process_x{2,4,8} / inv_process_x{2,4,8}   src/unordered.rs:222-293
+//   base FFT          Dif16 stockham_core (s = 1) + stockham_dif16_end   src/dif16.rs:449-827
+//
+// Mapping: n/16 threads per transform, 16 c64 (64 registers) per thread.  Every stage is one
+// radix-16 butterfly (or 16/r radix-r butterflies) per thread, entirely in registers.
+//   * HBM -> registers with 128-bit loads, lanes on consecutive c64 (512 B per warp request);
+//     registers -> HBM the same way: a transform moves exactly 2 * 16 * n bytes.
+//   * Exchanges between levels go through shared memory in natural order (conflict-free).
+//   * The 16x16 transpose between the two radix-16 passes of a 256-point base FFT stays inside
+//     one half-warp: XOR-swizzled shared memory + __syncwarp, no block barrier.
+//   * Twiddles come from plan tables re-laid out planar (w_k[p], lanes on consecutive p) so
+//     each request is one or two 128 B lines; they stay L1-resident.
+#include "c64_math.cuh"
+#include "plan.h"
+
+namespace cfft {
+namespace {
+
+__device__ __forceinline__ c64 ld_stream(const c64 *p)
+{
+    c64 v;
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream(c64 *p, c64 v)
+{
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ c64 ld_tw(const c64 *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
+
+template <int R> __device__ __forceinline__ constexpr int brev_c(int k)
+{
+    return R == 2 ? k : (R == 4 ? ((k & 1) << 1) | (k >> 1) : ((k & 1) << 2) | (k & 2) | (k >> 2));
+}
+
+// One unordered level of span NCUR on the 16 register values of a thread: B = 16/R butterflies,
+// butterfly j covers positions base_j + m*k.  Twiddles planar: tw[(k-1)*m + p].
+template <int R, int NCUR, int TPR, bool FWD, bool G_IN, bool G_OUT>
+__device__ __forceinline__ void level(const c64 *__restrict__ src, c64 *__restrict__ dst,
+                                      const c64 *__restrict__ tw, int t, c64 (&v)[16])
+{
+    constexpr int B = 16 / R, m = NCUR / R;
+    int base[B], p[B];
+#pragma unroll
+    for (int j = 0; j < B; j++) {
+        const int b = t + TPR * j;
+        const int blk = b / m;
+        p[j] = b - blk * m;
+        base[j] = blk * NCUR + p[j];
+    }
+#pragma unroll
+    for (int j = 0; j < B; j++)
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            const int pos = base[j] + m * (FWD ? k : brev_c<R>(k));
+            v[j * R + k] = G_IN ? ld_stream(src + pos) : src[pos];
+        }
+    if (!G_IN && !G_OUT) __syncthreads(); // everyone has read before anyone overwrites (in place)
+#pragma unroll
+    for (int j = 0; j < B; j++) {
+        c64 *x = &v[j * R];
+        if (!FWD) {
+#pragma unroll
+            for (int k = 1; k < R; k++) x[k] = cmul(ld_tw(tw + (k - 1) * m + p[j]), x[k]);
+        }
+        bfR<R, FWD>(x);
+        if (FWD) {
+#pragma unroll
+            for (int k = 1; k < R; k++) x[k] = cmul(ld_tw(tw + (k - 1) * m + p[j]), x[k]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < B; j++)
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            const int pos = base[j] + m * (FWD ? brev_c<R>(k) : k);
+            if (G_OUT) st_stream(dst + pos, v[j * R + k]);
+            else dst[pos] = v[j * R + k];
+        }
+}
+
+// 256-point base FFT (Dif16: radix-16 s=1 with twiddles, then radix-16 end) of the half-warp
+// that owns block `blk`; thread lane16 = p (first pass) = j (second pass).
+// FWD selects the butterfly direction only; the table passed in is the direction's table.
+template <bool FWD, bool G_IN, bool G_OUT>
+__device__ __forceinline__ void base256(const c64 *__restrict__ src, c64 *__restrict__ sm_blk, c64 *__restrict__ dst,
+                                        const c64 *__restrict__ tw_planar, int lane16, c64 (&v)[16])
+{
+    // pass 1: x[p + 16k] -> y[16p + k] = w[p + 16k] * DFT16(x)_k       src/dif16.rs:449-623
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = G_IN ? ld_stream(src + lane16 + 16 * k) : src[lane16 + 16 * k];
+    bf16<FWD>(v);
+#pragma unroll
+    for (int k = 1; k < 16; k++) v[k] = cmul(ld_tw(tw_planar + lane16 + 16 * k), v[k]);
+    __syncwarp(); // the half-warp has finished reading its block
+#pragma unroll
+    for (int k = 0; k < 16; k++) sm_blk[16 * lane16 + (k ^ lane16)] = v[k]; // XOR swizzle: conflict-free
+    __syncwarp();
+    // pass 2: terminal radix-16 on y[j + 16k]                           src/dif16.rs:649-827
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = sm_blk[16 * k + (lane16 ^ k)];
+    bf16<FWD>(v);
+    if (G_OUT) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) st_stream(dst + lane16 + 16 * k, v[k]);
+    } else {
+        __syncwarp(); // swizzled data consumed by the whole half-warp before natural-order overwrite
+#pragma unroll
+        for (int k = 0; k < 16; k++) dst[lane16 + 16 * k] = v[k];
+    }
+}
+
+struct FastTables {
+    const c64 *top1; // planar (R1-1) x n/R1
+    const c64 *top2; // planar (R2-1) x n/(R1 R2)
+    const c64 *base; // planar half of init_wt(16, 256): w[p + 16 k]
+};
+
+template <int N> struct FastCfg {
+    static constexpr int TPR = N / 16;                  // threads per transform
+    static constexpr int NT = TPR < 128 ? 128 : TPR;    // threads per CTA
+    static constexpr int ROWS = NT / TPR;               // transforms per CTA
+    static constexpr int MINB = (NT <= 128) ? 4 : (NT <= 256 ? 2 : 1);
+};
+
+template <int N, int R1, int R2, bool FWD>
+__global__ void __launch_bounds__(FastCfg<N>::NT, FastCfg<N>::MINB)
+c64_fast_b256_kernel(c64 *__restrict__ data, uint64_t batch, FastTables tb)
+{
+    static_assert(N == 256 * R1 * R2, "n = 256 * R1 * R2");
+    using Cfg = FastCfg<N>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int row = threadIdx.x / Cfg::TPR, t = threadIdx.x % Cfg::TPR;
+    const uint64_t grow = uint64_t(blockIdx.x) * Cfg::ROWS + row;
+    // rows are whole-warp aligned (TPR >= 16 and ROWS * TPR = NT), but a CTA may own fewer rows at
+    // the tail; inactive rows still take part in the block barriers below.
+    const bool active = grow < batch;
+    c64 *g = data + (active ? grow : 0) * N;
+    c64 *s = reinterpret_cast<c64 *>(smem_raw) + row * N;
+    c64 v[16];
+    constexpr int N2 = N / R1;      // span of the second level
+    const int blk = t / 16, lane16 = t % 16;
+
+    if (FWD) {
+        if (R1 > 1) {
+            if (active) level<R1, N, Cfg::TPR, true, true, false>(g, s, tb.top1, t, v);
+            __syncthreads();
+        }
+        if (R2 > 1) {
+            level<R2, N2, Cfg::TPR, true, false, false>(s, s, tb.top2, t, v);
+            __syncthreads();
+        }
+        if (active) {
+            if (R1 > 1) base256<true, false, true>(s + blk * 256, s + blk * 256, g + blk * 256, tb.base, lane16, v);
+            else base256<true, true, true>(g + blk * 256, s + blk * 256, g + blk * 256, tb.base, lane16, v);
+        }
+    } else {
+        if (active) {
+            if (R1 > 1) base256<false, true, false>(g + blk * 256, s + blk * 256, s + blk * 256, tb.base, lane16, v);
+            else base256<false, true, true>(g + blk * 256, s + blk * 256, g + blk * 256, tb.base, lane16, v);
+        }
+        if (R2 > 1) {
+            __syncthreads();
+            level<R2, N2, Cfg::TPR, false, false, false>(s, s, tb.top2, t, v);
+        }
+        if (R1 > 1) {
+            __syncthreads();
+            if (active) level<R1, N, Cfg::TPR, false, false, true>(s, g, tb.top1, t, v);
+        }
+    }
+}
+
+template <int N, int R1, int R2>
+cudaError_t launch_cfg(bool inverse, c64 *data, uint64_t batch, const FastTables &tb, cudaStream_t stream)
+{
+    using Cfg = FastCfg<N>;
+    const size_t smem = size_t(Cfg::ROWS) * N * sizeof(c64);
+    const uint64_t ctas = (batch + Cfg::ROWS - 1) / Cfg::ROWS;
+    auto fwd_k = c64_fast_b256_kernel<N, R1, R2, true>;
+    auto inv_k = c64_fast_b256_kernel<N, R1, R2, false>;
+    if (smem > 48 * 1024) {
+        static thread_local int configured_device = -1;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (configured_device != dev) {
+            cudaError_t e = cudaFuncSetAttribute(fwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(inv_k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            if (e != cudaSuccess) return e;
+            configured_device = dev;
+        }
+    }
+    if (inverse) inv_k<<<unsigned(ctas), Cfg::NT, smem, stream>>>(data, batch, tb);
+    else fwd_k<<<unsigned(ctas), Cfg::NT, smem, stream>>>(data, batch, tb);
+    count_launch();
+    return cudaGetLastError();
+}
+
+} // namespace
+
+// Does a plan qualify?  unordered, base (Dif16, 256), n = 256 .. 8192.
+bool fast_b256_supported(uint64_t n, int base_algo, uint64_t base_n)
+{
+    return base_algo == 6 /* Dif16 */ && base_n == 256 && n >= 256 && n <= 8192;
+}
+
+cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *data, uint64_t batch, cudaStream_t stream)
+{
+    if (batch == 0) return cudaSuccess;
+    const int d = inverse ? 1 : 0;
+    const c64 *base = plan->d_fast_tw[d];
+    FastTables tb;
+    tb.top1 = base + plan->fast_off[0];
+    tb.top2 = base + plan->fast_off[1];
+    tb.base = base + plan->fast_off[2];
+    switch (plan->n) {
+    case 256: return launch_cfg<256, 1, 1>(inverse, data, batch, tb, stream);
+    case 512: return launch_cfg<512, 2, 1>(inverse, data, batch, tb, stream);
+    case 1024: return launch_cfg<1024, 4, 1>(inverse, data, batch, tb, stream);
+    case 2048: return launch_cfg<2048, 8, 1>(inverse, data, batch, tb, stream);
+    case 4096: return launch_cfg<4096, 8, 2>(inverse, data, batch, tb, stream);
+    case 8192: return launch_cfg<8192, 8, 4>(inverse, data, batch, tb, stream);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+} // namespace cfft

@@ -165,7 +165,7 @@ cfft_status run_pipeline(const cfft_plan *plan, void *const *planes, int nplanes
                                 reinterpret_cast<double *>(d + 2 * chunk_plane_bytes),
                                 reinterpret_cast<double *>(d + 3 * chunk_plane_bytes), rows, s.stream);
             else
-                e = launch_c64_exact(plan, inverse, reinterpret_cast<double2 *>(d), rows, s.stream);
+                e = launch_c64(plan, inverse, reinterpret_cast<double2 *>(d), rows, s.stream);
         }
         if (e != cudaSuccess) break;
         what = "pipeline D2H";

@@ -53,7 +53,9 @@ struct cfft_plan {
     double2 *d_tw[2] = {nullptr, nullptr};
     double2 *d_monomial_tw = nullptr; // n entries, e^{-2 pi i k / n} (src/unordered.rs:714-720)
     cfft::StageProgram prog[2];       // [0] fwd, [1] inv: every stage in execution order
-    int fast_variant = 0;             // 0 = exact tile kernel only, else id of a specialised kernel
+    int fast_variant = 0;             // 0 = exact tile kernel only, 1 = c64_fast.cu (base Dif16/256)
+    double2 *d_fast_tw[2] = {nullptr, nullptr}; // planar re-layout of the same twiddle values
+    uint32_t fast_off[3] = {0, 0, 0};           // offsets of [level 1 | level 2 | base] inside d_fast_tw
 
     // fft128
     std::vector<double> h_f128_tw[4];
@@ -67,6 +69,11 @@ cudaError_t launch_c64_exact(const cfft_plan *plan, bool inverse, double2 *data,
 cudaError_t launch_monomial(const cfft_plan *plan, uint64_t degree, double2 *data, cudaStream_t st);
 cudaError_t launch_permute(const cfft_plan *plan, bool to_standard, const double2 *src, double2 *dst,
                            uint64_t batch, cudaStream_t st);
+// kernels (c64_fast.cu)
+bool fast_b256_supported(uint64_t n, int base_algo, uint64_t base_n);
+cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *data, uint64_t batch, cudaStream_t st);
+// dispatcher (api.cc): fast kernel when the plan has one, else the exact tile kernel
+cudaError_t launch_c64(const cfft_plan *plan, bool inverse, double2 *data, uint64_t batch, cudaStream_t st);
 // kernels (f128.cu)
 cudaError_t launch_f128(const cfft_plan *plan, bool inverse, double *re0, double *re1, double *im0, double *im1,
                         uint64_t batch, cudaStream_t st);

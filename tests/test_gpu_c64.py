@@ -292,3 +292,26 @@ def test_full_size_properties_n2048_batch65536(C, torch):
     torch.cuda.synchronize()
     err = float((y / n - x).abs().max())
     assert err < 1e-12
+
+
+@pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096, 8192])
+def test_fast_register_kernel_bit_exact(C, torch, n):
+    """c64_fast.cu (plans with base (Dif16, 256)): same bits and order as the reference plan, for
+    whole and ragged CTA tiles, and identical to the exact tile kernel."""
+    rng = np.random.default_rng(n)
+    plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(C.ordered.FftAlgo.Dif16, 256))
+    assert plan.kernel_name() == "fast-b256-regs"
+    ref = O.UnorderedPlan(n, O.DIF16, 256)
+    for batch in [1, 7, 8, 33]:
+        x = rand_c(rng, batch, n)
+        y = dev_run(torch, plan.fwd, x)
+        want = ref.fwd(x)
+        assert bits_equal(y, want), (n, batch)
+        assert bits_equal(dev_run(torch, plan.inv, y), ref.inv(want)), (n, batch)
+    os.environ["CFFT_B200_FORCE_EXACT"] = "1"
+    try:
+        exact = C.unordered.Plan(n, C.unordered.Method.UserProvided(C.ordered.FftAlgo.Dif16, 256))
+    finally:
+        del os.environ["CFFT_B200_FORCE_EXACT"]
+    assert exact.kernel_name() == "exact-tile"
+    assert bits_equal(dev_run(torch, exact.fwd, x), y)
