@@ -1,0 +1,81 @@
+//! Raw bindings of include/cfft_b200.h (one `extern "C"` item per declared symbol).
+#![allow(non_camel_case_types)]
+use core::ffi::{c_char, c_int, c_void};
+
+pub type cfft_status = i32;
+pub const CFFT_OK: cfft_status = 0;
+pub const CFFT_ELENGTH: cfft_status = -5;
+pub const CFFT_METHOD_USER: c_int = 0;
+pub const CFFT_METHOD_MEASURE: c_int = 1;
+
+#[repr(C)]
+pub struct cfft_plan {
+    _private: [u8; 0],
+}
+
+extern "C" {
+    pub fn cfft_ordered_plan_create(out: *mut *mut cfft_plan, device: c_int, n: u64, method: c_int, algo: c_int, allow_large: c_int) -> cfft_status;
+    pub fn cfft_unordered_plan_create(out: *mut *mut cfft_plan, device: c_int, n: u64, method: c_int, base_algo: c_int, base_n: u64) -> cfft_status;
+    pub fn cfft_f128_plan_create(out: *mut *mut cfft_plan, device: c_int, n: u64) -> cfft_status;
+    pub fn cfft_plan_destroy(plan: *mut cfft_plan);
+    pub fn cfft_plan_clone(plan: *const cfft_plan, out: *mut *mut cfft_plan) -> cfft_status;
+    pub fn cfft_plan_fft_size(plan: *const cfft_plan) -> u64;
+    pub fn cfft_plan_algo(plan: *const cfft_plan, algo: *mut c_int, base_n: *mut u64) -> cfft_status;
+    pub fn cfft_plan_scratch_req(plan: *const cfft_plan, bytes: *mut u64, align: *mut u64) -> cfft_status;
+    pub fn cfft_plan_kind(plan: *const cfft_plan) -> c_int;
+    pub fn cfft_plan_device(plan: *const cfft_plan) -> c_int;
+    pub fn cfft_plan_kernel_name(plan: *const cfft_plan) -> *const c_char;
+    pub fn cfft_c64_fwd(plan: *const cfft_plan, dev_buf: *mut c_void, batch: u64, stream: *mut c_void) -> cfft_status;
+    pub fn cfft_c64_inv(plan: *const cfft_plan, dev_buf: *mut c_void, batch: u64, stream: *mut c_void) -> cfft_status;
+    pub fn cfft_c64_fwd_host(plan: *const cfft_plan, host_buf: *mut c_void, len: u64, batch: u64) -> cfft_status;
+    pub fn cfft_c64_inv_host(plan: *const cfft_plan, host_buf: *mut c_void, len: u64, batch: u64) -> cfft_status;
+    pub fn cfft_c64_fwd_inv_host(plan: *const cfft_plan, host_buf: *mut c_void, len: u64, batch: u64) -> cfft_status;
+    pub fn cfft_unordered_fwd_monomial(plan: *const cfft_plan, degree: u64, dev_buf: *mut c_void, stream: *mut c_void) -> cfft_status;
+    pub fn cfft_unordered_fwd_monomial_host(plan: *const cfft_plan, degree: u64, host_buf: *mut c_void, len: u64) -> cfft_status;
+    pub fn cfft_unordered_permutation(plan: *const cfft_plan, out: *mut u64) -> cfft_status;
+    pub fn cfft_unordered_to_standard(plan: *const cfft_plan, dev_src: *const c_void, dev_dst: *mut c_void, batch: u64, stream: *mut c_void) -> cfft_status;
+    pub fn cfft_unordered_from_standard(plan: *const cfft_plan, dev_src: *const c_void, dev_dst: *mut c_void, batch: u64, stream: *mut c_void) -> cfft_status;
+    pub fn cfft_unordered_to_standard_host(plan: *const cfft_plan, src: *const c_void, dst: *mut c_void) -> cfft_status;
+    pub fn cfft_unordered_from_standard_host(plan: *const cfft_plan, src: *const c_void, count: u64, dst: *mut c_void) -> cfft_status;
+    pub fn cfft_f128_fwd(plan: *const cfft_plan, re0: *mut f64, re1: *mut f64, im0: *mut f64, im1: *mut f64, batch: u64, stream: *mut c_void) -> cfft_status;
+    pub fn cfft_f128_inv(plan: *const cfft_plan, re0: *mut f64, re1: *mut f64, im0: *mut f64, im1: *mut f64, batch: u64, stream: *mut c_void) -> cfft_status;
+    pub fn cfft_f128_fwd_host(plan: *const cfft_plan, re0: *mut f64, re1: *mut f64, im0: *mut f64, im1: *mut f64, len: u64, batch: u64) -> cfft_status;
+    pub fn cfft_f128_inv_host(plan: *const cfft_plan, re0: *mut f64, re1: *mut f64, im0: *mut f64, im1: *mut f64, len: u64, batch: u64) -> cfft_status;
+    pub fn cfft_status_string(st: cfft_status) -> *const c_char;
+    pub fn cfft_last_error() -> *const c_char;
+    pub fn cfft_launch_count() -> u64;
+    pub fn cfft_version() -> *const c_char;
+    pub fn cfft_plan_copy_twiddles(plan: *const cfft_plan, which: c_int, host_out: *mut c_void, bytes: u64) -> cfft_status;
+}
+
+/// Turns a non-zero status into the panic the reference would have raised at the same place.
+#[track_caller]
+pub fn check(st: cfft_status) {
+    if st != CFFT_OK {
+        let msg = unsafe { core::ffi::CStr::from_ptr(cfft_last_error()) };
+        panic!("cfft_b200: {} (status {st})", msg.to_string_lossy());
+    }
+}
+
+/// Owning handle: Drop -> cfft_plan_destroy, Clone -> cfft_plan_clone.  Plans are immutable
+/// after creation, so sharing `&Handle` across threads is sound (the reference's `&self`).
+pub struct Handle(pub *mut cfft_plan);
+unsafe impl Send for Handle {}
+unsafe impl Sync for Handle {}
+impl Drop for Handle {
+    fn drop(&mut self) {
+        unsafe { cfft_plan_destroy(self.0) }
+    }
+}
+impl Clone for Handle {
+    fn clone(&self) -> Self {
+        let mut out = core::ptr::null_mut();
+        check(unsafe { cfft_plan_clone(self.0, &mut out) });
+        Handle(out)
+    }
+}
+
+/// CUDA device new plans are created on (`CFFT_B200_DEVICE`, default 0).
+pub fn default_device() -> c_int {
+    std::env::var("CFFT_B200_DEVICE").ok().and_then(|s| s.parse().ok()).unwrap_or(0)
+}

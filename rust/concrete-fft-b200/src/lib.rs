@@ -1,0 +1,355 @@
+//! concrete-fft-b200: the public API of concrete-fft 0.5.1 (`ordered`, `unordered`, `fft128`)
+//! served by hand-written sm_100a CUDA kernels through the C ABI of `include/cfft_b200.h`.
+//!
+//! Every public item mirrors the item of the same name in concrete-fft (file:line citations
+//! refer to that crate); the bodies are single FFI calls.  Semantics kept:
+//! * in-place transforms on host slices, unnormalised, `&self` shareable across threads;
+//! * the unordered plan's permuted Fourier order for a given `(base_algo, base_n)`, index for
+//!   index, and results bit-identical to concrete-fft's for the same plan;
+//! * panics where concrete-fft asserts (sizes, lengths);
+//! * `fft_scratch()` still reports the reference's stack requirement so callers that size a
+//!   `PodStack` keep working (the device path does not use it).
+//!
+//! Extra, not in concrete-fft: `*_batch` methods (many polynomials per call) and `device`
+//! sub-modules taking raw device pointers + a CUDA stream.
+#![allow(non_camel_case_types)]
+
+pub mod ffi;
+
+/// `concrete_fft::c64`, src/lib.rs:84
+pub type c64 = num_complex::Complex64;
+
+pub mod ordered {
+    //! src/ordered.rs
+    use crate::{c64, ffi};
+    use aligned_vec::CACHELINE_ALIGN;
+    use dyn_stack::{PodStack, SizeOverflow, StackReq};
+
+    /// src/ordered.rs:28-45
+    #[derive(Clone, Copy, Debug, PartialEq, Eq)]
+    #[non_exhaustive]
+    pub enum FftAlgo {
+        Dif2,
+        Dit2,
+        Dif4,
+        Dit4,
+        Dif8,
+        Dit8,
+        Dif16,
+        Dit16,
+    }
+    impl FftAlgo {
+        pub(crate) fn from_raw(v: i32) -> Self {
+            use FftAlgo::*;
+            [Dif2, Dit2, Dif4, Dit4, Dif8, Dit8, Dif16, Dit16][v as usize]
+        }
+    }
+
+    /// src/ordered.rs:50-59
+    #[derive(Clone, Copy, Debug, PartialEq, Eq)]
+    #[non_exhaustive]
+    pub enum Method {
+        UserProvided(FftAlgo),
+        #[cfg(feature = "std")]
+        Measure(core::time::Duration),
+    }
+
+    /// src/ordered.rs:187-193
+    #[derive(Clone)]
+    pub struct Plan {
+        h: ffi::Handle,
+    }
+
+    impl core::fmt::Debug for Plan {
+        fn fmt(&self, f: &mut core::fmt::Formatter<'_>) -> core::fmt::Result {
+            f.debug_struct("Plan").field("algo", &self.algo()).field("fft_size", &self.fft_size()).finish()
+        }
+    }
+
+    impl Plan {
+        /// src/ordered.rs:242-278.  Panics if `n` is not a power of two or exceeds 2^10.
+        #[track_caller]
+        pub fn new(n: usize, method: Method) -> Self {
+            let (m, algo) = match method {
+                Method::UserProvided(a) => (ffi::CFFT_METHOD_USER, a as i32),
+                #[cfg(feature = "std")]
+                Method::Measure(_) => (ffi::CFFT_METHOD_MEASURE, 0),
+            };
+            let mut out = core::ptr::null_mut();
+            ffi::check(unsafe { ffi::cfft_ordered_plan_create(&mut out, ffi::default_device(), n as u64, m, algo, 0) });
+            Self { h: ffi::Handle(out) }
+        }
+        /// src/ordered.rs:291-293
+        pub fn fft_size(&self) -> usize {
+            unsafe { ffi::cfft_plan_fft_size(self.h.0) as usize }
+        }
+        /// src/ordered.rs:305-307
+        pub fn algo(&self) -> FftAlgo {
+            let (mut a, mut b) = (0, 0);
+            ffi::check(unsafe { ffi::cfft_plan_algo(self.h.0, &mut a, &mut b) });
+            FftAlgo::from_raw(a)
+        }
+        /// src/ordered.rs:320-322
+        pub fn fft_scratch(&self) -> Result<StackReq, SizeOverflow> {
+            StackReq::try_new_aligned::<c64>(self.fft_size(), CACHELINE_ALIGN)
+        }
+        /// src/ordered.rs:342-347
+        #[track_caller]
+        pub fn fwd(&self, buf: &mut [c64], stack: PodStack) {
+            let _ = stack;
+            ffi::check(unsafe { ffi::cfft_c64_fwd_host(self.h.0, buf.as_mut_ptr().cast(), buf.len() as u64, 1) });
+        }
+        /// src/ordered.rs:368-373
+        #[track_caller]
+        pub fn inv(&self, buf: &mut [c64], stack: PodStack) {
+            let _ = stack;
+            ffi::check(unsafe { ffi::cfft_c64_inv_host(self.h.0, buf.as_mut_ptr().cast(), buf.len() as u64, 1) });
+        }
+        /// Extension: `buf.len() / fft_size()` independent transforms in one call.
+        #[track_caller]
+        pub fn fwd_batch(&self, buf: &mut [c64]) {
+            let b = (buf.len() / self.fft_size()) as u64;
+            ffi::check(unsafe { ffi::cfft_c64_fwd_host(self.h.0, buf.as_mut_ptr().cast(), buf.len() as u64, b) });
+        }
+        #[track_caller]
+        pub fn inv_batch(&self, buf: &mut [c64]) {
+            let b = (buf.len() / self.fft_size()) as u64;
+            ffi::check(unsafe { ffi::cfft_c64_inv_host(self.h.0, buf.as_mut_ptr().cast(), buf.len() as u64, b) });
+        }
+    }
+}
+
+pub mod unordered {
+    //! src/unordered.rs
+    use crate::{c64, ffi, ordered::FftAlgo};
+    use aligned_vec::CACHELINE_ALIGN;
+    use dyn_stack::{PodStack, SizeOverflow, StackReq};
+
+    /// src/unordered.rs:526-537
+    #[derive(Clone, Copy, Debug)]
+    pub enum Method {
+        UserProvided { base_algo: FftAlgo, base_n: usize },
+        #[cfg(feature = "std")]
+        Measure(core::time::Duration),
+    }
+
+    /// src/unordered.rs:496-512
+    #[derive(Clone)]
+    pub struct Plan {
+        h: ffi::Handle,
+    }
+
+    impl core::fmt::Debug for Plan {
+        fn fmt(&self, f: &mut core::fmt::Formatter<'_>) -> core::fmt::Result {
+            let (a, b) = self.algo();
+            f.debug_struct("Plan").field("base_algo", &a).field("base_size", &b).field("fft_size", &self.fft_size()).finish()
+        }
+    }
+
+    impl Plan {
+        /// src/unordered.rs:659-747
+        #[track_caller]
+        pub fn new(n: usize, method: Method) -> Self {
+            let (m, algo, base_n) = match method {
+                Method::UserProvided { base_algo, base_n } => (ffi::CFFT_METHOD_USER, base_algo as i32, base_n as u64),
+                #[cfg(feature = "std")]
+                Method::Measure(_) => (ffi::CFFT_METHOD_MEASURE, 0, 0),
+            };
+            let mut out = core::ptr::null_mut();
+            ffi::check(unsafe { ffi::cfft_unordered_plan_create(&mut out, ffi::default_device(), n as u64, m, algo, base_n) });
+            Self { h: ffi::Handle(out) }
+        }
+        /// src/unordered.rs:760-762
+        pub fn fft_size(&self) -> usize {
+            unsafe { ffi::cfft_plan_fft_size(self.h.0) as usize }
+        }
+        /// src/unordered.rs:783-785
+        pub fn algo(&self) -> (FftAlgo, usize) {
+            let (mut a, mut b) = (0, 0);
+            ffi::check(unsafe { ffi::cfft_plan_algo(self.h.0, &mut a, &mut b) });
+            (FftAlgo::from_raw(a), b as usize)
+        }
+        /// src/unordered.rs:798-800
+        pub fn fft_scratch(&self) -> Result<StackReq, SizeOverflow> {
+            StackReq::try_new_aligned::<c64>(self.algo().1, CACHELINE_ALIGN)
+        }
+        /// src/unordered.rs:826-839.  Panics when `buf.len() != fft_size()`.
+        #[track_caller]
+        pub fn fwd(&self, buf: &mut [c64], stack: PodStack) {
+            let _ = stack;
+            ffi::check(unsafe { ffi::cfft_c64_fwd_host(self.h.0, buf.as_mut_ptr().cast(), buf.len() as u64, 1) });
+        }
+        /// src/unordered.rs:927-940
+        #[track_caller]
+        pub fn inv(&self, buf: &mut [c64], stack: PodStack) {
+            let _ = stack;
+            ffi::check(unsafe { ffi::cfft_c64_inv_host(self.h.0, buf.as_mut_ptr().cast(), buf.len() as u64, 1) });
+        }
+        /// src/unordered.rs:844-900
+        #[track_caller]
+        pub fn fwd_monomial(&self, degree: usize, buf: &mut [c64]) {
+            ffi::check(unsafe { ffi::cfft_unordered_fwd_monomial_host(self.h.0, degree as u64, buf.as_mut_ptr().cast(), buf.len() as u64) });
+        }
+        /// Extension: `buf.len() / fft_size()` polynomials per call (one upload, one download).
+        #[track_caller]
+        pub fn fwd_batch(&self, buf: &mut [c64]) {
+            let b = (buf.len() / self.fft_size()) as u64;
+            ffi::check(unsafe { ffi::cfft_c64_fwd_host(self.h.0, buf.as_mut_ptr().cast(), buf.len() as u64, b) });
+        }
+        #[track_caller]
+        pub fn inv_batch(&self, buf: &mut [c64]) {
+            let b = (buf.len() / self.fft_size()) as u64;
+            ffi::check(unsafe { ffi::cfft_c64_inv_host(self.h.0, buf.as_mut_ptr().cast(), buf.len() as u64, b) });
+        }
+
+        /// src/unordered.rs:951-972
+        #[cfg(feature = "serde")]
+        pub fn serialize_fourier_buffer<S: serde::Serializer>(&self, serializer: S, buf: &[c64]) -> Result<S::Ok, S::Error> {
+            use serde::ser::SerializeSeq;
+            let n = self.fft_size();
+            assert_eq!(n, buf.len());
+            let mut std_order = vec![c64::default(); n];
+            ffi::check(unsafe { ffi::cfft_unordered_to_standard_host(self.h.0, buf.as_ptr().cast(), std_order.as_mut_ptr().cast()) });
+            let mut seq = serializer.serialize_seq(Some(n))?;
+            for z in &std_order {
+                seq.serialize_element(z)?;
+            }
+            seq.end()
+        }
+
+        /// src/unordered.rs:982-1036
+        #[cfg(feature = "serde")]
+        pub fn deserialize_fourier_buffer<'de, D: serde::Deserializer<'de>>(&self, deserializer: D, buf: &mut [c64]) -> Result<(), D::Error> {
+            use serde::de::{SeqAccess, Visitor};
+            let n = self.fft_size();
+            assert_eq!(n, buf.len());
+            struct SeqVisitor<'a> {
+                plan: &'a Plan,
+                buf: &'a mut [c64],
+            }
+            impl<'de, 'a> Visitor<'de> for SeqVisitor<'a> {
+                type Value = ();
+                fn expecting(&self, f: &mut core::fmt::Formatter) -> core::fmt::Result {
+                    write!(f, "a sequence of {} 64-bit complex numbers", self.buf.len())
+                }
+                fn visit_seq<S: SeqAccess<'de>>(self, mut seq: S) -> Result<(), S::Error> {
+                    let n = self.buf.len();
+                    let mut std_order = Vec::with_capacity(n);
+                    let mut i = 0usize;
+                    while let Some(v) = seq.next_element::<c64>()? {
+                        if i < n {
+                            std_order.push(v);
+                        }
+                        i += 1;
+                    }
+                    let st = unsafe {
+                        ffi::cfft_unordered_from_standard_host(self.plan.h.0, std_order.as_ptr().cast(), i as u64, self.buf.as_mut_ptr().cast())
+                    };
+                    if st == ffi::CFFT_ELENGTH {
+                        Err(serde::de::Error::invalid_length(i, &self))
+                    } else {
+                        ffi::check(st);
+                        Ok(())
+                    }
+                }
+            }
+            deserializer.deserialize_seq(SeqVisitor { plan: self, buf })
+        }
+    }
+}
+
+#[cfg(feature = "fft128")]
+pub mod fft128 {
+    //! src/fft128/mod.rs
+    use crate::ffi;
+
+    /// src/fft128/mod.rs:3-7
+    #[derive(Copy, Clone, Debug)]
+    #[repr(C)]
+    pub struct f128(pub f64, pub f64);
+
+    /// src/fft128/mod.rs:1832-1838
+    #[derive(Clone)]
+    pub struct Plan {
+        h: ffi::Handle,
+    }
+
+    impl core::fmt::Debug for Plan {
+        fn fmt(&self, f: &mut core::fmt::Formatter<'_>) -> core::fmt::Result {
+            f.debug_struct("Plan").field("fft_size", &self.fft_size()).finish()
+        }
+    }
+
+    impl Plan {
+        /// src/fft128/mod.rs:1864-1881.  Panics unless `n` is a power of two >= 32.
+        #[track_caller]
+        pub fn new(n: usize) -> Self {
+            let mut out = core::ptr::null_mut();
+            ffi::check(unsafe { ffi::cfft_f128_plan_create(&mut out, ffi::default_device(), n as u64) });
+            Self { h: ffi::Handle(out) }
+        }
+        /// src/fft128/mod.rs:1891-1893
+        pub fn fft_size(&self) -> usize {
+            unsafe { ffi::cfft_plan_fft_size(self.h.0) as usize }
+        }
+        /// src/fft128/mod.rs:1905-1928
+        #[track_caller]
+        pub fn fwd(&self, buf_re0: &mut [f64], buf_re1: &mut [f64], buf_im0: &mut [f64], buf_im1: &mut [f64]) {
+            let n = self.fft_size();
+            assert_eq!(buf_re0.len(), n);
+            assert_eq!(buf_re1.len(), n);
+            assert_eq!(buf_im0.len(), n);
+            assert_eq!(buf_im1.len(), n);
+            ffi::check(unsafe {
+                ffi::cfft_f128_fwd_host(self.h.0, buf_re0.as_mut_ptr(), buf_re1.as_mut_ptr(), buf_im0.as_mut_ptr(), buf_im1.as_mut_ptr(), n as u64, 1)
+            });
+        }
+        /// src/fft128/mod.rs:1938-1960
+        #[track_caller]
+        pub fn inv(&self, buf_re0: &mut [f64], buf_re1: &mut [f64], buf_im0: &mut [f64], buf_im1: &mut [f64]) {
+            let n = self.fft_size();
+            assert_eq!(buf_re0.len(), n);
+            assert_eq!(buf_re1.len(), n);
+            assert_eq!(buf_im0.len(), n);
+            assert_eq!(buf_im1.len(), n);
+            ffi::check(unsafe {
+                ffi::cfft_f128_inv_host(self.h.0, buf_re0.as_mut_ptr(), buf_re1.as_mut_ptr(), buf_im0.as_mut_ptr(), buf_im1.as_mut_ptr(), n as u64, 1)
+            });
+        }
+        /// Extension: `len / fft_size()` transforms per call on planar arrays.
+        #[track_caller]
+        pub fn fwd_batch(&self, re0: &mut [f64], re1: &mut [f64], im0: &mut [f64], im1: &mut [f64]) {
+            let (len, n) = (re0.len(), self.fft_size());
+            assert!(re1.len() == len && im0.len() == len && im1.len() == len && len % n == 0);
+            ffi::check(unsafe {
+                ffi::cfft_f128_fwd_host(self.h.0, re0.as_mut_ptr(), re1.as_mut_ptr(), im0.as_mut_ptr(), im1.as_mut_ptr(), len as u64, (len / n) as u64)
+            });
+        }
+        #[track_caller]
+        pub fn inv_batch(&self, re0: &mut [f64], re1: &mut [f64], im0: &mut [f64], im1: &mut [f64]) {
+            let (len, n) = (re0.len(), self.fft_size());
+            assert!(re1.len() == len && im0.len() == len && im1.len() == len && len % n == 0);
+            ffi::check(unsafe {
+                ffi::cfft_f128_inv_host(self.h.0, re0.as_mut_ptr(), re1.as_mut_ptr(), im0.as_mut_ptr(), im1.as_mut_ptr(), len as u64, (len / n) as u64)
+            });
+        }
+    }
+}
+
+/// Device-pointer entry points (stream ordered, no host copies) for callers that keep their
+/// polynomials on the GPU.
+pub mod device {
+    use crate::ffi;
+    use core::ffi::c_void;
+
+    /// # Safety
+    /// `dev_buf` must point to `batch * fft_size` c64 on the plan's device; `stream` is a `cudaStream_t`.
+    pub unsafe fn c64_fwd(plan: *const ffi::cfft_plan, dev_buf: *mut c_void, batch: u64, stream: *mut c_void) {
+        ffi::check(ffi::cfft_c64_fwd(plan, dev_buf, batch, stream));
+    }
+    /// # Safety
+    /// See [`c64_fwd`].
+    pub unsafe fn c64_inv(plan: *const ffi::cfft_plan, dev_buf: *mut c_void, batch: u64, stream: *mut c_void) {
+        ffi::check(ffi::cfft_c64_inv(plan, dev_buf, batch, stream));
+    }
+}
