@@ -178,15 +178,14 @@ cfft_status check_device(int device)
     return CFFT_OK;
 }
 
-// Method::Measure replacement: deterministic per-size choice (see DESIGN.md "plan selection").
+// Method::Measure replacement: deterministic per-size choice.  The
+// Fourier-domain order is a function of base_n, so it must not depend on a timing race.
 void measure_choice(uint64_t n, int *algo, uint64_t *base_n)
 {
-    // the reference keeps base_n = n for n <= 256 (src/unordered.rs:561-564) and otherwise
-    // picks base_n in {512, 1024}; radix-16 stages minimise the number of shared-memory
-    // exchanges on the device.
-    *algo = CFFT_DIF16;
-    if (n <= 256) *base_n = n;
-    else *base_n = (n >= 1024) ? 1024 : 512;
+    *algo = CFFT_DIF16; // radix-16 stages minimise the number of shared-memory exchanges
+    if (n <= 256) *base_n = n;                       // as the reference, src/unordered.rs:561-564
+    else if (fast_b256_supported(n, CFFT_DIF16, 256)) *base_n = 256; // register kernel (c64_fast.cu)
+    else *base_n = 1024;
 }
 
 } // namespace
