@@ -332,10 +332,9 @@ def main():
     total_ms = t_begin.elapsed_time(t_end)
     fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
     inv_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
+    from concrete_fft_b200.sharding import max_over_ranks
+
+    total_ms = max_over_ranks(total_ms, dist, dev)
     value = 2.0 * batch * world * K / (total_ms * 1e-3)
 
     # ---- end to end through the host-memory API ----------------------------------------------
@@ -369,10 +368,7 @@ def main():
                 np.multiply(hnp[:1], inv_scale, out=hnp[:1])
         barrier()
         el = time.perf_counter() - t0
-        te = torch.tensor([el], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        el = float(te.item())
+        el = max_over_ranks(el, dist, dev)
         e2e = {"value": 2.0 * batch * world * args.e2e_steps / el, "unit": "transforms/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
                "ms_per_step": 1e3 * el / args.e2e_steps,
