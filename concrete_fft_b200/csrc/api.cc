@@ -137,33 +137,58 @@ cfft_status build_fast_tables(cfft_plan *p)
 {
     if (getenv("CFFT_B200_FORCE_EXACT")) return CFFT_OK;
     if (p->kind != KIND_UNORDERED || !fast_b256_supported(p->n, p->algo, p->base_n)) return CFFT_OK;
+    // levels top-down; forward offsets from prog[0], inverse offsets from prog[1] (stored bottom-up)
+    std::vector<Stage> tops_f, tops_i;
+    for (int i = 0; i < p->prog[0].count; i++) if (p->prog[0].st[i].kind == ST_TOP) tops_f.push_back(p->prog[0].st[i]);
+    for (int i = p->prog[1].count - 1; i >= 0; i--) if (p->prog[1].st[i].kind == ST_TOP) tops_i.push_back(p->prog[1].st[i]);
     for (int d = 0; d < 2; d++) {
         std::vector<cplx> out;
-        uint32_t off[3] = {0, 0, 0};
-        const StageProgram &pg = p->prog[0]; // level list top-down with forward offsets
-        int lvl = 0;
-        // inverse offsets of the same levels live in prog[1] in reverse order
-        std::vector<Stage> tops_f, tops_i;
-        for (int i = 0; i < pg.count; i++) if (pg.st[i].kind == ST_TOP) tops_f.push_back(pg.st[i]);
-        for (int i = p->prog[1].count - 1; i >= 0; i--) if (p->prog[1].st[i].kind == ST_TOP) tops_i.push_back(p->prog[1].st[i]);
-        for (size_t i = 0; i < tops_f.size() && lvl < 2; i++, lvl++) {
+        p->fast_levels.clear();
+        for (size_t i = 0; i < tops_f.size(); i++) {
             const Stage &st = d == 0 ? tops_f[i] : tops_i[i];
             const uint32_t r = uint32_t(st.radix), m = st.span / r;
-            off[lvl] = uint32_t(out.size());
+            p->fast_levels.push_back(cfft_plan::FastLevel{st.radix, st.span, uint32_t(out.size())});
             const cplx *src = p->h_tw[d].data() + st.tw_off;
             for (uint32_t k = 1; k < r; k++)
-                for (uint32_t q = 0; q < m; q++) out.push_back(src[(r - 1) * q + (k - 1)]);
+                for (uint32_t q = 0; q < m; q++) out.push_back(src[size_t(r - 1) * q + (k - 1)]);
         }
-        off[2] = uint32_t(out.size());
+        p->fast_base_off = uint32_t(out.size());
         // base table: forward at the end of the level tables, inverse at offset 0; planar half first
         const size_t base_off = d == 0 ? p->h_tw[0].size() - 2 * p->base_n : 0;
         for (uint64_t i = 0; i < p->base_n; i++) out.push_back(p->h_tw[d][base_off + i]);
         CU(cudaMalloc(reinterpret_cast<void **>(&p->d_fast_tw[d]), out.size() * sizeof(cplx)));
         CU(cudaMemcpy(p->d_fast_tw[d], out.data(), out.size() * sizeof(cplx), cudaMemcpyHostToDevice));
-        for (int i = 0; i < 3; i++) p->fast_off[i] = off[i];
     }
-    p->fast_variant = 1;
-    p->kernel_name = "fast-b256-regs";
+    if (p->n <= 8192) {
+        p->fast_variant = 1;
+        p->kernel_name = "fast-b256-regs";
+        return CFFT_OK;
+    }
+    // n > 8192: group the levels (8, 8, ..., 8, [4|2]) into HBM passes of combined radix <= 256:
+    // the last group takes the tail level plus up to two radix-8 levels, the rest pair up.
+    const int nl = int(p->fast_levels.size());
+    std::vector<std::pair<int, int>> spans; // [first, last] level index per group, built back to front
+    int hi = nl - 1;
+    {
+        int lo = hi;
+        const bool tail = p->fast_levels[size_t(hi)].radix != 8;
+        const int want = tail ? 3 : 2;
+        while (lo > 0 && hi - lo + 1 < want) lo--;
+        spans.push_back({lo, hi});
+        hi = lo - 1;
+    }
+    while (hi >= 0) {
+        const int lo = hi >= 1 ? hi - 1 : hi;
+        spans.push_back({lo, hi});
+        hi = lo - 1;
+    }
+    for (auto it = spans.rbegin(); it != spans.rend(); ++it) {
+        cfft_plan::FastGroup g{{1, 1, 1}, p->fast_levels[size_t(it->first)].span, it->first};
+        for (int i = it->first; i <= it->second; i++) g.radices[i - it->first] = p->fast_levels[size_t(i)].radix;
+        p->fast_groups.push_back(g);
+    }
+    p->fast_variant = 2;
+    p->kernel_name = "fast-b256-column+rows";
     return CFFT_OK;
 }
 
@@ -184,8 +209,7 @@ void measure_choice(uint64_t n, int *algo, uint64_t *base_n)
 {
     *algo = CFFT_DIF16; // radix-16 stages minimise the number of shared-memory exchanges
     if (n <= 256) *base_n = n;                       // as the reference, src/unordered.rs:561-564
-    else if (fast_b256_supported(n, CFFT_DIF16, 256)) *base_n = 256; // register kernel (c64_fast.cu)
-    else *base_n = 1024;
+    else *base_n = 256;                              // register / column kernels (c64_fast.cu)
 }
 
 } // namespace
@@ -193,7 +217,7 @@ void measure_choice(uint64_t n, int *algo, uint64_t *base_n)
 namespace cfft {
 cudaError_t launch_c64(const cfft_plan *plan, bool inverse, double2 *data, uint64_t batch, cudaStream_t st)
 {
-    if (plan->fast_variant == 1) return launch_c64_fast_b256(plan, inverse, data, batch, st);
+    if (plan->fast_variant != 0) return launch_c64_fast_b256(plan, inverse, data, batch, st);
     return launch_c64_exact(plan, inverse, data, batch, st);
 }
 void count_launch(uint64_t k) { g_launches.fetch_add(k, std::memory_order_relaxed); }

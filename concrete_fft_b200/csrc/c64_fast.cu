@@ -1,5 +1,7 @@
 // c64_fast.cu -- register-resident c64 kernels for unordered plans with base (Dif16, 256):
 //   n = 256 * R1 * R2,  R1, R2 in {1, 2, 4, 8}  ->  n = 256 .. 8192   (TFHE polynomial sizes)
+//   n > 8192: the levels run as column passes (c64_column.cu), then this file's N = 256 kernel
+//   runs the base FFTs on contiguous rows.
 //
 // Same butterflies, same twiddle values and same permuted output order as the reference for
 // Method::UserProvided { base_algo: Dif16, base_n: 256 }, so the result is bit-identical to
@@ -92,16 +94,17 @@ template <bool FWD, bool G_IN, bool G_OUT>
 __device__ __forceinline__ void base256(const c64 *__restrict__ src, c64 *__restrict__ sm_blk, c64 *__restrict__ dst,
                                         const c64 *__restrict__ tw_planar, int lane16, c64 (&v)[16])
 {
+    const unsigned hmask = 0xFFFFu << (threadIdx.x & 16); // the 16 lanes that own this block
     // pass 1: x[p + 16k] -> y[16p + k] = w[p + 16k] * DFT16(x)_k       src/dif16.rs:449-623
 #pragma unroll
     for (int k = 0; k < 16; k++) v[k] = G_IN ? ld_stream(src + lane16 + 16 * k) : src[lane16 + 16 * k];
     bf16<FWD>(v);
 #pragma unroll
     for (int k = 1; k < 16; k++) v[k] = cmul(ld_tw(tw_planar + lane16 + 16 * k), v[k]);
-    __syncwarp(); // the half-warp has finished reading its block
+    __syncwarp(hmask); // the half-warp has finished reading its block
 #pragma unroll
     for (int k = 0; k < 16; k++) sm_blk[16 * lane16 + (k ^ lane16)] = v[k]; // XOR swizzle: conflict-free
-    __syncwarp();
+    __syncwarp(hmask);
     // pass 2: terminal radix-16 on y[j + 16k]                           src/dif16.rs:649-827
 #pragma unroll
     for (int k = 0; k < 16; k++) v[k] = sm_blk[16 * k + (lane16 ^ k)];
@@ -110,7 +113,7 @@ __device__ __forceinline__ void base256(const c64 *__restrict__ src, c64 *__rest
 #pragma unroll
         for (int k = 0; k < 16; k++) st_stream(dst + lane16 + 16 * k, v[k]);
     } else {
-        __syncwarp(); // swizzled data consumed by the whole half-warp before natural-order overwrite
+        __syncwarp(hmask); // swizzled data consumed by the whole half-warp before natural-order overwrite
 #pragma unroll
         for (int k = 0; k < 16; k++) dst[lane16 + 16 * k] = v[k];
     }
@@ -203,10 +206,12 @@ cudaError_t launch_cfg(bool inverse, c64 *data, uint64_t batch, const FastTables
 
 } // namespace
 
-// Does a plan qualify?  unordered, base (Dif16, 256), n = 256 .. 8192.
+// Does a plan qualify?  unordered, base (Dif16, 256), n >= 256.
+//   n <= 8192 : one kernel (levels + base FFT fused, one HBM round trip)
+//   n >  8192 : column passes for the levels (c64_column.cu), then the base FFTs as rows of 256
 bool fast_b256_supported(uint64_t n, int base_algo, uint64_t base_n)
 {
-    return base_algo == 6 /* Dif16 */ && base_n == 256 && n >= 256 && n <= 8192;
+    return base_algo == 6 /* Dif16 */ && base_n == 256 && n >= 256 && n <= (uint64_t{1} << 26);
 }
 
 cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *data, uint64_t batch, cudaStream_t stream)
@@ -215,9 +220,28 @@ cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *d
     const int d = inverse ? 1 : 0;
     const c64 *base = plan->d_fast_tw[d];
     FastTables tb;
-    tb.top1 = base + plan->fast_off[0];
-    tb.top2 = base + plan->fast_off[1];
-    tb.base = base + plan->fast_off[2];
+    tb.top1 = plan->fast_levels.size() > 0 ? base + plan->fast_levels[0].off : base;
+    tb.top2 = plan->fast_levels.size() > 1 ? base + plan->fast_levels[1].off : base;
+    tb.base = base + plan->fast_base_off;
+    if (plan->fast_variant == 2) {
+        cudaError_t e;
+        const uint64_t rows = batch * (plan->n / 256);
+        auto run_group = [&](const cfft_plan::FastGroup &g) {
+            const double2 *tw[3] = {base, base, base};
+            for (int i = 0; i < 3; i++)
+                if (g.radices[i] > 1) tw[i] = base + plan->fast_levels[size_t(g.first_level + i)].off;
+            return launch_c64_column_group(inverse, data, batch, uint32_t(plan->n), g.span0, g.radices, tw, stream);
+        };
+        if (!inverse) {
+            for (const auto &g : plan->fast_groups)
+                if ((e = run_group(g)) != cudaSuccess) return e;
+            return launch_cfg<256, 1, 1>(false, data, rows, tb, stream);
+        }
+        if ((e = launch_cfg<256, 1, 1>(true, data, rows, tb, stream)) != cudaSuccess) return e;
+        for (auto it = plan->fast_groups.rbegin(); it != plan->fast_groups.rend(); ++it)
+            if ((e = run_group(*it)) != cudaSuccess) return e;
+        return cudaSuccess;
+    }
     switch (plan->n) {
     case 256: return launch_cfg<256, 1, 1>(inverse, data, batch, tb, stream);
     case 512: return launch_cfg<512, 2, 1>(inverse, data, batch, tb, stream);

@@ -55,7 +55,11 @@ struct cfft_plan {
     cfft::StageProgram prog[2];       // [0] fwd, [1] inv: every stage in execution order
     int fast_variant = 0;             // 0 = exact tile kernel only, 1 = c64_fast.cu (base Dif16/256)
     double2 *d_fast_tw[2] = {nullptr, nullptr}; // planar re-layout of the same twiddle values
-    uint32_t fast_off[3] = {0, 0, 0};           // offsets of [level 1 | level 2 | base] inside d_fast_tw
+    struct FastLevel { int radix; uint32_t span; uint32_t off; }; // off: planar table inside d_fast_tw
+    std::vector<FastLevel> fast_levels;         // unordered levels, outermost first
+    uint32_t fast_base_off = 0;                 // planar half of the base init_wt table
+    struct FastGroup { int radices[3]; uint32_t span0; int first_level; };
+    std::vector<FastGroup> fast_groups;         // fast_variant == 2: levels grouped per HBM pass
 
     // fft128
     std::vector<double> h_f128_tw[4];
@@ -72,6 +76,9 @@ cudaError_t launch_permute(const cfft_plan *plan, bool to_standard, const double
 // kernels (c64_fast.cu)
 bool fast_b256_supported(uint64_t n, int base_algo, uint64_t base_n);
 cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *data, uint64_t batch, cudaStream_t st);
+// kernels (c64_column.cu): one group of <= 3 unordered levels in one HBM pass
+cudaError_t launch_c64_column_group(bool inverse, double2 *data, uint64_t batch, uint32_t n, uint32_t span0,
+                                    const int radices[3], const double2 *const tw[3], cudaStream_t st);
 // dispatcher (api.cc): fast kernel when the plan has one, else the exact tile kernel
 cudaError_t launch_c64(const cfft_plan *plan, bool inverse, double2 *data, uint64_t batch, cudaStream_t st);
 // kernels (f128.cu)

@@ -147,8 +147,8 @@ def test_measure_method_is_deterministic_and_valid(C, torch):
         if n <= 256:
             assert base_n == n  # src/unordered.rs:561-564
         else:
-            assert base_n in (256, 1024) and base_n <= n
-            assert p1.kernel_name() == ("fast-b256-regs" if n <= 8192 else "exact-tile")
+            assert base_n == 256
+            assert p1.kernel_name() == ("fast-b256-regs" if n <= 8192 else "fast-b256-column+rows")
         x = rand_c(rng, 2, n)
         assert bits_equal(dev_run(torch, p1.fwd, x), O.UnorderedPlan(n, int(algo), base_n).fwd(x))
 
@@ -316,3 +316,23 @@ def test_fast_register_kernel_bit_exact(C, torch, n):
         del os.environ["CFFT_B200_FORCE_EXACT"]
     assert exact.kernel_name() == "exact-tile"
     assert bits_equal(dev_run(torch, exact.fwd, x), y)
+
+
+@pytest.mark.parametrize("logn", [14, 15, 16, 17, 18, 19, 20])
+def test_fast_large_n_column_passes_bit_exact(C, torch, logn):
+    """n = 2^14 .. 2^20 with base (Dif16, 256): levels as column passes (c64_column.cu) + base FFTs on
+    rows; same bits and same permuted order as the reference plan."""
+    n = 1 << logn
+    rng = np.random.default_rng(logn)
+    plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(C.ordered.FftAlgo.Dif16, 256))
+    assert plan.kernel_name() == "fast-b256-column+rows"
+    ref = O.UnorderedPlan(n, O.DIF16, 256)
+    for batch in ([1, 3] if logn <= 17 else [2]):
+        x = rand_c(rng, batch, n)
+        y = dev_run(torch, plan.fwd, x)
+        want = ref.fwd(x, threads=8)
+        assert bits_equal(y, want), (n, batch)
+        assert bits_equal(dev_run(torch, plan.inv, y), ref.inv(want, threads=8)), (n, batch)
+    pi = plan.permutation().astype(np.int64)
+    f = np.fft.fft(x[0])
+    assert np.linalg.norm(y[0][pi] - f) / np.linalg.norm(f) <= 1e-13 * logn
