@@ -45,15 +45,16 @@ __device__ __forceinline__ void col_level(c64 *__restrict__ g, c64 *__restrict__
 {
     constexpr int B = 16 / R, MROW = SG / R;
     const uint32_t m = uint32_t(MROW) * stride;
-    const int c = t & 15;
-    int row0[B];
+    int row0[B], col[B];
     uint32_t p[B];
 #pragma unroll
     for (int j = 0; j < B; j++) {
-        const int rb = (t + RG * j) >> 4; // butterfly index along rows, 0 .. RG/R - 1
+        const int b = t + RG * j;  // butterfly index inside the tile: 16 columns x RG/R row-butterflies
+        col[j] = b & 15;
+        const int rb = b >> 4;
         const int blk = rb / MROW, prow = rb - blk * MROW;
         row0[j] = blk * SG + prow;
-        p[j] = uint32_t(prow) * stride + col0 + uint32_t(c);
+        p[j] = uint32_t(prow) * stride + col0 + uint32_t(col[j]);
     }
     if (active || !G_IN) {
 #pragma unroll
@@ -61,7 +62,7 @@ __device__ __forceinline__ void col_level(c64 *__restrict__ g, c64 *__restrict__
 #pragma unroll
             for (int k = 0; k < R; k++) {
                 const int row = row0[j] + MROW * (FWD ? k : brev_c<R>(k));
-                v[j * R + k] = G_IN ? ld_stream(g + size_t(row) * stride + c) : s[row * 16 + c];
+                v[j * R + k] = G_IN ? ld_stream(g + size_t(row) * stride + col[j]) : s[row * 16 + col[j]];
             }
     }
     if (!G_IN && !G_OUT) __syncthreads(); // in place: all reads before any write
@@ -86,8 +87,8 @@ __device__ __forceinline__ void col_level(c64 *__restrict__ g, c64 *__restrict__
 #pragma unroll
             for (int k = 0; k < R; k++) {
                 const int row = row0[j] + MROW * (FWD ? brev_c<R>(k) : k);
-                if (G_OUT) st_stream(g + size_t(row) * stride + c, v[j * R + k]);
-                else s[row * 16 + c] = v[j * R + k];
+                if (G_OUT) st_stream(g + size_t(row) * stride + col[j], v[j * R + k]);
+                else s[row * 16 + col[j]] = v[j * R + k];
             }
     }
 }
