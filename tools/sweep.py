@@ -1,0 +1,100 @@
+#!/usr/bin/env python3
+"""Size sweep (BASELINE.json configs[4]): device-resident fwd / inv timing per size, one JSON
+line per (workload, n).  Batch = 2 GiB / bytes-per-transform (capped), inputs larger than L2.
+
+    python tools/sweep.py [--workload c64|f128|both] [--min 4] [--max 20] [--out gpurun_out/sweep.jsonl]
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def time_launches(torch, fn, reps):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    ev[0].record()
+    for i in range(reps):
+        fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(reps))
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="both")
+    ap.add_argument("--min", type=int, default=4)
+    ap.add_argument("--max", type=int, default=20)
+    ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--bytes", type=int, default=1 << 31)
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.jsonl"))
+    args = ap.parse_args()
+    import torch
+
+    import concrete_fft_b200 as C
+
+    peak = 6650.0
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    out = open(args.out, "a")
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(1)
+    if args.workload in ("c64", "both"):
+        for logn in range(args.min, args.max + 1):
+            n = 1 << logn
+            batch = max(1, args.bytes // (16 * n))
+            plan = C.unordered.Plan(n, C.unordered.Method.Measure())
+            algo, base_n = plan.algo()
+            data = torch.view_as_complex(torch.rand(batch, n, 2, dtype=torch.float64, device=dev, generator=g)).contiguous()
+            for _ in range(3):
+                plan.fwd(data); plan.inv(data); data.mul_(1.0 / n)
+            fwd_ms, fwd_best = time_launches(torch, lambda: plan.fwd(data), args.reps)
+            data.mul_(float(n) ** -args.reps)
+            inv_ms, inv_best = time_launches(torch, lambda: plan.inv(data), args.reps)
+            bytes_ = 2 * 16 * n * batch
+            rec = {"workload": "c64-unordered", "n": n, "batch": batch, "plan": "%s/%d" % (algo.name, base_n),
+                   "kernel": plan.kernel_name(), "fwd_ms": fwd_ms, "inv_ms": inv_ms,
+                   "fwd_gbs": bytes_ / fwd_ms / 1e6, "inv_gbs": bytes_ / inv_ms / 1e6,
+                   "frac_of_measured_hbm": bytes_ / fwd_ms / 1e6 / peak,
+                   "fwd_transforms_per_s": batch / fwd_ms * 1e3,
+                   "fwd_gflops_5nlog2n": 5.0 * n * logn * batch / fwd_ms / 1e6}
+            print(json.dumps(rec), flush=True)
+            out.write(json.dumps(rec) + "\n")
+            del data, plan
+            torch.cuda.empty_cache()
+    if args.workload in ("f128", "both"):
+        for logn in range(max(args.min, 5), min(args.max, 16) + 1):
+            n = 1 << logn
+            batch = max(1, (args.bytes // 2) // (32 * n))
+            plan = C.fft128.Plan(n)
+            planes = [torch.rand(batch, n, dtype=torch.float64, device=dev, generator=g), torch.zeros(batch, n, dtype=torch.float64, device=dev),
+                      torch.rand(batch, n, dtype=torch.float64, device=dev, generator=g), torch.zeros(batch, n, dtype=torch.float64, device=dev)]
+            for _ in range(3):
+                plan.fwd(*planes); plan.inv(*planes)
+                for p in planes:
+                    p.mul_(1.0 / n)
+            fwd_ms, _ = time_launches(torch, lambda: plan.fwd(*planes), 5)
+            for p in planes:
+                p.mul_(float(n) ** -5)
+            inv_ms, _ = time_launches(torch, lambda: plan.inv(*planes), 5)
+            instr = 94.0 * (n // 2) * logn
+            rec = {"workload": "fft128", "n": n, "batch": batch, "kernel": plan.kernel_name(), "fwd_ms": fwd_ms, "inv_ms": inv_ms,
+                   "fwd_transforms_per_s": batch / fwd_ms * 1e3, "inv_transforms_per_s": batch / inv_ms * 1e3,
+                   "fwd_fp64_pipe_frac_at_1965MHz": instr * batch / (fwd_ms * 1e-3) / (64 * 148 * 1965e6),
+                   "inv_fp64_pipe_frac_at_1965MHz": instr * batch / (inv_ms * 1e-3) / (64 * 148 * 1965e6),
+                   "fwd_gbs": 2 * 32 * n * batch / fwd_ms / 1e6}
+            print(json.dumps(rec), flush=True)
+            out.write(json.dumps(rec) + "\n")
+            del planes, plan
+            torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
