@@ -347,6 +347,14 @@ cfft_status cfft_f128_plan_create(cfft_plan **out, int device, uint64_t n)
             e = cudaMemcpy(p->d_f128_tw[i], p->h_f128_tw[i].data(), n * sizeof(double), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { cfft_plan_destroy(p); return cuda_fail(e, "f128 twiddle upload"); }
     }
+    {
+        std::vector<double> tw4(4 * n);
+        for (uint64_t i = 0; i < n; i++)
+            for (int k = 0; k < 4; k++) tw4[4 * i + k] = p->h_f128_tw[k][i];
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p->d_f128_tw4), 4 * n * sizeof(double));
+        if (e == cudaSuccess) e = cudaMemcpy(p->d_f128_tw4, tw4.data(), 4 * n * sizeof(double), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cfft_plan_destroy(p); return cuda_fail(e, "f128 twiddle upload"); }
+    }
     *out = p;
     return CFFT_OK;
 }
@@ -359,6 +367,7 @@ void cfft_plan_destroy(cfft_plan *p)
     for (int d = 0; d < 2; d++) if (p->d_fast_tw[d]) cudaFree(p->d_fast_tw[d]);
     if (p->d_monomial_tw) cudaFree(p->d_monomial_tw);
     for (int i = 0; i < 4; i++) if (p->d_f128_tw[i]) cudaFree(p->d_f128_tw[i]);
+    if (p->d_f128_tw4) cudaFree(p->d_f128_tw4);
     delete p;
 }
 

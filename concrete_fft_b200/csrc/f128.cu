@@ -91,15 +91,20 @@ F128_DEV void bfly_inv(ddc &z0, ddc &z1, ddc w)
 struct Planes { double *p[4]; };
 struct CPlanes { const double *p[4]; };
 
-F128_DEV ddc load_tw(const CPlanes &tw, uint32_t i)
+// twiddle k as one 32-byte record {re hi, re lo, im hi, im lo}: two 128-bit loads
+struct __align__(32) Tw4 { double re_hi, re_lo, im_hi, im_lo; };
+
+F128_DEV ddc load_tw(const Tw4 *__restrict__ tw, uint32_t i)
 {
-    return {{__ldg(tw.p[0] + i), __ldg(tw.p[1] + i)}, {__ldg(tw.p[2] + i), __ldg(tw.p[3] + i)}};
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(tw + i));
+    const double2 b = __ldg(reinterpret_cast<const double2 *>(tw + i) + 1);
+    return {{a.x, a.y}, {b.x, b.y}};
 }
 
 // Stages d0 .. d0+S-1 (t_d = n >> (d+1), m_d = 1 << d) on the G = 2^S elements
 // base + e*u, u = n >> (d0+S).  `row_pos` = position of element 0 inside its transform.
 template <int S, bool FWD>
-F128_DEV void run_group(ddc (&z)[1 << S], const CPlanes &tw, uint32_t row_pos, uint32_t logn, int d0)
+F128_DEV void run_group(ddc (&z)[1 << S], const Tw4 *__restrict__ tw, uint32_t row_pos, uint32_t logn, int d0)
 {
     constexpr int G = 1 << S;
     const uint32_t B = row_pos >> (logn - d0); // block index at stage d0
@@ -132,73 +137,138 @@ F128_DEV void run_group(ddc (&z)[1 << S], const CPlanes &tw, uint32_t row_pos, u
 
 constexpr int kThreads = 256;
 
-// one pass over a tile; src / dst are either the HBM tile or the shared-memory tile
-template <int S, bool FWD>
-F128_DEV void tile_pass(const Planes &src, const Planes &dst, uint32_t tile, uint32_t tile_row_off, uint32_t n,
-                        uint32_t logn, int d0, const CPlanes &tw)
+// Shared-memory tile: two arrays of double2 -- re = {hi, lo} and im = {hi, lo} per element -- so an
+// element moves with two 128-bit accesses.  Index swizzle i ^ ((i >> 3) & 7): for every pass
+// stride u = 2^a the eight lanes of a 128-bit phase land in eight different 16-byte banks.
+F128_DEV uint32_t swz(uint32_t i) { return i ^ ((i >> 3) & 7u); }
+
+// one pass over a tile; G_IN / G_OUT: that side is the HBM tile (four planar arrays), else smem
+template <int S, bool FWD, bool G_IN, bool G_OUT>
+F128_DEV void tile_pass(const Planes &g, double2 *__restrict__ sre, double2 *__restrict__ sim, uint32_t tile,
+                        uint32_t tile_row_off, uint32_t n, uint32_t logn, int d0, const Tw4 *__restrict__ tw, bool vec)
 {
     constexpr int G = 1 << S;
     const uint32_t u = n >> (d0 + S);
-    for (uint32_t g = threadIdx.x; g < tile / G; g += kThreads) {
-        const uint32_t hi = g / u, lo = g - hi * u;
+    for (uint32_t grp = threadIdx.x; grp < tile / G; grp += kThreads) {
+        const uint32_t hi = grp / u, lo = grp - hi * u;
         const uint32_t base = hi * (G * u) + lo;
         ddc z[G];
+        if (G_IN) {
+            if (vec && u == 1 && G >= 2) { // G consecutive doubles per plane: 128-bit loads
+                double buf[4][G];
 #pragma unroll
-        for (int e = 0; e < G; e++) {
-            const uint32_t i = base + e * u;
-            z[e] = {{src.p[0][i], src.p[1][i]}, {src.p[2][i], src.p[3][i]}};
+                for (int pl = 0; pl < 4; pl++)
+#pragma unroll
+                    for (int e = 0; e < G; e += 2) {
+                        const double2 t2 = *reinterpret_cast<const double2 *>(g.p[pl] + base + e);
+                        buf[pl][e] = t2.x;
+                        buf[pl][e + 1] = t2.y;
+                    }
+#pragma unroll
+                for (int e = 0; e < G; e++) z[e] = {{buf[0][e], buf[1][e]}, {buf[2][e], buf[3][e]}};
+            } else {
+#pragma unroll
+                for (int e = 0; e < G; e++) {
+                    const uint32_t i = base + e * u;
+                    z[e] = {{g.p[0][i], g.p[1][i]}, {g.p[2][i], g.p[3][i]}};
+                }
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < G; e++) {
+                const uint32_t i = swz(base + e * u);
+                const double2 a = sre[i], b = sim[i];
+                z[e] = {{a.x, a.y}, {b.x, b.y}};
+            }
         }
         run_group<S, FWD>(z, tw, (tile_row_off + base) & (n - 1), logn, d0);
+        if (G_OUT) {
+            if (vec && u == 1 && G >= 2) {
 #pragma unroll
-        for (int e = 0; e < G; e++) {
-            const uint32_t i = base + e * u;
-            dst.p[0][i] = z[e].re.hi;
-            dst.p[1][i] = z[e].re.lo;
-            dst.p[2][i] = z[e].im.hi;
-            dst.p[3][i] = z[e].im.lo;
+                for (int e = 0; e < G; e += 2) {
+                    *reinterpret_cast<double2 *>(g.p[0] + base + e) = make_double2(z[e].re.hi, z[e + 1].re.hi);
+                    *reinterpret_cast<double2 *>(g.p[1] + base + e) = make_double2(z[e].re.lo, z[e + 1].re.lo);
+                    *reinterpret_cast<double2 *>(g.p[2] + base + e) = make_double2(z[e].im.hi, z[e + 1].im.hi);
+                    *reinterpret_cast<double2 *>(g.p[3] + base + e) = make_double2(z[e].im.lo, z[e + 1].im.lo);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < G; e++) {
+                    const uint32_t i = base + e * u;
+                    g.p[0][i] = z[e].re.hi;
+                    g.p[1][i] = z[e].re.lo;
+                    g.p[2][i] = z[e].im.hi;
+                    g.p[3][i] = z[e].im.lo;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < G; e++) {
+                const uint32_t i = swz(base + e * u);
+                sre[i] = make_double2(z[e].re.hi, z[e].re.lo);
+                sim[i] = make_double2(z[e].im.hi, z[e].im.lo);
+            }
         }
     }
 }
 
+constexpr int kMaxPasses = 4; // tile <= 4096 elements = 12 stages = 4 passes of 3
 struct PassList {
     int count;
-    int d0[8];
-    int s[8];
+    int d0[kMaxPasses];
+    int s[kMaxPasses];
 };
+
+template <bool FWD, bool G_IN, bool G_OUT>
+F128_DEV void dispatch_pass(int s, const Planes &g, double2 *sre, double2 *sim, uint32_t tile, uint32_t row_off,
+                            uint32_t n, uint32_t logn, int d0, const Tw4 *tw, bool vec)
+{
+    if (s == 3) tile_pass<3, FWD, G_IN, G_OUT>(g, sre, sim, tile, row_off, n, logn, d0, tw, vec);
+    else if (s == 2) tile_pass<2, FWD, G_IN, G_OUT>(g, sre, sim, tile, row_off, n, logn, d0, tw, vec);
+    else tile_pass<1, FWD, G_IN, G_OUT>(g, sre, sim, tile, row_off, n, logn, d0, tw, vec);
+}
 
 template <bool FWD>
 __global__ void __launch_bounds__(kThreads, 2)
-f128_tile_kernel(Planes data, uint64_t total, uint32_t tile, uint32_t n, uint32_t logn, PassList passes, CPlanes tw)
+f128_tile_kernel(Planes data, uint64_t total, uint32_t tile, uint32_t n, uint32_t logn, PassList passes,
+                 const Tw4 *__restrict__ tw, bool vec)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *sm = reinterpret_cast<double *>(smem_raw);
+    double2 *sre = reinterpret_cast<double2 *>(smem_raw);
+    double2 *sim = sre + tile;
     const uint64_t start = uint64_t(blockIdx.x) * tile;
     const uint32_t valid = (total - start < tile) ? uint32_t(total - start) : tile;
     const uint32_t row_off = uint32_t(start & (n - 1));
-
-    Planes g, s;
+    Planes g;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        g.p[i] = data.p[i] + start;
-        s.p[i] = sm + size_t(i) * tile;
+    for (int i = 0; i < 4; i++) g.p[i] = data.p[i] + start;
+
+    const int last = passes.count - 1;
+    if (last == 0) {
+        dispatch_pass<FWD, true, true>(passes.s[0], g, sre, sim, valid, row_off, n, logn, passes.d0[0], tw, vec);
+        return;
     }
-    for (int pi = 0; pi < passes.count; pi++) {
-        const Planes &src = (pi == 0) ? g : s;
-        const Planes &dst = (pi == passes.count - 1) ? g : s;
-        const int d0 = passes.d0[pi];
-        switch (passes.s[pi]) {
-        case 3: tile_pass<3, FWD>(src, dst, valid, row_off, n, logn, d0, tw); break;
-        case 2: tile_pass<2, FWD>(src, dst, valid, row_off, n, logn, d0, tw); break;
-        default: tile_pass<1, FWD>(src, dst, valid, row_off, n, logn, d0, tw); break;
+    dispatch_pass<FWD, true, false>(passes.s[0], g, sre, sim, valid, row_off, n, logn, passes.d0[0], tw, vec);
+    __syncthreads();
+#pragma unroll
+    for (int pi = 1; pi < kMaxPasses - 1; pi++) {
+        if (pi < last) {
+            dispatch_pass<FWD, false, false>(passes.s[pi], g, sre, sim, valid, row_off, n, logn, passes.d0[pi], tw, vec);
+            __syncthreads();
         }
-        __syncthreads();
     }
+    // the last pass index is not a compile-time constant: select its parameters without indexing
+    int ls = passes.s[1], ld = passes.d0[1];
+#pragma unroll
+    for (int pi = 2; pi < kMaxPasses; pi++)
+        if (pi == last) { ls = passes.s[pi]; ld = passes.d0[pi]; }
+    dispatch_pass<FWD, false, true>(ls, g, sre, sim, valid, row_off, n, logn, ld, tw, vec);
 }
 
 // stages whose span exceeds a tile: one in-place pass through HBM
 template <int S, bool FWD>
 __global__ void __launch_bounds__(kThreads, 2)
-f128_global_pass(Planes data, uint64_t total, uint32_t n, uint32_t logn, int d0, CPlanes tw)
+f128_global_pass(Planes data, uint64_t total, uint32_t n, uint32_t logn, int d0, const Tw4 *__restrict__ tw)
 {
     constexpr int G = 1 << S;
     const uint32_t u = n >> (d0 + S);
@@ -226,7 +296,7 @@ f128_global_pass(Planes data, uint64_t total, uint32_t n, uint32_t logn, int d0,
 }
 
 template <bool FWD>
-cudaError_t launch_global(int S, Planes data, uint64_t total, uint32_t n, uint32_t logn, int d0, CPlanes tw,
+cudaError_t launch_global(int S, Planes data, uint64_t total, uint32_t n, uint32_t logn, int d0, const Tw4 *tw,
                           cudaStream_t stream)
 {
     uint64_t blocks = (total / (1u << S) + kThreads - 1) / kThreads;
@@ -263,7 +333,7 @@ cudaError_t launch_f128(const cfft_plan *plan, bool inverse, double *re0, double
     if (batch == 0) return cudaSuccess;
     const uint64_t total = uint64_t(n) * batch;
     Planes data = {{re0, re1, im0, im1}};
-    CPlanes tw = {{plan->d_f128_tw[0], plan->d_f128_tw[1], plan->d_f128_tw[2], plan->d_f128_tw[3]}};
+    const Tw4 *tw = reinterpret_cast<const Tw4 *>(plan->d_f128_tw4);
 
     // tile: whole transforms (up to 2048 elements) or a 4096-element sub-block of one transform
     uint32_t tile;
@@ -280,7 +350,7 @@ cudaError_t launch_f128(const cfft_plan *plan, bool inverse, double *re0, double
     }
 
     // global passes for d in [0, D0), at most 3 stages each; tile passes for d in [D0, logn)
-    int gd0[8], gs[8], gcount = 0;
+    int gd0[16], gs[16], gcount = 0;
     for (int d = 0; d < D0;) {
         const int s = (D0 - d >= 3) ? 3 : (D0 - d);
         gd0[gcount] = d;
@@ -296,6 +366,9 @@ cudaError_t launch_f128(const cfft_plan *plan, bool inverse, double *re0, double
         d += s;
     }
     const size_t smem = size_t(tile) * 4 * sizeof(double);
+    // 128-bit HBM accesses in the stride-1 pass need 16-byte aligned planes
+    const bool vec = ((reinterpret_cast<uintptr_t>(re0) | reinterpret_cast<uintptr_t>(re1) | reinterpret_cast<uintptr_t>(im0) |
+                       reinterpret_cast<uintptr_t>(im1)) & 15) == 0;
     const unsigned tiles = unsigned((total + tile - 1) / tile);
     cudaError_t e;
 
@@ -303,7 +376,7 @@ cudaError_t launch_f128(const cfft_plan *plan, bool inverse, double *re0, double
         for (int i = 0; i < gcount; i++)
             if ((e = launch_global<true>(gs[i], data, total, n, logn, gd0[i], tw, stream)) != cudaSuccess) return e;
         if ((e = configure_tile_kernel<true>()) != cudaSuccess) return e;
-        f128_tile_kernel<true><<<tiles, kThreads, smem, stream>>>(data, total, tile, n, logn, passes, tw);
+        f128_tile_kernel<true><<<tiles, kThreads, smem, stream>>>(data, total, tile, n, logn, passes, tw, vec);
         count_launch();
         return cudaGetLastError();
     }
@@ -315,7 +388,7 @@ cudaError_t launch_f128(const cfft_plan *plan, bool inverse, double *re0, double
         rev.s[i] = passes.s[passes.count - 1 - i];
     }
     if ((e = configure_tile_kernel<false>()) != cudaSuccess) return e;
-    f128_tile_kernel<false><<<tiles, kThreads, smem, stream>>>(data, total, tile, n, logn, rev, tw);
+    f128_tile_kernel<false><<<tiles, kThreads, smem, stream>>>(data, total, tile, n, logn, rev, tw, vec);
     count_launch();
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     for (int i = gcount - 1; i >= 0; i--)

@@ -64,6 +64,7 @@ struct cfft_plan {
     // fft128
     std::vector<double> h_f128_tw[4];
     double *d_f128_tw[4] = {nullptr, nullptr, nullptr, nullptr};
+    double *d_f128_tw4 = nullptr; // same values interleaved {re hi, re lo, im hi, im lo} per index
 };
 
 namespace cfft {

@@ -135,3 +135,20 @@ def test_full_size_n2048_batch16384_roundtrip(C, torch):
     err_re = ((w[0] / n - re0) + w[1] / n).abs().max()
     err_im = ((w[2] / n - im0) + w[3] / n).abs().max()
     assert float(err_re) < 1e-28 and float(err_im) < 1e-28
+
+
+def test_unaligned_planes_take_the_scalar_path(C, torch):
+    """Planes that are only 8-byte aligned must not use the 128-bit HBM accesses."""
+    rng = np.random.default_rng(30)
+    n, batch = 64, 5
+    planes = planes_random(rng, batch, n)
+    plan = C.fft128.Plan(n)
+    big = [torch.zeros(batch * n + 1, dtype=torch.float64, device="cuda") for _ in range(4)]
+    views = [b[1:] for b in big]  # data_ptr is 8 mod 16
+    for v, p in zip(views, planes):
+        v.copy_(torch.from_numpy(p.reshape(-1)))
+    assert views[0].data_ptr() % 16 == 8
+    plan.fwd(*views)
+    torch.cuda.synchronize()
+    want = O.F128Plan(n).fwd(*planes, variant=O.F128_FMA)
+    assert bits_equal([v.cpu().numpy().reshape(batch, n) for v in views], want)
