@@ -135,8 +135,11 @@ cfft_status upload_c64(cfft_plan *p)
 // (the reference itself lays the level tables out per SIMD width, src/unordered.rs:373-385).
 cfft_status build_fast_tables(cfft_plan *p)
 {
-    if (getenv("CFFT_B200_FORCE_EXACT")) return CFFT_OK;
-    if (p->kind != KIND_UNORDERED || !fast_b256_supported(p->n, p->algo, p->base_n)) return CFFT_OK;
+    const bool ordered_large = p->kind == KIND_ORDERED && p->allow_large;
+    if (!ordered_large) {
+        if (getenv("CFFT_B200_FORCE_EXACT")) return CFFT_OK;
+        if (p->kind != KIND_UNORDERED || !fast_b256_supported(p->n, p->algo, p->base_n)) return CFFT_OK;
+    }
     // levels top-down; forward offsets from prog[0], inverse offsets from prog[1] (stored bottom-up)
     std::vector<Stage> tops_f, tops_i;
     for (int i = 0; i < p->prog[0].count; i++) if (p->prog[0].st[i].kind == ST_TOP) tops_f.push_back(p->prog[0].st[i]);
@@ -159,7 +162,7 @@ cfft_status build_fast_tables(cfft_plan *p)
         CU(cudaMalloc(reinterpret_cast<void **>(&p->d_fast_tw[d]), out.size() * sizeof(cplx)));
         CU(cudaMemcpy(p->d_fast_tw[d], out.data(), out.size() * sizeof(cplx), cudaMemcpyHostToDevice));
     }
-    if (p->n <= 8192) {
+    if (p->n <= 8192 && !ordered_large) {
         p->fast_variant = 1;
         p->kernel_name = "fast-b256-regs";
         return CFFT_OK;
@@ -187,8 +190,8 @@ cfft_status build_fast_tables(cfft_plan *p)
         for (int i = it->first; i <= it->second; i++) g.radices[i - it->first] = p->fast_levels[size_t(i)].radix;
         p->fast_groups.push_back(g);
     }
-    p->fast_variant = 2;
-    p->kernel_name = "fast-b256-column+rows";
+    p->fast_variant = ordered_large ? 3 : 2;
+    p->kernel_name = ordered_large ? "ordered-b256-column+rows-std" : "fast-b256-column+rows";
     return CFFT_OK;
 }
 
@@ -248,7 +251,8 @@ cfft_status cfft_ordered_plan_create(cfft_plan **out, int device, uint64_t n, in
     *out = nullptr;
     if (!is_pow2(n)) return fail(CFFT_EINVAL, "n must be a power of two (src/ordered.rs:243)");
     if (ilog2(n) >= 11 && !allow_large) return fail(CFFT_EINVAL, "ordered plans need n <= 2^10 (src/ordered.rs:244)");
-    if (ilog2(n) >= 11) return fail(CFFT_EUNSUPPORTED, "ordered plans above 2^10 are not implemented yet");
+    if (ilog2(n) > 20) return fail(CFFT_EINVAL, "ordered plans are limited to n <= 2^20");
+    const bool large = ilog2(n) >= 11;
     if (method == CFFT_METHOD_MEASURE) algo = CFFT_DIF16;
     else if (method != CFFT_METHOD_USER) return fail(CFFT_EINVAL, "unknown method");
     if (algo < CFFT_DIF2 || algo > CFFT_DIT16) return fail(CFFT_EINVAL, "unknown FftAlgo");
@@ -266,6 +270,20 @@ cfft_status cfft_ordered_plan_create(cfft_plan **out, int device, uint64_t n, in
     p->base_n = n;
     p->method = method;
     p->kernel_name = "exact-tile";
+    if (large) {
+        // Extension (no reference implementation, src/ordered.rs:244): X = DFT(x) in standard order,
+        // computed as the unordered plan (Dif16, 256) with the un-permutation fused into the last pass.
+        p->allow_large = true;
+        p->algo = CFFT_DIF16;
+        p->base_n = 256; // internal base size; cfft_plan_algo reports n for ordered plans
+        init_unordered_twiddles(n, 256, 16, p->h_tw[0], p->h_tw[1]);
+        build_c64_programs(p);
+        st = upload_c64(p);
+        if (st == CFFT_OK) st = build_fast_tables(p);
+        if (st != CFFT_OK) { cfft_plan_destroy(p); return st; }
+        *out = p;
+        return CFFT_OK;
+    }
     // src/ordered.rs:259-270: zero-initialised 2n tables, filled by init_wt
     p->h_tw[0].assign(2 * n, cplx{0.0, 0.0});
     p->h_tw[1].assign(2 * n, cplx{0.0, 0.0});
@@ -390,7 +408,7 @@ cfft_status cfft_plan_algo(const cfft_plan *p, int *algo, uint64_t *base_n)
 {
     if (!p || p->kind == KIND_F128) return fail(CFFT_EINVAL, "not a c64 plan");
     if (algo) *algo = p->algo;
-    if (base_n) *base_n = p->base_n;
+    if (base_n) *base_n = (p->kind == KIND_ORDERED) ? p->n : p->base_n;
     return CFFT_OK;
 }
 
@@ -399,7 +417,7 @@ cfft_status cfft_plan_scratch_req(const cfft_plan *p, uint64_t *bytes, uint64_t 
     if (!p) return fail(CFFT_EINVAL, "null plan");
     // ordered: n c64 (src/ordered.rs:320-322); unordered: base_n c64 (src/unordered.rs:798-800);
     // fft128 needs none.  CACHELINE_ALIGN of aligned-vec 0.5 is 128 on x86-64.
-    if (bytes) *bytes = (p->kind == KIND_F128) ? 0 : p->base_n * sizeof(cplx);
+    if (bytes) *bytes = (p->kind == KIND_F128) ? 0 : (p->kind == KIND_ORDERED ? p->n : p->base_n) * sizeof(cplx);
     if (align) *align = 128;
     return CFFT_OK;
 }
@@ -477,7 +495,7 @@ cfft_status cfft_unordered_fwd_monomial(const cfft_plan *p, uint64_t degree, voi
 cfft_status cfft_unordered_permutation(const cfft_plan *p, uint64_t *out)
 {
     if (!p || p->kind == KIND_F128 || !out) return fail(CFFT_EINVAL, "not a c64 plan / null out");
-    const unsigned nb = ilog2(p->n), bb = ilog2(p->base_n);
+    const unsigned nb = ilog2(p->n), bb = ilog2(p->kind == KIND_ORDERED ? p->n : p->base_n);
     for (uint64_t i = 0; i < p->n; i++) out[i] = bit_rev_twice(nb, bb, i);
     return CFFT_OK;
 }
@@ -505,7 +523,7 @@ cfft_status cfft_unordered_from_standard(const cfft_plan *p, const void *src, vo
 cfft_status cfft_unordered_to_standard_host(const cfft_plan *p, const void *src, void *dst)
 {
     if (!p || p->kind == KIND_F128 || !src || !dst) return fail(CFFT_EINVAL, "bad argument");
-    const unsigned nb = ilog2(p->n), bb = ilog2(p->base_n);
+    const unsigned nb = ilog2(p->n), bb = p->kind == KIND_ORDERED ? nb : ilog2(p->base_n);
     const cplx *s = static_cast<const cplx *>(src);
     cplx *d = static_cast<cplx *>(dst);
     for (uint64_t i = 0; i < p->n; i++) d[i] = s[bit_rev_twice(nb, bb, i)]; // src/unordered.rs:967-969
@@ -514,7 +532,7 @@ cfft_status cfft_unordered_to_standard_host(const cfft_plan *p, const void *src,
 cfft_status cfft_unordered_from_standard_host(const cfft_plan *p, const void *src, uint64_t count, void *dst)
 {
     if (!p || p->kind == KIND_F128 || !src || !dst) return fail(CFFT_EINVAL, "bad argument");
-    const unsigned nb = ilog2(p->n), bb = ilog2(p->base_n);
+    const unsigned nb = ilog2(p->n), bb = p->kind == KIND_ORDERED ? nb : ilog2(p->base_n);
     const cplx *s = static_cast<const cplx *>(src);
     cplx *d = static_cast<cplx *>(dst);
     for (uint64_t i = 0; i < count && i < p->n; i++) d[bit_rev_twice(nb, bb, i)] = s[i]; // :1019-1022

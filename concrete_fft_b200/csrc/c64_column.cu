@@ -35,13 +35,15 @@ template <int R> __device__ __forceinline__ constexpr int brev_c(int k)
 }
 
 // One level of radix R whose blocks span SG rows of the tile (RG rows x 16 columns).
-//   g      : first element of the tile in HBM, element (row, c) at g[row * stride + c]
+//   g/gout : first element of the tile in the HBM source / destination (same buffer when in place),
+//            element (row, c) at [row * stride + c]
 //   s      : the tile in shared memory, element (row, c) at s[row * 16 + c]
 //   tw     : planar twiddles of this level, w_k[p] at tw[(k-1) * m + p], m = SG/R * stride
 //   col0   : column of the tile's first element inside the chunk
 template <int R, int SG, int RG, bool FWD, bool G_IN, bool G_OUT>
-__device__ __forceinline__ void col_level(c64 *__restrict__ g, c64 *__restrict__ s, const c64 *__restrict__ tw,
-                                          uint32_t stride, uint32_t col0, int t, bool active, c64 (&v)[16])
+__device__ __forceinline__ void col_level(const c64 *__restrict__ g, c64 *__restrict__ gout, c64 *__restrict__ s,
+                                          const c64 *__restrict__ tw, uint32_t stride, uint32_t col0, int t, bool active,
+                                          c64 (&v)[16])
 {
     constexpr int B = 16 / R, MROW = SG / R;
     const uint32_t m = uint32_t(MROW) * stride;
@@ -87,7 +89,7 @@ __device__ __forceinline__ void col_level(c64 *__restrict__ g, c64 *__restrict__
 #pragma unroll
             for (int k = 0; k < R; k++) {
                 const int row = row0[j] + MROW * (FWD ? brev_c<R>(k) : k);
-                if (G_OUT) st_stream(g + size_t(row) * stride + col[j], v[j * R + k]);
+                if (G_OUT) st_stream(gout + size_t(row) * stride + col[j], v[j * R + k]);
                 else s[row * 16 + col[j]] = v[j * R + k];
             }
     }
@@ -111,7 +113,7 @@ template <int RG> struct ColCfg {
 
 template <int RA, int RB, int RC, bool FWD>
 __global__ void __launch_bounds__(ColCfg<RA * RB * RC>::NT, ColCfg<RA * RB * RC>::MINB)
-c64_column_kernel(c64 *__restrict__ data, ColParams prm)
+c64_column_kernel(const c64 *__restrict__ src, c64 *__restrict__ dst, ColParams prm)
 {
     constexpr int RG = RA * RB * RC;
     using Cfg = ColCfg<RG>;
@@ -125,40 +127,42 @@ c64_column_kernel(c64 *__restrict__ data, ColParams prm)
     const uint32_t tt = uint32_t(tl - row * prm.tiles_per_row);
     const uint32_t chunk = tt / prm.tiles_per_chunk;
     const uint32_t col0 = (tt - chunk * prm.tiles_per_chunk) * 16;
-    c64 *g = data + row * prm.n + size_t(chunk) * prm.span0 + col0;
+    const size_t goff = row * prm.n + size_t(chunk) * prm.span0 + col0;
+    const c64 *g = src + goff;
+    c64 *go = dst + goff;
     c64 *s = reinterpret_cast<c64 *>(smem_raw) + size_t(lt) * RG * 16;
     c64 v[16];
     const uint32_t st = prm.stride;
 
     if (FWD) {
-        col_level<RA, SG0, RG, true, true, (RB == 1)>(g, s, prm.tw[0], st, col0, t, active, v);
+        col_level<RA, SG0, RG, true, true, (RB == 1)>(g, go, s, prm.tw[0], st, col0, t, active, v);
         if (RB > 1) {
             __syncthreads();
-            col_level<RB, SG1, RG, true, false, (RC == 1)>(g, s, prm.tw[1], st, col0, t, active, v);
+            col_level<RB, SG1, RG, true, false, (RC == 1)>(g, go, s, prm.tw[1], st, col0, t, active, v);
         }
         if (RC > 1) {
             __syncthreads();
-            col_level<RC, SG2, RG, true, false, true>(g, s, prm.tw[2], st, col0, t, active, v);
+            col_level<RC, SG2, RG, true, false, true>(g, go, s, prm.tw[2], st, col0, t, active, v);
         }
     } else {
         if (RC > 1) {
-            col_level<RC, SG2, RG, false, true, false>(g, s, prm.tw[2], st, col0, t, active, v);
+            col_level<RC, SG2, RG, false, true, false>(g, go, s, prm.tw[2], st, col0, t, active, v);
             __syncthreads();
-            col_level<RB, SG1, RG, false, false, false>(g, s, prm.tw[1], st, col0, t, active, v);
+            col_level<RB, SG1, RG, false, false, false>(g, go, s, prm.tw[1], st, col0, t, active, v);
             __syncthreads();
-            col_level<RA, SG0, RG, false, false, true>(g, s, prm.tw[0], st, col0, t, active, v);
+            col_level<RA, SG0, RG, false, false, true>(g, go, s, prm.tw[0], st, col0, t, active, v);
         } else if (RB > 1) {
-            col_level<RB, SG1, RG, false, true, false>(g, s, prm.tw[1], st, col0, t, active, v);
+            col_level<RB, SG1, RG, false, true, false>(g, go, s, prm.tw[1], st, col0, t, active, v);
             __syncthreads();
-            col_level<RA, SG0, RG, false, false, true>(g, s, prm.tw[0], st, col0, t, active, v);
+            col_level<RA, SG0, RG, false, false, true>(g, go, s, prm.tw[0], st, col0, t, active, v);
         } else {
-            col_level<RA, SG0, RG, false, true, true>(g, s, prm.tw[0], st, col0, t, active, v);
+            col_level<RA, SG0, RG, false, true, true>(g, go, s, prm.tw[0], st, col0, t, active, v);
         }
     }
 }
 
 template <int RA, int RB, int RC>
-cudaError_t launch_group(bool inverse, c64 *data, const ColParams &prm, cudaStream_t stream)
+cudaError_t launch_group(bool inverse, const c64 *src, c64 *dst, const ColParams &prm, cudaStream_t stream)
 {
     constexpr int RG = RA * RB * RC;
     using Cfg = ColCfg<RG>;
@@ -177,16 +181,16 @@ cudaError_t launch_group(bool inverse, c64 *data, const ColParams &prm, cudaStre
         }
     }
     const uint64_t ctas = (prm.total_tiles + Cfg::TPC - 1) / Cfg::TPC;
-    if (inverse) ik<<<unsigned(ctas), Cfg::NT, smem, stream>>>(data, prm);
-    else fk<<<unsigned(ctas), Cfg::NT, smem, stream>>>(data, prm);
+    if (inverse) ik<<<unsigned(ctas), Cfg::NT, smem, stream>>>(src, dst, prm);
+    else fk<<<unsigned(ctas), Cfg::NT, smem, stream>>>(src, dst, prm);
     count_launch();
     return cudaGetLastError();
 }
 
 } // namespace
 
-// radices: outermost level first; 1 = absent
-cudaError_t launch_c64_column_group(bool inverse, double2 *data, uint64_t batch, uint32_t n, uint32_t span0,
+// radices: outermost level first; 1 = absent.  src == dst: in place; else out of place (ordered plans)
+cudaError_t launch_c64_column_group(bool inverse, const double2 *src, double2 *dst, uint64_t batch, uint32_t n, uint32_t span0,
                                     const int radices[3], const double2 *const tw[3], cudaStream_t stream)
 {
     const int ra = radices[0], rb = radices[1], rc = radices[2];
@@ -201,14 +205,14 @@ cudaError_t launch_c64_column_group(bool inverse, double2 *data, uint64_t batch,
     for (int i = 0; i < 3; i++) prm.tw[i] = tw[i];
     const int key = ra * 100 + rb * 10 + rc;
     switch (key) {
-    case 811: return launch_group<8, 1, 1>(inverse, data, prm, stream);
-    case 411: return launch_group<4, 1, 1>(inverse, data, prm, stream);
-    case 211: return launch_group<2, 1, 1>(inverse, data, prm, stream);
-    case 821: return launch_group<8, 2, 1>(inverse, data, prm, stream);
-    case 841: return launch_group<8, 4, 1>(inverse, data, prm, stream);
-    case 881: return launch_group<8, 8, 1>(inverse, data, prm, stream);
-    case 882: return launch_group<8, 8, 2>(inverse, data, prm, stream);
-    case 884: return launch_group<8, 8, 4>(inverse, data, prm, stream);
+    case 811: return launch_group<8, 1, 1>(inverse, src, dst, prm, stream);
+    case 411: return launch_group<4, 1, 1>(inverse, src, dst, prm, stream);
+    case 211: return launch_group<2, 1, 1>(inverse, src, dst, prm, stream);
+    case 821: return launch_group<8, 2, 1>(inverse, src, dst, prm, stream);
+    case 841: return launch_group<8, 4, 1>(inverse, src, dst, prm, stream);
+    case 881: return launch_group<8, 8, 1>(inverse, src, dst, prm, stream);
+    case 882: return launch_group<8, 8, 2>(inverse, src, dst, prm, stream);
+    case 884: return launch_group<8, 8, 4>(inverse, src, dst, prm, stream);
     default: return cudaErrorInvalidValue;
     }
 }

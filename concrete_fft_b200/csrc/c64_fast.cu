@@ -18,6 +18,8 @@
 //     one half-warp: XOR-swizzled shared memory + __syncwarp, no block barrier.
 //   * Twiddles come from plan tables re-laid out planar (w_k[p], lanes on consecutive p) so
 //     each request is one or two 128 B lines; they stay L1-resident.
+#include <cstdlib>
+
 #include "c64_math.cuh"
 #include "plan.h"
 
@@ -204,6 +206,75 @@ cudaError_t launch_cfg(bool inverse, c64 *data, uint64_t batch, const FastTables
     return cudaGetLastError();
 }
 
+
+// ---- standard-order ("ordered") transforms above the reference's 2^10 cap ---------------------
+// X_i of an n = 256 M transform sits, in the unordered layout, at row c = bitrev_L(i mod M),
+// column i / M (src/unordered.rs:1046-1051 with base_n = 256).  These kernels run the 256-point
+// base FFTs on TW rows whose `lo = i mod M` values are consecutive and move the tile between row
+// order and standard order through a padded shared-memory transpose, so both the row side and the
+// standard-order side of the pass are 256-byte-coalesced.
+template <int TW, bool FWD>
+__global__ void __launch_bounds__(16 * TW, TW == 16 ? 2 : 4)
+c64_rows256_std_kernel(const c64 *__restrict__ src, c64 *__restrict__ dst, uint32_t n, uint32_t logm,
+                       const c64 *__restrict__ tw_base)
+{
+    constexpr int PITCH = 257; // c64 per staged row: lanes that differ in `d` hit different banks
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c64 *s = reinterpret_cast<c64 *>(smem_raw);
+    const uint32_t m = 1u << logm;
+    const uint32_t tiles_per_row = m / TW;
+    const uint32_t b = blockIdx.x / tiles_per_row;
+    const uint32_t lo0 = (blockIdx.x - b * tiles_per_row) * TW;
+    const int d = threadIdx.x >> 4, lane16 = threadIdx.x & 15;
+    const uint32_t c = __brev(lo0 + uint32_t(d)) >> (32 - logm); // row that holds lo = lo0 + d
+    const size_t row_base = size_t(b) * n;
+    c64 v[16];
+    if (FWD) {
+        // rows (unordered layout) -> base FFT -> staged natural order -> standard-order scatter
+        base256<true, true, false>(src + row_base + size_t(c) * 256, s + d * PITCH, s + d * PITCH, tw_base, lane16, v);
+        __syncthreads();
+        const int dd = threadIdx.x % TW, h0 = threadIdx.x / TW;
+#pragma unroll 4
+        for (int hi = h0; hi < 256; hi += 16 * TW / TW)
+            st_stream(dst + row_base + size_t(hi) * m + lo0 + dd, s[dd * PITCH + hi]);
+    } else {
+        const int dd = threadIdx.x % TW, h0 = threadIdx.x / TW;
+#pragma unroll 4
+        for (int hi = h0; hi < 256; hi += 16 * TW / TW)
+            s[dd * PITCH + hi] = ld_stream(src + row_base + size_t(hi) * m + lo0 + dd);
+        __syncthreads();
+        base256<false, false, true>(s + d * PITCH, s + d * PITCH, dst + row_base + size_t(c) * 256, tw_base, lane16, v);
+    }
+}
+
+template <int TW>
+cudaError_t launch_rows_std(bool inverse, const c64 *src, c64 *dst, uint64_t batch, uint32_t n, const c64 *tw_base,
+                            cudaStream_t stream)
+{
+    const uint32_t m = n / 256;
+    uint32_t logm = 0;
+    while ((1u << logm) < m) logm++;
+    const size_t smem = size_t(TW) * 257 * sizeof(c64);
+    auto fk = c64_rows256_std_kernel<TW, true>;
+    auto ik = c64_rows256_std_kernel<TW, false>;
+    if (smem > 48 * 1024) {
+        static thread_local int configured_device = -1;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (configured_device != dev) {
+            cudaError_t e = cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(ik, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            if (e != cudaSuccess) return e;
+            configured_device = dev;
+        }
+    }
+    const uint64_t ctas = batch * (m / TW);
+    if (inverse) ik<<<unsigned(ctas), 16 * TW, smem, stream>>>(src, dst, n, logm, tw_base);
+    else fk<<<unsigned(ctas), 16 * TW, smem, stream>>>(src, dst, n, logm, tw_base);
+    count_launch();
+    return cudaGetLastError();
+}
+
 } // namespace
 
 // Does a plan qualify?  unordered, base (Dif16, 256), n >= 256.
@@ -223,23 +294,68 @@ cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *d
     tb.top1 = plan->fast_levels.size() > 0 ? base + plan->fast_levels[0].off : base;
     tb.top2 = plan->fast_levels.size() > 1 ? base + plan->fast_levels[1].off : base;
     tb.base = base + plan->fast_base_off;
-    if (plan->fast_variant == 2) {
-        cudaError_t e;
-        const uint64_t rows = batch * (plan->n / 256);
-        auto run_group = [&](const cfft_plan::FastGroup &g) {
+    if (plan->fast_variant == 3) {
+        // ordered: levels as column passes (the last one out of place into a workspace), then the base
+        // FFTs read the workspace rows and write standard order back into the caller's buffer.
+        c64 *ws = nullptr;
+        cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&ws), batch * plan->n * sizeof(c64), stream);
+        if (e != cudaSuccess) return e;
+        const uint32_t n32 = uint32_t(plan->n);
+        auto group = [&](const cfft_plan::FastGroup &g, const c64 *src, c64 *dst) {
             const double2 *tw[3] = {base, base, base};
             for (int i = 0; i < 3; i++)
                 if (g.radices[i] > 1) tw[i] = base + plan->fast_levels[size_t(g.first_level + i)].off;
-            return launch_c64_column_group(inverse, data, batch, uint32_t(plan->n), g.span0, g.radices, tw, stream);
+            return launch_c64_column_group(inverse, src, dst, batch, n32, g.span0, g.radices, tw, stream);
         };
+        auto rows = [&](const c64 *src, c64 *dst) {
+            return n32 / 256 >= 16 ? launch_rows_std<16>(inverse, src, dst, batch, n32, tb.base, stream)
+                                   : launch_rows_std<8>(inverse, src, dst, batch, n32, tb.base, stream);
+        };
+        const size_t ng = plan->fast_groups.size();
         if (!inverse) {
-            for (const auto &g : plan->fast_groups)
-                if ((e = run_group(g)) != cudaSuccess) return e;
-            return launch_cfg<256, 1, 1>(false, data, rows, tb, stream);
+            for (size_t i = 0; i < ng && e == cudaSuccess; i++)
+                e = group(plan->fast_groups[i], data, i + 1 == ng ? ws : data);
+            if (e == cudaSuccess) e = rows(ws, data);
+        } else {
+            e = rows(data, ws);
+            for (size_t i = ng; i-- > 0 && e == cudaSuccess;)
+                e = group(plan->fast_groups[i], i + 1 == ng ? ws : data, data);
         }
-        if ((e = launch_cfg<256, 1, 1>(true, data, rows, tb, stream)) != cudaSuccess) return e;
-        for (auto it = plan->fast_groups.rbegin(); it != plan->fast_groups.rend(); ++it)
-            if ((e = run_group(*it)) != cudaSuccess) return e;
+        cudaError_t e2 = cudaFreeAsync(ws, stream);
+        return e != cudaSuccess ? e : e2;
+    }
+    if (plan->fast_variant == 2) {
+        // Optional (CFFT_B200_L2_CHUNK_MB): run the passes chunk by chunk hoping the chunk written by one
+        // pass is still L2-resident for the next.  Measured on B200: slower at every chunk size
+        // (8..128 MB) than whole-batch passes, so it is off by default.
+        static const uint64_t chunk_bytes = [] {
+            const char *e = getenv("CFFT_B200_L2_CHUNK_MB");
+            const long mb = e ? atol(e) : 0; // default off: measured slower on B200
+            return uint64_t(mb > 0 ? mb : 1 << 20) << 20;
+        }();
+        uint64_t rows_per_chunk = chunk_bytes / (plan->n * sizeof(c64));
+        if (rows_per_chunk < 1) rows_per_chunk = 1;
+        const uint64_t per_row = plan->n / 256;
+        auto run_group = [&](const cfft_plan::FastGroup &g, c64 *d0, uint64_t rows) {
+            const double2 *tw[3] = {base, base, base};
+            for (int i = 0; i < 3; i++)
+                if (g.radices[i] > 1) tw[i] = base + plan->fast_levels[size_t(g.first_level + i)].off;
+            return launch_c64_column_group(inverse, d0, d0, rows, uint32_t(plan->n), g.span0, g.radices, tw, stream);
+        };
+        for (uint64_t r0 = 0; r0 < batch; r0 += rows_per_chunk) {
+            const uint64_t rows = (batch - r0 < rows_per_chunk) ? batch - r0 : rows_per_chunk;
+            c64 *d0 = data + r0 * plan->n;
+            cudaError_t e;
+            if (!inverse) {
+                for (const auto &g : plan->fast_groups)
+                    if ((e = run_group(g, d0, rows)) != cudaSuccess) return e;
+                if ((e = launch_cfg<256, 1, 1>(false, d0, rows * per_row, tb, stream)) != cudaSuccess) return e;
+            } else {
+                if ((e = launch_cfg<256, 1, 1>(true, d0, rows * per_row, tb, stream)) != cudaSuccess) return e;
+                for (auto it = plan->fast_groups.rbegin(); it != plan->fast_groups.rend(); ++it)
+                    if ((e = run_group(*it, d0, rows)) != cudaSuccess) return e;
+            }
+        }
         return cudaSuccess;
     }
     switch (plan->n) {

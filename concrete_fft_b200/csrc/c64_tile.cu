@@ -329,7 +329,7 @@ cudaError_t launch_permute(const cfft_plan *plan, bool to_standard, const double
     if (total == 0) return cudaSuccess;
     uint64_t blocks = (total + 255) / 256;
     if (blocks > 148ull * 32) blocks = 148ull * 32;
-    const uint32_t nbits = ilog2(plan->n), bbits = ilog2(plan->base_n);
+    const uint32_t nbits = ilog2(plan->n), bbits = plan->kind == KIND_ORDERED ? nbits : ilog2(plan->base_n);
     if (to_standard)
         permute_kernel<true><<<unsigned(blocks), 256, 0, stream>>>(src, dst, total, uint32_t(plan->n), nbits, bbits);
     else

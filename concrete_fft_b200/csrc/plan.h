@@ -53,7 +53,8 @@ struct cfft_plan {
     double2 *d_tw[2] = {nullptr, nullptr};
     double2 *d_monomial_tw = nullptr; // n entries, e^{-2 pi i k / n} (src/unordered.rs:714-720)
     cfft::StageProgram prog[2];       // [0] fwd, [1] inv: every stage in execution order
-    int fast_variant = 0;             // 0 = exact tile kernel only, 1 = c64_fast.cu (base Dif16/256)
+    int fast_variant = 0;             // 0 exact tile kernel; 1 fused register kernel; 2 column passes + rows;
+                                      // 3 ordered (standard order in/out) above 2^10: column passes + transposing rows
     double2 *d_fast_tw[2] = {nullptr, nullptr}; // planar re-layout of the same twiddle values
     struct FastLevel { int radix; uint32_t span; uint32_t off; }; // off: planar table inside d_fast_tw
     std::vector<FastLevel> fast_levels;         // unordered levels, outermost first
@@ -78,7 +79,7 @@ cudaError_t launch_permute(const cfft_plan *plan, bool to_standard, const double
 bool fast_b256_supported(uint64_t n, int base_algo, uint64_t base_n);
 cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *data, uint64_t batch, cudaStream_t st);
 // kernels (c64_column.cu): one group of <= 3 unordered levels in one HBM pass
-cudaError_t launch_c64_column_group(bool inverse, double2 *data, uint64_t batch, uint32_t n, uint32_t span0,
+cudaError_t launch_c64_column_group(bool inverse, const double2 *src, double2 *dst, uint64_t batch, uint32_t n, uint32_t span0,
                                     const int radices[3], const double2 *const tw[3], cudaStream_t st);
 // dispatcher (api.cc): fast kernel when the plan has one, else the exact tile kernel
 cudaError_t launch_c64(const cfft_plan *plan, bool inverse, double2 *data, uint64_t batch, cudaStream_t st);

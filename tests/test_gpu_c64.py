@@ -336,3 +336,33 @@ def test_fast_large_n_column_passes_bit_exact(C, torch, logn):
     pi = plan.permutation().astype(np.int64)
     f = np.fft.fft(x[0])
     assert np.linalg.norm(y[0][pi] - f) / np.linalg.norm(f) <= 1e-13 * logn
+
+
+@pytest.mark.parametrize("logn", [11, 12, 13, 14, 16, 17, 19, 20])
+def test_ordered_above_reference_cap(C, torch, logn):
+    """BASELINE configs[2]: standard-order transforms for n > 2^10.  The reference cannot build these
+    (src/ordered.rs:244), so the oracle is the DFT definition: the unordered reference plan
+    (Dif16, 256) un-permuted (SURVEY.md 8c caveat) -- bit-exact -- and numpy's FFT within tolerance."""
+    n = 1 << logn
+    rng = np.random.default_rng(1000 + logn)
+    with pytest.raises(C.PanicError):
+        C.ordered.Plan(n, C.ordered.Method.UserProvided(C.ordered.FftAlgo.Dif16))  # reference behaviour
+    plan = C.ordered.Plan(n, C.ordered.Method.Measure(), allow_large=True)
+    assert plan.fft_size() == n and plan.kernel_name() == "ordered-b256-column+rows-std"
+    ref = O.UnorderedPlan(n, O.DIF16, 256)
+    pi = O.permutation(n, 256)
+    batch = 3 if logn <= 16 else 2
+    x = rand_c(rng, batch, n)
+    y = dev_run(torch, plan.fwd, x)
+    want = ref.fwd(x, threads=8)[:, pi]
+    assert bits_equal(y, want)
+    f = np.fft.fft(x, axis=1)
+    assert (np.linalg.norm(y - f, axis=1) / np.linalg.norm(f, axis=1)).max() <= 1e-13 * logn
+    z = dev_run(torch, plan.inv, y)
+    perm_in = np.empty_like(y)
+    perm_in[:, pi] = y
+    assert bits_equal(z, ref.inv(perm_in, threads=8))
+    assert np.abs(z / n - x).max() < 1e-11
+    h = x.copy()
+    plan.fwd(h)  # host-memory entry
+    assert bits_equal(h, want)
