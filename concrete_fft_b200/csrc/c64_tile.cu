@@ -21,6 +21,11 @@ namespace {
 
 constexpr int kThreads = 256;
 
+// Shared-memory index swizzle: XOR the low three bits (the 16-byte bank group) with bits 3..5 and
+// 6..8.  Stage patterns touch either consecutive elements or elements R = 2..16 apart across lanes;
+// both become conflict-free for the eight lanes of a 128-bit phase.
+__device__ __forceinline__ uint32_t swz(uint32_t i) { return i ^ ((i >> 3) & 7u) ^ ((i >> 6) & 7u); }
+
 __device__ __forceinline__ uint32_t brev_small(uint32_t k, int bits)
 {
     return __brev(k) >> (32 - bits);
@@ -38,23 +43,23 @@ __device__ __forceinline__ void stage_top(c64 *buf, uint32_t valid, uint32_t n_c
     const uint32_t m = n_cur / R;
     for (uint32_t b = threadIdx.x; b < valid / R; b += kThreads) {
         const uint32_t blk = b / m, p = b - blk * m;
-        c64 *z = buf + blk * n_cur + p;
+        const uint32_t z = blk * n_cur + p;
         const c64 *wp = w + (R - 1) * p;
         c64 v[R];
         if (FWD) {
 #pragma unroll
-            for (int k = 0; k < R; k++) v[k] = z[m * k];
+            for (int k = 0; k < R; k++) v[k] = buf[swz(z + m * k)];
             bfR<R, true>(v);
-            z[0] = v[0];
+            buf[swz(z)] = v[0];
 #pragma unroll
-            for (int k = 1; k < R; k++) z[m * brev_small(k, RB)] = cmul(wp[k - 1], v[k]);
+            for (int k = 1; k < R; k++) buf[swz(z + m * brev_small(k, RB))] = cmul(wp[k - 1], v[k]);
         } else {
-            v[0] = z[0];
+            v[0] = buf[swz(z)];
 #pragma unroll
-            for (int k = 1; k < R; k++) v[k] = cmul(wp[k - 1], z[m * brev_small(k, RB)]);
+            for (int k = 1; k < R; k++) v[k] = cmul(wp[k - 1], buf[swz(z + m * brev_small(k, RB))]);
             bfR<R, false>(v);
 #pragma unroll
-            for (int k = 0; k < R; k++) z[m * k] = v[k];
+            for (int k = 0; k < R; k++) buf[swz(z + m * k)] = v[k];
         }
     }
 }
@@ -69,16 +74,16 @@ __device__ __forceinline__ void stage_core_dif(const c64 *x, c64 *y, uint32_t va
     for (uint32_t b = threadIdx.x; b < valid / R; b += kThreads) {
         const uint32_t blk = b / per_blk, rem = b - blk * per_blk;
         const uint32_t p = rem / s, q = rem - p * s;
-        const c64 *xi = x + blk * base_n + q + s * p;
-        c64 *yo = y + blk * base_n + q + s * R * p;
+        const uint32_t xi = blk * base_n + q + s * p;
+        const uint32_t yo = blk * base_n + q + s * R * p;
         const c64 *wp = w + R * p * s;
         c64 v[R];
 #pragma unroll
-        for (int k = 0; k < R; k++) v[k] = xi[s * m * k];
+        for (int k = 0; k < R; k++) v[k] = x[swz(xi + s * m * k)];
         bfR<R, FWD>(v);
-        yo[0] = v[0];
+        y[swz(yo)] = v[0];
 #pragma unroll
-        for (int k = 1; k < R; k++) yo[s * k] = cmul(wp[k], v[k]);
+        for (int k = 1; k < R; k++) y[swz(yo + s * k)] = cmul(wp[k], v[k]);
     }
 }
 
@@ -92,16 +97,16 @@ __device__ __forceinline__ void stage_core_dit(const c64 *y, c64 *x, uint32_t va
     for (uint32_t b = threadIdx.x; b < valid / R; b += kThreads) {
         const uint32_t blk = b / per_blk, rem = b - blk * per_blk;
         const uint32_t p = rem / s, q = rem - p * s;
-        const c64 *yi = y + blk * base_n + q + s * R * p;
-        c64 *xo = x + blk * base_n + q + s * p;
+        const uint32_t yi = blk * base_n + q + s * R * p;
+        const uint32_t xo = blk * base_n + q + s * p;
         const c64 *wp = w + R * p * s;
         c64 v[R];
-        v[0] = yi[0];
+        v[0] = y[swz(yi)];
 #pragma unroll
-        for (int k = 1; k < R; k++) v[k] = cmul(wp[k], yi[s * k]);
+        for (int k = 1; k < R; k++) v[k] = cmul(wp[k], y[swz(yi + s * k)]);
         bfR<R, FWD>(v);
 #pragma unroll
-        for (int k = 0; k < R; k++) xo[s * m * k] = v[k];
+        for (int k = 0; k < R; k++) x[swz(xo + s * m * k)] = v[k];
     }
 }
 
@@ -112,13 +117,13 @@ __device__ __forceinline__ void stage_end(c64 *buf, uint32_t valid, uint32_t bas
     const uint32_t part = base_n / R;
     for (uint32_t b = threadIdx.x; b < valid / R; b += kThreads) {
         const uint32_t blk = b / part, j = b - blk * part;
-        c64 *z = buf + blk * base_n + j;
+        const uint32_t z = blk * base_n + j;
         c64 v[R];
 #pragma unroll
-        for (int k = 0; k < R; k++) v[k] = z[part * k];
+        for (int k = 0; k < R; k++) v[k] = buf[swz(z + part * k)];
         bfR<R, FWD>(v);
 #pragma unroll
-        for (int k = 0; k < R; k++) z[part * k] = v[k];
+        for (int k = 0; k < R; k++) buf[swz(z + part * k)] = v[k];
     }
 }
 
@@ -129,13 +134,13 @@ c64_tile_kernel(c64 *__restrict__ data, uint64_t total, uint32_t tile, uint32_t 
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c64 *cur = reinterpret_cast<c64 *>(smem_raw);
-    c64 *oth = cur + tile;
+    c64 *oth = cur + ((tile + 7u) & ~7u); // swz() permutes inside aligned groups of 8 elements
 
     const uint64_t start = uint64_t(blockIdx.x) * tile;
     const uint32_t valid = (total - start < tile) ? uint32_t(total - start) : tile;
     c64 *g = data + start;
 
-    for (uint32_t i = threadIdx.x; i < valid; i += kThreads) cur[i] = g[i];
+    for (uint32_t i = threadIdx.x; i < valid; i += kThreads) cur[swz(i)] = g[i];
     __syncthreads();
 
     for (int si = 0; si < prog.count; si++) {
@@ -167,7 +172,7 @@ c64_tile_kernel(c64 *__restrict__ data, uint64_t total, uint32_t tile, uint32_t 
         __syncthreads();
     }
 
-    for (uint32_t i = threadIdx.x; i < valid; i += kThreads) g[i] = cur[i];
+    for (uint32_t i = threadIdx.x; i < valid; i += kThreads) g[i] = cur[swz(i)];
 }
 
 // ---- unordered level through HBM (span > tile) ----------------------------------------------
@@ -255,7 +260,7 @@ template <bool FWD>
 cudaError_t launch_tile(const StageProgram &prog, c64 *data, uint64_t total, uint32_t tile, uint32_t base_n,
                         const c64 *tw, cudaStream_t stream)
 {
-    const size_t smem = size_t(tile) * sizeof(c64) * 2;
+    const size_t smem = size_t((tile + 7u) & ~7u) * sizeof(c64) * 2;
     static thread_local int configured_device = -1;
     int dev = 0;
     cudaGetDevice(&dev);

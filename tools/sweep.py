@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--bytes", type=int, default=1 << 31)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.jsonl"))
+    ap.add_argument("--cufft", action="store_true", help="also time torch.fft.fft (cuFFT) as a reference point")
     args = ap.parse_args()
     import torch
 
@@ -59,12 +60,43 @@ def main():
             data.mul_(float(n) ** -args.reps)
             inv_ms, inv_best = time_launches(torch, lambda: plan.inv(data), args.reps)
             bytes_ = 2 * 16 * n * batch
+            # cuFFT (through torch.fft) as a GPU reference point only -- never on the product path
+            cufft_ms = None
+            if args.cufft and n >= 2:
+                try:
+                    outb = torch.fft.fft(data, dim=1)
+                    cufft_ms, _ = time_launches(torch, lambda: torch.fft.fft(data, dim=1, out=outb), 5)
+                    del outb
+                except Exception:
+                    cufft_ms = None
             rec = {"workload": "c64-unordered", "n": n, "batch": batch, "plan": "%s/%d" % (algo.name, base_n),
+                   "cufft_z2z_out_of_place_ms": cufft_ms, "cufft_gbs": (2 * 16 * n * batch / cufft_ms / 1e6) if cufft_ms else None,
                    "kernel": plan.kernel_name(), "fwd_ms": fwd_ms, "inv_ms": inv_ms,
                    "fwd_gbs": bytes_ / fwd_ms / 1e6, "inv_gbs": bytes_ / inv_ms / 1e6,
                    "frac_of_measured_hbm": bytes_ / fwd_ms / 1e6 / peak,
                    "fwd_transforms_per_s": batch / fwd_ms * 1e3,
                    "fwd_gflops_5nlog2n": 5.0 * n * logn * batch / fwd_ms / 1e6}
+            print(json.dumps(rec), flush=True)
+            out.write(json.dumps(rec) + "\n")
+            del data, plan
+            torch.cuda.empty_cache()
+    if args.workload in ("ordered", "both"):
+        for logn in range(max(args.min, 1), args.max + 1):
+            n = 1 << logn
+            batch = max(1, args.bytes // (16 * n))
+            if n > 1024:
+                batch = max(1, batch // 2)  # leave room for the out-of-place workspace
+            plan = C.ordered.Plan(n, C.ordered.Method.Measure(), allow_large=n > 1024)
+            data = torch.view_as_complex(torch.rand(batch, n, 2, dtype=torch.float64, device=dev, generator=g)).contiguous()
+            for _ in range(3):
+                plan.fwd(data); plan.inv(data); data.mul_(1.0 / n)
+            fwd_ms, _ = time_launches(torch, lambda: plan.fwd(data), args.reps)
+            data.mul_(float(n) ** -args.reps)
+            inv_ms, _ = time_launches(torch, lambda: plan.inv(data), args.reps)
+            bytes_ = 2 * 16 * n * batch
+            rec = {"workload": "c64-ordered", "n": n, "batch": batch, "plan": plan.algo().name, "kernel": plan.kernel_name(),
+                   "fwd_ms": fwd_ms, "inv_ms": inv_ms, "fwd_gbs": bytes_ / fwd_ms / 1e6, "inv_gbs": bytes_ / inv_ms / 1e6,
+                   "frac_of_measured_hbm": bytes_ / fwd_ms / 1e6 / peak, "fwd_transforms_per_s": batch / fwd_ms * 1e3}
             print(json.dumps(rec), flush=True)
             out.write(json.dumps(rec) + "\n")
             del data, plan
