@@ -49,6 +49,8 @@ _SIGNATURES = {
     "cfft_plan_kind": (_int, [_vp]),
     "cfft_plan_device": (_int, [_vp]),
     "cfft_plan_kernel_name": (ctypes.c_char_p, [_vp]),
+    "cfft_plan_autotune": (ctypes.c_int32, [_vp, _u64]),
+    "cfft_plan_tuning_report": (_u64, [_vp, ctypes.c_char_p, _u64]),
     "cfft_c64_fwd": (ctypes.c_int32, [_vp, _vp, _u64, _vp]),
     "cfft_c64_inv": (ctypes.c_int32, [_vp, _vp, _u64, _vp]),
     "cfft_c64_fwd_host": (ctypes.c_int32, [_vp, _vp, _u64, _u64]),

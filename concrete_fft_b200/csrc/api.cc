@@ -162,7 +162,7 @@ cfft_status build_fast_tables(cfft_plan *p)
         CU(cudaMalloc(reinterpret_cast<void **>(&p->d_fast_tw[d]), out.size() * sizeof(cplx)));
         CU(cudaMemcpy(p->d_fast_tw[d], out.data(), out.size() * sizeof(cplx), cudaMemcpyHostToDevice));
     }
-    if (p->n <= 8192 && !ordered_large) {
+    if (p->n == 256) {
         p->fast_variant = 1;
         p->kernel_name = "fast-b256-regs";
         return CFFT_OK;
@@ -190,8 +190,12 @@ cfft_status build_fast_tables(cfft_plan *p)
         for (int i = it->first; i <= it->second; i++) g.radices[i - it->first] = p->fast_levels[size_t(i)].radix;
         p->fast_groups.push_back(g);
     }
-    p->fast_variant = ordered_large ? 3 : 2;
-    p->kernel_name = ordered_large ? "ordered-b256-column+rows-std" : "fast-b256-column+rows";
+    // n <= 8192 also has the fused single-kernel variant, the default there (autotune may switch)
+    p->fast_variant = ordered_large ? 3 : (p->n <= 8192 ? 1 : 2);
+    if (const char *fv = getenv("CFFT_B200_FAST_VARIANT")) // testing hook: force the multi-pass variant
+        if (!ordered_large && atoi(fv) == 2) p->fast_variant = 2;
+    p->kernel_name = ordered_large ? "ordered-b256-column+rows-std"
+                                   : (p->fast_variant == 1 ? "fast-b256-regs" : "fast-b256-column+rows");
     return CFFT_OK;
 }
 
@@ -213,6 +217,38 @@ void measure_choice(uint64_t n, int *algo, uint64_t *base_n)
     *algo = CFFT_DIF16; // radix-16 stages minimise the number of shared-memory exchanges
     if (n <= 256) *base_n = n;                       // as the reference, src/unordered.rs:561-564
     else *base_n = 256;                              // register / column kernels (c64_fast.cu)
+}
+
+} // namespace
+
+namespace {
+
+// time fwd+inv of the plan's current variant on a scratch batch: best of 3 after one warm-up
+cfft_status time_variant(cfft_plan *p, void *scratch, uint64_t batch, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1,
+                         float *ms_out)
+{
+    float best = 1e30f;
+    for (int it = 0; it < 4; it++) {
+        CU(cudaEventRecord(e0, st));
+        for (int dir = 0; dir < 2; dir++) {
+            cudaError_t e;
+            if (p->kind == KIND_F128) {
+                double *b = static_cast<double *>(scratch);
+                const uint64_t pl = batch * p->n;
+                e = launch_f128(p, dir == 1, b, b + pl, b + 2 * pl, b + 3 * pl, batch, st);
+            } else {
+                e = launch_c64(p, dir == 1, static_cast<double2 *>(scratch), batch, st);
+            }
+            if (e != cudaSuccess) return cuda_fail(e, "autotune launch");
+        }
+        CU(cudaEventRecord(e1, st));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (it > 0 && ms < best) best = ms;
+    }
+    *ms_out = best;
+    return CFFT_OK;
 }
 
 } // namespace
@@ -332,6 +368,7 @@ cfft_status cfft_unordered_plan_create(cfft_plan **out, int device, uint64_t n, 
     build_c64_programs(p);
     st = upload_c64(p);
     if (st == CFFT_OK) st = build_fast_tables(p);
+    if (st == CFFT_OK && method == CFFT_METHOD_MEASURE && !getenv("CFFT_B200_NO_AUTOTUNE")) st = cfft_plan_autotune(p, 0);
     if (st != CFFT_OK) { cfft_plan_destroy(p); return st; }
     *out = p;
     return CFFT_OK;
@@ -392,11 +429,20 @@ void cfft_plan_destroy(cfft_plan *p)
 cfft_status cfft_plan_clone(const cfft_plan *p, cfft_plan **out)
 {
     if (!p || !out) return fail(CFFT_EINVAL, "null argument");
+    cfft_status st;
     switch (p->kind) {
-    case KIND_ORDERED: return cfft_ordered_plan_create(out, p->device, p->n, CFFT_METHOD_USER, p->algo, p->allow_large);
-    case KIND_UNORDERED: return cfft_unordered_plan_create(out, p->device, p->n, CFFT_METHOD_USER, p->algo, p->base_n);
-    default: return cfft_f128_plan_create(out, p->device, p->n);
+    case KIND_ORDERED: st = cfft_ordered_plan_create(out, p->device, p->n, CFFT_METHOD_USER, p->algo, p->allow_large); break;
+    case KIND_UNORDERED: st = cfft_unordered_plan_create(out, p->device, p->n, CFFT_METHOD_USER, p->algo, p->base_n); break;
+    default: st = cfft_f128_plan_create(out, p->device, p->n); break;
     }
+    if (st == CFFT_OK) { // keep the source plan's tuned variant
+        (*out)->method = p->method;
+        (*out)->fast_variant = p->fast_variant;
+        (*out)->tile_elems = p->tile_elems;
+        (*out)->kernel_name = p->kernel_name;
+        (*out)->tuning_report = p->tuning_report;
+    }
+    return st;
 }
 
 uint64_t cfft_plan_fft_size(const cfft_plan *p) { return p ? p->n : 0; }
@@ -420,6 +466,90 @@ cfft_status cfft_plan_scratch_req(const cfft_plan *p, uint64_t *bytes, uint64_t 
     if (bytes) *bytes = (p->kind == KIND_F128) ? 0 : (p->kind == KIND_ORDERED ? p->n : p->base_n) * sizeof(cplx);
     if (align) *align = 128;
     return CFFT_OK;
+}
+
+cfft_status cfft_plan_autotune(cfft_plan *p, uint64_t batch_hint)
+{
+    if (!p) return fail(CFFT_EINVAL, "null plan");
+    if (p->n < 2) return CFFT_OK;
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
+    const uint64_t bytes_per = p->n * (p->kind == KIND_F128 ? 32u : 16u);
+    uint64_t batch = batch_hint ? batch_hint : std::max<uint64_t>(1, (uint64_t{128} << 20) / bytes_per);
+    if (batch * bytes_per > (uint64_t{1} << 30)) batch = std::max<uint64_t>(1, (uint64_t{1} << 30) / bytes_per);
+
+    struct Cand { std::string name; int fast_variant; uint32_t tile; };
+    std::vector<Cand> cands;
+    if (p->kind == KIND_F128 || p->fast_variant == 0) {
+        const char *fam = p->kind == KIND_F128 ? "f128-radix8-tile" : "exact-tile";
+        if (p->n <= 2048)
+            for (uint32_t t : {1024u, 2048u, 4096u})
+                if (t >= p->n) cands.push_back({std::string(fam) + "/" + std::to_string(t), p->fast_variant, t});
+    } else if (p->fast_variant == 1 || p->fast_variant == 2) {
+        if (p->n > 256 && p->n <= 8192) {
+            cands.push_back({"fast-b256-regs", 1, 0});
+            cands.push_back({"fast-b256-column+rows", 2, 0});
+        }
+    }
+    if (cands.size() < 2) {
+        p->tuning_report = p->kernel_name + ": only variant\n";
+        return CFFT_OK;
+    }
+    void *scratch = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cfft_status rc = CFFT_OK;
+    auto cleanup = [&] {
+        if (scratch) cudaFree(scratch);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        if (st) cudaStreamDestroy(st);
+    };
+    cudaError_t ce = cudaMalloc(&scratch, batch * bytes_per);
+    if (ce == cudaSuccess) ce = cudaMemset(scratch, 0, batch * bytes_per);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&e0);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&e1);
+    if (ce != cudaSuccess) { cleanup(); return cuda_fail(ce, "autotune setup"); }
+
+    const int keep_variant = p->fast_variant;
+    const uint32_t keep_tile = p->tile_elems;
+    std::string report;
+    float best_ms = 1e30f;
+    size_t best = 0;
+    for (size_t i = 0; i < cands.size() && rc == CFFT_OK; i++) {
+        p->fast_variant = cands[i].fast_variant;
+        p->tile_elems = cands[i].tile;
+        float ms = 0;
+        rc = time_variant(p, scratch, batch, st, e0, e1, &ms);
+        if (rc != CFFT_OK) break;
+        char line[160];
+        snprintf(line, sizeof line, "%s: %.4f ms (fwd+inv, batch %llu)\n", cands[i].name.c_str(), ms,
+                 static_cast<unsigned long long>(batch));
+        report += line;
+        if (ms < best_ms) { best_ms = ms; best = i; }
+    }
+    cleanup();
+    if (rc != CFFT_OK) {
+        p->fast_variant = keep_variant;
+        p->tile_elems = keep_tile;
+        return rc;
+    }
+    p->fast_variant = cands[best].fast_variant;
+    p->tile_elems = cands[best].tile;
+    if (p->kind != KIND_F128 && p->fast_variant != 0)
+        p->kernel_name = p->fast_variant == 1 ? "fast-b256-regs" : "fast-b256-column+rows";
+    p->tuning_report = report + "selected: " + cands[best].name + "\n";
+    return CFFT_OK;
+}
+
+uint64_t cfft_plan_tuning_report(const cfft_plan *p, char *buf, uint64_t buf_len)
+{
+    if (!p || !buf || buf_len == 0) return 0;
+    const uint64_t nbytes = std::min<uint64_t>(buf_len - 1, p->tuning_report.size());
+    memcpy(buf, p->tuning_report.data(), nbytes);
+    buf[nbytes] = 0;
+    return nbytes;
 }
 
 cfft_status cfft_plan_copy_twiddles(const cfft_plan *p, int which, void *host_out, uint64_t bytes)

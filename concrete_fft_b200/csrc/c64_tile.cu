@@ -291,7 +291,7 @@ cudaError_t launch_c64_exact(const cfft_plan *plan, bool inverse, double2 *data,
     uint32_t tile;
     if (n >= kTileMax) tile = kTileMax;
     else {
-        uint64_t rows = 2048 / n;
+        uint64_t rows = (plan->tile_elems ? plan->tile_elems : 2048u) / n;
         if (rows < 1) rows = 1;
         if (rows > batch) rows = batch;
         tile = uint32_t(rows * n);

@@ -341,10 +341,11 @@ cudaError_t launch_f128(const cfft_plan *plan, bool inverse, double *re0, double
     if (n > kF128TileMax) {
         tile = kF128TileMax;
         D0 = int(logn - ilog2(kF128TileMax));
-    } else if (n >= 2048) {
+    } else if (n >= 2048 && !(plan->tile_elems > n)) {
         tile = n;
     } else {
-        uint64_t rows = 2048 / n;
+        uint64_t rows = (plan->tile_elems ? plan->tile_elems : 2048u) / n;
+        if (rows < 1) rows = 1;
         if (rows > batch) rows = batch;
         tile = uint32_t(rows * n);
     }

@@ -47,6 +47,8 @@ struct cfft_plan {
     int method = 0;
     bool allow_large = false;
     std::string kernel_name;
+    std::string tuning_report;
+    uint32_t tile_elems = 0; // exact / fft128 tile size override chosen by the autotuner (0 = default)
 
     // c64
     std::vector<cfft::cplx> h_tw[2]; // [0] fwd, [1] inv (host copies, kept for clone / tests)

@@ -45,6 +45,12 @@ class Plan:
     def __repr__(self):
         return "Plan { fft_size: %d }" % self.fft_size()
 
+    def autotune(self, batch_hint=0):
+        N.check(N.lib.cfft_plan_autotune(self._h, batch_hint))
+        buf = ctypes.create_string_buffer(4096)
+        N.lib.cfft_plan_tuning_report(self._h, buf, 4096)
+        return buf.value.decode()
+
     def _run(self, planes, inverse):
         n = self.fft_size()
         views = [f64_view(p) for p in planes]

@@ -75,6 +75,19 @@ class _PlanBase:
     def device(self):
         return int(N.lib.cfft_plan_device(self._h))
 
+    def autotune(self, batch_hint=0):
+        """Time this plan's kernel variants on the device and keep the fastest (never changes the
+        plan's (base_algo, base_n) or any output bit).  Returns the report text."""
+        N.check(N.lib.cfft_plan_autotune(self._h, batch_hint))
+        return self.tuning_report()
+
+    def tuning_report(self):
+        import ctypes as _c
+
+        buf = _c.create_string_buffer(4096)
+        N.lib.cfft_plan_tuning_report(self._h, buf, 4096)
+        return buf.value.decode()
+
     def _algo(self):
         a, b = ctypes.c_int(), ctypes.c_uint64()
         N.check(N.lib.cfft_plan_algo(self._h, ctypes.byref(a), ctypes.byref(b)))

@@ -101,6 +101,19 @@ int cfft_plan_device(const cfft_plan *plan);
 /* Which kernel family serves this plan: "exact-tile", "fast-..." (see DESIGN.md). */
 const char *cfft_plan_kernel_name(const cfft_plan *plan);
 
+/* ---- on-device autotune ------------------------------------------------------------ */
+
+/* Replaces measure_fastest (src/ordered.rs:99-180, src/unordered.rs:553-640): times every kernel
+ * VARIANT available for this plan (fused vs multi-pass kernels, tile sizes) on `batch_hint`
+ * synthetic transforms with CUDA events and keeps the fastest (batch_hint = 0: 128 MiB worth).
+ * It never changes (base_algo, base_n) -- the Fourier-domain order -- nor any output bit: all
+ * variants of a plan are bit-identical.  Runs implicitly when a plan is created with
+ * CFFT_METHOD_MEASURE (skip with env CFFT_B200_NO_AUTOTUNE=1).  Must not race with transforms on
+ * the same plan. */
+cfft_status cfft_plan_autotune(cfft_plan *plan, uint64_t batch_hint);
+/* "variant-name: ms" lines of the last autotune ("" if none); returns bytes written (excl. NUL) */
+uint64_t cfft_plan_tuning_report(const cfft_plan *plan, char *buf, uint64_t buf_len);
+
 /* ---- c64 transforms --------------------------------------------------------------- */
 
 /* {ordered,unordered}::Plan::fwd / inv on device memory, in place, stream ordered.

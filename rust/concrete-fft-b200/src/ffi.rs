@@ -25,6 +25,8 @@ extern "C" {
     pub fn cfft_plan_kind(plan: *const cfft_plan) -> c_int;
     pub fn cfft_plan_device(plan: *const cfft_plan) -> c_int;
     pub fn cfft_plan_kernel_name(plan: *const cfft_plan) -> *const c_char;
+    pub fn cfft_plan_autotune(plan: *mut cfft_plan, batch_hint: u64) -> cfft_status;
+    pub fn cfft_plan_tuning_report(plan: *const cfft_plan, buf: *mut c_char, buf_len: u64) -> u64;
     pub fn cfft_c64_fwd(plan: *const cfft_plan, dev_buf: *mut c_void, batch: u64, stream: *mut c_void) -> cfft_status;
     pub fn cfft_c64_inv(plan: *const cfft_plan, dev_buf: *mut c_void, batch: u64, stream: *mut c_void) -> cfft_status;
     pub fn cfft_c64_fwd_host(plan: *const cfft_plan, host_buf: *mut c_void, len: u64, batch: u64) -> cfft_status;

@@ -366,3 +366,42 @@ def test_ordered_above_reference_cap(C, torch, logn):
     h = x.copy()
     plan.fwd(h)  # host-memory entry
     assert bits_equal(h, want)
+
+
+def test_autotune_keeps_bits_and_order(C, torch):
+    """cfft_plan_autotune (the Method::Measure replacement) switches kernel VARIANTS only: every
+    variant of a plan gives the same bits in the same order."""
+    rng = np.random.default_rng(77)
+    A = C.ordered.FftAlgo
+    for n in [512, 2048, 8192]:
+        x = rand_c(rng, 5, n)
+        want = O.UnorderedPlan(n, O.DIF16, 256).fwd(x)
+        os.environ["CFFT_B200_FAST_VARIANT"] = "2"
+        try:
+            multi = C.unordered.Plan(n, C.unordered.Method.UserProvided(A.Dif16, 256))
+        finally:
+            del os.environ["CFFT_B200_FAST_VARIANT"]
+        assert multi.kernel_name() == "fast-b256-column+rows"
+        y = dev_run(torch, multi.fwd, x)
+        assert bits_equal(y, want)
+        assert bits_equal(dev_run(torch, multi.inv, y), O.UnorderedPlan(n, O.DIF16, 256).inv(want))
+        report = multi.autotune()
+        assert "selected:" in report and "fast-b256-regs" in report and "fast-b256-column+rows" in report
+        assert multi.algo() == (A.Dif16, 256)
+        assert bits_equal(dev_run(torch, multi.fwd, x), want)
+        twin = multi.clone()
+        assert twin.kernel_name() == multi.kernel_name()
+    # tile-size variants of the exact kernel and of fft128
+    p = C.unordered.Plan(128, C.unordered.Method.Measure())
+    assert "exact-tile/" in p.tuning_report() and "selected:" in p.tuning_report()
+    x = rand_c(rng, 300, 128)
+    assert bits_equal(dev_run(torch, p.fwd, x), O.UnorderedPlan(128, O.DIF16, 128).fwd(x))
+    fp = C.fft128.Plan(256)
+    rep = fp.autotune()
+    assert "f128-radix8-tile/" in rep and "selected:" in rep
+    planes = [rng.random((37, 256)), np.zeros((37, 256)), rng.random((37, 256)), np.zeros((37, 256))]
+    d = [torch.from_numpy(a.copy()).cuda() for a in planes]
+    fp.fwd(*d)
+    torch.cuda.synchronize()
+    ref = O.F128Plan(256).fwd(*planes, variant=O.F128_FMA)
+    assert all(np.array_equal(a.cpu().numpy().view(np.uint64), b.view(np.uint64)) for a, b in zip(d, ref))
