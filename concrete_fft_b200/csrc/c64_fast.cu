@@ -89,6 +89,58 @@ __device__ __forceinline__ void level(const c64 *__restrict__ src, c64 *__restri
         }
 }
 
+// Two consecutive unordered levels (radix 8 on span NCUR, then radix 2 on span NCUR/8) fused in
+// registers: a thread's two radix-8 butterflies sit at p = t and t + NCUR/16, which is exactly the
+// pair the radix-2 level combines inside every chunk, so no exchange is needed between them.
+// Arithmetic per butterfly is unchanged (src/unordered.rs:24-43, 98-219).
+template <int NCUR, int TPR, bool FWD>
+__device__ __forceinline__ void level_8x2(const c64 *__restrict__ gsrc, c64 *__restrict__ gdst, c64 *__restrict__ s,
+                                          const c64 *__restrict__ tw8, const c64 *__restrict__ tw2, int t, c64 (&v)[16])
+{
+    static_assert(TPR * 16 == NCUR, "thread t owns p = t and p = t + NCUR/16");
+    constexpr int m = NCUR / 8;  // 8 chunks of m after the radix-8 level
+    constexpr int h = NCUR / 16; // half a chunk = span of the radix-2 level's butterflies
+    if (FWD) {
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[j * 8 + k] = ld_stream(gsrc + t + h * j + m * k);
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            c64 *x = &v[j * 8];
+            bf8<true>(x);
+#pragma unroll
+            for (int k = 1; k < 8; k++) x[k] = cmul(ld_tw(tw8 + (k - 1) * m + t + h * j), x[k]);
+        }
+        const c64 w = ld_tw(tw2 + t);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const c64 a = v[k], b = v[8 + k];
+            const int chunk = m * brev_c<8>(k);
+            s[chunk + t] = cadd(a, b);              // fwd_butterfly_x2
+            s[chunk + h + t] = cmul(w, csub(a, b));
+        }
+    } else {
+        const c64 w = ld_tw(tw2 + t);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int chunk = m * brev_c<8>(k);
+            const c64 a = s[chunk + t], b = cmul(w, s[chunk + h + t]); // inv_butterfly_x2
+            v[k] = cadd(a, b);
+            v[8 + k] = csub(a, b);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            c64 *x = &v[j * 8];
+#pragma unroll
+            for (int k = 1; k < 8; k++) x[k] = cmul(ld_tw(tw8 + (k - 1) * m + t + h * j), x[k]);
+            bf8<false>(x);
+#pragma unroll
+            for (int k = 0; k < 8; k++) st_stream(gdst + t + h * j + m * k, x[k]);
+        }
+    }
+}
+
 // 256-point base FFT (Dif16: radix-16 s=1 with twiddles, then radix-16 end) of the half-warp
 // that owns block `blk`; thread lane16 = p (first pass) = j (second pass).
 // FWD selects the butterfly direction only; the table passed in is the direction's table.
@@ -152,12 +204,16 @@ c64_fast_b256_kernel(c64 *__restrict__ data, uint64_t batch, FastTables tb)
     constexpr int N2 = N / R1;      // span of the second level
     const int blk = t / 16, lane16 = t % 16;
 
+    constexpr bool FUSED = (R1 == 8 && R2 == 2); // both levels in registers, see level_8x2
     if (FWD) {
-        if (R1 > 1) {
+        if (FUSED) {
+            if (active) level_8x2<N, Cfg::TPR, true>(g, g, s, tb.top1, tb.top2, t, v);
+            __syncthreads();
+        } else if (R1 > 1) {
             if (active) level<R1, N, Cfg::TPR, true, true, false>(g, s, tb.top1, t, v);
             __syncthreads();
         }
-        if (R2 > 1) {
+        if (R2 > 1 && !FUSED) {
             level<R2, N2, Cfg::TPR, true, false, false>(s, s, tb.top2, t, v);
             __syncthreads();
         }
@@ -170,13 +226,18 @@ c64_fast_b256_kernel(c64 *__restrict__ data, uint64_t batch, FastTables tb)
             if (R1 > 1) base256<false, true, false>(g + blk * 256, s + blk * 256, s + blk * 256, tb.base, lane16, v);
             else base256<false, true, true>(g + blk * 256, s + blk * 256, g + blk * 256, tb.base, lane16, v);
         }
-        if (R2 > 1) {
+        if (FUSED) {
             __syncthreads();
-            level<R2, N2, Cfg::TPR, false, false, false>(s, s, tb.top2, t, v);
-        }
-        if (R1 > 1) {
-            __syncthreads();
-            if (active) level<R1, N, Cfg::TPR, false, false, true>(s, g, tb.top1, t, v);
+            if (active) level_8x2<N, Cfg::TPR, false>(g, g, s, tb.top1, tb.top2, t, v);
+        } else {
+            if (R2 > 1) {
+                __syncthreads();
+                level<R2, N2, Cfg::TPR, false, false, false>(s, s, tb.top2, t, v);
+            }
+            if (R1 > 1) {
+                __syncthreads();
+                if (active) level<R1, N, Cfg::TPR, false, false, true>(s, g, tb.top1, t, v);
+            }
         }
     }
 }

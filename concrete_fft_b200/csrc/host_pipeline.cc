@@ -8,6 +8,7 @@
 // through internal pinned buffers.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -20,8 +21,25 @@ using namespace cfft;
 
 namespace {
 
-constexpr int kSlots = 3;
-constexpr size_t kChunkBytes = size_t(32) << 20;
+constexpr int kSlots = 4; // capacity; the number in use comes from pipe_slots()
+size_t pipe_chunk_bytes()
+{
+    static const size_t v = [] {
+        const char *e = getenv("CFFT_B200_PIPE_CHUNK_MB");
+        const long mb = e ? atol(e) : 32;
+        return size_t(mb > 0 ? mb : 32) << 20;
+    }();
+    return v;
+}
+int pipe_slots()
+{
+    static const int v = [] {
+        const char *e = getenv("CFFT_B200_PIPE_SLOTS");
+        const int k = e ? atoi(e) : 3;
+        return k < 1 ? 1 : (k > kSlots ? kSlots : k);
+    }();
+    return v;
+}
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -114,7 +132,8 @@ cfft_status run_pipeline(const cfft_plan *plan, void *const *planes, int nplanes
     bool pinned = true;
     for (int i = 0; i < nplanes; i++) pinned = pinned && is_pinned(planes[i]);
 
-    size_t rows_per_chunk = kChunkBytes / (row_bytes * size_t(nplanes));
+    const int nslots = pipe_slots();
+    size_t rows_per_chunk = pipe_chunk_bytes() / (row_bytes * size_t(nplanes));
     if (rows_per_chunk < 1) rows_per_chunk = 1;
     if (rows_per_chunk > batch) rows_per_chunk = size_t(batch);
     const size_t chunk_plane_bytes = rows_per_chunk * row_bytes;
@@ -133,7 +152,7 @@ cfft_status run_pipeline(const cfft_plan *plan, void *const *planes, int nplanes
 
     const size_t nchunks = (size_t(batch) + rows_per_chunk - 1) / rows_per_chunk;
     for (size_t c = 0; c < nchunks && e == cudaSuccess; c++) {
-        Slot &s = ctx->slot[c % kSlots];
+        Slot &s = ctx->slot[c % size_t(nslots)];
         what = "pipeline slot setup";
         if ((e = ensure_slot(s, chunk_bytes, pinned ? 0 : chunk_bytes)) != cudaSuccess) break;
         const size_t row0 = c * rows_per_chunk;
@@ -141,7 +160,7 @@ cfft_status run_pipeline(const cfft_plan *plan, void *const *planes, int nplanes
         if (!pinned) {
             // the slot's previous D2H must have landed before its staging buffer is reused
             what = "pipeline event sync";
-            if (c >= kSlots && (e = cudaEventSynchronize(s.done)) != cudaSuccess) break;
+            if (c >= size_t(nslots) && (e = cudaEventSynchronize(s.done)) != cudaSuccess) break;
             flush_pending(s);
             for (int pl = 0; pl < nplanes; pl++)
                 std::memcpy(static_cast<char *>(s.pinned) + size_t(pl) * chunk_plane_bytes,
