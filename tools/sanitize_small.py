@@ -1,0 +1,49 @@
+#!/usr/bin/env python3
+"""Small invocation of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+import concrete_fft_b200 as C
+
+A = C.ordered.FftAlgo
+rng = np.random.default_rng(0)
+
+
+def run_c64(plan, n, batch):
+    x = torch.from_numpy(rng.random((batch, n)) + 1j * rng.random((batch, n))).cuda()
+    plan.fwd(x)
+    plan.inv(x)
+    torch.cuda.synchronize()
+
+
+for n in [256, 512, 1024, 2048, 4096, 8192, 16384, 131072]:
+    run_c64(C.unordered.Plan(n, C.unordered.Method.UserProvided(A.Dif16, 256)), n, 3)
+for n, algo, base in [(2048, A.Dif4, 32), (1024, A.Dit8, 64), (16384, A.Dit16, 1024), (64, A.Dif2, 64), (8, A.Dif16, 8)]:
+    run_c64(C.unordered.Plan(n, C.unordered.Method.UserProvided(algo, base)), n, 5)
+for n in [512, 1024]:
+    run_c64(C.ordered.Plan(n, C.ordered.Method.UserProvided(A.Dit16)), n, 3)
+for n in [2048, 4096, 65536, 131072]:
+    run_c64(C.ordered.Plan(n, C.ordered.Method.Measure(), allow_large=True), n, 2)
+os.environ["CFFT_B200_FAST_VARIANT"] = "2"
+run_c64(C.unordered.Plan(2048, C.unordered.Method.UserProvided(A.Dif16, 256)), 2048, 3)
+del os.environ["CFFT_B200_FAST_VARIANT"]
+for n in [32, 256, 2048, 4096, 16384]:
+    p = C.fft128.Plan(n)
+    planes = [torch.rand(3, n, dtype=torch.float64, device="cuda") for _ in range(4)]
+    p.fwd(*planes)
+    p.inv(*planes)
+    torch.cuda.synchronize()
+p = C.unordered.Plan(1024, C.unordered.Method.UserProvided(A.Dif4, 32))
+buf = torch.zeros(1024, dtype=torch.complex128, device="cuda")
+p.fwd_monomial(5, buf)
+std = p.serialize_fourier_buffer(buf)
+p.deserialize_fourier_buffer(std, buf)
+h = rng.random((7, 1024)) + 0j
+p.fwd(h)
+torch.cuda.synchronize()
+print("sanitize_small done, launches =", C.launch_count())
