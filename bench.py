@@ -381,10 +381,18 @@ def main():
         return
 
     peak, peak_src, _ = measured_peaks()
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        rec = tj.get("%s:%d:%d" % (args.workload, n, batch))
+        if rec:
+            traffic, traffic_src = rec["traffic_bytes"], "profiles/traffic.json (ncu dram__bytes_read+write, %s)" % rec["kernel"]
+    except Exception:
+        pass
     dom_ms = min(fwd_ms, inv_ms) if False else fwd_ms
     achieved = bytes_per_launch / (dom_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": plan.kernel_name() + " (fwd launch)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch,
                 "fwd_ms": fwd_ms, "inv_ms": inv_ms,
                 "inv_achieved": bytes_per_launch / (inv_ms * 1e-3) / 1e9,
