@@ -405,3 +405,55 @@ def test_autotune_keeps_bits_and_order(C, torch):
     torch.cuda.synchronize()
     ref = O.F128Plan(256).fwd(*planes, variant=O.F128_FMA)
     assert all(np.array_equal(a.cpu().numpy().view(np.uint64), b.view(np.uint64)) for a, b in zip(d, ref))
+
+
+def test_concurrent_host_calls_share_one_plan(C, torch):
+    """`&self` semantics: many host threads call fwd on ONE plan at the same time (TFHE-rs keeps plans
+    in a global cache and calls them from worker threads)."""
+    import threading
+
+    rng = np.random.default_rng(55)
+    n = 1024
+    plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(C.ordered.FftAlgo.Dif16, 256))
+    ref = O.UnorderedPlan(n, O.DIF16, 256)
+    inputs = [rand_c(rng, 1 + 37 * i, n) for i in range(8)]
+    wants = [ref.fwd(x) for x in inputs]
+    outs = [x.copy() for x in inputs]
+    errors = []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                outs[i][...] = inputs[i]
+                plan.fwd(outs[i])
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors
+    for got, want in zip(outs, wants):
+        assert bits_equal(got, want)
+
+
+def test_plan_on_second_device(C, torch):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.default_rng(56)
+    n = 2048
+    plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(C.ordered.FftAlgo.Dif16, 256), device=1)
+    assert plan.device() == 1
+    x = rand_c(rng, 4, n)
+    d = torch.from_numpy(x.copy()).to("cuda:1")
+    plan.fwd(d)  # current device stays cuda:0
+    torch.cuda.synchronize(1)
+    assert torch.cuda.current_device() == 0
+    assert bits_equal(d.cpu().numpy(), O.UnorderedPlan(n, O.DIF16, 256).fwd(x))
+    with pytest.raises(ValueError):
+        plan.fwd(torch.from_numpy(x.copy()).to("cuda:0"))
+    h = x.copy()
+    plan.fwd(h)
+    assert bits_equal(h, d.cpu().numpy())
