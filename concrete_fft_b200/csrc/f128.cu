@@ -14,6 +14,8 @@
 // by the FP64 pipe.  Stages whose span exceeds a tile (n > 4096) run as separate HBM passes.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "plan.h"
 
 namespace cfft {
@@ -143,13 +145,13 @@ constexpr int kThreads = 256;
 F128_DEV uint32_t swz(uint32_t i) { return i ^ ((i >> 3) & 7u); }
 
 // one pass over a tile; G_IN / G_OUT: that side is the HBM tile (four planar arrays), else smem
-template <int S, bool FWD, bool G_IN, bool G_OUT>
+template <int S, bool FWD, bool G_IN, bool G_OUT, int NT>
 F128_DEV void tile_pass(const Planes &g, double2 *__restrict__ sre, double2 *__restrict__ sim, uint32_t tile,
                         uint32_t tile_row_off, uint32_t n, uint32_t logn, int d0, const Tw4 *__restrict__ tw, bool vec)
 {
     constexpr int G = 1 << S;
     const uint32_t u = n >> (d0 + S);
-    for (uint32_t grp = threadIdx.x; grp < tile / G; grp += kThreads) {
+    for (uint32_t grp = threadIdx.x; grp < tile / G; grp += NT) {
         const uint32_t hi = grp / u, lo = grp - hi * u;
         const uint32_t base = hi * (G * u) + lo;
         ddc z[G];
@@ -219,17 +221,17 @@ struct PassList {
     int s[kMaxPasses];
 };
 
-template <bool FWD, bool G_IN, bool G_OUT>
+template <bool FWD, bool G_IN, bool G_OUT, int NT>
 F128_DEV void dispatch_pass(int s, const Planes &g, double2 *sre, double2 *sim, uint32_t tile, uint32_t row_off,
                             uint32_t n, uint32_t logn, int d0, const Tw4 *tw, bool vec)
 {
-    if (s == 3) tile_pass<3, FWD, G_IN, G_OUT>(g, sre, sim, tile, row_off, n, logn, d0, tw, vec);
-    else if (s == 2) tile_pass<2, FWD, G_IN, G_OUT>(g, sre, sim, tile, row_off, n, logn, d0, tw, vec);
-    else tile_pass<1, FWD, G_IN, G_OUT>(g, sre, sim, tile, row_off, n, logn, d0, tw, vec);
+    if (s == 3) tile_pass<3, FWD, G_IN, G_OUT, NT>(g, sre, sim, tile, row_off, n, logn, d0, tw, vec);
+    else if (s == 2) tile_pass<2, FWD, G_IN, G_OUT, NT>(g, sre, sim, tile, row_off, n, logn, d0, tw, vec);
+    else tile_pass<1, FWD, G_IN, G_OUT, NT>(g, sre, sim, tile, row_off, n, logn, d0, tw, vec);
 }
 
-template <bool FWD>
-__global__ void __launch_bounds__(kThreads, 2)
+template <bool FWD, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT)
 f128_tile_kernel(Planes data, uint64_t total, uint32_t tile, uint32_t n, uint32_t logn, PassList passes,
                  const Tw4 *__restrict__ tw, bool vec)
 {
@@ -245,15 +247,15 @@ f128_tile_kernel(Planes data, uint64_t total, uint32_t tile, uint32_t n, uint32_
 
     const int last = passes.count - 1;
     if (last == 0) {
-        dispatch_pass<FWD, true, true>(passes.s[0], g, sre, sim, valid, row_off, n, logn, passes.d0[0], tw, vec);
+        dispatch_pass<FWD, true, true, NT>(passes.s[0], g, sre, sim, valid, row_off, n, logn, passes.d0[0], tw, vec);
         return;
     }
-    dispatch_pass<FWD, true, false>(passes.s[0], g, sre, sim, valid, row_off, n, logn, passes.d0[0], tw, vec);
+    dispatch_pass<FWD, true, false, NT>(passes.s[0], g, sre, sim, valid, row_off, n, logn, passes.d0[0], tw, vec);
     __syncthreads();
 #pragma unroll
     for (int pi = 1; pi < kMaxPasses - 1; pi++) {
         if (pi < last) {
-            dispatch_pass<FWD, false, false>(passes.s[pi], g, sre, sim, valid, row_off, n, logn, passes.d0[pi], tw, vec);
+            dispatch_pass<FWD, false, false, NT>(passes.s[pi], g, sre, sim, valid, row_off, n, logn, passes.d0[pi], tw, vec);
             __syncthreads();
         }
     }
@@ -262,7 +264,7 @@ f128_tile_kernel(Planes data, uint64_t total, uint32_t tile, uint32_t n, uint32_
 #pragma unroll
     for (int pi = 2; pi < kMaxPasses; pi++)
         if (pi == last) { ls = passes.s[pi]; ld = passes.d0[pi]; }
-    dispatch_pass<FWD, false, true>(ls, g, sre, sim, valid, row_off, n, logn, ld, tw, vec);
+    dispatch_pass<FWD, false, true, NT>(ls, g, sre, sim, valid, row_off, n, logn, ld, tw, vec);
 }
 
 // stages whose span exceeds a tile: one in-place pass through HBM
@@ -311,14 +313,14 @@ cudaError_t launch_global(int S, Planes data, uint64_t total, uint32_t n, uint32
 
 constexpr uint32_t kF128TileMax = 4096; // 4 planes x 8 B x 4096 = 128 KiB of shared memory
 
-template <bool FWD>
+template <bool FWD, int NT>
 cudaError_t configure_tile_kernel()
 {
     static thread_local int configured_device = -1;
     int dev = 0;
     cudaGetDevice(&dev);
     if (configured_device == dev) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(f128_tile_kernel<FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(f128_tile_kernel<FWD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          int(kF128TileMax * 4 * sizeof(double)));
     if (e == cudaSuccess) configured_device = dev;
     return e;
@@ -335,12 +337,22 @@ cudaError_t launch_f128(const cfft_plan *plan, bool inverse, double *re0, double
     Planes data = {{re0, re1, im0, im1}};
     const Tw4 *tw = reinterpret_cast<const Tw4 *>(plan->d_f128_tw4);
 
-    // tile: whole transforms (up to 2048 elements) or a 4096-element sub-block of one transform
+    // Stage split.  n <= 4096: every stage runs in the tile kernel.  Larger n: the widest stages run
+    // as HBM passes of three stages each (a 3-stage pass does as much FP64 work as its HBM traffic
+    // costs, so it keeps both busy), the rest on sub-blocks of n >> D0 elements in the tile kernel.
     uint32_t tile;
-    int D0 = 0; // stages d < D0 span more than a tile
-    if (n > kF128TileMax) {
-        tile = kF128TileMax;
-        D0 = int(logn - ilog2(kF128TileMax));
+    int D0 = 0; // stages d < D0 run as HBM passes
+    static const uint32_t tile_max = [] {
+        const char *e = getenv("CFFT_B200_F128_TILEMAX");
+        const long v = e ? atol(e) : 0;
+        return (v == 2048 || v == 4096) ? uint32_t(v) : kF128TileMax;
+    }();
+    if (n > tile_max) {
+        const int over = int(logn - ilog2(tile_max));
+        D0 = 3 * ((over + 2) / 3);
+        const uint32_t sub = n >> D0;
+        tile = sub < 2048 ? 2048 : sub; // whole sub-blocks, 2048 or 4096 elements
+        if (uint64_t(tile) > uint64_t(n) * batch) tile = sub;
     } else if (n >= 2048 && !(plan->tile_elems > n)) {
         tile = n;
     } else {
@@ -350,21 +362,23 @@ cudaError_t launch_f128(const cfft_plan *plan, bool inverse, double *re0, double
         tile = uint32_t(rows * n);
     }
 
-    // global passes for d in [0, D0), at most 3 stages each; tile passes for d in [D0, logn)
     int gd0[16], gs[16], gcount = 0;
-    for (int d = 0; d < D0;) {
-        const int s = (D0 - d >= 3) ? 3 : (D0 - d);
+    for (int d = 0; d < D0; d += 3) {
         gd0[gcount] = d;
-        gs[gcount++] = s;
-        d += s;
+        gs[gcount++] = 3;
     }
+    // tile passes: ceil(k / 3) passes with the stages spread evenly (3,3,2,2 rather than 3,3,3,1)
     PassList passes;
     passes.count = 0;
-    for (int d = D0; d < int(logn);) {
-        const int s = (int(logn) - d >= 3) ? 3 : (int(logn) - d);
-        passes.d0[passes.count] = d;
-        passes.s[passes.count++] = s;
-        d += s;
+    {
+        const int k = int(logn) - D0;
+        const int np = (k + 2) / 3, lo = k / np, extra = k % np;
+        for (int i = 0, d = D0; i < np; i++) {
+            const int sz = lo + (i < extra ? 1 : 0);
+            passes.d0[passes.count] = d;
+            passes.s[passes.count++] = sz;
+            d += sz;
+        }
     }
     const size_t smem = size_t(tile) * 4 * sizeof(double);
     // 128-bit HBM accesses in the stride-1 pass need 16-byte aligned planes
@@ -376,8 +390,14 @@ cudaError_t launch_f128(const cfft_plan *plan, bool inverse, double *re0, double
     if (!inverse) {
         for (int i = 0; i < gcount; i++)
             if ((e = launch_global<true>(gs[i], data, total, n, logn, gd0[i], tw, stream)) != cudaSuccess) return e;
-        if ((e = configure_tile_kernel<true>()) != cudaSuccess) return e;
-        f128_tile_kernel<true><<<tiles, kThreads, smem, stream>>>(data, total, tile, n, logn, passes, tw, vec);
+        // 8 elements per thread and pass: a 4096-element tile gets 512 threads (16 warps per SM)
+        if (tile > 2048) {
+            if ((e = configure_tile_kernel<true, 512>()) != cudaSuccess) return e;
+            f128_tile_kernel<true, 512><<<tiles, 512, smem, stream>>>(data, total, tile, n, logn, passes, tw, vec);
+        } else {
+            if ((e = configure_tile_kernel<true, 256>()) != cudaSuccess) return e;
+            f128_tile_kernel<true, 256><<<tiles, 256, smem, stream>>>(data, total, tile, n, logn, passes, tw, vec);
+        }
         count_launch();
         return cudaGetLastError();
     }
@@ -388,8 +408,13 @@ cudaError_t launch_f128(const cfft_plan *plan, bool inverse, double *re0, double
         rev.d0[i] = passes.d0[passes.count - 1 - i];
         rev.s[i] = passes.s[passes.count - 1 - i];
     }
-    if ((e = configure_tile_kernel<false>()) != cudaSuccess) return e;
-    f128_tile_kernel<false><<<tiles, kThreads, smem, stream>>>(data, total, tile, n, logn, rev, tw, vec);
+    if (tile > 2048) {
+        if ((e = configure_tile_kernel<false, 512>()) != cudaSuccess) return e;
+        f128_tile_kernel<false, 512><<<tiles, 512, smem, stream>>>(data, total, tile, n, logn, rev, tw, vec);
+    } else {
+        if ((e = configure_tile_kernel<false, 256>()) != cudaSuccess) return e;
+        f128_tile_kernel<false, 256><<<tiles, 256, smem, stream>>>(data, total, tile, n, logn, rev, tw, vec);
+    }
     count_launch();
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     for (int i = gcount - 1; i >= 0; i--)
