@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c64", choices=["c64", "f128"])
+    ap.add_argument("--workload", default="c64", choices=["c64", "ordered", "f128"])
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--base-n", type=int, default=0)
@@ -115,6 +115,12 @@ class ClockSampler:
 
 
 def workload_defaults(args):
+    if args.workload == "ordered":
+        # BASELINE.json configs[2]: standard-order N = 2^16, batch 4096 in total, sharded across the GPUs
+        n = args.n or 65536
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        batch = args.batch or max(1, 4096 // world)
+        return n, batch, 256, "Dif16"
     if args.workload == "c64":
         n = args.n or 2048
         batch = args.batch or 65536
@@ -142,7 +148,9 @@ def cpu_port_rate(workload, n, base_n, algo, threads, seconds):
 
     rng = np.random.default_rng(0)
     rows = max(threads * 8, 256)
-    if workload == "c64":
+    if workload in ("c64", "ordered"):
+        if n >= 16384:
+            rows = max(threads, 16)
         plan = O.UnorderedPlan(n, O.ALGO_NAMES.index(algo), base_n, fast=True)
         buf = rng.random((rows, n)) + 1j * rng.random((rows, n))
 
@@ -185,7 +193,7 @@ def run_reference(args):
     rng = np.random.default_rng(0)
     # each step = fwd+inv over a bounded sample of the workload's batch
     rows = min(batch, max(threads * 16, 512)) if args.workload == "c64" else min(batch, max(threads * 4, 64))
-    if args.workload == "c64":
+    if args.workload in ("c64", "ordered"):
         plan = O.UnorderedPlan(n, O.ALGO_NAMES.index(algo), base_n, fast=True)
         buf = rng.random((rows, n)) + 1j * rng.random((rows, n))
 
@@ -212,10 +220,11 @@ def run_reference(args):
     sample = "%d of %d polynomials per step, fwd+inv, %d host threads" % (rows, batch, threads)
     line = {
         "impl": "reference",
-        "metric": "batched %s FFT transforms/s (fwd+inv)" % ("c64" if args.workload == "c64" else "fft128"),
+        "metric": "batched %s FFT transforms/s (fwd+inv)" % METRIC_NAME[args.workload],
         "value": value, "unit": "transforms/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64" if args.workload == "c64" else "f64x2 (double-double)", "data": "synthetic",
+        "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
+        "scaling": "strong" if args.workload == "ordered" else "weak", "vs_baseline": None,
+        "dtype": "f64x2 (double-double)" if args.workload == "f128" else "f64", "data": "synthetic",
         "config": config_dict(args.workload, n, batch, base_n, algo, args.gpus),
         "cpu_baseline": {"value": value, "unit": "transforms/s", "cores": threads, "kind": "port", "sample": sample,
                          "note": "C restatement of the reference algorithm (oracle/, -O3 build, bit-identical "
@@ -226,7 +235,16 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+METRIC_NAME = {"c64": "c64", "ordered": "standard-order c64", "f128": "fft128"}
+
+
 def config_dict(workload, n, batch, base_n, algo, gpus):
+    if workload == "ordered":
+        return {"workload": "ordered (standard order in/out) c64 fwd+inv N=%d, batch %d in total = %d per GPU (BASELINE.json configs[2])" % (n, batch * gpus, batch),
+                "n": n, "batch_per_gpu": batch, "plan": "ordered, allow_large (extension: the reference caps ordered plans at 2^10, src/ordered.rs:244); "
+                "CPU arm = the reference's unordered plan {Dif16, 256} (no ordered reference exists at this size)",
+                "sharding": "batch split across %d GPU(s), no collective" % gpus,
+                "l2": "inputs (%.2f GiB per GPU) larger than L2, no flush" % (batch * n * 16 / 2**30)}
     if workload == "c64":
         return {"workload": "unordered c64 fwd+inv N=%d batch %d per GPU (BASELINE.json configs[1], TFHE bootstrapping shape)" % (n, batch),
                 "n": n, "batch_per_gpu": batch, "plan": "UserProvided{base_algo: %s, base_n: %d}" % (algo, base_n),
@@ -264,8 +282,11 @@ def main():
     g = torch.Generator(device=dev).manual_seed(0x5EED0000 + rank)
     A = C.ordered.FftAlgo
 
-    if args.workload == "c64":
-        plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(A[algo], base_n), device=local)
+    if args.workload in ("c64", "ordered"):
+        if args.workload == "ordered":
+            plan = C.ordered.Plan(n, C.ordered.Method.Measure(), device=local, allow_large=n > 1024)
+        else:
+            plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(A[algo], base_n), device=local)
         data = torch.view_as_complex(torch.rand(batch, n, 2, dtype=torch.float64, device=dev, generator=g)).contiguous()
         bytes_per_launch = 2 * 16 * n * batch
         inv_scale = 1.0 / n
@@ -340,7 +361,7 @@ def main():
     # ---- end to end through the host-memory API ----------------------------------------------
     e2e = None
     if not args.no_e2e:
-        if args.workload == "c64":
+        if args.workload in ("c64", "ordered"):
             host = torch.view_as_complex(torch.rand(batch, n, 2, dtype=torch.float64)).contiguous().pin_memory()
             hnp = host.numpy()
             h2d = d2h = batch * n * 16
@@ -358,13 +379,13 @@ def main():
                 plan.inv(*hn)
                 return float(hn[0][0, 0])
         e2e_step()
-        if args.workload == "c64":
+        if args.workload in ("c64", "ordered"):
             np.multiply(hnp, inv_scale, out=hnp)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             e2e_step()
-            if args.workload == "c64":
+            if args.workload in ("c64", "ordered"):
                 np.multiply(hnp[:1], inv_scale, out=hnp[:1])
         barrier()
         el = time.perf_counter() - t0
@@ -372,7 +393,7 @@ def main():
         e2e = {"value": 2.0 * batch * world * args.e2e_steps / el, "unit": "transforms/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
                "ms_per_step": 1e3 * el / args.e2e_steps,
-               "api": "Plan.fwd_inv_host -> cfft_c64_fwd_inv_host (pinned host buffers)" if args.workload == "c64"
+               "api": "Plan.fwd_inv_host -> cfft_c64_fwd_inv_host (pinned host buffers)" if args.workload in ("c64", "ordered")
                       else "fft128.Plan.fwd + inv on pinned host planes -> cfft_f128_{fwd,inv}_host"}
 
     if rank != 0:
@@ -417,10 +438,11 @@ def main():
                "sample": "%d polynomials x %d fwd+inv steps in %.1f s (same n / plan as the GPU run)" % (rows, steps, el)}
 
     line = {
-        "metric": "batched %s FFT transforms/s (fwd+inv)" % ("c64" if args.workload == "c64" else "fft128"),
+        "metric": "batched %s FFT transforms/s (fwd+inv)" % METRIC_NAME[args.workload],
         "value": value, "unit": "transforms/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
-        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64" if args.workload == "c64" else "f64x2 (double-double)", "data": "synthetic",
+        "ms_per_step": total_ms / K, "higher_is_better": True,
+        "scaling": "strong" if args.workload == "ordered" else "weak", "vs_baseline": None,
+        "dtype": "f64x2 (double-double)" if args.workload == "f128" else "f64", "data": "synthetic",
         "config": config_dict(args.workload, n, batch, base_n, algo, world),
         "hbm_gbs_whole_step": 2 * bytes_per_launch * world * K / (total_ms * 1e-3) / 1e9,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
