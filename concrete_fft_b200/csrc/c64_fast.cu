@@ -19,6 +19,7 @@
 //   * Twiddles come from plan tables re-laid out planar (w_k[p], lanes on consecutive p) so
 //     each request is one or two 128 B lines; they stay L1-resident.
 #include <cstdlib>
+#include <mutex>
 
 #include "c64_math.cuh"
 #include "plan.h"
@@ -338,6 +339,30 @@ cudaError_t launch_rows_std(bool inverse, const c64 *src, c64 *dst, uint64_t bat
 
 } // namespace
 
+// Stream-ordered workspace for the out-of-place (ordered) path: one private pool per device that keeps
+// its memory between calls (release threshold = max), so steady-state calls never touch the OS allocator.
+static cudaError_t workspace_pool(int device, cudaMemPool_t *out)
+{
+    static std::mutex mu;
+    static cudaMemPool_t pools[64] = {};
+    if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!pools[device]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaError_t e = cudaMemPoolCreate(&pools[device], &props);
+        if (e != cudaSuccess) return e;
+        uint64_t keep = ~uint64_t{0};
+        e = cudaMemPoolSetAttribute(pools[device], cudaMemPoolAttrReleaseThreshold, &keep);
+        if (e != cudaSuccess) return e;
+    }
+    *out = pools[device];
+    return cudaSuccess;
+}
+
 // Does a plan qualify?  unordered, base (Dif16, 256), n >= 256.
 //   n <= 8192 : one kernel (levels + base FFT fused, one HBM round trip)
 //   n >  8192 : column passes for the levels (c64_column.cu), then the base FFTs as rows of 256
@@ -359,7 +384,10 @@ cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *d
         // ordered: levels as column passes (the last one out of place into a workspace), then the base
         // FFTs read the workspace rows and write standard order back into the caller's buffer.
         c64 *ws = nullptr;
-        cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&ws), batch * plan->n * sizeof(c64), stream);
+        cudaMemPool_t pool = nullptr;
+        cudaError_t e = workspace_pool(plan->device, &pool);
+        if (e == cudaSuccess)
+            e = cudaMallocFromPoolAsync(reinterpret_cast<void **>(&ws), batch * plan->n * sizeof(c64), pool, stream);
         if (e != cudaSuccess) return e;
         const uint32_t n32 = uint32_t(plan->n);
         auto group = [&](const cfft_plan::FastGroup &g, const c64 *src, c64 *dst) {
