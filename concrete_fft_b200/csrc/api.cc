@@ -136,9 +136,11 @@ cfft_status upload_c64(cfft_plan *p)
 cfft_status build_fast_tables(cfft_plan *p)
 {
     const bool ordered_large = p->kind == KIND_ORDERED && p->allow_large;
+    // the ordered Dif16 plan of size 256 IS the 256-point base FFT of the register kernel
+    const bool ordered_256 = p->kind == KIND_ORDERED && !p->allow_large && p->n == 256 && p->algo == CFFT_DIF16;
     if (!ordered_large) {
         if (getenv("CFFT_B200_FORCE_EXACT")) return CFFT_OK;
-        if (p->kind != KIND_UNORDERED || !fast_b256_supported(p->n, p->algo, p->base_n)) return CFFT_OK;
+        if (!ordered_256 && (p->kind != KIND_UNORDERED || !fast_b256_supported(p->n, p->algo, p->base_n))) return CFFT_OK;
     }
     // levels top-down; forward offsets from prog[0], inverse offsets from prog[1] (stored bottom-up)
     std::vector<Stage> tops_f, tops_i;
@@ -330,6 +332,7 @@ cfft_status cfft_ordered_plan_create(cfft_plan **out, int device, uint64_t n, in
     append_base_stages(f, algo, n, uint32_t(n));
     append_base_stages(v, algo, n, uint32_t(n));
     st = upload_c64(p);
+    if (st == CFFT_OK) st = build_fast_tables(p);
     if (st != CFFT_OK) { cfft_plan_destroy(p); return st; }
     *out = p;
     return CFFT_OK;
@@ -609,6 +612,36 @@ cfft_status cfft_f128_inv(const cfft_plan *p, double *re0, double *re1, double *
                           void *stream)
 {
     return run_f128(p, true, re0, re1, im0, im1, batch, stream);
+}
+
+cfft_status cfft_f128_binary_op(int device, int op, const double *a_hi, const double *a_lo, const double *b_hi,
+                                const double *b_lo, double *out_hi, double *out_lo, uint64_t len, void *stream)
+{
+    if (op < CFFT_F128_ADD || op > CFFT_F128_DIV_ESTIMATE) return fail(CFFT_EINVAL, "unknown f128 operator");
+    if (len && (!a_hi || !a_lo || !b_hi || !b_lo || !out_hi || !out_lo)) return fail(CFFT_EINVAL, "null buffer");
+    cfft_status st = check_device(device);
+    if (st != CFFT_OK) return st;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
+    cudaError_t e = launch_f128_binary(op, a_hi, a_lo, b_hi, b_lo, out_hi, out_lo, len, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "f128 binary op launch");
+    return CFFT_OK;
+}
+
+cfft_status cfft_f128_cplx_mul_scale(int device, double *l_re0, double *l_re1, double *l_im0, double *l_im1,
+                                     const double *r_re0, const double *r_re1, const double *r_im0, const double *r_im1,
+                                     double factor, uint64_t len, void *stream)
+{
+    if (len && (!l_re0 || !l_re1 || !l_im0 || !l_im1 || !r_re0 || !r_re1 || !r_im0 || !r_im1))
+        return fail(CFFT_EINVAL, "null buffer");
+    cfft_status st = check_device(device);
+    if (st != CFFT_OK) return st;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
+    cudaError_t e = launch_f128_cplx_mul_scale(l_re0, l_re1, l_im0, l_im1, r_re0, r_re1, r_im0, r_im1, factor, len,
+                                               static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "f128 pointwise product launch");
+    return CFFT_OK;
 }
 
 cfft_status cfft_unordered_fwd_monomial(const cfft_plan *p, uint64_t degree, void *dev_buf, void *stream)

@@ -87,3 +87,35 @@ class Plan:
             N.check(N.lib.cfft_plan_copy_twiddles(self._h, w, a.ctypes.data, a.nbytes))
             out.append(a)
         return out
+
+
+# ---- the scalar f128 operators on device arrays (src/fft128/f128_ops.rs) ---------------------------
+_OPS = {"add": 0, "sub": 1, "mul": 2, "div": 3, "add_estimate": 4, "sub_estimate": 5, "div_estimate": 6}
+
+
+def f128_op(op, a_hi, a_lo, b_hi, b_lo):
+    """Element-wise f128 operator on CUDA float64 tensors; returns (hi, lo).  `op` is one of
+    add, sub, mul, div (f128::add_f128_f128 ... div_f128_f128) or add_estimate, sub_estimate,
+    div_estimate; bit-exact with the reference's scalar functions."""
+    import torch
+
+    views = [f64_view(t) for t in (a_hi, a_lo, b_hi, b_lo)]
+    if any(v[0] != "device" for v in views) or len({v[2] for v in views}) != 1:
+        raise TypeError("f128_op takes four CUDA float64 tensors of equal length")
+    dev = views[0][3]
+    out_hi, out_lo = torch.empty_like(a_hi), torch.empty_like(a_hi)
+    N.check(N.lib.cfft_f128_binary_op(dev, _OPS[op], views[0][1], views[1][1], views[2][1], views[3][1],
+                                      out_hi.data_ptr(), out_lo.data_ptr(), views[0][2], current_stream_ptr(dev)))
+    return out_hi, out_lo
+
+
+def cplx_mul_scale(lhs, rhs, factor):
+    """lhs <- (lhs * rhs) * factor point-wise on planar (re0, re1, im0, im1) CUDA tensors: the step
+    between fwd and inv of a negacyclic product (src/fft128/mod.rs:2033-2047)."""
+    lv = [f64_view(t) for t in lhs]
+    rv = [f64_view(t) for t in rhs]
+    if any(v[0] != "device" for v in lv + rv) or len({v[2] for v in lv + rv}) != 1:
+        raise TypeError("cplx_mul_scale takes eight CUDA float64 tensors of equal length")
+    dev = lv[0][3]
+    N.check(N.lib.cfft_f128_cplx_mul_scale(dev, *[v[1] for v in lv], *[v[1] for v in rv], float(factor), lv[0][2],
+                                           current_stream_ptr(dev)))

@@ -174,6 +174,29 @@ cfft_status cfft_f128_fwd_host(const cfft_plan *plan, double *re0, double *re1, 
 cfft_status cfft_f128_inv_host(const cfft_plan *plan, double *re0, double *re1, double *im0,
                                double *im1, uint64_t len, uint64_t batch);
 
+/* ---- f128 operators around the transform ---------------------------- */
+
+/* The scalar `f128` operators of src/fft128/f128_ops.rs applied element-wise to device arrays
+ * (hi / lo planes), bit-exact with the reference's scalar functions:
+ *   ADD add_f128_f128 :311-321, SUB sub_f128_f128 :360-370, MUL mul_f128_f128 :395-400,
+ *   DIV div_f128_f128 :477-491, ADD_ESTIMATE :302-307, SUB_ESTIMATE :350-356, DIV_ESTIMATE :457-474.
+ * out may alias an input.  Stream ordered on `device`. */
+enum {
+    CFFT_F128_ADD = 0, CFFT_F128_SUB, CFFT_F128_MUL, CFFT_F128_DIV,
+    CFFT_F128_ADD_ESTIMATE, CFFT_F128_SUB_ESTIMATE, CFFT_F128_DIV_ESTIMATE
+};
+cfft_status cfft_f128_binary_op(int device, int op, const double *a_hi, const double *a_lo,
+                                const double *b_hi, const double *b_lo, double *out_hi,
+                                double *out_lo, uint64_t len, void *stream);
+
+/* lhs <- (lhs * rhs) * factor, point-wise on planar double-double complex arrays: the step between
+ * fwd and inv of a negacyclic product exactly as the reference's tests do it (scalar cplx_mul,
+ * src/fft128/mod.rs:310-326, loop at :2033-2047; factor = 2 / N there). */
+cfft_status cfft_f128_cplx_mul_scale(int device, double *l_re0, double *l_re1, double *l_im0,
+                                     double *l_im1, const double *r_re0, const double *r_re1,
+                                     const double *r_im0, const double *r_im1, double factor,
+                                     uint64_t len, void *stream);
+
 /* ---- diagnostics ------------------------------------------------------------------- */
 
 const char *cfft_status_string(cfft_status st);

@@ -106,6 +106,87 @@ of128 orc_f128_mul(of128 a, of128 b, int variant)
     return r;
 }
 
+/* f128_ops.rs:286-291 / :380-385 */
+static of128 add_f128_f64(of128 a, double b)
+{
+    double s1, s2;
+    two_sum(a.hi, b, &s1, &s2);
+    s2 = s2 + a.lo;
+    of128 r;
+    quick_two_sum(s1, s2, &r.hi, &r.lo);
+    return r;
+}
+static of128 mul_f128_f64(of128 a, double b)
+{
+    double p1, p2;
+    two_prod(a.hi, b, &p1, &p2);
+    p2 = p2 + (a.lo * b);
+    of128 r;
+    quick_two_sum(p1, p2, &r.hi, &r.lo);
+    return r;
+}
+
+/* f128_ops.rs:477-491 */
+of128 orc_f128_div(of128 a, of128 b)
+{
+    double q1 = a.hi / b.hi;
+    of128 r = orc_f128_sub(a, mul_f128_f64(b, q1));
+    double q2 = r.hi / b.hi;
+    r = orc_f128_sub(r, mul_f128_f64(b, q2));
+    double q3 = r.hi / b.hi;
+    of128 q;
+    quick_two_sum(q1, q2, &q.hi, &q.lo);
+    return add_f128_f64(q, q3);
+}
+
+/* f128_ops.rs:457-474 */
+of128 orc_f128_div_estimate(of128 a, of128 b)
+{
+    double q1 = a.hi / b.hi;
+    of128 r = mul_f128_f64(b, q1);
+    double s1, s2;
+    two_diff(a.hi, r.hi, &s1, &s2);
+    s2 = s2 - r.lo;
+    s2 = s2 + a.lo;
+    double q2 = (s1 + s2) / b.hi;
+    of128 q;
+    quick_two_sum(q1, q2, &q.hi, &q.lo);
+    return q;
+}
+
+void orc_f128_binary_op(int op, const double *a_hi, const double *a_lo, const double *b_hi, const double *b_lo,
+                        double *out_hi, double *out_lo, size_t len)
+{
+    for (size_t i = 0; i < len; i++) {
+        of128 a = { a_hi[i], a_lo[i] }, b = { b_hi[i], b_lo[i] }, r;
+        switch (op) {
+        case 0: r = orc_f128_add(a, b); break;
+        case 1: r = orc_f128_sub(a, b); break;
+        case 2: r = orc_f128_mul(a, b, ORC_F128_SCALAR); break;
+        case 3: r = orc_f128_div(a, b); break;
+        case 4: r = orc_f128_add_estimate(a, b); break;
+        case 5: r = orc_f128_sub_estimate(a, b); break;
+        default: r = orc_f128_div_estimate(a, b); break;
+        }
+        out_hi[i] = r.hi;
+        out_lo[i] = r.lo;
+    }
+}
+
+void orc_f128_cplx_mul_scale(double *l_re0, double *l_re1, double *l_im0, double *l_im1, const double *r_re0,
+                             const double *r_re1, const double *r_im0, const double *r_im1, double factor, size_t len)
+{
+    for (size_t i = 0; i < len; i++) {
+        of128 ar = { l_re0[i], l_re1[i] }, ai = { l_im0[i], l_im1[i] };
+        of128 br = { r_re0[i], r_re1[i] }, bi = { r_im0[i], r_im1[i] };
+        of128 rr = orc_f128_mul(ar, br, ORC_F128_SCALAR), ri = orc_f128_mul(ar, bi, ORC_F128_SCALAR);
+        of128 ir = orc_f128_mul(ai, br, ORC_F128_SCALAR), ii = orc_f128_mul(ai, bi, ORC_F128_SCALAR);
+        of128 pr = orc_f128_sub_estimate(rr, ii), pi = orc_f128_add_estimate(ir, ri);
+        l_re0[i] = pr.hi * factor; l_re1[i] = pr.lo * factor;
+        l_im0[i] = pi.hi * factor; l_im1[i] = pi.lo * factor;
+    }
+}
+
 /* helpers used by sincospi only (scalar operator impls, f128_ops.rs:60-230) */
 static inline of128 mul_ss(of128 a, of128 b) { return orc_f128_mul(a, b, ORC_F128_SCALAR); }
 
@@ -120,6 +201,7 @@ static of128 sub_f128_f64(of128 a, double b)
     return r;
 }
 
+of128 orc_f128_sqr(of128 a);
 /* f128_ops.rs:404-409 (sqr) */
 static of128 sqr_f128(of128 a)
 {
@@ -359,3 +441,5 @@ void orc_f128_inv_batch(const orc_f128_plan *p, double *re0, double *re1, double
     struct fbatch f = { p, { re0, re1, im0, im1 }, 1, variant };
     orc_parallel_rows(threads, batch, fbatch_rows, &f);
 }
+
+of128 orc_f128_sqr(of128 a) { return sqr_f128(a); }

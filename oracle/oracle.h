@@ -78,6 +78,18 @@ of128 orc_f128_add(of128 a, of128 b);          /* f128_ops.rs:311-321 */
 of128 orc_f128_sub(of128 a, of128 b);          /* f128_ops.rs:360-370 */
 of128 orc_f128_mul(of128 a, of128 b, int variant);
 void orc_f128_sincospi(of128 x, of128 *s, of128 *c); /* f128_ops.rs:514-575 */
+of128 orc_f128_div(of128 a, of128 b);          /* f128_ops.rs:477-491 */
+of128 orc_f128_div_estimate(of128 a, of128 b); /* f128_ops.rs:457-474 */
+of128 orc_f128_sqr(of128 a);                   /* f128_ops.rs:404-409 */
+
+/* element-wise array forms of the scalar f128 operators; op codes match include/cfft_b200.h:
+ * 0 add, 1 sub, 2 mul (scalar form :395-400), 3 div, 4 add_estimate, 5 sub_estimate, 6 div_estimate */
+void orc_f128_binary_op(int op, const double *a_hi, const double *a_lo, const double *b_hi, const double *b_lo,
+                        double *out_hi, double *out_lo, size_t len);
+/* lhs <- (lhs * rhs) * factor on planar double-double complex arrays, scalar cplx_mul
+ * (src/fft128/mod.rs:310-326) then four f64 scalings, exactly the loop at src/fft128/mod.rs:2033-2047 */
+void orc_f128_cplx_mul_scale(double *l_re0, double *l_re1, double *l_im0, double *l_im1, const double *r_re0,
+                             const double *r_re1, const double *r_im0, const double *r_im1, double factor, size_t len);
 
 /* src/fft128/mod.rs:1805-1828: four arrays of n doubles, entry 0 untouched (0.0). */
 void orc_f128_init_twiddles(size_t n, double *re0, double *re1, double *im0, double *im1);

@@ -57,6 +57,8 @@ def lib(fast=False):
         "orc_f128_fwd_batch": (None, [vp, vp, vp, vp, vp, sz, ci, ci]),
         "orc_f128_inv_batch": (None, [vp, vp, vp, vp, vp, sz, ci, ci]),
         "orc_f128_twiddles": (vp, [vp, ci]),
+        "orc_f128_binary_op": (None, [ci, vp, vp, vp, vp, vp, vp, sz]),
+        "orc_f128_cplx_mul_scale": (None, [vp, vp, vp, vp, vp, vp, vp, vp, dbl, sz]),
     }
     for k, (res, args) in sig.items():
         f = getattr(L, k)
@@ -186,3 +188,20 @@ class F128Plan:
             p = self.L.orc_f128_twiddles(self.h, w)
             out.append(np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_double)), (self.n,)).copy())
         return out
+
+
+F128_OPS = {"add": 0, "sub": 1, "mul": 2, "div": 3, "add_estimate": 4, "sub_estimate": 5, "div_estimate": 6}
+
+
+def f128_binary_op(op, a_hi, a_lo, b_hi, b_lo):
+    arrs = [np.ascontiguousarray(x, dtype=np.float64) for x in (a_hi, a_lo, b_hi, b_lo)]
+    out_hi, out_lo = np.empty_like(arrs[0]), np.empty_like(arrs[0])
+    lib().orc_f128_binary_op(F128_OPS[op], *[_ptr(x) for x in arrs], _ptr(out_hi), _ptr(out_lo), arrs[0].size)
+    return out_hi, out_lo
+
+
+def f128_cplx_mul_scale(lhs, rhs, factor):
+    L = [np.ascontiguousarray(x, dtype=np.float64).copy() for x in lhs]
+    R = [np.ascontiguousarray(x, dtype=np.float64) for x in rhs]
+    lib().orc_f128_cplx_mul_scale(*[_ptr(x) for x in L], *[_ptr(x) for x in R], float(factor), L[0].size)
+    return L

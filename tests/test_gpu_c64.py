@@ -78,6 +78,8 @@ def test_ordered_all_algos_bit_exact(C, torch, algo):
         assert np.abs(y - np.fft.fft(x, axis=1)).max() < 1e-12
         assert bits_equal(dev_run(torch, plan.inv, y), ref.inv(y)), (algo, n)
         # twiddle tables are the reference's init_wt tables, bit for bit (NaN slots included)
+        if n == 256 and algo == O.DIF16:
+            assert plan.kernel_name() == "fast-b256-regs"  # ordered Dif16/256 == the register kernel's base FFT
         tw = np.zeros((2, 2 * n), np.complex128)
         if n >= (2 << (algo >> 1)):
             O.lib().orc_init_wt(2 << (algo >> 1), n, tw[0].ctypes.data, tw[1].ctypes.data)

@@ -107,3 +107,26 @@ def test_scalar_and_fma_variants_differ_only_in_last_bits():
                for h1, l1, h2, l2 in zip(a[0], a[1], b[0], b[1]))
     scale = float(np.abs(a[0]).max())
     assert diff < scale * 2.0 ** -95
+
+
+def test_operator_set_error_bounds():
+    """src/fft128/f128_ops.rs:1043-1215 re-expressed with mpmath: exact ops <= 2^-104 relative,
+    *_estimate <= 2^-101."""
+    mpmath.mp.prec = 1024
+    rng = np.random.default_rng(5)
+    n = 300
+    a_hi = rng.uniform(-4, 4, n)
+    b_hi = rng.uniform(0.25, 4, n) * rng.choice([-1.0, 1.0], n)
+    a_lo = (rng.random(n) - 0.5) * np.spacing(a_hi)
+    b_lo = (rng.random(n) - 0.5) * np.spacing(b_hi)
+    fns = {"add": lambda x, y: x + y, "sub": lambda x, y: x - y, "mul": lambda x, y: x * y, "div": lambda x, y: x / y}
+    for op in ["add", "sub", "mul", "div", "add_estimate", "sub_estimate", "div_estimate"]:
+        hi, lo = O.f128_binary_op(op, a_hi, a_lo, b_hi, b_lo)
+        bound = mpmath.mpf(2) ** (-101 if op.endswith("estimate") else -104)
+        for i in range(n):
+            A = mpmath.mpf(float(a_hi[i])) + mpmath.mpf(float(a_lo[i]))
+            B = mpmath.mpf(float(b_hi[i])) + mpmath.mpf(float(b_lo[i]))
+            want = fns[op.split("_")[0]](A, B)
+            got = mpmath.mpf(float(hi[i])) + mpmath.mpf(float(lo[i]))
+            scale = max(abs(want), abs(A) if op.startswith(("add", "sub")) else abs(want))
+            assert abs(got - want) <= bound * scale, (op, i)
