@@ -194,10 +194,13 @@ cfft_status build_fast_tables(cfft_plan *p)
     }
     // n <= 8192 also has the fused single-kernel variant, the default there (autotune may switch)
     p->fast_variant = ordered_large ? 3 : (p->n <= 8192 ? 1 : 2);
-    if (const char *fv = getenv("CFFT_B200_FAST_VARIANT")) // testing hook: force the multi-pass variant
+    if (const char *fv = getenv("CFFT_B200_FAST_VARIANT")) { // testing hook: force a variant
         if (!ordered_large && atoi(fv) == 2) p->fast_variant = 2;
+        if (!ordered_large && atoi(fv) == 4 && (p->n == 8192 || p->n == 16384)) p->fast_variant = 4;
+    }
     p->kernel_name = ordered_large ? "ordered-b256-column+rows-std"
-                                   : (p->fast_variant == 1 ? "fast-b256-regs" : "fast-b256-column+rows");
+                                   : (p->fast_variant == 1 ? "fast-b256-regs"
+                                      : p->fast_variant == 4 ? "fast-b256-cluster" : "fast-b256-column+rows");
     return CFFT_OK;
 }
 
@@ -488,11 +491,10 @@ cfft_status cfft_plan_autotune(cfft_plan *p, uint64_t batch_hint)
         if (p->n <= 2048)
             for (uint32_t t : {1024u, 2048u, 4096u})
                 if (t >= p->n) cands.push_back({std::string(fam) + "/" + std::to_string(t), p->fast_variant, t});
-    } else if (p->fast_variant == 1 || p->fast_variant == 2) {
-        if (p->n > 256 && p->n <= 8192) {
-            cands.push_back({"fast-b256-regs", 1, 0});
-            cands.push_back({"fast-b256-column+rows", 2, 0});
-        }
+    } else if (p->fast_variant == 1 || p->fast_variant == 2 || p->fast_variant == 4) {
+        if (p->n > 256 && p->n <= 8192) cands.push_back({"fast-b256-regs", 1, 0});
+        if (p->n > 256 && p->n <= 16384) cands.push_back({"fast-b256-column+rows", 2, 0});
+        if (p->n == 8192 || p->n == 16384) cands.push_back({"fast-b256-cluster", 4, 0});
     }
     if (cands.size() < 2) {
         p->tuning_report = p->kernel_name + ": only variant\n";
@@ -541,7 +543,8 @@ cfft_status cfft_plan_autotune(cfft_plan *p, uint64_t batch_hint)
     p->fast_variant = cands[best].fast_variant;
     p->tile_elems = cands[best].tile;
     if (p->kind != KIND_F128 && p->fast_variant != 0)
-        p->kernel_name = p->fast_variant == 1 ? "fast-b256-regs" : "fast-b256-column+rows";
+        p->kernel_name = p->fast_variant == 1 ? "fast-b256-regs"
+                         : p->fast_variant == 4 ? "fast-b256-cluster" : "fast-b256-column+rows";
     p->tuning_report = report + "selected: " + cands[best].name + "\n";
     return CFFT_OK;
 }

@@ -18,6 +18,8 @@
 //     one half-warp: XOR-swizzled shared memory + __syncwarp, no block barrier.
 //   * Twiddles come from plan tables re-laid out planar (w_k[p], lanes on consecutive p) so
 //     each request is one or two 128 B lines; they stay L1-resident.
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 #include <mutex>
 
@@ -243,6 +245,116 @@ c64_fast_b256_kernel(c64 *__restrict__ data, uint64_t batch, FastTables tb)
     }
 }
 
+// ---- n = 8192 / 16384: one transform per thread-block CLUSTER --------------------------------
+// A 128 / 256 KiB transform does not fit one SM with room for a second CTA, so the fused kernel above
+// runs one CTA per SM and its load / compute / store phases cannot overlap.  Here CSZ = 2 / 4 CTAs of
+// 256 threads and 64 KiB each own one transform: the first level (radix 8) reads HBM and scatters
+// its eight output chunks into the owning CTA's shared memory over DSMEM (about 30 GB/s per SM on
+// B200, tools/dsmem_probe.cu; half / three quarters of the data crosses once), then every CTA
+// finishes its 4096 contiguous elements locally (second level + 256-point base FFTs) exactly like
+// the single-CTA kernel.  Two CTAs of different clusters share an SM, so HBM, DSMEM and FP64 phases
+// overlap.  Same butterflies and twiddles => same bits.
+namespace cg = cooperative_groups;
+
+template <int N, int CSZ, int R2, bool FWD>
+__global__ void __launch_bounds__(256, 2)
+c64_cluster_kernel(c64 *__restrict__ data, FastTables tb)
+{
+    constexpr int NL = N / CSZ;   // elements finished by one CTA (4096)
+    constexpr int M1 = N / 8;     // chunk size after the radix-8 level
+    constexpr int CPC = 8 / CSZ;  // chunks owned per CTA
+    constexpr int PPC = M1 / CSZ; // first-level butterflies (values of p) per CTA = 512
+    static_assert(NL == 4096 && PPC == 512 && R2 * 256 == M1, "cluster layout");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c64 *s = reinterpret_cast<c64 *>(smem_raw);
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = int(cluster.block_rank());
+    const int t = threadIdx.x;
+    c64 *g = data + size_t(blockIdx.x / CSZ) * N;
+    c64 v[16];
+    const int blk = t / 16, lane16 = t % 16;
+
+    if (FWD) {
+        cluster.sync(); // every CTA of the cluster is resident before anyone writes remote shared memory
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[j * 8 + k] = ld_stream(g + rank * PPC + t + 256 * j + M1 * k);
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            c64 *x = &v[j * 8];
+            const int p = rank * PPC + t + 256 * j;
+            bf8<true>(x);
+#pragma unroll
+            for (int k = 1; k < 8; k++) x[k] = cmul(ld_tw(tb.top1 + (k - 1) * M1 + p), x[k]);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int c = brev_c<8>(k);
+                c64 *dst = cluster.map_shared_rank(s, unsigned(c / CPC));
+                dst[(c % CPC) * M1 + p] = x[k];
+            }
+        }
+        cluster.sync();
+        level<R2, M1, 256, true, false, false>(s, s, tb.top2, t, v);
+        __syncthreads();
+        base256<true, false, true>(s + blk * 256, s + blk * 256, g + rank * NL + blk * 256, tb.base, lane16, v);
+    } else {
+        base256<false, true, false>(g + rank * NL + blk * 256, s + blk * 256, s + blk * 256, tb.base, lane16, v);
+        __syncthreads();
+        level<R2, M1, 256, false, false, false>(s, s, tb.top2, t, v);
+        cluster.sync();
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            c64 *x = &v[j * 8];
+            const int p = rank * PPC + t + 256 * j;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int c = brev_c<8>(k);
+                const c64 *src = cluster.map_shared_rank(s, unsigned(c / CPC));
+                x[k] = src[(c % CPC) * M1 + p];
+            }
+#pragma unroll
+            for (int k = 1; k < 8; k++) x[k] = cmul(ld_tw(tb.top1 + (k - 1) * M1 + p), x[k]);
+            bf8<false>(x);
+#pragma unroll
+            for (int k = 0; k < 8; k++) st_stream(g + p + M1 * k, x[k]);
+        }
+        cluster.sync(); // peers may still be reading this CTA's shared memory
+    }
+}
+
+template <int N, int CSZ, int R2>
+cudaError_t launch_cluster(bool inverse, c64 *data, uint64_t batch, const FastTables &tb, cudaStream_t stream)
+{
+    constexpr size_t smem = size_t(N / CSZ) * sizeof(c64);
+    auto fk = c64_cluster_kernel<N, CSZ, R2, true>;
+    auto ik = c64_cluster_kernel<N, CSZ, R2, false>;
+    static thread_local int configured_device = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured_device != dev) {
+        cudaError_t e = cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ik, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return e;
+        configured_device = dev;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(batch * CSZ));
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = CSZ;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = inverse ? cudaLaunchKernelEx(&cfg, ik, data, tb) : cudaLaunchKernelEx(&cfg, fk, data, tb);
+    count_launch();
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
 template <int N, int R1, int R2>
 cudaError_t launch_cfg(bool inverse, c64 *data, uint64_t batch, const FastTables &tb, cudaStream_t stream)
 {
@@ -446,6 +558,11 @@ cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *d
             }
         }
         return cudaSuccess;
+    }
+    if (plan->fast_variant == 4) {
+        if (plan->n == 8192) return launch_cluster<8192, 2, 4>(inverse, data, batch, tb, stream);
+        if (plan->n == 16384) return launch_cluster<16384, 4, 8>(inverse, data, batch, tb, stream);
+        return cudaErrorInvalidValue;
     }
     switch (plan->n) {
     case 256: return launch_cfg<256, 1, 1>(inverse, data, batch, tb, stream);

@@ -57,6 +57,7 @@ struct cfft_plan {
     cfft::StageProgram prog[2];       // [0] fwd, [1] inv: every stage in execution order
     int fast_variant = 0;             // 0 exact tile kernel; 1 fused register kernel; 2 column passes + rows;
                                       // 3 ordered (standard order in/out) above 2^10: column passes + transposing rows
+                                      // 4 one transform per thread-block cluster (n = 8192, 16384), DSMEM exchange
     double2 *d_fast_tw[2] = {nullptr, nullptr}; // planar re-layout of the same twiddle values
     struct FastLevel { int radix; uint32_t span; uint32_t off; }; // off: planar table inside d_fast_tw
     std::vector<FastLevel> fast_levels;         // unordered levels, outermost first

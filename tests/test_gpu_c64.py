@@ -459,3 +459,23 @@ def test_plan_on_second_device(C, torch):
     h = x.copy()
     plan.fwd(h)
     assert bits_equal(h, d.cpu().numpy())
+
+
+@pytest.mark.parametrize("n", [8192, 16384])
+def test_cluster_kernel_bit_exact(C, torch, n):
+    """One transform per thread-block cluster (DSMEM exchange after the first level): same bits."""
+    rng = np.random.default_rng(n + 1)
+    os.environ["CFFT_B200_FAST_VARIANT"] = "4"
+    try:
+        plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(C.ordered.FftAlgo.Dif16, 256))
+    finally:
+        del os.environ["CFFT_B200_FAST_VARIANT"]
+    assert plan.kernel_name() == "fast-b256-cluster"
+    ref = O.UnorderedPlan(n, O.DIF16, 256)
+    for batch in [1, 2, 37]:
+        x = rand_c(rng, batch, n)
+        y = dev_run(torch, plan.fwd, x)
+        want = ref.fwd(x, threads=8)
+        assert bits_equal(y, want), (n, batch)
+        assert bits_equal(dev_run(torch, plan.inv, y), ref.inv(want, threads=8)), (n, batch)
+    assert "fast-b256-cluster" in plan.autotune()
