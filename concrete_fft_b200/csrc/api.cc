@@ -445,6 +445,8 @@ cfft_status cfft_plan_clone(const cfft_plan *p, cfft_plan **out)
         (*out)->method = p->method;
         (*out)->fast_variant = p->fast_variant;
         (*out)->tile_elems = p->tile_elems;
+        (*out)->l2_chunk_mb = p->l2_chunk_mb;
+        (*out)->l2_streams = p->l2_streams;
         (*out)->kernel_name = p->kernel_name;
         (*out)->tuning_report = p->tuning_report;
     }
@@ -481,10 +483,10 @@ cfft_status cfft_plan_autotune(cfft_plan *p, uint64_t batch_hint)
     DeviceGuard guard(p->device);
     if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
     const uint64_t bytes_per = p->n * (p->kind == KIND_F128 ? 32u : 16u);
-    uint64_t batch = batch_hint ? batch_hint : std::max<uint64_t>(1, (uint64_t{128} << 20) / bytes_per);
+    uint64_t batch = batch_hint ? batch_hint : std::max<uint64_t>(1, (uint64_t{p->n >= 16384 ? 512 : 128} << 20) / bytes_per);
     if (batch * bytes_per > (uint64_t{1} << 30)) batch = std::max<uint64_t>(1, (uint64_t{1} << 30) / bytes_per);
 
-    struct Cand { std::string name; int fast_variant; uint32_t tile; };
+    struct Cand { std::string name; int fast_variant; uint32_t tile; uint32_t l2_mb = 0, l2_streams = 1; };
     std::vector<Cand> cands;
     if (p->kind == KIND_F128 || p->fast_variant == 0) {
         const char *fam = p->kind == KIND_F128 ? "f128-radix8-tile" : "exact-tile";
@@ -495,6 +497,12 @@ cfft_status cfft_plan_autotune(cfft_plan *p, uint64_t batch_hint)
         if (p->n > 256 && p->n <= 8192) cands.push_back({"fast-b256-regs", 1, 0});
         if (p->n > 256 && p->n <= 16384) cands.push_back({"fast-b256-column+rows", 2, 0});
         if (p->n == 8192 || p->n == 16384) cands.push_back({"fast-b256-cluster", 4, 0});
+        if (p->n >= 16384) {
+            if (p->n > 16384) cands.push_back({"fast-b256-column+rows", 2, 0});
+            cands.push_back({"fast-b256-column+rows/L2-16MBx4", 2, 0, 16, 4});
+            cands.push_back({"fast-b256-column+rows/L2-24MBx3", 2, 0, 24, 3});
+            cands.push_back({"fast-b256-column+rows/L2-32MBx2", 2, 0, 32, 2});
+        }
     }
     if (cands.size() < 2) {
         p->tuning_report = p->kernel_name + ": only variant\n";
@@ -518,13 +526,15 @@ cfft_status cfft_plan_autotune(cfft_plan *p, uint64_t batch_hint)
     if (ce != cudaSuccess) { cleanup(); return cuda_fail(ce, "autotune setup"); }
 
     const int keep_variant = p->fast_variant;
-    const uint32_t keep_tile = p->tile_elems;
+    const uint32_t keep_tile = p->tile_elems, keep_mb = p->l2_chunk_mb, keep_st = p->l2_streams;
     std::string report;
     float best_ms = 1e30f;
     size_t best = 0;
     for (size_t i = 0; i < cands.size() && rc == CFFT_OK; i++) {
         p->fast_variant = cands[i].fast_variant;
         p->tile_elems = cands[i].tile;
+        p->l2_chunk_mb = cands[i].l2_mb;
+        p->l2_streams = cands[i].l2_streams;
         float ms = 0;
         rc = time_variant(p, scratch, batch, st, e0, e1, &ms);
         if (rc != CFFT_OK) break;
@@ -538,13 +548,18 @@ cfft_status cfft_plan_autotune(cfft_plan *p, uint64_t batch_hint)
     if (rc != CFFT_OK) {
         p->fast_variant = keep_variant;
         p->tile_elems = keep_tile;
+        p->l2_chunk_mb = keep_mb;
+        p->l2_streams = keep_st;
         return rc;
     }
     p->fast_variant = cands[best].fast_variant;
     p->tile_elems = cands[best].tile;
+    p->l2_chunk_mb = cands[best].l2_mb;
+    p->l2_streams = cands[best].l2_streams;
     if (p->kind != KIND_F128 && p->fast_variant != 0)
         p->kernel_name = p->fast_variant == 1 ? "fast-b256-regs"
                          : p->fast_variant == 4 ? "fast-b256-cluster" : "fast-b256-column+rows";
+    if (p->l2_chunk_mb) p->kernel_name += "/L2-chunked";
     p->tuning_report = report + "selected: " + cands[best].name + "\n";
     return CFFT_OK;
 }

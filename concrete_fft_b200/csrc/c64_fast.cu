@@ -526,14 +526,17 @@ cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *d
         return e != cudaSuccess ? e : e2;
     }
     if (plan->fast_variant == 2) {
-        // Optional (CFFT_B200_L2_CHUNK_MB): run the passes chunk by chunk hoping the chunk written by one
-        // pass is still L2-resident for the next.  Measured on B200: slower at every chunk size
-        // (8..128 MB) than whole-batch passes, so it is off by default.
-        static const uint64_t chunk_bytes = [] {
-            const char *e = getenv("CFFT_B200_L2_CHUNK_MB");
-            const long mb = e ? atol(e) : 0; // default off: measured slower on B200
-            return uint64_t(mb > 0 ? mb : 1 << 20) << 20;
-        }();
+        // Optional L2-resident scheduling (plan->l2_chunk_mb, chosen by the autotuner or forced with
+        // CFFT_B200_L2_CHUNK_MB / CFFT_B200_L2_STREAMS): the passes run chunk by chunk so that what one
+        // pass wrote is still in the 126 MB L2 when the next pass reads it.  Back-to-back chunks on ONE
+        // stream lose more to launch gaps than they gain; alternating chunks over 2-4 streams gains
+        // 10-18 % at n = 2^14 .. 2^16.
+        static const long env_mb = [] { const char *e = getenv("CFFT_B200_L2_CHUNK_MB"); return e ? atol(e) : -1; }();
+        static const int env_streams = [] { const char *e = getenv("CFFT_B200_L2_STREAMS"); return e ? atoi(e) : -1; }();
+        const long mb = env_mb >= 0 ? env_mb : long(plan->l2_chunk_mb);
+        int nstreams = env_streams >= 0 ? env_streams : int(plan->l2_streams);
+        nstreams = nstreams < 1 ? 1 : (nstreams > 4 ? 4 : nstreams);
+        const uint64_t chunk_bytes = uint64_t(mb > 0 ? mb : 1 << 20) << 20;
         uint64_t rows_per_chunk = chunk_bytes / (plan->n * sizeof(c64));
         if (rows_per_chunk < 1) rows_per_chunk = 1;
         const uint64_t per_row = plan->n / 256;
@@ -543,7 +546,27 @@ cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *d
                 if (g.radices[i] > 1) tw[i] = base + plan->fast_levels[size_t(g.first_level + i)].off;
             return launch_c64_column_group(inverse, d0, d0, rows, uint32_t(plan->n), g.span0, g.radices, tw, stream);
         };
-        for (uint64_t r0 = 0; r0 < batch; r0 += rows_per_chunk) {
+        // chunks are independent: with CFFT_B200_L2_STREAMS > 1 they alternate over auxiliary streams so
+        // that one chunk's second pass overlaps the next chunk's first pass (fork / join on events)
+        struct Aux { int device = -1; cudaStream_t st[4] = {}; cudaEvent_t done[4] = {}; cudaEvent_t start = nullptr; };
+        static thread_local Aux aux;
+        const bool fork = nstreams > 1 && rows_per_chunk < batch;
+        if (fork && aux.device != plan->device) {
+            for (int i = 0; i < 4; i++) {
+                if (cudaStreamCreateWithFlags(&aux.st[i], cudaStreamNonBlocking) != cudaSuccess) return cudaGetLastError();
+                if (cudaEventCreateWithFlags(&aux.done[i], cudaEventDisableTiming) != cudaSuccess) return cudaGetLastError();
+            }
+            if (cudaEventCreateWithFlags(&aux.start, cudaEventDisableTiming) != cudaSuccess) return cudaGetLastError();
+            aux.device = plan->device;
+        }
+        cudaStream_t user_stream = stream;
+        if (fork) {
+            cudaEventRecord(aux.start, user_stream);
+            for (int i = 0; i < nstreams; i++) cudaStreamWaitEvent(aux.st[i], aux.start, 0);
+        }
+        uint64_t chunk_index = 0;
+        for (uint64_t r0 = 0; r0 < batch; r0 += rows_per_chunk, chunk_index++) {
+            if (fork) stream = aux.st[chunk_index % uint64_t(nstreams)];
             const uint64_t rows = (batch - r0 < rows_per_chunk) ? batch - r0 : rows_per_chunk;
             c64 *d0 = data + r0 * plan->n;
             cudaError_t e;
@@ -557,7 +580,13 @@ cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *d
                     if ((e = run_group(*it, d0, rows)) != cudaSuccess) return e;
             }
         }
-        return cudaSuccess;
+        if (fork) {
+            for (int i = 0; i < nstreams; i++) {
+                cudaEventRecord(aux.done[i], aux.st[i]);
+                cudaStreamWaitEvent(user_stream, aux.done[i], 0);
+            }
+        }
+        return cudaGetLastError();
     }
     if (plan->fast_variant == 4) {
         if (plan->n == 8192) return launch_cluster<8192, 2, 4>(inverse, data, batch, tb, stream);

