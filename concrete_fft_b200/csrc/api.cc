@@ -321,6 +321,7 @@ cfft_status cfft_ordered_plan_create(cfft_plan **out, int device, uint64_t n, in
         build_c64_programs(p);
         st = upload_c64(p);
         if (st == CFFT_OK) st = build_fast_tables(p);
+        if (st == CFFT_OK && method == CFFT_METHOD_MEASURE && !getenv("CFFT_B200_NO_AUTOTUNE")) st = cfft_plan_autotune(p, 0);
         if (st != CFFT_OK) { cfft_plan_destroy(p); return st; }
         *out = p;
         return CFFT_OK;
@@ -483,7 +484,7 @@ cfft_status cfft_plan_autotune(cfft_plan *p, uint64_t batch_hint)
     DeviceGuard guard(p->device);
     if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
     const uint64_t bytes_per = p->n * (p->kind == KIND_F128 ? 32u : 16u);
-    uint64_t batch = batch_hint ? batch_hint : std::max<uint64_t>(1, (uint64_t{p->n >= 16384 ? 512 : 128} << 20) / bytes_per);
+    uint64_t batch = batch_hint ? batch_hint : std::max<uint64_t>(1, (uint64_t{(p->n >= 16384 || p->fast_variant == 3) ? 512 : 128} << 20) / bytes_per);
     if (batch * bytes_per > (uint64_t{1} << 30)) batch = std::max<uint64_t>(1, (uint64_t{1} << 30) / bytes_per);
 
     struct Cand { std::string name; int fast_variant; uint32_t tile; uint32_t l2_mb = 0, l2_streams = 1; };
@@ -493,6 +494,10 @@ cfft_status cfft_plan_autotune(cfft_plan *p, uint64_t batch_hint)
         if (p->n <= 2048)
             for (uint32_t t : {1024u, 2048u, 4096u})
                 if (t >= p->n) cands.push_back({std::string(fam) + "/" + std::to_string(t), p->fast_variant, t});
+    } else if (p->fast_variant == 3) {
+        cands.push_back({"ordered-b256-column+rows-std", 3, 0});
+        cands.push_back({"ordered-b256-column+rows-std/L2-16MBx4", 3, 0, 16, 4});
+        cands.push_back({"ordered-b256-column+rows-std/L2-32MBx2", 3, 0, 32, 2});
     } else if (p->fast_variant == 1 || p->fast_variant == 2 || p->fast_variant == 4) {
         if (p->n > 256 && p->n <= 8192) cands.push_back({"fast-b256-regs", 1, 0});
         if (p->n > 256 && p->n <= 16384) cands.push_back({"fast-b256-column+rows", 2, 0});
@@ -556,7 +561,8 @@ cfft_status cfft_plan_autotune(cfft_plan *p, uint64_t batch_hint)
     p->tile_elems = cands[best].tile;
     p->l2_chunk_mb = cands[best].l2_mb;
     p->l2_streams = cands[best].l2_streams;
-    if (p->kind != KIND_F128 && p->fast_variant != 0)
+    if (p->kind != KIND_F128 && p->fast_variant == 3) p->kernel_name = "ordered-b256-column+rows-std";
+    else if (p->kind != KIND_F128 && p->fast_variant != 0)
         p->kernel_name = p->fast_variant == 1 ? "fast-b256-regs"
                          : p->fast_variant == 4 ? "fast-b256-cluster" : "fast-b256-column+rows";
     if (p->l2_chunk_mb) p->kernel_name += "/L2-chunked";

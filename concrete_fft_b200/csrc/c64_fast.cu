@@ -492,65 +492,76 @@ cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *d
     tb.top1 = plan->fast_levels.size() > 0 ? base + plan->fast_levels[0].off : base;
     tb.top2 = plan->fast_levels.size() > 1 ? base + plan->fast_levels[1].off : base;
     tb.base = base + plan->fast_base_off;
-    if (plan->fast_variant == 3) {
-        // ordered: levels as column passes (the last one out of place into a workspace), then the base
-        // FFTs read the workspace rows and write standard order back into the caller's buffer.
-        c64 *ws = nullptr;
-        cudaMemPool_t pool = nullptr;
-        cudaError_t e = workspace_pool(plan->device, &pool);
-        if (e == cudaSuccess)
-            e = cudaMallocFromPoolAsync(reinterpret_cast<void **>(&ws), batch * plan->n * sizeof(c64), pool, stream);
-        if (e != cudaSuccess) return e;
-        const uint32_t n32 = uint32_t(plan->n);
-        auto group = [&](const cfft_plan::FastGroup &g, const c64 *src, c64 *dst) {
-            const double2 *tw[3] = {base, base, base};
-            for (int i = 0; i < 3; i++)
-                if (g.radices[i] > 1) tw[i] = base + plan->fast_levels[size_t(g.first_level + i)].off;
-            return launch_c64_column_group(inverse, src, dst, batch, n32, g.span0, g.radices, tw, stream);
-        };
-        auto rows = [&](const c64 *src, c64 *dst) {
-            return n32 / 256 >= 16 ? launch_rows_std<16>(inverse, src, dst, batch, n32, tb.base, stream)
-                                   : launch_rows_std<8>(inverse, src, dst, batch, n32, tb.base, stream);
-        };
-        const size_t ng = plan->fast_groups.size();
-        if (!inverse) {
-            for (size_t i = 0; i < ng && e == cudaSuccess; i++)
-                e = group(plan->fast_groups[i], data, i + 1 == ng ? ws : data);
-            if (e == cudaSuccess) e = rows(ws, data);
-        } else {
-            e = rows(data, ws);
-            for (size_t i = ng; i-- > 0 && e == cudaSuccess;)
-                e = group(plan->fast_groups[i], i + 1 == ng ? ws : data, data);
-        }
-        cudaError_t e2 = cudaFreeAsync(ws, stream);
-        return e != cudaSuccess ? e : e2;
-    }
-    if (plan->fast_variant == 2) {
-        // Optional L2-resident scheduling (plan->l2_chunk_mb, chosen by the autotuner or forced with
-        // CFFT_B200_L2_CHUNK_MB / CFFT_B200_L2_STREAMS): the passes run chunk by chunk so that what one
-        // pass wrote is still in the 126 MB L2 when the next pass reads it.  Back-to-back chunks on ONE
-        // stream lose more to launch gaps than they gain; alternating chunks over 2-4 streams gains
-        // 10-18 % at n = 2^14 .. 2^16.
+    if (plan->fast_variant == 2 || plan->fast_variant == 3) {
+        // Multi-pass variants: unordered (2, in place) and ordered (3: the last column pass goes out of
+        // place into a workspace and the base-FFT pass writes standard order back).
+        //
+        // Scheduling (plan->l2_chunk_mb / l2_streams, chosen by the autotuner or forced with
+        // CFFT_B200_L2_CHUNK_MB / CFFT_B200_L2_STREAMS): by default each pass covers the whole batch.
+        // Otherwise the passes run chunk by chunk so that what one pass wrote is still in the 126 MB L2
+        // when the next reads it; chunks alternate over 2-4 auxiliary streams (fork / join on events)
+        // because back-to-back small kernels on ONE stream lose more to launch gaps than L2 gains.
         static const long env_mb = [] { const char *e = getenv("CFFT_B200_L2_CHUNK_MB"); return e ? atol(e) : -1; }();
         static const int env_streams = [] { const char *e = getenv("CFFT_B200_L2_STREAMS"); return e ? atoi(e) : -1; }();
+        const bool ordered = plan->fast_variant == 3;
         const long mb = env_mb >= 0 ? env_mb : long(plan->l2_chunk_mb);
         int nstreams = env_streams >= 0 ? env_streams : int(plan->l2_streams);
         nstreams = nstreams < 1 ? 1 : (nstreams > 4 ? 4 : nstreams);
         const uint64_t chunk_bytes = uint64_t(mb > 0 ? mb : 1 << 20) << 20;
         uint64_t rows_per_chunk = chunk_bytes / (plan->n * sizeof(c64));
         if (rows_per_chunk < 1) rows_per_chunk = 1;
-        const uint64_t per_row = plan->n / 256;
-        auto run_group = [&](const cfft_plan::FastGroup &g, c64 *d0, uint64_t rows) {
-            const double2 *tw[3] = {base, base, base};
-            for (int i = 0; i < 3; i++)
-                if (g.radices[i] > 1) tw[i] = base + plan->fast_levels[size_t(g.first_level + i)].off;
-            return launch_c64_column_group(inverse, d0, d0, rows, uint32_t(plan->n), g.span0, g.radices, tw, stream);
+        const uint32_t n32 = uint32_t(plan->n);
+        const size_t ng = plan->fast_groups.size();
+        cudaMemPool_t pool = nullptr;
+        if (ordered) {
+            cudaError_t e = workspace_pool(plan->device, &pool);
+            if (e != cudaSuccess) return e;
+        }
+
+        // all passes of `rows` transforms starting at d0, on stream st
+        auto process = [&](c64 *d0, uint64_t rows, cudaStream_t st) -> cudaError_t {
+            auto group = [&](const cfft_plan::FastGroup &g, const c64 *src, c64 *dst) {
+                const double2 *tw[3] = {base, base, base};
+                for (int i = 0; i < 3; i++)
+                    if (g.radices[i] > 1) tw[i] = base + plan->fast_levels[size_t(g.first_level + i)].off;
+                return launch_c64_column_group(inverse, src, dst, rows, n32, g.span0, g.radices, tw, st);
+            };
+            cudaError_t e = cudaSuccess;
+            if (!ordered) {
+                if (!inverse) {
+                    for (size_t i = 0; i < ng && e == cudaSuccess; i++) e = group(plan->fast_groups[i], d0, d0);
+                    if (e == cudaSuccess) e = launch_cfg<256, 1, 1>(false, d0, rows * (n32 / 256), tb, st);
+                } else {
+                    e = launch_cfg<256, 1, 1>(true, d0, rows * (n32 / 256), tb, st);
+                    for (size_t i = ng; i-- > 0 && e == cudaSuccess;) e = group(plan->fast_groups[i], d0, d0);
+                }
+                return e;
+            }
+            c64 *ws = nullptr;
+            e = cudaMallocFromPoolAsync(reinterpret_cast<void **>(&ws), rows * plan->n * sizeof(c64), pool, st);
+            if (e != cudaSuccess) return e;
+            auto rows_pass = [&](const c64 *src, c64 *dst) {
+                return n32 / 256 >= 16 ? launch_rows_std<16>(inverse, src, dst, rows, n32, tb.base, st)
+                                       : launch_rows_std<8>(inverse, src, dst, rows, n32, tb.base, st);
+            };
+            if (!inverse) {
+                for (size_t i = 0; i < ng && e == cudaSuccess; i++)
+                    e = group(plan->fast_groups[i], d0, i + 1 == ng ? ws : d0);
+                if (e == cudaSuccess) e = rows_pass(ws, d0);
+            } else {
+                e = rows_pass(d0, ws);
+                for (size_t i = ng; i-- > 0 && e == cudaSuccess;)
+                    e = group(plan->fast_groups[i], i + 1 == ng ? ws : d0, d0);
+            }
+            const cudaError_t e2 = cudaFreeAsync(ws, st);
+            return e != cudaSuccess ? e : e2;
         };
-        // chunks are independent: with CFFT_B200_L2_STREAMS > 1 they alternate over auxiliary streams so
-        // that one chunk's second pass overlaps the next chunk's first pass (fork / join on events)
+
+        if (rows_per_chunk >= batch) return process(data, batch, stream);
+
         struct Aux { int device = -1; cudaStream_t st[4] = {}; cudaEvent_t done[4] = {}; cudaEvent_t start = nullptr; };
         static thread_local Aux aux;
-        const bool fork = nstreams > 1 && rows_per_chunk < batch;
+        const bool fork = nstreams > 1;
         if (fork && aux.device != plan->device) {
             for (int i = 0; i < 4; i++) {
                 if (cudaStreamCreateWithFlags(&aux.st[i], cudaStreamNonBlocking) != cudaSuccess) return cudaGetLastError();
@@ -559,34 +570,23 @@ cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *d
             if (cudaEventCreateWithFlags(&aux.start, cudaEventDisableTiming) != cudaSuccess) return cudaGetLastError();
             aux.device = plan->device;
         }
-        cudaStream_t user_stream = stream;
         if (fork) {
-            cudaEventRecord(aux.start, user_stream);
+            cudaEventRecord(aux.start, stream);
             for (int i = 0; i < nstreams; i++) cudaStreamWaitEvent(aux.st[i], aux.start, 0);
         }
+        cudaError_t e = cudaSuccess;
         uint64_t chunk_index = 0;
-        for (uint64_t r0 = 0; r0 < batch; r0 += rows_per_chunk, chunk_index++) {
-            if (fork) stream = aux.st[chunk_index % uint64_t(nstreams)];
+        for (uint64_t r0 = 0; r0 < batch && e == cudaSuccess; r0 += rows_per_chunk, chunk_index++) {
             const uint64_t rows = (batch - r0 < rows_per_chunk) ? batch - r0 : rows_per_chunk;
-            c64 *d0 = data + r0 * plan->n;
-            cudaError_t e;
-            if (!inverse) {
-                for (const auto &g : plan->fast_groups)
-                    if ((e = run_group(g, d0, rows)) != cudaSuccess) return e;
-                if ((e = launch_cfg<256, 1, 1>(false, d0, rows * per_row, tb, stream)) != cudaSuccess) return e;
-            } else {
-                if ((e = launch_cfg<256, 1, 1>(true, d0, rows * per_row, tb, stream)) != cudaSuccess) return e;
-                for (auto it = plan->fast_groups.rbegin(); it != plan->fast_groups.rend(); ++it)
-                    if ((e = run_group(*it, d0, rows)) != cudaSuccess) return e;
-            }
+            e = process(data + r0 * plan->n, rows, fork ? aux.st[chunk_index % uint64_t(nstreams)] : stream);
         }
         if (fork) {
             for (int i = 0; i < nstreams; i++) {
                 cudaEventRecord(aux.done[i], aux.st[i]);
-                cudaStreamWaitEvent(user_stream, aux.done[i], 0);
+                cudaStreamWaitEvent(stream, aux.done[i], 0);
             }
         }
-        return cudaGetLastError();
+        return e != cudaSuccess ? e : cudaGetLastError();
     }
     if (plan->fast_variant == 4) {
         if (plan->n == 8192) return launch_cluster<8192, 2, 4>(inverse, data, batch, tb, stream);

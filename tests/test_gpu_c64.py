@@ -350,7 +350,7 @@ def test_ordered_above_reference_cap(C, torch, logn):
     with pytest.raises(C.PanicError):
         C.ordered.Plan(n, C.ordered.Method.UserProvided(C.ordered.FftAlgo.Dif16))  # reference behaviour
     plan = C.ordered.Plan(n, C.ordered.Method.Measure(), allow_large=True)
-    assert plan.fft_size() == n and plan.kernel_name() == "ordered-b256-column+rows-std"
+    assert plan.fft_size() == n and plan.kernel_name().startswith("ordered-b256-column+rows-std")
     ref = O.UnorderedPlan(n, O.DIF16, 256)
     pi = O.permutation(n, 256)
     batch = 3 if logn <= 16 else 2
