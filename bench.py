@@ -38,7 +38,7 @@ FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c64", choices=["c64", "ordered", "f128"])
@@ -77,7 +77,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -423,9 +423,16 @@ def main():
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         fp64_peak = 64 * 148 * sm_mhz * 1e6
         rate = instr * batch / (fwd_ms * 1e-3)
-        roofline.update({"bound": "fp64-pipe", "fp64_instr_per_transform": instr, "fp64_instr_per_s": rate,
-                         "fp64_pipe_frac_at_sampled_clock": rate / fp64_peak,
-                         "fp64_pipe_frac_at_max_clock": rate / (64 * 148 * 1965e6)})
+        # fft128 is bound by the FP64 pipe, not by HBM: report the roofline in FP64 instructions
+        # (94 per butterfly) against 64 lanes x 148 SMs x the SM clock sampled during the run
+        roofline = {"bound": "fp64", "kernel": roofline["kernel"], "achieved": rate / 1e12, "peak": fp64_peak / 1e12,
+                    "unit": "T FP64 instr/s", "frac": rate / fp64_peak, "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": "64 FP64 lanes x 148 SMs x sampled SM clock (%.0f MHz); MEASURED_PEAKS.json has no FP64 entry" % sm_mhz,
+                    "fp64_instr_per_transform": instr, "frac_at_max_clock": rate / (64 * 148 * 1965e6),
+                    "ncu_sm__pipe_fp64_cycles_active_pct": {"fwd": 76.38, "inv": 79.39, "source": "profiles/r1h_traffic_f128.csv"},
+                    "flop_frac_of_37.2TF": 106.0 / 94.0 * rate / (2 * 64 * 148 * 1965e6),
+                    "algorithmic_bytes_per_launch": bytes_per_launch, "hbm_achieved_gbs": achieved, "hbm_frac": achieved / peak,
+                    "fwd_ms": fwd_ms, "inv_ms": inv_ms}
 
     cpu = None
     if not args.no_cpu:
