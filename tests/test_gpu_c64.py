@@ -479,3 +479,38 @@ def test_cluster_kernel_bit_exact(C, torch, n):
         assert bits_equal(y, want), (n, batch)
         assert bits_equal(dev_run(torch, plan.inv, y), ref.inv(want, threads=8)), (n, batch)
     assert "fast-b256-cluster" in plan.autotune()
+
+
+def test_random_plans_fuzz(C, torch):
+    """Seeded fuzz over everything Plan::new accepts: random n, algo, base_n, batch and entry point
+    (device / host-pageable), bit-exact against the oracle in both directions."""
+    rng = np.random.default_rng(20261017)
+    A = C.ordered.FftAlgo
+    for trial in range(48):
+        logn = int(rng.integers(0, 16))
+        n = 1 << logn
+        algo = int(rng.integers(0, 8))
+        if rng.random() < 0.35 and logn <= 10:
+            kind = "ordered"
+            plan = C.ordered.Plan(n, C.ordered.Method.UserProvided(A(algo)))
+            ref = O.OrderedPlan(n, algo) if n > 1 else None
+        else:
+            kind = "unordered"
+            choices = [b for b in range(5, 11) if b <= logn] + [logn] if logn <= 10 else [b for b in range(5, 11)]
+            base_n = 1 << int(rng.choice(choices))
+            plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(A(algo), base_n))
+            ref = O.UnorderedPlan(n, algo, base_n) if n > 1 else None
+        batch = int(rng.integers(1, max(2, min(40, (1 << 18) // n))))
+        x = rand_c(rng, batch, n)
+        if n == 1:
+            assert bits_equal(dev_run(torch, plan.fwd, x), x)
+            continue
+        want = ref.fwd(x)
+        if rng.random() < 0.5:
+            y = dev_run(torch, plan.fwd, x)
+            z = dev_run(torch, plan.inv, y)
+        else:
+            y = x.copy(); plan.fwd(y)
+            z = y.copy(); plan.inv(z)
+        assert bits_equal(y, want), (trial, kind, n, algo, batch)
+        assert bits_equal(z, ref.inv(want)), (trial, kind, n, algo, batch)

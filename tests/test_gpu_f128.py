@@ -208,3 +208,22 @@ def test_pointwise_product_bit_exact_and_full_size_convolution(C, torch):
         lo = np.concatenate([L[1][r].cpu().numpy(), L[3][r].cpu().numpy()])
         err = max(abs(dd_to_fraction(h, l) - e) for h, l, e in zip(hi, lo, exact))
         assert float(err) < 1e-30 * npoly  # src/fft128/mod.rs:2062
+
+
+def test_random_sizes_fuzz(C, torch):
+    rng = np.random.default_rng(424242)
+    for trial in range(16):
+        logn = int(rng.integers(5, 16))
+        n = 1 << logn
+        batch = int(rng.integers(1, max(2, min(50, (1 << 17) // n))))
+        planes = planes_random(rng, batch, n, full_width=bool(rng.integers(0, 2)))
+        plan = C.fft128.Plan(n)
+        ref = O.F128Plan(n)
+        if rng.random() < 0.5:
+            y = dev_run(torch, plan.fwd, planes)
+        else:
+            y = [p.copy() for p in planes]
+            plan.fwd(*y)
+        want = ref.fwd(*planes, variant=O.F128_FMA)
+        assert bits_equal(y, want), (trial, n, batch)
+        assert bits_equal(dev_run(torch, plan.inv, y), ref.inv(*want, variant=O.F128_FMA)), (trial, n, batch)
