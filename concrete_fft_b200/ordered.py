@@ -62,9 +62,12 @@ class _PlanBase:
     _h = None
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            N.lib.cfft_plan_destroy(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None):
+                N.lib.cfft_plan_destroy(self._h)
+                self._h = None
+        except Exception:  # interpreter shutdown: the library handle may already be gone
+            pass
 
     def fft_size(self):
         return int(N.lib.cfft_plan_fft_size(self._h))
