@@ -142,6 +142,53 @@ cfft_status run_pipeline(const cfft_plan *plan, void *const *planes, int nplanes
     PipeCtx *ctx = acquire_ctx(plan->device);
     cudaError_t e = cudaSuccess;
     const char *what = "";
+
+    // Small calls (the literal one-polynomial Plan::fwd): skip the copy engines.  The kernels read and
+    // write the caller's pinned memory -- or a pinned bounce buffer for pageable memory -- directly
+    // over PCIe (zero copy), which saves two DMA submissions and their latencies per call.
+    const size_t total_bytes = size_t(batch) * row_bytes * size_t(nplanes);
+    static const size_t zero_copy_max = [] {
+        const char *ev = getenv("CFFT_B200_ZERO_COPY_MAX_KB");
+        return size_t(ev ? atol(ev) : 512) << 10;
+    }();
+    if (total_bytes <= zero_copy_max) {
+        Slot &s = ctx->slot[0];
+        what = "zero-copy setup";
+        e = ensure_slot(s, 0, pinned ? 0 : total_bytes);
+        char *base[4] = {nullptr, nullptr, nullptr, nullptr};
+        const size_t plane_bytes = size_t(batch) * row_bytes;
+        if (e == cudaSuccess) {
+            for (int pl = 0; pl < nplanes; pl++) {
+                if (pinned) base[pl] = static_cast<char *>(planes[pl]);
+                else {
+                    base[pl] = static_cast<char *>(s.pinned) + size_t(pl) * plane_bytes;
+                    std::memcpy(base[pl], planes[pl], plane_bytes);
+                }
+            }
+            what = "zero-copy launch";
+            for (int pass = 0; pass < (op == 2 ? 2 : 1) && e == cudaSuccess; pass++) {
+                const bool inverse = (op == 1) || (op == 2 && pass == 1);
+                if (plan->kind == KIND_F128)
+                    e = launch_f128(plan, inverse, reinterpret_cast<double *>(base[0]), reinterpret_cast<double *>(base[1]),
+                                    reinterpret_cast<double *>(base[2]), reinterpret_cast<double *>(base[3]), batch, s.stream);
+                else
+                    e = launch_c64(plan, inverse, reinterpret_cast<double2 *>(base[0]), batch, s.stream);
+            }
+        }
+        if (e == cudaSuccess) {
+            what = "zero-copy sync";
+            e = cudaStreamSynchronize(s.stream);
+        }
+        if (e == cudaSuccess && !pinned)
+            for (int pl = 0; pl < nplanes; pl++) std::memcpy(planes[pl], base[pl], plane_bytes);
+        release_ctx(ctx);
+        if (prev_dev >= 0 && prev_dev != plan->device) cudaSetDevice(prev_dev);
+        if (e != cudaSuccess) {
+            err = std::string(what) + ": " + cudaGetErrorString(e);
+            return CFFT_ECUDA;
+        }
+        return CFFT_OK;
+    }
     auto flush_pending = [&](Slot &s) {
         if (!s.pending) return;
         for (int pl = 0; pl < nplanes; pl++)
@@ -199,11 +246,12 @@ cfft_status run_pipeline(const cfft_plan *plan, void *const *planes, int nplanes
             s.pending = true;
             s.pend_row0 = row0;
             s.pend_rows = rows;
+            e = cudaEventRecord(s.done, s.stream); // staging-buffer reuse waits on this
         }
-        e = cudaEventRecord(s.done, s.stream);
     }
-    // drain
-    for (int i = 0; i < kSlots; i++) {
+    // drain the slots this call used
+    const int used = int(nchunks < size_t(nslots) ? nchunks : size_t(nslots));
+    for (int i = 0; i < used; i++) {
         Slot &s = ctx->slot[i];
         if (!s.stream) continue;
         cudaError_t e2 = cudaStreamSynchronize(s.stream);
