@@ -81,3 +81,22 @@ def test_method_and_enum_surface(C):
     m = C.unordered.Method.UserProvided(A.Dif16, 256)
     assert (m.base_algo, m.base_n) == (A.Dif16, 256)
     assert "cfft_b200" in C.version()
+
+
+def test_header_is_plain_c_and_demo_links(C, tmp_path):
+    """include/cfft_b200.h must compile as C99 with warnings as errors, and a C program must link
+    against the shared library using nothing but that header."""
+    import subprocess
+
+    exe = tmp_path / "c_api_demo"
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "c_api_demo.c"), "-L", os.path.join(ROOT, "concrete_fft_b200"), "-lcfft_b200",
+           "-Wl,-rpath," + os.path.join(ROOT, "concrete_fft_b200"), "-lm", "-o", str(exe)]
+    subprocess.run(cmd, check=True)
+    rc = subprocess.run([str(exe)], capture_output=True, text=True)
+    import torch
+
+    if torch.cuda.is_available():
+        assert rc.returncode == 0, rc.stdout + rc.stderr
+    else:
+        assert rc.returncode == 77, rc.stdout + rc.stderr  # fails loudly without a GPU: no CPU fallback
