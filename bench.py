@@ -287,6 +287,7 @@ def main():
             plan = C.ordered.Plan(n, C.ordered.Method.Measure(), device=local, allow_large=n > 1024)
         else:
             plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(A[algo], base_n), device=local)
+            plan.autotune()  # kernel variant only; the plan (order, bits) is fixed by UserProvided
         data = torch.view_as_complex(torch.rand(batch, n, 2, dtype=torch.float64, device=dev, generator=g)).contiguous()
         bytes_per_launch = 2 * 16 * n * batch
         inv_scale = 1.0 / n
