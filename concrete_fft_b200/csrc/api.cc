@@ -599,6 +599,7 @@ static cfft_status run_c64(const cfft_plan *p, bool inverse, void *dev_buf, uint
 {
     if (!p || p->kind == KIND_F128) return fail(CFFT_EINVAL, "not a c64 plan");
     if (!dev_buf && batch) return fail(CFFT_EINVAL, "null buffer");
+    if (reinterpret_cast<uintptr_t>(dev_buf) & 15) return fail(CFFT_EINVAL, "device buffer must be 16-byte aligned (128-bit accesses)");
     DeviceGuard guard(p->device);
     if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
     cudaError_t e = launch_c64(p, inverse, static_cast<double2 *>(dev_buf), batch, static_cast<cudaStream_t>(stream));

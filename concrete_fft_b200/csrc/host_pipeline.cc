@@ -131,6 +131,10 @@ cfft_status run_pipeline(const cfft_plan *plan, void *const *planes, int nplanes
     }
     bool pinned = true;
     for (int i = 0; i < nplanes; i++) pinned = pinned && is_pinned(planes[i]);
+    // c64 kernels use 128-bit accesses: a caller slice that is only 8-byte aligned (Rust's Complex64
+    // alignment) cannot be touched in place by the zero-copy path; DMA into our aligned buffers is fine
+    bool aligned16 = true;
+    for (int i = 0; i < nplanes; i++) aligned16 = aligned16 && (reinterpret_cast<uintptr_t>(planes[i]) & 15) == 0;
 
     const int nslots = pipe_slots();
     size_t rows_per_chunk = pipe_chunk_bytes() / (row_bytes * size_t(nplanes));
@@ -154,12 +158,13 @@ cfft_status run_pipeline(const cfft_plan *plan, void *const *planes, int nplanes
     if (total_bytes <= zero_copy_max) {
         Slot &s = ctx->slot[0];
         what = "zero-copy setup";
-        e = ensure_slot(s, 0, pinned ? 0 : total_bytes);
+        const bool in_place = pinned && (aligned16 || plan->kind == KIND_F128);
+        e = ensure_slot(s, 0, in_place ? 0 : total_bytes);
         char *base[4] = {nullptr, nullptr, nullptr, nullptr};
         const size_t plane_bytes = size_t(batch) * row_bytes;
         if (e == cudaSuccess) {
             for (int pl = 0; pl < nplanes; pl++) {
-                if (pinned) base[pl] = static_cast<char *>(planes[pl]);
+                if (in_place) base[pl] = static_cast<char *>(planes[pl]);
                 else {
                     base[pl] = static_cast<char *>(s.pinned) + size_t(pl) * plane_bytes;
                     std::memcpy(base[pl], planes[pl], plane_bytes);
@@ -179,7 +184,7 @@ cfft_status run_pipeline(const cfft_plan *plan, void *const *planes, int nplanes
             what = "zero-copy sync";
             e = cudaStreamSynchronize(s.stream);
         }
-        if (e == cudaSuccess && !pinned)
+        if (e == cudaSuccess && !in_place)
             for (int pl = 0; pl < nplanes; pl++) std::memcpy(planes[pl], base[pl], plane_bytes);
         release_ctx(ctx);
         if (prev_dev >= 0 && prev_dev != plan->device) cudaSetDevice(prev_dev);

@@ -118,7 +118,8 @@ uint64_t cfft_plan_tuning_report(const cfft_plan *plan, char *buf, uint64_t buf_
 
 /* {ordered,unordered}::Plan::fwd / inv on device memory, in place, stream ordered.
  * src/ordered.rs:342-373, src/unordered.rs:826-839, 927-940.
- * dev_buf: batch * n c64 on the plan's device.  Unordered: fwd output / inv input are in the
+ * dev_buf: batch * n c64 on the plan's device, 16-byte aligned (CFFT_EINVAL otherwise; host
+ * entry points accept any c64 alignment).  Unordered: fwd output / inv input are in the
  * plan's permuted order, index for index as the reference (src/unordered.rs:1046-1051). */
 cfft_status cfft_c64_fwd(const cfft_plan *plan, void *dev_buf, uint64_t batch, void *stream);
 cfft_status cfft_c64_inv(const cfft_plan *plan, void *dev_buf, uint64_t batch, void *stream);

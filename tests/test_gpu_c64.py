@@ -514,3 +514,31 @@ def test_random_plans_fuzz(C, torch):
             z = y.copy(); plan.inv(z)
         assert bits_equal(y, want), (trial, kind, n, algo, batch)
         assert bits_equal(z, ref.inv(want)), (trial, kind, n, algo, batch)
+
+
+def test_alignment_rules(C, torch):
+    """Device buffers must be 16-byte aligned (128-bit accesses); host slices may be 8-byte aligned
+    like a Rust &mut [Complex64] -- pageable or pinned."""
+    rng = np.random.default_rng(31)
+    n = 2048
+    plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(C.ordered.FftAlgo.Dif16, 256))
+    ref = O.UnorderedPlan(n, O.DIF16, 256)
+    x = rand_c(rng, 2, n)
+    want = ref.fwd(x)
+    raw = np.zeros(2 * (2 * n) + 1, np.float64)
+    view = raw[1:].view(np.complex128).reshape(2, n)  # 8 mod 16
+    if view.ctypes.data % 16 == 0:
+        raw = np.zeros(2 * (2 * n) + 2, np.float64)
+        view = raw[2:][: 4 * n].view(np.complex128).reshape(2, n)
+    view[...] = x
+    if view.ctypes.data % 16 == 8:
+        plan.fwd(view)
+        assert bits_equal(view, want)
+    pinned = torch.zeros(2 * (2 * n) + 1, dtype=torch.float64).pin_memory()
+    pv = pinned.numpy()[1:].view(np.complex128).reshape(2, n)
+    pv[...] = x
+    plan.fwd(pv)
+    assert bits_equal(pv, want)
+    dev = torch.zeros(2 * n * 2 + 2, dtype=torch.float64, device="cuda")
+    st = C._native.lib.cfft_c64_fwd(plan._h, dev.data_ptr() + 8, 2, None)
+    assert st == C._native.EINVAL
