@@ -484,7 +484,7 @@ cfft_status cfft_plan_autotune(cfft_plan *p, uint64_t batch_hint)
     DeviceGuard guard(p->device);
     if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
     const uint64_t bytes_per = p->n * (p->kind == KIND_F128 ? 32u : 16u);
-    uint64_t batch = batch_hint ? batch_hint : std::max<uint64_t>(1, (uint64_t{(p->n >= 16384 || p->fast_variant == 3) ? 512 : 128} << 20) / bytes_per);
+    uint64_t batch = batch_hint ? batch_hint : std::max<uint64_t>(1, (uint64_t((p->n >= 16384 || p->fast_variant == 3) ? 512 : 128) << 20) / bytes_per);
     if (batch * bytes_per > (uint64_t{1} << 30)) batch = std::max<uint64_t>(1, (uint64_t{1} << 30) / bytes_per);
 
     struct Cand { std::string name; int fast_variant; uint32_t tile; uint32_t l2_mb = 0, l2_streams = 1; };

@@ -91,7 +91,6 @@ F128_DEV void bfly_inv(ddc &z0, ddc &z1, ddc w)
 }
 
 struct Planes { double *p[4]; };
-struct CPlanes { const double *p[4]; };
 
 // twiddle k as one 32-byte record {re hi, re lo, im hi, im lo}: two 128-bit loads
 struct __align__(32) Tw4 { double re_hi, re_lo, im_hi, im_lo; };
@@ -179,8 +178,9 @@ F128_DEV void tile_pass(const Planes &g, double2 *__restrict__ sre, double2 *__r
 #pragma unroll
             for (int e = 0; e < G; e++) {
                 const uint32_t i = swz(base + e * u);
-                const double2 a = sre[i], b = sim[i];
-                z[e] = {{a.x, a.y}, {b.x, b.y}};
+                const double2 re2 = sre[i], im2 = sim[i];
+                z[e].re.hi = re2.x; z[e].re.lo = re2.y;
+                z[e].im.hi = im2.x; z[e].im.lo = im2.y;
             }
         }
         run_group<S, FWD>(z, tw, (tile_row_off + base) & (n - 1), logn, d0);
