@@ -331,6 +331,12 @@ cfft_status cfft_f128_inv_host(const cfft_plan *p, double *re0, double *re1, dou
     return f128_host(p, re0, re1, im0, im1, len, batch, 1);
 }
 
+cfft_status cfft_f128_fwd_inv_host(const cfft_plan *p, double *re0, double *re1, double *im0, double *im1, uint64_t len,
+                                   uint64_t batch)
+{
+    return f128_host(p, re0, re1, im0, im1, len, batch, 2);
+}
+
 cfft_status cfft_unordered_fwd_monomial_host(const cfft_plan *p, uint64_t degree, void *host_buf, uint64_t len)
 {
     if (!p || p->kind != KIND_UNORDERED) return set_last_error(CFFT_EINVAL, "not an unordered plan");

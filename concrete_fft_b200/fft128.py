@@ -81,6 +81,14 @@ class Plan:
         """src/fft128/mod.rs:1938-1960: bit-reversed order in, standard order out, unnormalised."""
         self._run((buf_re0, buf_re1, buf_im0, buf_im1), True)
 
+    def fwd_inv_host(self, buf_re0, buf_re1, buf_im0, buf_im1):
+        """fwd then inv on the device between one upload and one download (bench `e2e` step)."""
+        n = self.fft_size()
+        views = [f64_view(p) for p in (buf_re0, buf_re1, buf_im0, buf_im1)]
+        if any(v[0] != "host" for v in views) or any(v[2] != views[0][2] or v[2] % n for v in views):
+            raise N.PanicError("fwd_inv_host needs four host planes of batch * n doubles")
+        N.check(N.lib.cfft_f128_fwd_inv_host(self._h, *[v[1] for v in views], views[0][2], views[0][2] // n))
+
     def twiddles(self):
         import numpy as np
 

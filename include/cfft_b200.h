@@ -174,6 +174,9 @@ cfft_status cfft_f128_fwd_host(const cfft_plan *plan, double *re0, double *re1, 
                                double *im1, uint64_t len, uint64_t batch);
 cfft_status cfft_f128_inv_host(const cfft_plan *plan, double *re0, double *re1, double *im0,
                                double *im1, uint64_t len, uint64_t batch);
+/* fwd immediately followed by inv on the device between one upload and one download */
+cfft_status cfft_f128_fwd_inv_host(const cfft_plan *plan, double *re0, double *re1, double *im0,
+                                   double *im1, uint64_t len, uint64_t batch);
 
 /* ---- f128 operators around the transform ---------------------------- */
 

@@ -227,3 +227,24 @@ def test_random_sizes_fuzz(C, torch):
         want = ref.fwd(*planes, variant=O.F128_FMA)
         assert bits_equal(y, want), (trial, n, batch)
         assert bits_equal(dev_run(torch, plan.inv, y), ref.inv(*want, variant=O.F128_FMA)), (trial, n, batch)
+
+
+def test_host_entry_points(C, torch):
+    rng = np.random.default_rng(50)
+    n, batch = 1024, 300  # > one zero-copy call, exercises the chunked pipeline too
+    planes = planes_random(rng, batch, n)
+    plan = C.fft128.Plan(n)
+    ref = O.F128Plan(n)
+    want = ref.fwd(*planes, variant=O.F128_FMA, threads=8)
+    h = [p.copy() for p in planes]
+    plan.fwd(*h)
+    assert bits_equal(h, want)
+    back = ref.inv(*want, variant=O.F128_FMA, threads=8)
+    plan.inv(*h)
+    assert bits_equal(h, back)
+    both = [p.copy() for p in planes]
+    plan.fwd_inv_host(*both)
+    assert bits_equal(both, back)
+    one = [p[:1].copy() for p in planes]  # single transform: zero-copy path
+    plan.fwd(*one)
+    assert bits_equal(one, [w[:1] for w in want])
