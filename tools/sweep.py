@@ -24,6 +24,41 @@ def time_launches(torch, fn, reps):
     return ts[len(ts) // 2], ts[0]
 
 
+def cpu_rate(kind, n, algo_name, base_n, seconds=0.6):
+    """forward transforms/s of the oracle port (-O3 build) on all host threads; test infrastructure
+    used as the reported CPU baseline only."""
+    import time
+
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except Exception:
+        threads = os.cpu_count() or 1
+    rng = np.random.default_rng(0)
+    rows = max(threads * 4, min(4096, (1 << 22) // n))
+    if kind == "f128":
+        plan = O.F128Plan(n, fast=True)
+        rows = max(threads, min(512, (1 << 19) // n))
+        planes = [rng.random((rows, n)), np.zeros((rows, n)), rng.random((rows, n)), np.zeros((rows, n))]
+        step = lambda: plan.fwd_inplace(planes, O.F128_FMA, threads)
+        rescale = lambda: [p.__imul__(1.0 / n) for p in planes]
+    else:
+        plan = O.UnorderedPlan(n, O.ALGO_NAMES.index(algo_name), base_n, fast=True)
+        buf = rng.random((rows, n)) + 1j * rng.random((rows, n))
+        step = lambda: plan.fwd_inplace(buf, threads)
+        rescale = lambda: buf.__imul__(1.0 / n)
+    step(); rescale()
+    t0, done = time.perf_counter(), 0
+    while time.perf_counter() - t0 < seconds:
+        step(); rescale()
+        done += 1
+    return rows * done / (time.perf_counter() - t0), threads
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="both")
@@ -33,6 +68,8 @@ def main():
     ap.add_argument("--bytes", type=int, default=1 << 31)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.jsonl"))
     ap.add_argument("--cufft", action="store_true", help="also time torch.fft.fft (cuFFT) as a reference point")
+    ap.add_argument("--cpu", action="store_true", help="also time the CPU port of the reference algorithm (oracle/, all host threads)")
+    ap.add_argument("--table", default="", help="write a markdown table of the results to this path")
     args = ap.parse_args()
     import torch
 
@@ -45,6 +82,7 @@ def main():
         pass
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     out = open(args.out, "a")
+    rows_out = []
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev).manual_seed(1)
     if args.workload in ("c64", "both"):
@@ -76,6 +114,9 @@ def main():
                    "frac_of_measured_hbm": bytes_ / fwd_ms / 1e6 / peak,
                    "fwd_transforms_per_s": batch / fwd_ms * 1e3,
                    "fwd_gflops_5nlog2n": 5.0 * n * logn * batch / fwd_ms / 1e6}
+            if args.cpu and n >= 2:
+                rec["cpu_port_fwd_transforms_per_s"], rec["cpu_threads"] = cpu_rate("c64", n, algo.name, base_n)
+            rows_out.append(rec)
             print(json.dumps(rec), flush=True)
             out.write(json.dumps(rec) + "\n")
             del data, plan
@@ -97,6 +138,7 @@ def main():
             rec = {"workload": "c64-ordered", "n": n, "batch": batch, "plan": plan.algo().name, "kernel": plan.kernel_name(),
                    "fwd_ms": fwd_ms, "inv_ms": inv_ms, "fwd_gbs": bytes_ / fwd_ms / 1e6, "inv_gbs": bytes_ / inv_ms / 1e6,
                    "frac_of_measured_hbm": bytes_ / fwd_ms / 1e6 / peak, "fwd_transforms_per_s": batch / fwd_ms * 1e3}
+            rows_out.append(rec)
             print(json.dumps(rec), flush=True)
             out.write(json.dumps(rec) + "\n")
             del data, plan
@@ -122,10 +164,34 @@ def main():
                    "fwd_fp64_pipe_frac_at_1965MHz": instr * batch / (fwd_ms * 1e-3) / (64 * 148 * 1965e6),
                    "inv_fp64_pipe_frac_at_1965MHz": instr * batch / (inv_ms * 1e-3) / (64 * 148 * 1965e6),
                    "fwd_gbs": 2 * 32 * n * batch / fwd_ms / 1e6}
+            if args.cpu:
+                rec["cpu_port_fwd_transforms_per_s"], rec["cpu_threads"] = cpu_rate("f128", n, "", n)
+            rows_out.append(rec)
             print(json.dumps(rec), flush=True)
             out.write(json.dumps(rec) + "\n")
             del planes, plan
             torch.cuda.empty_cache()
+
+
+    if args.table:
+        with open(args.table, "w") as f:
+            f.write("| workload | n | plan / kernel | fwd transforms/s | fwd GB/s (algorithmic) | fraction of roofline | inv GB/s | GFLOP/s (5 n log2 n) | cuFFT GB/s | CPU port transforms/s (threads) | GPU / CPU |\n")
+            f.write("|---|---|---|---|---|---|---|---|---|---|---|\n")
+            for r in rows_out:
+                cpu = r.get("cpu_port_fwd_transforms_per_s")
+                if r["workload"] == "fft128":
+                    frac = "%.2f of FP64 issue" % r["fwd_fp64_pipe_frac_at_1965MHz"]
+                    plan = r["kernel"]
+                else:
+                    frac = "%.2f of measured HBM" % r["frac_of_measured_hbm"]
+                    plan = "%s / %s" % (r.get("plan", ""), r["kernel"])
+                f.write("| %s | %d | %s | %.3g | %.0f | %s | %s | %s | %s | %s | %s |\n" % (
+                    r["workload"], r["n"], plan, r["fwd_transforms_per_s"], r["fwd_gbs"], frac,
+                    ("%.0f" % r["inv_gbs"]) if "inv_gbs" in r else "-",
+                    ("%.0f" % r["fwd_gflops_5nlog2n"]) if "fwd_gflops_5nlog2n" in r else "-",
+                    ("%.0f" % r["cufft_gbs"]) if r.get("cufft_gbs") else "-",
+                    ("%.3g (%d)" % (cpu, r["cpu_threads"])) if cpu else "-",
+                    ("%.0fx" % (r["fwd_transforms_per_s"] / cpu)) if cpu else "-"))
 
 
 if __name__ == "__main__":
