@@ -227,8 +227,9 @@ def run_reference(args):
         "dtype": "f64x2 (double-double)" if args.workload == "f128" else "f64", "data": "synthetic",
         "config": config_dict(args.workload, n, batch, base_n, algo, args.gpus),
         "cpu_baseline": {"value": value, "unit": "transforms/s", "cores": threads, "kind": "port", "sample": sample,
-                         "note": "C restatement of the reference algorithm (oracle/, -O3 build, bit-identical "
-                                 "to the reference's golden vector); the Rust crate cannot be built here"},
+                         "note": "C restatement of the reference algorithm (oracle/, -O3 AVX2+FMA build: two complex per "
+                                 "register like the reference's c64x2 path; bit-identical to the reference's golden "
+                                 "vector); the Rust crate cannot be built here"},
         "e2e": {"value": value, "unit": "transforms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

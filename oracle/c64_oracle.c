@@ -23,159 +23,96 @@ static const double H1X = 0.9238795325112867;       /* src/fft_simd.rs:50 */
 static const double H1Y = -0.38268343236508984;     /* src/fft_simd.rs:52 */
 
 static inline oc64 cx(double re, double im) { oc64 z = { re, im }; return z; }
-static inline oc64 cadd(oc64 a, oc64 b) { return cx(a.re + b.re, a.im + b.im); }
-static inline oc64 csub(oc64 a, oc64 b) { return cx(a.re - b.re, a.im - b.im); }
+static inline oc64 cadd_s(oc64 a, oc64 b) { return cx(a.re + b.re, a.im + b.im); }
+static inline oc64 csub_s(oc64 a, oc64 b) { return cx(a.re - b.re, a.im - b.im); }
 
 /* src/fft_simd.rs:220-233: w * z, re = fma(a, x, -(b*y)), im = fma(a, y, b*x) */
-static inline oc64 cmul(oc64 w, oc64 z)
+static inline oc64 cmul_s(oc64 w, oc64 z)
 {
     double a = w.re, b = w.im, x = z.re, y = z.im;
     return cx(fma(a, x, -b * y), fma(a, y, b * x));
 }
 
 /* src/fft_simd.rs:113-120 */
-static inline oc64 mulj(int fwd, oc64 z)
+static inline oc64 mulj_s(int fwd, oc64 z)
 {
     return fwd ? cx(-z.im, z.re) : cx(z.im, -z.re);
 }
 
 /* src/fft_simd.rs:122-131 */
-static inline oc64 mul_e8(int fwd, oc64 z)
+static inline oc64 mul_e8_s(int fwd, oc64 z)
 {
-    oc64 t = cadd(z, mulj(fwd, z));
+    oc64 t = cadd_s(z, mulj_s(fwd, z));
     return cx(INV_SQRT2 * t.re, INV_SQRT2 * t.im);
 }
-static inline oc64 mul_ne8(int fwd, oc64 z) { return mul_e8(!fwd, z); }
+static inline oc64 mul_ne8_s(int fwd, oc64 z) { return mul_e8_s(!fwd, z); }
 
 /* src/fft_simd.rs:133-159 */
-static inline oc64 mul_e16(int fwd, oc64 z) { return cmul(cx(H1X, fwd ? H1Y : -H1Y), z); }
-static inline oc64 mul_e17(int fwd, oc64 z) { return cmul(cx(-H1Y, fwd ? -H1X : H1X), z); }
-static inline oc64 mul_ne16(int fwd, oc64 z) { return mul_e16(!fwd, z); }
-static inline oc64 mul_ne17(int fwd, oc64 z) { return mul_e17(!fwd, z); }
+static inline oc64 mul_e16_s(int fwd, oc64 z) { return cmul_s(cx(H1X, fwd ? H1Y : -H1Y), z); }
+static inline oc64 mul_e17_s(int fwd, oc64 z) { return cmul_s(cx(-H1Y, fwd ? -H1X : H1X), z); }
+static inline oc64 mul_ne16_s(int fwd, oc64 z) { return mul_e16_s(!fwd, z); }
+static inline oc64 mul_ne17_s(int fwd, oc64 z) { return mul_e17_s(!fwd, z); }
 
-/* ------------------------------------------------------------------ */
-/* twiddle-free butterflies ("last_butterfly")                         */
-/* ------------------------------------------------------------------ */
-
-/* src/dif2.rs:106-113 */
-static inline void bf2(oc64 *v)
+#define CT oc64
+#define X(f) f##_s
+#include "butterflies.inc"
+#undef CT
+#undef X
+/* ---- AVX2 + FMA instantiation: a register holds two interleaved complex numbers, the reference's
+ * c64x2 (src/x86.rs:4-74: add/sub lane-wise, mul = fmaddsub(aa, xy, bb * yx), swap = permute 0b0101).
+ * Used only by the -O3 -march=x86-64-v3 build (the timed CPU baseline); same bits as the scalar code. */
+#if defined(__AVX2__) && defined(__FMA__)
+#include <immintrin.h>
+#define ORC_HAVE_AVX2 1
+typedef __m256d cv;
+static inline cv cadd_v(cv a, cv b) { return _mm256_add_pd(a, b); }
+static inline cv csub_v(cv a, cv b) { return _mm256_sub_pd(a, b); }
+static inline cv cmul_v(cv w, cv z)
 {
-    oc64 a = v[0], b = v[1];
-    v[0] = cadd(a, b);
-    v[1] = csub(a, b);
+    cv yx = _mm256_permute_pd(z, 0x5);
+    cv aa = _mm256_unpacklo_pd(w, w), bb = _mm256_unpackhi_pd(w, w);
+    return _mm256_fmaddsub_pd(aa, z, _mm256_mul_pd(bb, yx));
 }
-
-/* src/dif4.rs:195-214 */
-static inline void bf4(int fwd, oc64 *v)
+static inline cv mulj_v(int fwd, cv z)
 {
-    oc64 apc = cadd(v[0], v[2]);
-    oc64 amc = csub(v[0], v[2]);
-    oc64 bpd = cadd(v[1], v[3]);
-    oc64 jbmd = mulj(fwd, csub(v[1], v[3]));
-    v[0] = cadd(apc, bpd);
-    v[1] = csub(amc, jbmd);
-    v[2] = csub(apc, bpd);
-    v[3] = cadd(amc, jbmd);
+    cv sw = _mm256_permute_pd(z, 0x5); /* (im, re) */
+    const cv neg_even = _mm256_set_pd(0.0, -0.0, 0.0, -0.0), neg_odd = _mm256_set_pd(-0.0, 0.0, -0.0, 0.0);
+    return _mm256_xor_pd(sw, fwd ? neg_even : neg_odd); /* fwd: (-im, re); else (im, -re) */
 }
-
-/* src/dif8.rs:310-351 (== src/unordered.rs:98-153 without the twiddles) */
-static inline void bf8(int fwd, oc64 *v)
+static inline cv mul_e8_v(int fwd, cv z)
 {
-    oc64 a[4], s[4];
-    for (int i = 0; i < 4; i++) {
-        a[i] = cadd(v[i], v[i + 4]);
-        s[i] = csub(v[i], v[i + 4]);
-    }
-    oc64 js2 = mulj(fwd, s[2]);
-    oc64 js3 = mulj(fwd, s[3]);
-
-    oc64 a02p = cadd(a[0], a[2]);
-    oc64 s02m = csub(s[0], js2);
-    oc64 a02m = csub(a[0], a[2]);
-    oc64 s02p = cadd(s[0], js2);
-    oc64 a13p = cadd(a[1], a[3]);
-    oc64 w8 = mul_ne8(fwd, csub(s[1], js3));
-    oc64 ja13m = mulj(fwd, csub(a[1], a[3]));
-    oc64 v8 = mul_e8(fwd, cadd(s[1], js3));
-
-    v[0] = cadd(a02p, a13p);
-    v[1] = cadd(s02m, w8);
-    v[2] = csub(a02m, ja13m);
-    v[3] = csub(s02p, v8);
-    v[4] = csub(a02p, a13p);
-    v[5] = csub(s02m, w8);
-    v[6] = cadd(a02m, ja13m);
-    v[7] = cadd(s02p, v8);
+    return _mm256_mul_pd(_mm256_set1_pd(INV_SQRT2), cadd_v(z, mulj_v(fwd, z)));
 }
-
-/* src/dif16.rs:649-772 */
-static inline void bf16(int fwd, oc64 *v)
+static inline cv mul_ne8_v(int fwd, cv z) { return mul_e8_v(!fwd, z); }
+static inline cv cconst_v(double re, double im) { return _mm256_set_pd(im, re, im, re); }
+static inline cv mul_e16_v(int fwd, cv z) { return cmul_v(cconst_v(H1X, fwd ? H1Y : -H1Y), z); }
+static inline cv mul_e17_v(int fwd, cv z) { return cmul_v(cconst_v(-H1Y, fwd ? -H1X : H1X), z); }
+static inline cv mul_ne16_v(int fwd, cv z) { return mul_e16_v(!fwd, z); }
+static inline cv mul_ne17_v(int fwd, cv z) { return mul_e17_v(!fwd, z); }
+#define CT cv
+#define X(f) f##_v
+#include "butterflies.inc"
+#undef CT
+#undef X
+static inline cv ld2(const oc64 *p) { return _mm256_loadu_pd((const double *)p); }
+static inline cv ld11(const oc64 *p0, const oc64 *p1)
 {
-    oc64 a[8], s[8];
-    for (int i = 0; i < 8; i++) {
-        a[i] = cadd(v[i], v[i + 8]);
-        s[i] = csub(v[i], v[i + 8]);
-    }
-    oc64 ap[4], sm[4], am[4], sp[4];
-    for (int i = 0; i < 4; i++) {
-        oc64 js = mulj(fwd, s[i + 4]);
-        ap[i] = cadd(a[i], a[i + 4]);
-        sm[i] = csub(s[i], js);
-        am[i] = csub(a[i], a[i + 4]);
-        sp[i] = cadd(s[i], js);
-    }
-    /* E = even half (inputs 0,2 groups), O = odd half (inputs 1,3 groups) */
-    oc64 t[2][8];
-    for (int h = 0; h < 2; h++) {
-        int e = h, o = h + 2;
-        oc64 w8 = mul_ne8(fwd, sm[o]);
-        oc64 j_ = mulj(fwd, am[o]);
-        oc64 v8 = mul_e8(fwd, sp[o]);
-        t[h][0] = cadd(ap[e], ap[o]);
-        t[h][1] = cadd(sm[e], w8);
-        t[h][2] = csub(am[e], j_);
-        t[h][3] = csub(sp[e], v8);
-        t[h][4] = csub(ap[e], ap[o]);
-        t[h][5] = csub(sm[e], w8);
-        t[h][6] = cadd(am[e], j_);
-        t[h][7] = cadd(sp[e], v8);
-    }
-    const oc64 *E = t[0], *O = t[1];
-    oc64 u1 = mul_e16(fwd, O[1]);
-    oc64 u2 = mul_ne8(fwd, O[2]);
-    oc64 u3 = mul_e17(fwd, O[3]);
-    oc64 u4 = mulj(fwd, O[4]);
-    oc64 u5 = mul_ne17(fwd, O[5]);
-    oc64 u6 = mul_e8(fwd, O[6]);
-    oc64 u7 = mul_ne16(fwd, O[7]);
-
-    v[0] = cadd(E[0], O[0]);
-    v[1] = cadd(E[1], u1);
-    v[2] = cadd(E[2], u2);
-    v[3] = cadd(E[3], u3);
-    v[4] = csub(E[4], u4);
-    v[5] = csub(E[5], u5);
-    v[6] = csub(E[6], u6);
-    v[7] = csub(E[7], u7);
-    v[8] = csub(E[0], O[0]);
-    v[9] = csub(E[1], u1);
-    v[10] = csub(E[2], u2);
-    v[11] = csub(E[3], u3);
-    v[12] = cadd(E[4], u4);
-    v[13] = cadd(E[5], u5);
-    v[14] = cadd(E[6], u6);
-    v[15] = cadd(E[7], u7);
+    return _mm256_set_m128d(_mm_loadu_pd((const double *)p1), _mm_loadu_pd((const double *)p0));
 }
-
-static inline __attribute__((always_inline)) void bfR(const int R, const int fwd, oc64 *v)
+static inline cv splat1(const oc64 *p) { return _mm256_broadcast_pd((const __m128d *)p); }
+static inline void st2(oc64 *p, cv v) { _mm256_storeu_pd((double *)p, v); }
+static inline void st11(oc64 *p0, oc64 *p1, cv v)
 {
-    switch (R) {
-    case 2: bf2(v); break;
-    case 4: bf4(fwd, v); break;
-    case 8: bf8(fwd, v); break;
-    default: bf16(fwd, v); break;
-    }
+    _mm_storeu_pd((double *)p0, _mm256_castpd256_pd128(v));
+    _mm_storeu_pd((double *)p1, _mm256_extractf128_pd(v, 1));
 }
+#endif
+
+/* the scalar drivers below use the unsuffixed names */
+#define cadd cadd_s
+#define csub csub_s
+#define cmul cmul_s
+#define bfR bfR_s
 
 /* ------------------------------------------------------------------ */
 /* sincospi64 and twiddle tables                                       */
@@ -270,6 +207,36 @@ static inline __attribute__((always_inline)) void dif_core_impl(const int R, con
     }
 }
 
+#ifdef ORC_HAVE_AVX2
+/* two butterflies per iteration: pairs of q (s >= 2, twiddle splat) or pairs of p (s == 1) */
+static inline __attribute__((always_inline)) void dif_core_impl_v(const int R, const int fwd, size_t n, size_t s, const oc64 *x, oc64 *y, const oc64 *w)
+{
+    size_t m = n / ((size_t)R * s);
+    cv v[16];
+    if (s >= 2) {
+        for (size_t p = 0; p < m; p++) {
+            const oc64 *wp = w + (size_t)R * p * s;
+            for (size_t q = 0; q < s; q += 2) {
+                for (int k = 0; k < R; k++) v[k] = ld2(&x[q + s * (p + m * (size_t)k)]);
+                bfR_v(R, fwd, v);
+                st2(&y[q + s * ((size_t)R * p)], v[0]);
+                for (int k = 1; k < R; k++) st2(&y[q + s * ((size_t)R * p + (size_t)k)], cmul_v(splat1(&wp[k]), v[k]));
+            }
+        }
+    } else {
+        for (size_t p = 0; p < m; p += 2) {
+            const oc64 *w0 = w + (size_t)R * p, *w1 = w0 + R;
+            oc64 *y0 = y + (size_t)R * p, *y1 = y0 + R;
+            for (int k = 0; k < R; k++) v[k] = ld2(&x[p + m * (size_t)k]);
+            bfR_v(R, fwd, v);
+            st11(&y0[0], &y1[0], v[0]);
+            for (int k = 1; k < R; k++) st11(&y0[k], &y1[k], cmul_v(ld11(&w0[k], &w1[k]), v[k]));
+        }
+    }
+}
+#define dif_core_impl(R, F, n, s, x, y, w) (((n) / ((size_t)(R) * (s))) >= 2 || (s) >= 2 ? dif_core_impl_v(R, F, n, s, x, y, w) : dif_core_impl(R, F, n, s, x, y, w))
+#endif
+
 /* radix / direction become compile-time constants in each arm (speed only; same arithmetic) */
 static void dif_core(int R, int fwd, size_t n, size_t s, const oc64 *x, oc64 *y, const oc64 *w)
 {
@@ -298,6 +265,35 @@ static inline __attribute__((always_inline)) void dit_core_impl(const int R, con
 }
 
 /* radix / direction become compile-time constants in each arm (speed only; same arithmetic) */
+#ifdef ORC_HAVE_AVX2
+static inline __attribute__((always_inline)) void dit_core_impl_v(const int R, const int fwd, size_t n, size_t s, oc64 *x, const oc64 *y, const oc64 *w)
+{
+    size_t m = n / ((size_t)R * s);
+    cv v[16];
+    if (s >= 2) {
+        for (size_t p = 0; p < m; p++) {
+            const oc64 *wp = w + (size_t)R * p * s;
+            for (size_t q = 0; q < s; q += 2) {
+                v[0] = ld2(&y[q + s * ((size_t)R * p)]);
+                for (int k = 1; k < R; k++) v[k] = cmul_v(splat1(&wp[k]), ld2(&y[q + s * ((size_t)R * p + (size_t)k)]));
+                bfR_v(R, fwd, v);
+                for (int k = 0; k < R; k++) st2(&x[q + s * (p + m * (size_t)k)], v[k]);
+            }
+        }
+    } else {
+        for (size_t p = 0; p < m; p += 2) {
+            const oc64 *w0 = w + (size_t)R * p, *w1 = w0 + R;
+            const oc64 *y0 = y + (size_t)R * p, *y1 = y0 + R;
+            v[0] = ld11(&y0[0], &y1[0]);
+            for (int k = 1; k < R; k++) v[k] = cmul_v(ld11(&w0[k], &w1[k]), ld11(&y0[k], &y1[k]));
+            bfR_v(R, fwd, v);
+            for (int k = 0; k < R; k++) st2(&x[p + m * (size_t)k], v[k]);
+        }
+    }
+}
+#define dit_core_impl(R, F, n, s, x, y, w) (((n) / ((size_t)(R) * (s))) >= 2 || (s) >= 2 ? dit_core_impl_v(R, F, n, s, x, y, w) : dit_core_impl(R, F, n, s, x, y, w))
+#endif
+
 static void dit_core(int R, int fwd, size_t n, size_t s, oc64 *x, const oc64 *y, const oc64 *w)
 {
 #define ARM(r) case r: if (fwd) dit_core_impl(r, 1, n, s, x, y, w); else dit_core_impl(r, 0, n, s, x, y, w); break
@@ -320,6 +316,20 @@ static inline __attribute__((always_inline)) void end_stage_impl(const int R, co
 }
 
 /* radix / direction become compile-time constants in each arm (speed only; same arithmetic) */
+#ifdef ORC_HAVE_AVX2
+static inline __attribute__((always_inline)) void end_stage_impl_v(const int R, const int fwd, size_t n, const oc64 *src, oc64 *dst)
+{
+    size_t part = n / (size_t)R;
+    cv v[16];
+    for (size_t j = 0; j < part; j += 2) {
+        for (int k = 0; k < R; k++) v[k] = ld2(&src[(size_t)k * part + j]);
+        bfR_v(R, fwd, v);
+        for (int k = 0; k < R; k++) st2(&dst[(size_t)k * part + j], v[k]);
+    }
+}
+#define end_stage_impl(R, F, n, src, dst) ((n) / (size_t)(R) >= 2 ? end_stage_impl_v(R, F, n, src, dst) : end_stage_impl(R, F, n, src, dst))
+#endif
+
 static void end_stage(int R, int fwd, size_t n, const oc64 *src, oc64 *dst)
 {
 #define ARM(r) case r: if (fwd) end_stage_impl(r, 1, n, src, dst); else end_stage_impl(r, 0, n, src, dst); break
@@ -479,6 +489,37 @@ static inline __attribute__((always_inline)) void fwd_top_stage_impl(const int r
     }
 }
 
+#ifdef ORC_HAVE_AVX2
+/* pairs of p: n / r >= base_n >= 32 here, so it is always even */
+static inline __attribute__((always_inline)) void fwd_top_stage_impl_v(const int r, size_t n, oc64 *z, const oc64 *w)
+{
+    size_t m = n / (size_t)r;
+    unsigned rb = ilog2((size_t)r);
+    cv v[8];
+    for (size_t p = 0; p < m; p += 2) {
+        const oc64 *w0 = w + (size_t)(r - 1) * p, *w1 = w0 + (r - 1);
+        for (int k = 0; k < r; k++) v[k] = ld2(&z[p + m * (size_t)k]);
+        bfR_v(r, 1, v);
+        st2(&z[p], v[0]);
+        for (int k = 1; k < r; k++) st2(&z[p + m * brev(rb, (size_t)k)], cmul_v(ld11(&w0[k - 1], &w1[k - 1]), v[k]));
+    }
+}
+static inline __attribute__((always_inline)) void inv_top_stage_impl_v(const int r, size_t n, oc64 *z, const oc64 *w)
+{
+    size_t m = n / (size_t)r;
+    unsigned rb = ilog2((size_t)r);
+    cv v[8];
+    for (size_t p = 0; p < m; p += 2) {
+        const oc64 *w0 = w + (size_t)(r - 1) * p, *w1 = w0 + (r - 1);
+        v[0] = ld2(&z[p]);
+        for (int k = 1; k < r; k++) v[k] = cmul_v(ld11(&w0[k - 1], &w1[k - 1]), ld2(&z[p + m * brev(rb, (size_t)k)]));
+        bfR_v(r, 0, v);
+        for (int k = 0; k < r; k++) st2(&z[p + m * (size_t)k], v[k]);
+    }
+}
+#define fwd_top_stage_impl fwd_top_stage_impl_v
+#endif
+
 static void fwd_top_stage(int r, size_t n, oc64 *z, const oc64 *w)
 {
     switch (r) {
@@ -505,6 +546,9 @@ static inline __attribute__((always_inline)) void inv_top_stage_impl(const int r
     }
 }
 
+#ifdef ORC_HAVE_AVX2
+#define inv_top_stage_impl inv_top_stage_impl_v
+#endif
 static void inv_top_stage(int r, size_t n, oc64 *z, const oc64 *w)
 {
     switch (r) {

@@ -358,6 +358,59 @@ void orc_f128_plan_free(orc_f128_plan *p)
 
 const double *orc_f128_twiddles(const orc_f128_plan *p, int which) { return p->tw[which & 3]; }
 
+
+/* Inner loops of one butterfly block written on plain doubles so that gcc -O3 vectorises them (the
+ * reference's AVX2 path, src/fft128/mod.rs:406-662, does the same work four lanes at a time).  Same
+ * operations in the same order as orc_f128_{add,sub}_estimate / orc_f128_mul(FMA): same bits. */
+#define DD_TWO_SUM(a, b, s, e) do { double t_ = (a) + (b); double bb_ = t_ - (a); (e) = ((a) - (t_ - bb_)) + ((b) - bb_); (s) = t_; } while (0)
+#define DD_TWO_DIFF(a, b, s, e) do { double t_ = (a) - (b); double bb_ = t_ - (a); (e) = ((a) - (t_ - bb_)) - ((b) + bb_); (s) = t_; } while (0)
+#define DD_QTS(a, b, s, e) do { double t_ = (a) + (b); (e) = (b) - (t_ - (a)); (s) = t_; } while (0)
+#define DD_ADD(ah, al, bh, bl, rh, rl) do { double s_, e_; DD_TWO_SUM(ah, bh, s_, e_); e_ = e_ + ((al) + (bl)); DD_QTS(s_, e_, rh, rl); } while (0)
+#define DD_SUB(ah, al, bh, bl, rh, rl) do { double s_, e_; DD_TWO_DIFF(ah, bh, s_, e_); e_ = e_ + (al); e_ = e_ - (bl); DD_QTS(s_, e_, rh, rl); } while (0)
+#define DD_MUL(ah, al, bh, bl, rh, rl) do { double p_ = (ah) * (bh); double e_ = fma(ah, bh, -p_); e_ = fma(ah, bl, fma(al, bh, e_)); DD_QTS(p_, e_, rh, rl); } while (0)
+
+static void fwd_block_fma(double *restrict re0, double *restrict re1, double *restrict im0, double *restrict im1,
+                          size_t start, size_t t, double wrh, double wrl, double wih, double wil)
+{
+    for (size_t j = start; j < start + t; j++) {
+        double z1rh = re0[j + t], z1rl = re1[j + t], z1ih = im0[j + t], z1il = im1[j + t];
+        double rrh, rrl, rih, ril, irh, irl, iih, iil, zwrh, zwrl, zwih, zwil;
+        DD_MUL(z1rh, z1rl, wrh, wrl, rrh, rrl);
+        DD_MUL(z1rh, z1rl, wih, wil, rih, ril);
+        DD_MUL(z1ih, z1il, wrh, wrl, irh, irl);
+        DD_MUL(z1ih, z1il, wih, wil, iih, iil);
+        DD_SUB(rrh, rrl, iih, iil, zwrh, zwrl);
+        DD_ADD(irh, irl, rih, ril, zwih, zwil);
+        double z0rh = re0[j], z0rl = re1[j], z0ih = im0[j], z0il = im1[j];
+        double a, b;
+        DD_ADD(z0rh, z0rl, zwrh, zwrl, a, b); re0[j] = a; re1[j] = b;
+        DD_ADD(z0ih, z0il, zwih, zwil, a, b); im0[j] = a; im1[j] = b;
+        DD_SUB(z0rh, z0rl, zwrh, zwrl, a, b); re0[j + t] = a; re1[j + t] = b;
+        DD_SUB(z0ih, z0il, zwih, zwil, a, b); im0[j + t] = a; im1[j + t] = b;
+    }
+}
+
+static void inv_block_fma(double *restrict re0, double *restrict re1, double *restrict im0, double *restrict im1,
+                          size_t start, size_t t, double wrh, double wrl, double wih, double wil)
+{
+    for (size_t j = start; j < start + t; j++) {
+        double z0rh = re0[j], z0rl = re1[j], z0ih = im0[j], z0il = im1[j];
+        double z1rh = re0[j + t], z1rl = re1[j + t], z1ih = im0[j + t], z1il = im1[j + t];
+        double drh, drl, dih, dil, a, b;
+        DD_SUB(z0rh, z0rl, z1rh, z1rl, drh, drl);
+        DD_SUB(z0ih, z0il, z1ih, z1il, dih, dil);
+        DD_ADD(z0rh, z0rl, z1rh, z1rl, a, b); re0[j] = a; re1[j] = b;
+        DD_ADD(z0ih, z0il, z1ih, z1il, a, b); im0[j] = a; im1[j] = b;
+        double rrh, rrl, rih, ril, irh, irl, iih, iil;
+        DD_MUL(drh, drl, wrh, wrl, rrh, rrl);
+        DD_MUL(drh, drl, wih, wil, rih, ril);
+        DD_MUL(dih, dil, wrh, wrl, irh, irl);
+        DD_MUL(dih, dil, wih, wil, iih, iil);
+        DD_ADD(rrh, rrl, iih, iil, a, b); re0[j + t] = a; re1[j + t] = b;
+        DD_SUB(irh, irl, rih, ril, a, b); im0[j + t] = a; im1[j + t] = b;
+    }
+}
+
 /* src/fft128/mod.rs:352-402 (cplx_mul :310-326) */
 void orc_f128_fwd(const orc_f128_plan *p, double *re0, double *re1, double *im0, double *im1, int variant)
 {
@@ -368,6 +421,10 @@ void orc_f128_fwd(const orc_f128_plan *p, double *re0, double *re1, double *im0,
             of128 wr = dd(p->tw[0][m + i], p->tw[1][m + i]);
             of128 wi = dd(p->tw[2][m + i], p->tw[3][m + i]);
             size_t start = 2 * i * t;
+            if (variant == ORC_F128_FMA) {
+                fwd_block_fma(re0, re1, im0, im1, start, t, wr.hi, wr.lo, wi.hi, wi.lo);
+                continue;
+            }
             for (size_t j = start; j < start + t; j++) {
                 of128 z0r = dd(re0[j], re1[j]), z0i = dd(im0[j], im1[j]);
                 of128 z1r = dd(re0[j + t], re1[j + t]), z1i = dd(im0[j + t], im1[j + t]);
@@ -396,6 +453,10 @@ void orc_f128_inv(const orc_f128_plan *p, double *re0, double *re1, double *im0,
             of128 wr = dd(p->tw[0][m + i], p->tw[1][m + i]);
             of128 wi = dd(p->tw[2][m + i], p->tw[3][m + i]);
             size_t start = 2 * i * t;
+            if (variant == ORC_F128_FMA) {
+                inv_block_fma(re0, re1, im0, im1, start, t, wr.hi, wr.lo, wi.hi, wi.lo);
+                continue;
+            }
             for (size_t j = start; j < start + t; j++) {
                 of128 z0r = dd(re0[j], re1[j]), z0i = dd(im0[j], im1[j]);
                 of128 z1r = dd(re0[j + t], re1[j + t]), z1i = dd(im0[j + t], im1[j + t]);

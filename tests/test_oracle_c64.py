@@ -176,3 +176,20 @@ def test_batch_threads_same_bits():
     assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
     c = O.UnorderedPlan(2048, O.DIF16, 256, fast=True).fwd(x, threads=3)
     assert np.array_equal(a.view(np.uint64), c.view(np.uint64))
+
+
+@pytest.mark.parametrize("algo", range(8))
+def test_avx2_build_same_bits_as_scalar(algo):
+    """The timed CPU baseline (-O3 -march=x86-64-v3: two interleaved complex per AVX2 register, the
+    reference's c64x2 form) must give the scalar oracle's bits for every algorithm and direction."""
+    rng = np.random.default_rng(900 + algo)
+    for n, base in [(32, 32), (64, 64), (256, 256), (512, 512), (1024, 32), (2048, 256), (4096, 1024), (8192, 512)]:
+        x = rand_c(rng, 3, n)
+        slow, fast = O.UnorderedPlan(n, algo, base), O.UnorderedPlan(n, algo, base, fast=True)
+        y = slow.fwd(x)
+        assert np.array_equal(y.view(np.uint64), fast.fwd(x).view(np.uint64)), (algo, n, base)
+        assert np.array_equal(slow.inv(y).view(np.uint64), fast.inv(y).view(np.uint64)), (algo, n, base)
+    for n in [2, 4, 8, 16, 128, 1024]:
+        x = rand_c(rng, 2, n)
+        assert np.array_equal(O.OrderedPlan(n, algo).fwd(x).view(np.uint64), O.OrderedPlan(n, algo, fast=True).fwd(x).view(np.uint64))
+        assert np.array_equal(O.OrderedPlan(n, algo).inv(x).view(np.uint64), O.OrderedPlan(n, algo, fast=True).inv(x).view(np.uint64))

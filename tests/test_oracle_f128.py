@@ -130,3 +130,15 @@ def test_operator_set_error_bounds():
             got = mpmath.mpf(float(hi[i])) + mpmath.mpf(float(lo[i]))
             scale = max(abs(want), abs(A) if op.startswith(("add", "sub")) else abs(want))
             assert abs(got - want) <= bound * scale, (op, i)
+
+
+def test_vectorised_build_same_bits():
+    rng = np.random.default_rng(77)
+    for n in [32, 64, 256, 2048]:
+        planes = [rng.random((3, n)), (rng.random((3, n)) - 0.5) * 1e-17, rng.random((3, n)), (rng.random((3, n)) - 0.5) * 1e-17]
+        a = O.F128Plan(n).fwd(*planes, variant=O.F128_FMA)
+        b = O.F128Plan(n, fast=True).fwd(*planes, variant=O.F128_FMA)
+        assert all(np.array_equal(x.view(np.uint64), y.view(np.uint64)) for x, y in zip(a, b))
+        a2 = O.F128Plan(n).inv(*a, variant=O.F128_FMA)
+        b2 = O.F128Plan(n, fast=True).inv(*a, variant=O.F128_FMA)
+        assert all(np.array_equal(x.view(np.uint64), y.view(np.uint64)) for x, y in zip(a2, b2))
