@@ -130,6 +130,20 @@ cfft_status upload_c64(cfft_plan *p)
     return CFFT_OK;
 }
 
+const char *variant_name(const cfft_plan *p)
+{
+    if (p->kind == KIND_F128) return "f128-radix8-tile";
+    switch (p->fast_variant) {
+    case 1: return "fast-b256-regs";
+    case 2: return "fast-b256-column+rows";
+    case 3: return "ordered-b256-column+rows-std";
+    case 4: return "fast-b256-cluster";
+    case 5: return "ordered-b256-regs-std";
+    case 6: return "ord16-regs";
+    default: return "exact-tile";
+    }
+}
+
 // Planar copies of the plan's twiddles for c64_fast.cu: per unordered level w_k[p] (k-major,
 // (r-1) x m), then the planar half of the base init_wt table.  Same values, different layout
 // (the reference itself lays the level tables out per SIMD width, src/unordered.rs:373-385).
@@ -140,6 +154,13 @@ cfft_status build_fast_tables(cfft_plan *p)
     const bool ordered_256 = p->kind == KIND_ORDERED && !p->allow_large && p->n == 256 && p->algo == CFFT_DIF16;
     if (!ordered_large) {
         if (getenv("CFFT_B200_FORCE_EXACT")) return CFFT_OK;
+        // whole-transform Dif16 plans of the other sizes: c64_ord16.cu, straight from the plan's own table
+        const bool whole = p->kind == KIND_ORDERED || (p->kind == KIND_UNORDERED && p->base_n == p->n);
+        if (whole && ord16_supported(p->n, p->algo)) {
+            p->fast_variant = 6;
+            p->kernel_name = variant_name(p);
+            return CFFT_OK;
+        }
         if (!ordered_256 && (p->kind != KIND_UNORDERED || !fast_b256_supported(p->n, p->algo, p->base_n))) return CFFT_OK;
     }
     // levels top-down; forward offsets from prog[0], inverse offsets from prog[1] (stored bottom-up)
@@ -166,7 +187,7 @@ cfft_status build_fast_tables(cfft_plan *p)
     }
     if (p->n == 256) {
         p->fast_variant = 1;
-        p->kernel_name = "fast-b256-regs";
+        p->kernel_name = variant_name(p);
         return CFFT_OK;
     }
     // n > 8192: group the levels (8, 8, ..., 8, [4|2]) into HBM passes of combined radix <= 256:
@@ -193,14 +214,13 @@ cfft_status build_fast_tables(cfft_plan *p)
         p->fast_groups.push_back(g);
     }
     // n <= 8192 also has the fused single-kernel variant, the default there (autotune may switch)
-    p->fast_variant = ordered_large ? 3 : (p->n <= 8192 ? 1 : 2);
+    p->fast_variant = ordered_large ? (p->n <= 8192 ? 5 : 3) : (p->n <= 8192 ? 1 : 2);
     if (const char *fv = getenv("CFFT_B200_FAST_VARIANT")) { // testing hook: force a variant
+        if (ordered_large && atoi(fv) == 3) p->fast_variant = 3;
         if (!ordered_large && atoi(fv) == 2) p->fast_variant = 2;
         if (!ordered_large && atoi(fv) == 4 && (p->n == 8192 || p->n == 16384)) p->fast_variant = 4;
     }
-    p->kernel_name = ordered_large ? "ordered-b256-column+rows-std"
-                                   : (p->fast_variant == 1 ? "fast-b256-regs"
-                                      : p->fast_variant == 4 ? "fast-b256-cluster" : "fast-b256-column+rows");
+    p->kernel_name = variant_name(p);
     return CFFT_OK;
 }
 
@@ -261,6 +281,7 @@ cfft_status time_variant(cfft_plan *p, void *scratch, uint64_t batch, cudaStream
 namespace cfft {
 cudaError_t launch_c64(const cfft_plan *plan, bool inverse, double2 *data, uint64_t batch, cudaStream_t st)
 {
+    if (plan->fast_variant == 6) return launch_c64_ord16(plan, inverse, data, batch, st);
     if (plan->fast_variant != 0) return launch_c64_fast_b256(plan, inverse, data, batch, st);
     return launch_c64_exact(plan, inverse, data, batch, st);
 }
@@ -484,17 +505,19 @@ cfft_status cfft_plan_autotune(cfft_plan *p, uint64_t batch_hint)
     DeviceGuard guard(p->device);
     if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
     const uint64_t bytes_per = p->n * (p->kind == KIND_F128 ? 32u : 16u);
-    uint64_t batch = batch_hint ? batch_hint : std::max<uint64_t>(1, (uint64_t((p->n >= 16384 || p->fast_variant == 3) ? 512 : 128) << 20) / bytes_per);
+    uint64_t batch = batch_hint ? batch_hint : std::max<uint64_t>(1, (uint64_t((p->n >= 16384 || p->fast_variant == 3 || p->fast_variant == 5) ? 512 : 128) << 20) / bytes_per);
     if (batch * bytes_per > (uint64_t{1} << 30)) batch = std::max<uint64_t>(1, (uint64_t{1} << 30) / bytes_per);
 
     struct Cand { std::string name; int fast_variant; uint32_t tile; uint32_t l2_mb = 0, l2_streams = 1; };
     std::vector<Cand> cands;
-    if (p->kind == KIND_F128 || p->fast_variant == 0) {
+    if (p->kind == KIND_F128 || p->fast_variant == 0 || p->fast_variant == 6) {
         const char *fam = p->kind == KIND_F128 ? "f128-radix8-tile" : "exact-tile";
+        if (p->fast_variant == 6) cands.push_back({"ord16-regs", 6, 0});
         if (p->n <= 2048)
             for (uint32_t t : {1024u, 2048u, 4096u})
-                if (t >= p->n) cands.push_back({std::string(fam) + "/" + std::to_string(t), p->fast_variant, t});
-    } else if (p->fast_variant == 3) {
+                if (t >= p->n) cands.push_back({std::string(fam) + "/" + std::to_string(t), p->kind == KIND_F128 ? p->fast_variant : 0, t});
+    } else if (p->fast_variant == 3 || p->fast_variant == 5) {
+        if (p->n <= 8192) cands.push_back({"ordered-b256-regs-std", 5, 0});
         cands.push_back({"ordered-b256-column+rows-std", 3, 0});
         cands.push_back({"ordered-b256-column+rows-std/L2-16MBx4", 3, 0, 16, 4});
         cands.push_back({"ordered-b256-column+rows-std/L2-32MBx2", 3, 0, 32, 2});
@@ -561,10 +584,7 @@ cfft_status cfft_plan_autotune(cfft_plan *p, uint64_t batch_hint)
     p->tile_elems = cands[best].tile;
     p->l2_chunk_mb = cands[best].l2_mb;
     p->l2_streams = cands[best].l2_streams;
-    if (p->kind != KIND_F128 && p->fast_variant == 3) p->kernel_name = "ordered-b256-column+rows-std";
-    else if (p->kind != KIND_F128 && p->fast_variant != 0)
-        p->kernel_name = p->fast_variant == 1 ? "fast-b256-regs"
-                         : p->fast_variant == 4 ? "fast-b256-cluster" : "fast-b256-column+rows";
+    p->kernel_name = variant_name(p);
     if (p->l2_chunk_mb) p->kernel_name += "/L2-chunked";
     p->tuning_report = report + "selected: " + cands[best].name + "\n";
     return CFFT_OK;

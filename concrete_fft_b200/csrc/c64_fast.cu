@@ -147,14 +147,16 @@ __device__ __forceinline__ void level_8x2(const c64 *__restrict__ gsrc, c64 *__r
 // 256-point base FFT (Dif16: radix-16 s=1 with twiddles, then radix-16 end) of the half-warp
 // that owns block `blk`; thread lane16 = p (first pass) = j (second pass).
 // FWD selects the butterfly direction only; the table passed in is the direction's table.
+// `sw_in` / `sw_out` (0..7) XOR the natural-order shared-memory positions read / written; the standard-order
+// kernels use it so that the transposing pass that follows / precedes is bank-conflict free.
 template <bool FWD, bool G_IN, bool G_OUT>
 __device__ __forceinline__ void base256(const c64 *__restrict__ src, c64 *__restrict__ sm_blk, c64 *__restrict__ dst,
-                                        const c64 *__restrict__ tw_planar, int lane16, c64 (&v)[16])
+                                        const c64 *__restrict__ tw_planar, int lane16, c64 (&v)[16], int sw_in = 0, int sw_out = 0)
 {
     const unsigned hmask = 0xFFFFu << (threadIdx.x & 16); // the 16 lanes that own this block
     // pass 1: x[p + 16k] -> y[16p + k] = w[p + 16k] * DFT16(x)_k       src/dif16.rs:449-623
 #pragma unroll
-    for (int k = 0; k < 16; k++) v[k] = G_IN ? ld_stream(src + lane16 + 16 * k) : src[lane16 + 16 * k];
+    for (int k = 0; k < 16; k++) v[k] = G_IN ? ld_stream(src + lane16 + 16 * k) : src[(lane16 + 16 * k) ^ sw_in];
     bf16<FWD>(v);
 #pragma unroll
     for (int k = 1; k < 16; k++) v[k] = cmul(ld_tw(tw_planar + lane16 + 16 * k), v[k]);
@@ -172,7 +174,7 @@ __device__ __forceinline__ void base256(const c64 *__restrict__ src, c64 *__rest
     } else {
         __syncwarp(hmask); // swizzled data consumed by the whole half-warp before natural-order overwrite
 #pragma unroll
-        for (int k = 0; k < 16; k++) dst[lane16 + 16 * k] = v[k];
+        for (int k = 0; k < 16; k++) dst[(lane16 + 16 * k) ^ sw_out] = v[k];
     }
 }
 
@@ -189,11 +191,17 @@ template <int N> struct FastCfg {
     static constexpr int MINB = (NT <= 128) ? 4 : (NT <= 256 ? 2 : 1);
 };
 
-template <int N, int R1, int R2, bool FWD>
+// STD = true: standard-order ("ordered") in / out.  X_i sits in the unordered layout at chunk
+// c = bitrev_L(i mod M), offset i / M (M = N / 256 chunks, src/unordered.rs:1046-1051), so the kernel
+// adds one more shared-memory exchange: chunk c keeps offset hi at (hi ^ (lo & 7)), lo = bitrev_L(c),
+// which makes both the base FFT's 16-consecutive accesses and the transposing pass (lanes on
+// consecutive i, i.e. on consecutive lo first) conflict-free; HBM sees consecutive i only.
+template <int N, int R1, int R2, bool FWD, bool STD = false>
 __global__ void __launch_bounds__(FastCfg<N>::NT, FastCfg<N>::MINB)
 c64_fast_b256_kernel(c64 *__restrict__ data, uint64_t batch, FastTables tb)
 {
     static_assert(N == 256 * R1 * R2, "n = 256 * R1 * R2");
+    static_assert(!STD || N >= 2048, "standard-order variant: M = N / 256 >= 8 chunks");
     using Cfg = FastCfg<N>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int row = threadIdx.x / Cfg::TPR, t = threadIdx.x % Cfg::TPR;
@@ -206,6 +214,13 @@ c64_fast_b256_kernel(c64 *__restrict__ data, uint64_t batch, FastTables tb)
     c64 v[16];
     constexpr int N2 = N / R1;      // span of the second level
     const int blk = t / 16, lane16 = t % 16;
+
+    constexpr int M = N / 256, LOGM = (M == 8 ? 3 : (M == 16 ? 4 : 5));
+    const int sw = STD ? int(__brev(unsigned(blk)) >> (32 - LOGM)) & 7 : 0; // (lo & 7) of this thread's chunk
+    auto std_pos = [](int i) { // shared-memory position of standard index i
+        const int lo = i & (M - 1), hi = i / M;
+        return int(__brev(unsigned(lo)) >> (32 - LOGM)) * 256 + (hi ^ (lo & 7));
+    };
 
     constexpr bool FUSED = (R1 == 8 && R2 == 2); // both levels in registers, see level_8x2
     if (FWD) {
@@ -220,12 +235,30 @@ c64_fast_b256_kernel(c64 *__restrict__ data, uint64_t batch, FastTables tb)
             level<R2, N2, Cfg::TPR, true, false, false>(s, s, tb.top2, t, v);
             __syncthreads();
         }
-        if (active) {
+        if (STD) {
+            base256<true, false, false>(s + blk * 256, s + blk * 256, s + blk * 256, tb.base, lane16, v, 0, sw);
+            __syncthreads();
+            if (active) {
+#pragma unroll
+                for (int j = 0; j < 16; j++) v[j] = s[std_pos(t + Cfg::TPR * j)];
+#pragma unroll
+                for (int j = 0; j < 16; j++) st_stream(g + t + Cfg::TPR * j, v[j]);
+            }
+        } else if (active) {
             if (R1 > 1) base256<true, false, true>(s + blk * 256, s + blk * 256, g + blk * 256, tb.base, lane16, v);
             else base256<true, true, true>(g + blk * 256, s + blk * 256, g + blk * 256, tb.base, lane16, v);
         }
     } else {
-        if (active) {
+        if (STD) {
+            if (active) {
+#pragma unroll
+                for (int j = 0; j < 16; j++) v[j] = ld_stream(g + t + Cfg::TPR * j);
+#pragma unroll
+                for (int j = 0; j < 16; j++) s[std_pos(t + Cfg::TPR * j)] = v[j];
+            }
+            __syncthreads();
+            base256<false, false, false>(s + blk * 256, s + blk * 256, s + blk * 256, tb.base, lane16, v, sw, 0);
+        } else if (active) {
             if (R1 > 1) base256<false, true, false>(g + blk * 256, s + blk * 256, s + blk * 256, tb.base, lane16, v);
             else base256<false, true, true>(g + blk * 256, s + blk * 256, g + blk * 256, tb.base, lane16, v);
         }
@@ -355,14 +388,14 @@ cudaError_t launch_cluster(bool inverse, c64 *data, uint64_t batch, const FastTa
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
-template <int N, int R1, int R2>
+template <int N, int R1, int R2, bool STD = false>
 cudaError_t launch_cfg(bool inverse, c64 *data, uint64_t batch, const FastTables &tb, cudaStream_t stream)
 {
     using Cfg = FastCfg<N>;
     const size_t smem = size_t(Cfg::ROWS) * N * sizeof(c64);
     const uint64_t ctas = (batch + Cfg::ROWS - 1) / Cfg::ROWS;
-    auto fwd_k = c64_fast_b256_kernel<N, R1, R2, true>;
-    auto inv_k = c64_fast_b256_kernel<N, R1, R2, false>;
+    auto fwd_k = c64_fast_b256_kernel<N, R1, R2, true, STD>;
+    auto inv_k = c64_fast_b256_kernel<N, R1, R2, false, STD>;
     if (smem > 48 * 1024) {
         static thread_local int configured_device = -1;
         int dev = 0;
@@ -587,6 +620,14 @@ cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *d
             }
         }
         return e != cudaSuccess ? e : cudaGetLastError();
+    }
+    if (plan->fast_variant == 5) { // standard-order in / out, one kernel (ordered plans 2^11 <= n <= 2^13)
+        switch (plan->n) {
+        case 2048: return launch_cfg<2048, 8, 1, true>(inverse, data, batch, tb, stream);
+        case 4096: return launch_cfg<4096, 8, 2, true>(inverse, data, batch, tb, stream);
+        case 8192: return launch_cfg<8192, 8, 4, true>(inverse, data, batch, tb, stream);
+        default: return cudaErrorInvalidValue;
+        }
     }
     if (plan->fast_variant == 4) {
         if (plan->n == 8192) return launch_cluster<8192, 2, 4>(inverse, data, batch, tb, stream);

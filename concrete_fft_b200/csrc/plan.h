@@ -62,6 +62,8 @@ struct cfft_plan {
     int fast_variant = 0;             // 0 exact tile kernel; 1 fused register kernel; 2 column passes + rows;
                                       // 3 ordered (standard order in/out) above 2^10: column passes + transposing rows
                                       // 4 one transform per thread-block cluster (n = 8192, 16384), DSMEM exchange
+                                      // 5 ordered above 2^10, n <= 8192: fused register kernel with standard-order in / out
+                                      // 6 whole-transform Dif16 plans, n = 32..128, 512, 1024 (c64_ord16.cu)
     double2 *d_fast_tw[2] = {nullptr, nullptr}; // planar re-layout of the same twiddle values
     struct FastLevel { int radix; uint32_t span; uint32_t off; }; // off: planar table inside d_fast_tw
     std::vector<FastLevel> fast_levels;         // unordered levels, outermost first
@@ -85,6 +87,9 @@ cudaError_t launch_permute(const cfft_plan *plan, bool to_standard, const double
 // kernels (c64_fast.cu)
 bool fast_b256_supported(uint64_t n, int base_algo, uint64_t base_n);
 cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *data, uint64_t batch, cudaStream_t st);
+// kernels (c64_ord16.cu)
+bool ord16_supported(uint64_t n, int algo);
+cudaError_t launch_c64_ord16(const cfft_plan *plan, bool inverse, double2 *data, uint64_t batch, cudaStream_t st);
 // kernels (c64_column.cu): one group of <= 3 unordered levels in one HBM pass
 cudaError_t launch_c64_column_group(bool inverse, const double2 *src, double2 *dst, uint64_t batch, uint32_t n, uint32_t span0,
                                     const int radices[3], const double2 *const tw[3], cudaStream_t st);

@@ -350,7 +350,9 @@ def test_ordered_above_reference_cap(C, torch, logn):
     with pytest.raises(C.PanicError):
         C.ordered.Plan(n, C.ordered.Method.UserProvided(C.ordered.FftAlgo.Dif16))  # reference behaviour
     plan = C.ordered.Plan(n, C.ordered.Method.Measure(), allow_large=True)
-    assert plan.fft_size() == n and plan.kernel_name().startswith("ordered-b256-column+rows-std")
+    want_kernel = "ordered-b256-regs-std" if logn <= 13 else "ordered-b256-column+rows-std"
+    assert plan.fft_size() == n and plan.kernel_name().startswith(("ordered-b256-regs-std", "ordered-b256-column+rows-std"))
+    assert C.ordered.Plan(n, C.ordered.Method.UserProvided(C.ordered.FftAlgo.Dif16), allow_large=True).kernel_name() == want_kernel
     ref = O.UnorderedPlan(n, O.DIF16, 256)
     pi = O.permutation(n, 256)
     batch = 3 if logn <= 16 else 2
@@ -368,6 +370,73 @@ def test_ordered_above_reference_cap(C, torch, logn):
     h = x.copy()
     plan.fwd(h)  # host-memory entry
     assert bits_equal(h, want)
+
+
+@pytest.mark.parametrize("n", [2048, 4096, 8192])
+def test_ordered_fused_standard_order_kernel(C, torch, n):
+    """Standard-order plans 2^11 <= n <= 2^13 run as ONE kernel (levels + base FFTs + the transposing
+    exchange in shared memory).  Same bits as the unordered reference plan un-permuted, for ragged
+    batches, in place, fwd and inv; and the same bits as the multi-pass variant."""
+    rng = np.random.default_rng(1500 + n)
+    plan = C.ordered.Plan(n, C.ordered.Method.UserProvided(C.ordered.FftAlgo.Dif16), allow_large=True)
+    assert plan.kernel_name() == "ordered-b256-regs-std"
+    ref = O.UnorderedPlan(n, O.DIF16, 256)
+    pi = O.permutation(n, 256)
+    for batch in (1, 5, 37):
+        x = rand_c(rng, batch, n)
+        y = dev_run(torch, plan.fwd, x)
+        assert bits_equal(y, ref.fwd(x, threads=8)[:, pi]), (n, batch)
+        perm_in = np.empty_like(y)
+        perm_in[:, pi] = y
+        assert bits_equal(dev_run(torch, plan.inv, y), ref.inv(perm_in, threads=8)), (n, batch)
+    os.environ["CFFT_B200_FAST_VARIANT"] = "3"
+    try:
+        multi = C.ordered.Plan(n, C.ordered.Method.UserProvided(C.ordered.FftAlgo.Dif16), allow_large=True)
+    finally:
+        del os.environ["CFFT_B200_FAST_VARIANT"]
+    assert multi.kernel_name() == "ordered-b256-column+rows-std"
+    x = rand_c(rng, 9, n)
+    assert bits_equal(dev_run(torch, multi.fwd, x), dev_run(torch, plan.fwd, x))
+    assert bits_equal(dev_run(torch, multi.inv, x), dev_run(torch, plan.inv, x))
+
+
+@pytest.mark.parametrize("n", [32, 64, 128, 512, 1024])
+def test_ord16_register_kernel_bit_exact(C, torch, n):
+    """Whole-transform Dif16 plans (ordered, and unordered with base_n == n) on the register kernel of
+    c64_ord16.cu: bit-exact vs the oracle for ragged batches (tail CTAs, single rows), fwd and inv,
+    and identical to the exact tile kernel."""
+    rng = np.random.default_rng(1600 + n)
+    A = C.ordered.FftAlgo
+    po = C.ordered.Plan(n, C.ordered.Method.UserProvided(A.Dif16))
+    pu = C.unordered.Plan(n, C.unordered.Method.UserProvided(A.Dif16, n))
+    assert po.kernel_name() == "ord16-regs" and pu.kernel_name() == "ord16-regs"
+    assert C.ordered.Plan(n, C.ordered.Method.UserProvided(A.Dit16)).kernel_name() == "exact-tile"
+    assert np.array_equal(pu.permutation(), np.arange(n))
+    ref = O.OrderedPlan(n, O.DIF16)
+    uref = O.UnorderedPlan(n, O.DIF16, n)
+    for batch in (1, 2, 3, 63, 64, 65, 1000):
+        x = rand_c(rng, batch, n)
+        y = dev_run(torch, po.fwd, x)
+        want = ref.fwd(x)
+        assert bits_equal(y, want), (n, batch)
+        assert bits_equal(want, uref.fwd(x))
+        assert bits_equal(dev_run(torch, pu.fwd, x), want), (n, batch)
+        z = dev_run(torch, po.inv, y)
+        assert bits_equal(z, ref.inv(y)), (n, batch)
+        assert bits_equal(dev_run(torch, pu.inv, y), z)
+        assert np.abs(z / n - x).max() < 1e-12
+    f = np.fft.fft(x, axis=1)
+    assert (np.linalg.norm(y - f, axis=1) / np.linalg.norm(f, axis=1)).max() <= 1e-13 * np.log2(n)
+    os.environ["CFFT_B200_FORCE_EXACT"] = "1"
+    try:
+        exact = C.ordered.Plan(n, C.ordered.Method.UserProvided(A.Dif16))
+    finally:
+        del os.environ["CFFT_B200_FORCE_EXACT"]
+    assert exact.kernel_name() == "exact-tile"
+    assert bits_equal(dev_run(torch, exact.fwd, x), y)
+    h = x.copy()
+    po.fwd(h)  # host-memory entry
+    assert bits_equal(h, y)
 
 
 def test_autotune_keeps_bits_and_order(C, torch):
