@@ -467,6 +467,7 @@ cfft_status cfft_plan_clone(const cfft_plan *p, cfft_plan **out)
         (*out)->method = p->method;
         (*out)->fast_variant = p->fast_variant;
         (*out)->tile_elems = p->tile_elems;
+        (*out)->f128_smax = p->f128_smax;
         (*out)->l2_chunk_mb = p->l2_chunk_mb;
         (*out)->l2_streams = p->l2_streams;
         (*out)->kernel_name = p->kernel_name;
@@ -508,7 +509,7 @@ cfft_status cfft_plan_autotune(cfft_plan *p, uint64_t batch_hint)
     uint64_t batch = batch_hint ? batch_hint : std::max<uint64_t>(1, (uint64_t((p->n >= 16384 || p->fast_variant == 3 || p->fast_variant == 5) ? 512 : 128) << 20) / bytes_per);
     if (batch * bytes_per > (uint64_t{1} << 30)) batch = std::max<uint64_t>(1, (uint64_t{1} << 30) / bytes_per);
 
-    struct Cand { std::string name; int fast_variant; uint32_t tile; uint32_t l2_mb = 0, l2_streams = 1; };
+    struct Cand { std::string name; int fast_variant; uint32_t tile; uint32_t l2_mb = 0, l2_streams = 1; int smax = 3; };
     std::vector<Cand> cands;
     if (p->kind == KIND_F128 || p->fast_variant == 0 || p->fast_variant == 6) {
         const char *fam = p->kind == KIND_F128 ? "f128-radix8-tile" : "exact-tile";
@@ -516,6 +517,8 @@ cfft_status cfft_plan_autotune(cfft_plan *p, uint64_t batch_hint)
         if (p->n <= 2048)
             for (uint32_t t : {1024u, 2048u, 4096u})
                 if (t >= p->n) cands.push_back({std::string(fam) + "/" + std::to_string(t), p->kind == KIND_F128 ? p->fast_variant : 0, t});
+        if (p->kind == KIND_F128 && p->n <= 2048) // two-stage groups in 80 registers: three CTAs per SM
+            cands.push_back({std::string(fam) + "/2048/3-per-SM", p->fast_variant, 2048u, 0, 1, 2});
     } else if (p->fast_variant == 3 || p->fast_variant == 5) {
         if (p->n <= 8192) cands.push_back({"ordered-b256-regs-std", 5, 0});
         cands.push_back({"ordered-b256-column+rows-std", 3, 0});
@@ -555,12 +558,14 @@ cfft_status cfft_plan_autotune(cfft_plan *p, uint64_t batch_hint)
 
     const int keep_variant = p->fast_variant;
     const uint32_t keep_tile = p->tile_elems, keep_mb = p->l2_chunk_mb, keep_st = p->l2_streams;
+    const int keep_smax = p->f128_smax;
     std::string report;
     float best_ms = 1e30f;
     size_t best = 0;
     for (size_t i = 0; i < cands.size() && rc == CFFT_OK; i++) {
         p->fast_variant = cands[i].fast_variant;
         p->tile_elems = cands[i].tile;
+        p->f128_smax = cands[i].smax;
         p->l2_chunk_mb = cands[i].l2_mb;
         p->l2_streams = cands[i].l2_streams;
         float ms = 0;
@@ -576,12 +581,14 @@ cfft_status cfft_plan_autotune(cfft_plan *p, uint64_t batch_hint)
     if (rc != CFFT_OK) {
         p->fast_variant = keep_variant;
         p->tile_elems = keep_tile;
+        p->f128_smax = keep_smax;
         p->l2_chunk_mb = keep_mb;
         p->l2_streams = keep_st;
         return rc;
     }
     p->fast_variant = cands[best].fast_variant;
     p->tile_elems = cands[best].tile;
+    p->f128_smax = cands[best].smax;
     p->l2_chunk_mb = cands[best].l2_mb;
     p->l2_streams = cands[best].l2_streams;
     p->kernel_name = variant_name(p);

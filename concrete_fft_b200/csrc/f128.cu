@@ -143,14 +143,22 @@ constexpr int kThreads = 256;
 // stride u = 2^a the eight lanes of a 128-bit phase land in eight different 16-byte banks.
 F128_DEV uint32_t swz(uint32_t i) { return i ^ ((i >> 3) & 7u); }
 
-// one pass over a tile; G_IN / G_OUT: that side is the HBM tile (four planar arrays), else smem
+// one pass over a tile; G_IN / G_OUT: that side is the HBM tile (four planar arrays), else smem.
+// Groups are dealt to warps in contiguous runs (warp w owns groups [w gpw, (w+1) gpw) of the FULL tile),
+// so a pass whose groups span G u <= full_tile / warps elements stays inside the warp's own contiguous
+// block of the tile: consecutive such passes need no block barrier (see pass_is_warp_local).
 template <int S, bool FWD, bool G_IN, bool G_OUT, int NT>
 F128_DEV void tile_pass(const Planes &g, double2 *__restrict__ sre, double2 *__restrict__ sim, uint32_t tile,
-                        uint32_t tile_row_off, uint32_t n, uint32_t logn, int d0, const Tw4 *__restrict__ tw, bool vec)
+                        uint32_t full_tile, uint32_t tile_row_off, uint32_t n, uint32_t logn, int d0,
+                        const Tw4 *__restrict__ tw, bool vec)
 {
     constexpr int G = 1 << S;
     const uint32_t u = n >> (d0 + S);
-    for (uint32_t grp = threadIdx.x; grp < tile / G; grp += NT) {
+    // groups per warp, rounded up to whole 32-lane rounds (exact for power-of-two tiles >= 256 per warp)
+    const uint32_t gpw = ((full_tile / G + (NT / 32) - 1) / (NT / 32) + 31u) & ~31u;
+    const uint32_t g0 = (threadIdx.x >> 5) * gpw + (threadIdx.x & 31);
+    for (uint32_t grp = g0; grp < g0 + gpw; grp += 32) {
+        if (grp >= tile / G) break;
         const uint32_t hi = grp / u, lo = grp - hi * u;
         const uint32_t base = hi * (G * u) + lo;
         ddc z[G];
@@ -214,27 +222,42 @@ F128_DEV void tile_pass(const Planes &g, double2 *__restrict__ sre, double2 *__r
     }
 }
 
-constexpr int kMaxPasses = 4; // tile <= 4096 elements = 12 stages = 4 passes of 3
+constexpr int kMaxPasses = 6; // tile <= 4096 elements = 12 stages = 4 passes of 3 (or 6 of 2)
 struct PassList {
     int count;
     int d0[kMaxPasses];
     int s[kMaxPasses];
 };
 
-template <bool FWD, bool G_IN, bool G_OUT, int NT>
-F128_DEV void dispatch_pass(int s, const Planes &g, double2 *sre, double2 *sim, uint32_t tile, uint32_t row_off,
-                            uint32_t n, uint32_t logn, int d0, const Tw4 *tw, bool vec)
+template <bool FWD, bool G_IN, bool G_OUT, int NT, int SMAX = 3>
+F128_DEV void dispatch_pass(int s, const Planes &g, double2 *sre, double2 *sim, uint32_t tile, uint32_t full_tile,
+                            uint32_t row_off, uint32_t n, uint32_t logn, int d0, const Tw4 *tw, bool vec)
 {
-    if (s == 3) tile_pass<3, FWD, G_IN, G_OUT, NT>(g, sre, sim, tile, row_off, n, logn, d0, tw, vec);
-    else if (s == 2) tile_pass<2, FWD, G_IN, G_OUT, NT>(g, sre, sim, tile, row_off, n, logn, d0, tw, vec);
-    else tile_pass<1, FWD, G_IN, G_OUT, NT>(g, sre, sim, tile, row_off, n, logn, d0, tw, vec);
+    if (SMAX >= 3 && s == 3) tile_pass<3, FWD, G_IN, G_OUT, NT>(g, sre, sim, tile, full_tile, row_off, n, logn, d0, tw, vec);
+    else if (s == 2) tile_pass<2, FWD, G_IN, G_OUT, NT>(g, sre, sim, tile, full_tile, row_off, n, logn, d0, tw, vec);
+    else tile_pass<1, FWD, G_IN, G_OUT, NT>(g, sre, sim, tile, full_tile, row_off, n, logn, d0, tw, vec);
 }
 
-template <bool FWD, int NT>
-__global__ void __launch_bounds__(NT, 512 / NT)
+// Stages d0 .. d0+s-1 couple elements inside aligned blocks of n >> d0 = G u elements; with the
+// warp-contiguous group mapping a warp owns an aligned block of full_tile / warps elements.
+template <int NT> F128_DEV bool pass_is_warp_local(uint32_t n, int d0, uint32_t full_tile)
+{
+    const bool regular = (full_tile & (full_tile - 1)) == 0 && full_tile >= 256u * (NT / 32); // exact dealing for S <= 3
+    return regular && (n >> d0) <= full_tile / (NT / 32);
+}
+// barrier between two consecutive shared-memory passes: a block barrier unless both are warp-local
+template <int NT> F128_DEV void pass_barrier(uint32_t n, int d0_a, int d0_b, uint32_t full_tile)
+{
+    if (pass_is_warp_local<NT>(n, d0_a, full_tile) && pass_is_warp_local<NT>(n, d0_b, full_tile)) __syncwarp();
+    else __syncthreads();
+}
+
+template <bool FWD, int NT, int MINB = 512 / NT>
+__global__ void __launch_bounds__(NT, MINB)
 f128_tile_kernel(Planes data, uint64_t total, uint32_t tile, uint32_t n, uint32_t logn, PassList passes,
                  const Tw4 *__restrict__ tw, bool vec)
 {
+    constexpr int SMAX = MINB == 3 ? 2 : 3; // three CTAs per SM leave 80 registers: two-stage groups only
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2 *sre = reinterpret_cast<double2 *>(smem_raw);
     double2 *sim = sre + tile;
@@ -247,16 +270,17 @@ f128_tile_kernel(Planes data, uint64_t total, uint32_t tile, uint32_t n, uint32_
 
     const int last = passes.count - 1;
     if (last == 0) {
-        dispatch_pass<FWD, true, true, NT>(passes.s[0], g, sre, sim, valid, row_off, n, logn, passes.d0[0], tw, vec);
+        dispatch_pass<FWD, true, true, NT, SMAX>(passes.s[0], g, sre, sim, valid, tile, row_off, n, logn, passes.d0[0], tw, vec);
         return;
     }
-    dispatch_pass<FWD, true, false, NT>(passes.s[0], g, sre, sim, valid, row_off, n, logn, passes.d0[0], tw, vec);
-    __syncthreads();
+    dispatch_pass<FWD, true, false, NT, SMAX>(passes.s[0], g, sre, sim, valid, tile, row_off, n, logn, passes.d0[0], tw, vec);
+    int prev_d0 = passes.d0[0];
 #pragma unroll
     for (int pi = 1; pi < kMaxPasses - 1; pi++) {
         if (pi < last) {
-            dispatch_pass<FWD, false, false, NT>(passes.s[pi], g, sre, sim, valid, row_off, n, logn, passes.d0[pi], tw, vec);
-            __syncthreads();
+            pass_barrier<NT>(n, prev_d0, passes.d0[pi], tile);
+            dispatch_pass<FWD, false, false, NT, SMAX>(passes.s[pi], g, sre, sim, valid, tile, row_off, n, logn, passes.d0[pi], tw, vec);
+            prev_d0 = passes.d0[pi];
         }
     }
     // the last pass index is not a compile-time constant: select its parameters without indexing
@@ -264,7 +288,8 @@ f128_tile_kernel(Planes data, uint64_t total, uint32_t tile, uint32_t n, uint32_
 #pragma unroll
     for (int pi = 2; pi < kMaxPasses; pi++)
         if (pi == last) { ls = passes.s[pi]; ld = passes.d0[pi]; }
-    dispatch_pass<FWD, false, true, NT>(ls, g, sre, sim, valid, row_off, n, logn, ld, tw, vec);
+    pass_barrier<NT>(n, prev_d0, ld, tile);
+    dispatch_pass<FWD, false, true, NT, SMAX>(ls, g, sre, sim, valid, tile, row_off, n, logn, ld, tw, vec);
 }
 
 // stages whose span exceeds a tile: one in-place pass through HBM
@@ -313,14 +338,14 @@ cudaError_t launch_global(int S, Planes data, uint64_t total, uint32_t n, uint32
 
 constexpr uint32_t kF128TileMax = 4096; // 4 planes x 8 B x 4096 = 128 KiB of shared memory
 
-template <bool FWD, int NT>
+template <bool FWD, int NT, int MINB = 512 / NT>
 cudaError_t configure_tile_kernel()
 {
     static thread_local int configured_device = -1;
     int dev = 0;
     cudaGetDevice(&dev);
     if (configured_device == dev) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(f128_tile_kernel<FWD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(f128_tile_kernel<FWD, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          int(kF128TileMax * 4 * sizeof(double)));
     if (e == cudaSuccess) configured_device = dev;
     return e;
@@ -368,11 +393,13 @@ cudaError_t launch_f128(const cfft_plan *plan, bool inverse, double *re0, double
         gs[gcount++] = 3;
     }
     // tile passes: ceil(k / 3) passes with the stages spread evenly (3,3,2,2 rather than 3,3,3,1)
+    static const int env_smax = [] { const char *e = getenv("CFFT_B200_F128_SMAX"); return e ? atoi(e) : 0; }();
+    const int smax = (env_smax == 2 || env_smax == 3) ? env_smax : (plan->f128_smax == 2 ? 2 : 3);
     PassList passes;
     passes.count = 0;
     {
         const int k = int(logn) - D0;
-        const int np = (k + 2) / 3, lo = k / np, extra = k % np;
+        const int np = (k + smax - 1) / smax, lo = k / np, extra = k % np;
         for (int i = 0, d = D0; i < np; i++) {
             const int sz = lo + (i < extra ? 1 : 0);
             passes.d0[passes.count] = d;
@@ -394,6 +421,9 @@ cudaError_t launch_f128(const cfft_plan *plan, bool inverse, double *re0, double
         if (tile > 2048) {
             if ((e = configure_tile_kernel<true, 512>()) != cudaSuccess) return e;
             f128_tile_kernel<true, 512><<<tiles, 512, smem, stream>>>(data, total, tile, n, logn, passes, tw, vec);
+        } else if (smax == 2) {
+            if ((e = configure_tile_kernel<true, 256, 3>()) != cudaSuccess) return e;
+            f128_tile_kernel<true, 256, 3><<<tiles, 256, smem, stream>>>(data, total, tile, n, logn, passes, tw, vec);
         } else {
             if ((e = configure_tile_kernel<true, 256>()) != cudaSuccess) return e;
             f128_tile_kernel<true, 256><<<tiles, 256, smem, stream>>>(data, total, tile, n, logn, passes, tw, vec);
@@ -411,6 +441,9 @@ cudaError_t launch_f128(const cfft_plan *plan, bool inverse, double *re0, double
     if (tile > 2048) {
         if ((e = configure_tile_kernel<false, 512>()) != cudaSuccess) return e;
         f128_tile_kernel<false, 512><<<tiles, 512, smem, stream>>>(data, total, tile, n, logn, rev, tw, vec);
+    } else if (smax == 2) {
+        if ((e = configure_tile_kernel<false, 256, 3>()) != cudaSuccess) return e;
+        f128_tile_kernel<false, 256, 3><<<tiles, 256, smem, stream>>>(data, total, tile, n, logn, rev, tw, vec);
     } else {
         if ((e = configure_tile_kernel<false, 256>()) != cudaSuccess) return e;
         f128_tile_kernel<false, 256><<<tiles, 256, smem, stream>>>(data, total, tile, n, logn, rev, tw, vec);

@@ -49,6 +49,7 @@ struct cfft_plan {
     std::string kernel_name;
     std::string tuning_report;
     uint32_t tile_elems = 0; // exact / fft128 tile size override chosen by the autotuner (0 = default)
+    int f128_smax = 3;       // fft128 tile kernel: 3 = three-stage groups, 2 CTAs per SM; 2 = two-stage groups, 3 CTAs per SM
     // multi-pass (variant 2) scheduling: 0 = whole batch per pass; else passes run chunk by chunk
     // (chunk <= l2_chunk_mb MiB, alternating over l2_streams auxiliary streams) so that a chunk stays
     // L2-resident between its passes
