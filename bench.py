@@ -157,7 +157,9 @@ def cpu_port_rate(workload, n, base_n, algo, threads, seconds):
         def step():
             plan.fwd_inplace(buf, threads)
             plan.inv_inplace(buf, threads)
-            np.multiply(buf, 1.0 / n, out=buf)
+
+        def rescale(k):  # fwd+inv multiplies by n: one exact power-of-two rescale every k steps, as in the GPU arm
+            np.multiply(buf, float(n) ** -k, out=buf)
     else:
         rows = max(threads * 2, 32)
         plan = O.F128Plan(n, fast=True)
@@ -166,14 +168,20 @@ def cpu_port_rate(workload, n, base_n, algo, threads, seconds):
         def step():
             plan.fwd_inplace(planes, O.F128_FMA, threads)
             plan.inv_inplace(planes, O.F128_FMA, threads)
+
+        def rescale(k):
             for p in planes:
-                p *= 1.0 / n
+                p *= float(n) ** -k
+    every = max(1, 900 // max(1, n.bit_length() - 1))
     step()
+    rescale(1)
     t0 = time.perf_counter()
     steps = 0
     while True:
         step()
         steps += 1
+        if steps % every == 0:
+            rescale(every)
         el = time.perf_counter() - t0
         if el >= seconds or steps >= 100000:
             break
@@ -200,7 +208,9 @@ def run_reference(args):
         def step():
             plan.fwd_inplace(buf, threads)
             plan.inv_inplace(buf, threads)
-            np.multiply(buf, 1.0 / n, out=buf)
+
+        def rescale(k):  # fwd+inv multiplies by n: one exact power-of-two rescale every k steps, as in the GPU arm
+            np.multiply(buf, float(n) ** -k, out=buf)
     else:
         plan = O.F128Plan(n, fast=True)
         planes = [rng.random((rows, n)), np.zeros((rows, n)), rng.random((rows, n)), np.zeros((rows, n))]
@@ -208,13 +218,19 @@ def run_reference(args):
         def step():
             plan.fwd_inplace(planes, O.F128_FMA, threads)
             plan.inv_inplace(planes, O.F128_FMA, threads)
+
+        def rescale(k):
             for p in planes:
-                p *= 1.0 / n
+                p *= float(n) ** -k
+    every = max(1, 900 // max(1, n.bit_length() - 1))
     for _ in range(args.warmup):
         step()
+        rescale(1)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         step()
+        if (i + 1) % every == 0:
+            rescale(every)
     el = time.perf_counter() - t0
     value = 2.0 * rows * args.steps / el
     sample = "%d of %d polynomials per step, fwd+inv, %d host threads" % (rows, batch, threads)
