@@ -140,6 +140,7 @@ const char *variant_name(const cfft_plan *p)
     case 4: return "fast-b256-cluster";
     case 5: return "ordered-b256-regs-std";
     case 6: return "ord16-regs";
+    case 8: return "fast-b256-persistent-2pass";
     default: return "exact-tile";
     }
 }
@@ -219,6 +220,7 @@ cfft_status build_fast_tables(cfft_plan *p)
         if (ordered_large && atoi(fv) == 3) p->fast_variant = 3;
         if (!ordered_large && atoi(fv) == 2) p->fast_variant = 2;
         if (!ordered_large && atoi(fv) == 4 && (p->n == 8192 || p->n == 16384)) p->fast_variant = 4;
+        if (!ordered_large && atoi(fv) == 8 && p->n >= 16384 && p->n <= 65536) p->fast_variant = 8;
     }
     p->kernel_name = variant_name(p);
     return CFFT_OK;
@@ -524,7 +526,8 @@ cfft_status cfft_plan_autotune(cfft_plan *p, uint64_t batch_hint)
         cands.push_back({"ordered-b256-column+rows-std", 3, 0});
         cands.push_back({"ordered-b256-column+rows-std/L2-16MBx4", 3, 0, 16, 4});
         cands.push_back({"ordered-b256-column+rows-std/L2-32MBx2", 3, 0, 32, 2});
-    } else if (p->fast_variant == 1 || p->fast_variant == 2 || p->fast_variant == 4) {
+    } else if (p->fast_variant == 1 || p->fast_variant == 2 || p->fast_variant == 4 || p->fast_variant == 8) {
+        if (p->n >= 16384 && p->n <= 65536) cands.push_back({"fast-b256-persistent-2pass", 8, 0});
         if (p->n > 256 && p->n <= 8192) cands.push_back({"fast-b256-regs", 1, 0});
         if (p->n > 256 && p->n <= 16384) cands.push_back({"fast-b256-column+rows", 2, 0});
         if (p->n == 8192 || p->n == 16384) cands.push_back({"fast-b256-cluster", 4, 0});

@@ -23,28 +23,12 @@
 #include <cstdlib>
 #include <mutex>
 
-#include "c64_math.cuh"
+#include "c64_dev.cuh"
 #include "plan.h"
 
 namespace cfft {
+using namespace dev;
 namespace {
-
-__device__ __forceinline__ c64 ld_stream(const c64 *p)
-{
-    c64 v;
-    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ void st_stream(c64 *p, c64 v)
-{
-    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
-}
-__device__ __forceinline__ c64 ld_tw(const c64 *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
-
-template <int R> __device__ __forceinline__ constexpr int brev_c(int k)
-{
-    return R == 2 ? k : (R == 4 ? ((k & 1) << 1) | (k >> 1) : ((k & 1) << 2) | (k & 2) | (k >> 2));
-}
 
 // One unordered level of span NCUR on the 16 register values of a thread: B = 16/R butterflies,
 // butterfly j covers positions base_j + m*k.  Twiddles planar: tw[(k-1)*m + p].
@@ -141,40 +125,6 @@ __device__ __forceinline__ void level_8x2(const c64 *__restrict__ gsrc, c64 *__r
 #pragma unroll
             for (int k = 0; k < 8; k++) st_stream(gdst + t + h * j + m * k, x[k]);
         }
-    }
-}
-
-// 256-point base FFT (Dif16: radix-16 s=1 with twiddles, then radix-16 end) of the half-warp
-// that owns block `blk`; thread lane16 = p (first pass) = j (second pass).
-// FWD selects the butterfly direction only; the table passed in is the direction's table.
-// `sw_in` / `sw_out` (0..7) XOR the natural-order shared-memory positions read / written; the standard-order
-// kernels use it so that the transposing pass that follows / precedes is bank-conflict free.
-template <bool FWD, bool G_IN, bool G_OUT>
-__device__ __forceinline__ void base256(const c64 *__restrict__ src, c64 *__restrict__ sm_blk, c64 *__restrict__ dst,
-                                        const c64 *__restrict__ tw_planar, int lane16, c64 (&v)[16], int sw_in = 0, int sw_out = 0)
-{
-    const unsigned hmask = 0xFFFFu << (threadIdx.x & 16); // the 16 lanes that own this block
-    // pass 1: x[p + 16k] -> y[16p + k] = w[p + 16k] * DFT16(x)_k       src/dif16.rs:449-623
-#pragma unroll
-    for (int k = 0; k < 16; k++) v[k] = G_IN ? ld_stream(src + lane16 + 16 * k) : src[(lane16 + 16 * k) ^ sw_in];
-    bf16<FWD>(v);
-#pragma unroll
-    for (int k = 1; k < 16; k++) v[k] = cmul(ld_tw(tw_planar + lane16 + 16 * k), v[k]);
-    __syncwarp(hmask); // the half-warp has finished reading its block
-#pragma unroll
-    for (int k = 0; k < 16; k++) sm_blk[16 * lane16 + (k ^ lane16)] = v[k]; // XOR swizzle: conflict-free
-    __syncwarp(hmask);
-    // pass 2: terminal radix-16 on y[j + 16k]                           src/dif16.rs:649-827
-#pragma unroll
-    for (int k = 0; k < 16; k++) v[k] = sm_blk[16 * k + (lane16 ^ k)];
-    bf16<FWD>(v);
-    if (G_OUT) {
-#pragma unroll
-        for (int k = 0; k < 16; k++) st_stream(dst + lane16 + 16 * k, v[k]);
-    } else {
-        __syncwarp(hmask); // swizzled data consumed by the whole half-warp before natural-order overwrite
-#pragma unroll
-        for (int k = 0; k < 16; k++) dst[(lane16 + 16 * k) ^ sw_out] = v[k];
     }
 }
 
@@ -486,7 +436,7 @@ cudaError_t launch_rows_std(bool inverse, const c64 *src, c64 *dst, uint64_t bat
 
 // Stream-ordered workspace for the out-of-place (ordered) path: one private pool per device that keeps
 // its memory between calls (release threshold = max), so steady-state calls never touch the OS allocator.
-static cudaError_t workspace_pool(int device, cudaMemPool_t *out)
+cudaError_t workspace_pool(int device, cudaMemPool_t *out)
 {
     static std::mutex mu;
     static cudaMemPool_t pools[64] = {};
@@ -620,6 +570,16 @@ cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *d
             }
         }
         return e != cudaSuccess ? e : cudaGetLastError();
+    }
+    if (plan->fast_variant == 8) { // n = 2^14 .. 2^16, one persistent kernel for both passes
+        static const int env_lag = [] { const char *e = getenv("CFFT_B200_TWOPASS_LAG"); return e ? atoi(e) : 0; }();
+        if (plan->fast_groups.size() != 1) return cudaErrorInvalidValue;
+        const cfft_plan::FastGroup &g = plan->fast_groups[0];
+        const double2 *tw[3] = {base, base, base};
+        for (int i = 0; i < 3; i++)
+            if (g.radices[i] > 1) tw[i] = base + plan->fast_levels[size_t(g.first_level + i)].off;
+        return launch_c64_twopass(inverse, data, batch, uint32_t(plan->n), g.radices, tw, tb.base, uint32_t(env_lag > 0 ? env_lag : 0),
+                                  plan->device, stream);
     }
     if (plan->fast_variant == 5) { // standard-order in / out, one kernel (ordered plans 2^11 <= n <= 2^13)
         switch (plan->n) {

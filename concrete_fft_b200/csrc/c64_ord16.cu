@@ -17,23 +17,12 @@
 // XOR-swizzled shared memory.  n >= 512 reads and writes HBM directly (lanes on consecutive c64);
 // n <= 128 would touch only 32..128 contiguous bytes per request that way, so a CTA first stages 2048
 // contiguous elements (64 / 32 / 16 transforms) through shared memory with fully coalesced accesses.
-#include "c64_math.cuh"
+#include "c64_dev.cuh"
 #include "plan.h"
 
 namespace cfft {
+using namespace dev;
 namespace {
-
-__device__ __forceinline__ c64 ld_stream(const c64 *p)
-{
-    c64 v;
-    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ void st_stream(c64 *p, c64 v)
-{
-    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
-}
-__device__ __forceinline__ c64 ld_tw(const c64 *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
 
 constexpr int kNT = 128; // threads per CTA
 

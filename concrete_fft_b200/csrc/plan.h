@@ -64,6 +64,7 @@ struct cfft_plan {
                                       // 3 ordered (standard order in/out) above 2^10: column passes + transposing rows
                                       // 4 one transform per thread-block cluster (n = 8192, 16384), DSMEM exchange
                                       // 5 ordered above 2^10, n <= 8192: fused register kernel with standard-order in / out
+                                      // 8 n = 2^14 .. 2^16: both HBM passes in one persistent kernel, intermediate kept in L2
                                       // 6 whole-transform Dif16 plans, n = 32..128, 512, 1024 (c64_ord16.cu)
     double2 *d_fast_tw[2] = {nullptr, nullptr}; // planar re-layout of the same twiddle values
     struct FastLevel { int radix; uint32_t span; uint32_t off; }; // off: planar table inside d_fast_tw
@@ -94,6 +95,11 @@ cudaError_t launch_c64_ord16(const cfft_plan *plan, bool inverse, double2 *data,
 // kernels (c64_column.cu): one group of <= 3 unordered levels in one HBM pass
 cudaError_t launch_c64_column_group(bool inverse, const double2 *src, double2 *dst, uint64_t batch, uint32_t n, uint32_t span0,
                                     const int radices[3], const double2 *const tw[3], cudaStream_t st);
+// n = 2^14 .. 2^16: column group + base FFTs in one persistent kernel (c64_column.cu)
+cudaError_t launch_c64_twopass(bool inverse, double2 *data, uint64_t batch, uint32_t n, const int radices[3],
+                               const double2 *const tw[3], const double2 *tw_base, uint32_t lag, int device, cudaStream_t st);
+// stream-ordered scratch pool, one per device, keeps its memory between calls (c64_fast.cu)
+cudaError_t workspace_pool(int device, cudaMemPool_t *out);
 // dispatcher (api.cc): fast kernel when the plan has one, else the exact tile kernel
 cudaError_t launch_c64(const cfft_plan *plan, bool inverse, double2 *data, uint64_t batch, cudaStream_t st);
 // kernels (f128.cu)

@@ -550,6 +550,29 @@ def test_cluster_kernel_bit_exact(C, torch, n):
     assert "fast-b256-cluster" in plan.autotune()
 
 
+@pytest.mark.parametrize("logn", [14, 15, 16])
+def test_persistent_two_phase_kernel_bit_exact(C, torch, logn):
+    """n = 2^14 .. 2^16 with both HBM passes in one persistent kernel (work queue, per-transform
+    release / acquire counters): same bits as the reference plan for batches smaller than, equal to and
+    larger than the lag between the phases, and larger than the number of resident CTAs' items."""
+    n = 1 << logn
+    rng = np.random.default_rng(logn)
+    os.environ["CFFT_B200_FAST_VARIANT"] = "8"
+    try:
+        plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(C.ordered.FftAlgo.Dif16, 256))
+    finally:
+        del os.environ["CFFT_B200_FAST_VARIANT"]
+    assert plan.kernel_name() == "fast-b256-persistent-2pass"
+    ref = O.UnorderedPlan(n, O.DIF16, 256)
+    for batch in [1, 2, 37, 1 << (22 - logn)]:
+        x = rand_c(rng, batch, n)
+        y = dev_run(torch, plan.fwd, x)
+        want = ref.fwd(x, threads=8)
+        assert bits_equal(y, want), (n, batch)
+        assert bits_equal(dev_run(torch, plan.inv, y), ref.inv(want, threads=8)), (n, batch)
+    assert "fast-b256-persistent-2pass" in plan.autotune()
+
+
 def test_random_plans_fuzz(C, torch):
     """Seeded fuzz over everything Plan::new accepts: random n, algo, base_n, batch and entry point
     (device / host-pageable), bit-exact against the oracle in both directions."""
