@@ -32,7 +32,18 @@ for n in [2048, 4096, 65536, 131072]:
 os.environ["CFFT_B200_FAST_VARIANT"] = "2"
 run_c64(C.unordered.Plan(2048, C.unordered.Method.UserProvided(A.Dif16, 256)), 2048, 3)
 del os.environ["CFFT_B200_FAST_VARIANT"]
-for n in [32, 256, 2048, 4096, 16384]:
+# round-1 additions: whole-transform Dif16 register kernels, fused standard-order kernel, cluster and
+# persistent two-phase kernels
+for n in [32, 64, 128, 512, 1024]:
+    run_c64(C.ordered.Plan(n, C.ordered.Method.UserProvided(A.Dif16)), n, 70)
+for n in [2048, 4096, 8192]:
+    run_c64(C.ordered.Plan(n, C.ordered.Method.UserProvided(A.Dif16), allow_large=True), n, 3)
+for var, sizes in [("4", [8192, 16384]), ("8", [16384, 32768, 65536])]:
+    os.environ["CFFT_B200_FAST_VARIANT"] = var
+    for n in sizes:
+        run_c64(C.unordered.Plan(n, C.unordered.Method.UserProvided(A.Dif16, 256)), n, 5)
+    del os.environ["CFFT_B200_FAST_VARIANT"]
+for n in [32, 256, 1024, 2048, 4096, 16384]:
     p = C.fft128.Plan(n)
     planes = [torch.rand(3, n, dtype=torch.float64, device="cuda") for _ in range(4)]
     p.fwd(*planes)
