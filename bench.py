@@ -140,19 +140,17 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def cpu_port_rate(workload, n, base_n, algo, threads, seconds):
-    """transforms/s of the oracle port (fast build) on `threads` host threads: fwd+inv steps over
-    a bounded sample until ~`seconds` of wall time."""
+def cpu_workload(workload, n, base_n, algo, rows, threads):
+    """(step, rescale) closures of the oracle port (fast build) over `rows` polynomials in host memory:
+    step = fwd pass then inv pass over all rows on `threads` threads (the GPU step's shape)."""
     import numpy as np
     import oracle_lib as O
 
     rng = np.random.default_rng(0)
-    rows = max(threads * 8, 256)
     if workload in ("c64", "ordered"):
-        if n >= 16384:
-            rows = max(threads, 16)
         plan = O.UnorderedPlan(n, O.ALGO_NAMES.index(algo), base_n, fast=True)
-        buf = rng.random((rows, n)) + 1j * rng.random((rows, n))
+        buf = np.empty((rows, n), np.complex128)
+        rng.random(out=buf.view(np.float64).reshape(rows, 2 * n))
 
         def step():
             plan.fwd_inplace(buf, threads)
@@ -161,7 +159,6 @@ def cpu_port_rate(workload, n, base_n, algo, threads, seconds):
         def rescale(k):  # fwd+inv multiplies by n: one exact power-of-two rescale every k steps, as in the GPU arm
             np.multiply(buf, float(n) ** -k, out=buf)
     else:
-        rows = max(threads * 2, 32)
         plan = O.F128Plan(n, fast=True)
         planes = [rng.random((rows, n)), np.zeros((rows, n)), rng.random((rows, n)), np.zeros((rows, n))]
 
@@ -172,6 +169,25 @@ def cpu_port_rate(workload, n, base_n, algo, threads, seconds):
         def rescale(k):
             for p in planes:
                 p *= float(n) ** -k
+    return step, rescale
+
+
+def cpu_sample_rows(workload, n, batch, max_bytes):
+    """rows of the CPU sample: the whole per-GPU batch when it fits `max_bytes`, else the largest
+    power-of-two slice that does -- always far larger than the host's last-level cache, so the CPU
+    streams from DRAM like the real workload (a cache-resident sample would flatter it by ~1.4x)."""
+    per = n * (32 if workload == "f128" else 16)
+    rows = batch
+    while rows > 1 and rows * per > max_bytes:
+        rows //= 2
+    return max(1, rows)
+
+
+def cpu_port_rate(workload, n, batch, base_n, algo, threads, seconds):
+    """transforms/s of the oracle port on `threads` host threads: fwd+inv steps over a DRAM-sized
+    sample (<= 512 MiB) of the workload until ~`seconds` of wall time."""
+    rows = cpu_sample_rows(workload, n, batch, 512 << 20)
+    step, rescale = cpu_workload(workload, n, base_n, algo, rows, threads)
     every = max(1, 900 // max(1, n.bit_length() - 1))
     step()
     rescale(1)
@@ -194,34 +210,23 @@ def run_reference(args):
         return
     n, batch, base_n, algo = workload_defaults(args)
     threads = host_threads()
-    import numpy as np
     import oracle_lib as O
 
     O.build()
-    rng = np.random.default_rng(0)
-    # each step = fwd+inv over a bounded sample of the workload's batch
-    rows = min(batch, max(threads * 16, 512)) if args.workload == "c64" else min(batch, max(threads * 4, 64))
-    if args.workload in ("c64", "ordered"):
-        plan = O.UnorderedPlan(n, O.ALGO_NAMES.index(algo), base_n, fast=True)
-        buf = rng.random((rows, n)) + 1j * rng.random((rows, n))
-
-        def step():
-            plan.fwd_inplace(buf, threads)
-            plan.inv_inplace(buf, threads)
-
-        def rescale(k):  # fwd+inv multiplies by n: one exact power-of-two rescale every k steps, as in the GPU arm
-            np.multiply(buf, float(n) ** -k, out=buf)
-    else:
-        plan = O.F128Plan(n, fast=True)
-        planes = [rng.random((rows, n)), np.zeros((rows, n)), rng.random((rows, n)), np.zeros((rows, n))]
-
-        def step():
-            plan.fwd_inplace(planes, O.F128_FMA, threads)
-            plan.inv_inplace(planes, O.F128_FMA, threads)
-
-        def rescale(k):
-            for p in planes:
-                p *= float(n) ** -k
+    # Each step = fwd+inv over the WHOLE per-GPU batch when `--steps` of them finish in about a minute
+    # (the default c64 workload does: 200 x 2 GiB); otherwise over the largest power-of-two slice that does.
+    probe_rows = cpu_sample_rows(args.workload, n, batch, 64 << 20)
+    step, rescale = cpu_workload(args.workload, n, base_n, algo, probe_rows, threads)
+    step()
+    t0 = time.perf_counter()
+    step()
+    per_row = (time.perf_counter() - t0) / probe_rows
+    del step, rescale
+    rows = batch
+    while rows > probe_rows and rows * per_row * (args.steps + args.warmup) > 75.0:
+        rows //= 2
+    rows = max(rows, probe_rows)
+    step, rescale = cpu_workload(args.workload, n, base_n, algo, rows, threads)
     every = max(1, 900 // max(1, n.bit_length() - 1))
     for _ in range(args.warmup):
         step()
@@ -233,7 +238,9 @@ def run_reference(args):
             rescale(every)
     el = time.perf_counter() - t0
     value = 2.0 * rows * args.steps / el
-    sample = "%d of %d polynomials per step, fwd+inv, %d host threads" % (rows, batch, threads)
+    bytes_per = n * (32 if args.workload == "f128" else 16)
+    sample = "%d of %d polynomials per step (%.0f MiB, streamed from host DRAM), fwd+inv, %d host threads" % (
+        rows, batch, rows * bytes_per / 2 ** 20, threads)
     line = {
         "impl": "reference",
         "metric": "batched %s FFT transforms/s (fwd+inv)" % METRIC_NAME[args.workload],
@@ -245,7 +252,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "transforms/s", "cores": threads, "kind": "port", "sample": sample,
                          "note": "C restatement of the reference algorithm (oracle/, -O3 AVX2+FMA build: two complex per "
                                  "register like the reference's c64x2 path; bit-identical to the reference's golden "
-                                 "vector); the Rust crate cannot be built here"},
+                                 "vector; persistent thread pool); the Rust crate cannot be built here"},
         "e2e": {"value": value, "unit": "transforms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -467,9 +474,9 @@ def main():
 
         O.build()
         threads = host_threads()
-        rate, rows, steps, el = cpu_port_rate(args.workload, n, base_n, algo, threads, args.cpu_seconds)
+        rate, rows, steps, el = cpu_port_rate(args.workload, n, batch, base_n, algo, threads, args.cpu_seconds)
         cpu = {"value": rate, "unit": "transforms/s", "cores": threads, "kind": "port",
-               "sample": "%d polynomials x %d fwd+inv steps in %.1f s (same n / plan as the GPU run)" % (rows, steps, el)}
+               "sample": "%d polynomials (DRAM-sized sample) x %d fwd+inv steps in %.1f s (same n / plan as the GPU run)" % (rows, steps, el)}
 
     line = {
         "metric": "batched %s FFT transforms/s (fwd+inv)" % METRIC_NAME[args.workload],
