@@ -1,10 +1,11 @@
 // c64_ord16.cu -- register-resident kernels for standard-order Dif16 plans below and above the
 // 256-point case that c64_fast.cu covers:
-//   ordered::Plan::new(n, UserProvided(Dif16)) / Measure,  n = 32, 64, 128, 512, 1024
+//   ordered::Plan::new(n, UserProvided(Dif16)) / Measure,  n = 16, 32, 64, 128, 512, 1024
 //   unordered::Plan with base_n == n and base_algo == Dif16 (the same transform, src/unordered.rs:561-564)
 //
 // Stage schedule of the reference for these sizes (src/dif16.rs:449-623 stockham_core_generic,
 // :649-827 stockham_dif16_end, recursion as src/dif4.rs:285-303):
+//   n = 16                   :  terminal radix-16 only
 //   n = 16 R3  (R3 = 2, 4, 8):  radix-16 at stride 1 with twiddles, terminal radix-R3 at stride 16
 //   n = 256 R3 (R3 = 2, 4)   :  radix-16 at stride 1, radix-16 at stride 16 (both with twiddles),
 //                               terminal radix-R3 at stride 256
@@ -150,6 +151,54 @@ c64_ord16_small_kernel(c64 *__restrict__ data, uint64_t total, const c64 *__rest
     }
 }
 
+// ---- n = 16: the whole transform is the terminal radix-16 butterfly (src/dif16.rs:649-827) ------
+template <bool FWD>
+__global__ void __launch_bounds__(kNT, 4)
+c64_ord16_n16_kernel(c64 *__restrict__ data, uint64_t total)
+{
+    constexpr int TILE = 2048; // 128 transforms per CTA, one per thread
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c64 *s = reinterpret_cast<c64 *>(smem_raw);
+    const uint64_t base = uint64_t(blockIdx.x) * TILE;
+    c64 *g = data + base;
+    const uint32_t valid = total - base < TILE ? uint32_t(total - base) : TILE;
+    auto swz = [](int e) { return (e & ~15) | ((e ^ (e >> 4)) & 15); }; // element k of transform L at 16 L + (k ^ (L & 15))
+    c64 v[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const uint32_t idx = threadIdx.x + kNT * j;
+        v[j] = idx < valid ? ld_stream(g + idx) : mk(0.0, 0.0);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j++) s[swz(int(threadIdx.x) + kNT * j)] = v[j];
+    __syncthreads();
+    const int L = threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = s[16 * L + (k ^ (L & 15))];
+    bf16<FWD>(v);
+#pragma unroll
+    for (int k = 0; k < 16; k++) s[16 * L + (k ^ (L & 15))] = v[k];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 16; j++) v[j] = s[swz(int(threadIdx.x) + kNT * j)];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const uint32_t idx = threadIdx.x + kNT * j;
+        if (idx < valid) st_stream(g + idx, v[j]);
+    }
+}
+
+cudaError_t launch_n16(bool inverse, c64 *data, uint64_t batch, cudaStream_t st)
+{
+    const uint64_t total = batch * 16;
+    const size_t smem = 2048 * sizeof(c64);
+    const unsigned ctas = unsigned((total + 2047) / 2048);
+    if (inverse) c64_ord16_n16_kernel<false><<<ctas, kNT, smem, st>>>(data, total);
+    else c64_ord16_n16_kernel<true><<<ctas, kNT, smem, st>>>(data, total);
+    count_launch();
+    return cudaGetLastError();
+}
+
 template <int N> cudaError_t launch_mid(bool inverse, c64 *data, uint64_t batch, const c64 *tw, cudaStream_t st)
 {
     constexpr int ROWS = kNT / (N / 16);
@@ -176,7 +225,7 @@ template <int N> cudaError_t launch_small(bool inverse, c64 *data, uint64_t batc
 
 bool ord16_supported(uint64_t n, int algo)
 {
-    return algo == 6 /* Dif16 */ && (n == 32 || n == 64 || n == 128 || n == 512 || n == 1024);
+    return algo == 6 /* Dif16 */ && (n == 16 || n == 32 || n == 64 || n == 128 || n == 512 || n == 1024);
 }
 
 // tw: the plan's table for the direction; its first n entries are the planar half of init_wt(16, n)
@@ -185,6 +234,7 @@ cudaError_t launch_c64_ord16(const cfft_plan *plan, bool inverse, double2 *data,
     if (batch == 0) return cudaSuccess;
     const c64 *tw = plan->d_tw[inverse ? 1 : 0];
     switch (plan->n) {
+    case 16: return launch_n16(inverse, data, batch, st);
     case 32: return launch_small<32>(inverse, data, batch, tw, st);
     case 64: return launch_small<64>(inverse, data, batch, tw, st);
     case 128: return launch_small<128>(inverse, data, batch, tw, st);

@@ -297,6 +297,43 @@ def test_full_size_properties_n2048_batch65536(C, torch):
     assert err < 1e-12
 
 
+@pytest.mark.parametrize("npoly,base_n", [(64, 32), (1024, 256), (4096, 256), (4096, 32)])
+def test_negacyclic_product_through_unordered_plan(C, torch, npoly, base_n):
+    """What the crate is for (README.md:10-17, src/lib.rs:9-16): polynomial products modulo X^N + 1 with
+    only element-wise work in the (permuted) Fourier domain.  Fold N real coefficients into N/2 complex
+    points, twist by e^{i pi k / N}, unordered fwd, point-wise product on the device, unordered inv,
+    untwist, unfold -- equals the integer schoolbook negacyclic convolution.  The c64 counterpart of the
+    reference's fft128 `test_product` (src/fft128/mod.rs:1990-2066)."""
+    n = npoly // 2
+    rng = np.random.default_rng(npoly + base_n)
+    batch = 6
+    a = rng.integers(-(1 << 20), 1 << 20, size=(batch, npoly))
+    b = rng.integers(-(1 << 10), 1 << 10, size=(batch, npoly))
+    # schoolbook in exact integer arithmetic: c_k = sum_{i+j=k} a_i b_j - sum_{i+j=k+N} a_i b_j
+    want = np.zeros((batch, npoly), dtype=object)
+    for r in range(batch):
+        full = np.convolve(a[r].astype(object), b[r].astype(object))
+        want[r] = full[:npoly]
+        want[r][: npoly - 1] -= full[npoly:]
+    twist = np.exp(1j * np.pi * np.arange(n) / npoly)
+
+    def fold(p):
+        return (p[:, :n] + 1j * p[:, n:]) * twist
+
+    plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(C.ordered.FftAlgo.Dif16, min(base_n, n)))
+    fa = torch.from_numpy(fold(a)).cuda()
+    fb = torch.from_numpy(fold(b)).cuda()
+    plan.fwd(fa)
+    plan.fwd(fb)
+    fa.mul_(fb)  # same permutation on both operands: the order never has to be undone
+    plan.inv(fa)
+    torch.cuda.synchronize()
+    z = fa.cpu().numpy() / n * np.conj(twist)
+    got = np.concatenate([z.real, z.imag], axis=1)
+    assert np.array_equal(np.rint(got).astype(np.int64), want.astype(np.int64))
+    assert np.abs(got - want.astype(np.float64)).max() < 0.05  # |c| < 2^42: far inside f64
+
+
 @pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096, 8192])
 def test_fast_register_kernel_bit_exact(C, torch, n):
     """c64_fast.cu (plans with base (Dif16, 256)): same bits and order as the reference plan, for
@@ -400,7 +437,7 @@ def test_ordered_fused_standard_order_kernel(C, torch, n):
     assert bits_equal(dev_run(torch, multi.inv, x), dev_run(torch, plan.inv, x))
 
 
-@pytest.mark.parametrize("n", [32, 64, 128, 512, 1024])
+@pytest.mark.parametrize("n", [16, 32, 64, 128, 512, 1024])
 def test_ord16_register_kernel_bit_exact(C, torch, n):
     """Whole-transform Dif16 plans (ordered, and unordered with base_n == n) on the register kernel of
     c64_ord16.cu: bit-exact vs the oracle for ragged batches (tail CTAs, single rows), fwd and inv,
