@@ -130,6 +130,31 @@ cfft_status upload_c64(cfft_plan *p)
     return CFFT_OK;
 }
 
+// Planar copies w_k[p] (k-major) of the unordered level tables for the register kernel of c64_regs.cu:
+// lanes on consecutive p then read consecutive entries.  Same values as h_tw (the reference lays these
+// tables out per SIMD width itself, src/unordered.rs:373-385).
+cfft_status build_top_planar(cfft_plan *p)
+{
+    for (int d = 0; d < 2; d++) {
+        std::vector<cplx> out;
+        StageProgram &pg = p->prog[d];
+        for (int i = 0; i < pg.count; i++) {
+            Stage &st = pg.st[i];
+            st.tw2 = 0;
+            if (st.kind != ST_TOP) continue;
+            st.tw2 = uint32_t(out.size());
+            const uint32_t r = uint32_t(st.radix), m = st.span / r;
+            const cplx *src = p->h_tw[d].data() + st.tw_off;
+            for (uint32_t k = 1; k < r; k++)
+                for (uint32_t q = 0; q < m; q++) out.push_back(src[size_t(r - 1) * q + (k - 1)]);
+        }
+        if (out.empty()) continue;
+        CU(cudaMalloc(reinterpret_cast<void **>(&p->d_top_tw[d]), out.size() * sizeof(cplx)));
+        CU(cudaMemcpy(p->d_top_tw[d], out.data(), out.size() * sizeof(cplx), cudaMemcpyHostToDevice));
+    }
+    return CFFT_OK;
+}
+
 const char *variant_name(const cfft_plan *p)
 {
     if (p->kind == KIND_F128) return "f128-radix8-tile";
@@ -141,7 +166,7 @@ const char *variant_name(const cfft_plan *p)
     case 5: return "ordered-b256-regs-std";
     case 6: return "ord16-regs";
     case 8: return "fast-b256-persistent-2pass";
-    default: return "exact-tile";
+    default: return p->exact_regs ? "exact-regs" : "exact-tile";
     }
 }
 
@@ -333,7 +358,7 @@ cfft_status cfft_ordered_plan_create(cfft_plan **out, int device, uint64_t n, in
     p->algo = algo;
     p->base_n = n;
     p->method = method;
-    p->kernel_name = "exact-tile";
+    p->kernel_name = variant_name(p);
     if (large) {
         // Extension (no reference implementation, src/ordered.rs:244): X = DFT(x) in standard order,
         // computed as the unordered plan (Dif16, 256) with the un-permutation fused into the last pass.
@@ -343,6 +368,7 @@ cfft_status cfft_ordered_plan_create(cfft_plan **out, int device, uint64_t n, in
         init_unordered_twiddles(n, 256, 16, p->h_tw[0], p->h_tw[1]);
         build_c64_programs(p);
         st = upload_c64(p);
+        if (st == CFFT_OK) st = build_top_planar(p);
         if (st == CFFT_OK) st = build_fast_tables(p);
         if (st == CFFT_OK && method == CFFT_METHOD_MEASURE && !getenv("CFFT_B200_NO_AUTOTUNE")) st = cfft_plan_autotune(p, 0);
         if (st != CFFT_OK) { cfft_plan_destroy(p); return st; }
@@ -359,6 +385,7 @@ cfft_status cfft_ordered_plan_create(cfft_plan **out, int device, uint64_t n, in
     append_base_stages(f, algo, n, uint32_t(n));
     append_base_stages(v, algo, n, uint32_t(n));
     st = upload_c64(p);
+    if (st == CFFT_OK) st = build_top_planar(p);
     if (st == CFFT_OK) st = build_fast_tables(p);
     if (st != CFFT_OK) { cfft_plan_destroy(p); return st; }
     *out = p;
@@ -393,10 +420,11 @@ cfft_status cfft_unordered_plan_create(cfft_plan **out, int device, uint64_t n, 
     p->algo = base_algo;
     p->base_n = base_n;
     p->method = method;
-    p->kernel_name = "exact-tile";
+    p->kernel_name = variant_name(p);
     init_unordered_twiddles(n, base_n, size_t(algo_radix(base_algo)), p->h_tw[0], p->h_tw[1]);
     build_c64_programs(p);
     st = upload_c64(p);
+    if (st == CFFT_OK) st = build_top_planar(p);
     if (st == CFFT_OK) st = build_fast_tables(p);
     if (st == CFFT_OK && method == CFFT_METHOD_MEASURE && !getenv("CFFT_B200_NO_AUTOTUNE")) st = cfft_plan_autotune(p, 0);
     if (st != CFFT_OK) { cfft_plan_destroy(p); return st; }
@@ -450,6 +478,7 @@ void cfft_plan_destroy(cfft_plan *p)
     DeviceGuard guard(p->device);
     for (int d = 0; d < 2; d++) if (p->d_tw[d]) cudaFree(p->d_tw[d]);
     for (int d = 0; d < 2; d++) if (p->d_fast_tw[d]) cudaFree(p->d_fast_tw[d]);
+    for (int d = 0; d < 2; d++) if (p->d_top_tw[d]) cudaFree(p->d_top_tw[d]);
     if (p->d_monomial_tw) cudaFree(p->d_monomial_tw);
     for (int i = 0; i < 4; i++) if (p->d_f128_tw[i]) cudaFree(p->d_f128_tw[i]);
     if (p->d_f128_tw4) cudaFree(p->d_f128_tw4);
@@ -470,6 +499,7 @@ cfft_status cfft_plan_clone(const cfft_plan *p, cfft_plan **out)
         (*out)->fast_variant = p->fast_variant;
         (*out)->tile_elems = p->tile_elems;
         (*out)->f128_smax = p->f128_smax;
+        (*out)->exact_regs = p->exact_regs;
         (*out)->l2_chunk_mb = p->l2_chunk_mb;
         (*out)->l2_streams = p->l2_streams;
         (*out)->kernel_name = p->kernel_name;
@@ -511,14 +541,16 @@ cfft_status cfft_plan_autotune(cfft_plan *p, uint64_t batch_hint)
     uint64_t batch = batch_hint ? batch_hint : std::max<uint64_t>(1, (uint64_t((p->n >= 16384 || p->fast_variant == 3 || p->fast_variant == 5) ? 512 : 128) << 20) / bytes_per);
     if (batch * bytes_per > (uint64_t{1} << 30)) batch = std::max<uint64_t>(1, (uint64_t{1} << 30) / bytes_per);
 
-    struct Cand { std::string name; int fast_variant; uint32_t tile; uint32_t l2_mb = 0, l2_streams = 1; int smax = 3; };
+    struct Cand { std::string name; int fast_variant; uint32_t tile; uint32_t l2_mb = 0, l2_streams = 1; int smax = 3; bool regs = false; };
     std::vector<Cand> cands;
     if (p->kind == KIND_F128 || p->fast_variant == 0 || p->fast_variant == 6) {
         const char *fam = p->kind == KIND_F128 ? "f128-radix8-tile" : "exact-tile";
         if (p->fast_variant == 6) cands.push_back({"ord16-regs", 6, 0});
+        if (p->kind != KIND_F128) cands.push_back({"exact-regs", 0, 0, 0, 1, 3, true});
         if (p->n <= 2048)
             for (uint32_t t : {1024u, 2048u, 4096u})
                 if (t >= p->n) cands.push_back({std::string(fam) + "/" + std::to_string(t), p->kind == KIND_F128 ? p->fast_variant : 0, t});
+        if (p->kind != KIND_F128 && p->n > 2048) cands.push_back({"exact-tile/4096", 0, 0});
         if (p->kind == KIND_F128 && p->n <= 2048) // two-stage groups in 80 registers: three CTAs per SM
             cands.push_back({std::string(fam) + "/2048/3-per-SM", p->fast_variant, 2048u, 0, 1, 2});
     } else if (p->fast_variant == 3 || p->fast_variant == 5) {
@@ -562,6 +594,7 @@ cfft_status cfft_plan_autotune(cfft_plan *p, uint64_t batch_hint)
     const int keep_variant = p->fast_variant;
     const uint32_t keep_tile = p->tile_elems, keep_mb = p->l2_chunk_mb, keep_st = p->l2_streams;
     const int keep_smax = p->f128_smax;
+    const bool keep_regs = p->exact_regs;
     std::string report;
     float best_ms = 1e30f;
     size_t best = 0;
@@ -569,6 +602,7 @@ cfft_status cfft_plan_autotune(cfft_plan *p, uint64_t batch_hint)
         p->fast_variant = cands[i].fast_variant;
         p->tile_elems = cands[i].tile;
         p->f128_smax = cands[i].smax;
+        p->exact_regs = cands[i].regs;
         p->l2_chunk_mb = cands[i].l2_mb;
         p->l2_streams = cands[i].l2_streams;
         float ms = 0;
@@ -585,6 +619,7 @@ cfft_status cfft_plan_autotune(cfft_plan *p, uint64_t batch_hint)
         p->fast_variant = keep_variant;
         p->tile_elems = keep_tile;
         p->f128_smax = keep_smax;
+        p->exact_regs = keep_regs;
         p->l2_chunk_mb = keep_mb;
         p->l2_streams = keep_st;
         return rc;
@@ -592,6 +627,7 @@ cfft_status cfft_plan_autotune(cfft_plan *p, uint64_t batch_hint)
     p->fast_variant = cands[best].fast_variant;
     p->tile_elems = cands[best].tile;
     p->f128_smax = cands[best].smax;
+    p->exact_regs = cands[best].regs;
     p->l2_chunk_mb = cands[best].l2_mb;
     p->l2_streams = cands[best].l2_streams;
     p->kernel_name = variant_name(p);

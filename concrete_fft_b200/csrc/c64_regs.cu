@@ -1,0 +1,191 @@
+// c64_regs.cu -- register-resident execution of ANY plan's stage schedule (all 8 algorithms, every
+// base_n, ordered and unordered): the successor of the shared-memory "exact tile" kernel of c64_tile.cu.
+//
+// A CTA of NT threads owns a tile of 16 NT contiguous c64 (whole transforms, or a sub-block of one when
+// n exceeds the tile) and every thread always holds 16 of them in registers: a radix-R stage is 16/R
+// butterflies per thread, so EVERY stage of the reference's schedule keeps all threads busy --
+//   unordered levels   fwd_process_x{2,4,8} / inv_process_x{2,4,8}     src/unordered.rs:222-293
+//   Stockham stages    stockham_core_* of dif{2,4,8,16}.rs / dit{2,4,8,16}.rs (e.g. src/dif4.rs:118-168,
+//                      src/dit4.rs:96-145) and the terminal passes (e.g. src/dif4.rs:217-244)
+// -- with the first stage reading HBM and the last writing HBM directly (their access patterns are
+// lane-consecutive for every stage kind), stages in between exchanging through ONE swizzled shared-memory
+// copy of the tile (read all -> barrier -> compute -> write, so no ping-pong buffer: 32 KiB per 128
+// threads, four CTAs per SM), and twiddles read from planar tables (lanes on consecutive p) instead of
+// the reference's per-butterfly interleaved layout.  Same butterflies (c64_math.cuh), same table values,
+// same element order => bit-identical to the reference for the plan, like the kernel it replaces.
+#include "c64_dev.cuh"
+#include "plan.h"
+
+namespace cfft {
+using namespace dev;
+namespace {
+
+// conflict-free for every stage pattern (consecutive elements, or elements 2..16 apart across lanes)
+__device__ __forceinline__ uint32_t swz(uint32_t i) { return i ^ ((i >> 3) & 7u) ^ ((i >> 6) & 7u); }
+
+template <int R> __device__ __forceinline__ int brev_r(int k)
+{
+    return R == 16 ? ((k & 1) << 3) | ((k & 2) << 1) | ((k & 4) >> 1) | (k >> 3) : brev_c<R>(k);
+}
+
+struct TileIo {
+    c64 *g;         // tile start in HBM
+    c64 *s;         // tile in shared memory (swizzled)
+    uint32_t valid; // elements of the tile that exist (whole transforms)
+    bool in_g, out_g;
+};
+
+// One stage on the 16 register values of a thread.  in_idx / out_idx: tile positions of element k of
+// butterfly j; tw_idx: twiddle index of (j, k >= 1) or nullptr-equivalent when the stage has none.
+template <int R, bool FWD, bool TW_IN, bool TW_OUT, class FIn, class FOut, class FTw>
+__device__ __forceinline__ void stage_body(const TileIo &io, const c64 *__restrict__ tw, FIn in_idx, FOut out_idx, FTw tw_idx,
+                                           c64 (&v)[16])
+{
+    constexpr int B = 16 / R;
+    bool live[B];
+#pragma unroll
+    for (int j = 0; j < B; j++) {
+        live[j] = in_idx(j, 0) < io.valid;
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            const uint32_t i = in_idx(j, k);
+            v[j * R + k] = !live[j] ? mk(0.0, 0.0) : (io.in_g ? ld_stream(io.g + i) : io.s[swz(i)]);
+        }
+    }
+    if (!io.in_g && !io.out_g) __syncthreads(); // in place: every read before any write
+#pragma unroll
+    for (int j = 0; j < B; j++) {
+        c64 *x = &v[j * R];
+        if (TW_IN) {
+#pragma unroll
+            for (int k = 1; k < R; k++) x[k] = cmul(ld_tw(tw + tw_idx(j, k)), x[k]);
+        }
+        bfR<R, FWD>(x);
+        if (TW_OUT) {
+#pragma unroll
+            for (int k = 1; k < R; k++) x[k] = cmul(ld_tw(tw + tw_idx(j, k)), x[k]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < B; j++)
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            const uint32_t i = out_idx(j, k);
+            if (live[j]) {
+                if (io.out_g) st_stream(io.g + i, v[j * R + k]);
+                else io.s[swz(i)] = v[j * R + k];
+            }
+        }
+}
+
+__device__ __forceinline__ uint32_t lg2(uint32_t x) { return 31u - uint32_t(__clz(int(x))); }
+
+// Index maps are recomputed from the butterfly number b = t + NT j where they are used (a few integer
+// operations next to ~50 FP64 instructions per element) instead of being kept in registers.
+template <int R, bool FWD, int NT>
+__device__ __forceinline__ void run_stage(const Stage &st, uint32_t base_n, const c64 *tw_ref, const c64 *tw_top,
+                                          const TileIo &io, c64 (&v)[16])
+{
+    const uint32_t t = threadIdx.x;
+    if (st.kind == ST_TOP) {
+        // fwd: v = DFT_R(z[p + m k]); z[p + m brev(k)] = w_k v_k      inv: v_k = w_k z[p + m brev(k)]; z[p + m k] = DFT^-1
+        const uint32_t m = st.span / R, lm = lg2(m), span = st.span;
+        auto zof = [=](int j) { const uint32_t b = t + NT * j; return (b >> lm) * span + (b & (m - 1)); };
+        auto nat = [=](int j, int k) { return zof(j) + m * uint32_t(k); };
+        auto rev = [=](int j, int k) { return zof(j) + m * uint32_t(brev_r<R>(k)); };
+        auto twi = [=](int j, int k) { return uint32_t(k - 1) * m + ((t + NT * j) & (m - 1)); };
+        if (FWD) stage_body<R, true, false, true>(io, tw_top + st.tw2, nat, rev, twi, v);
+        else stage_body<R, false, true, false>(io, tw_top + st.tw2, rev, nat, twi, v);
+    } else if (st.kind == ST_END) {
+        const uint32_t part = base_n / R, lp = lg2(part);
+        auto idx = [=](int j, int k) { const uint32_t b = t + NT * j; return (b >> lp) * base_n + (b & (part - 1)) + part * uint32_t(k); };
+        auto twi = [](int, int) { return 0u; };
+        stage_body<R, FWD, false, false>(io, tw_ref, idx, idx, twi, v);
+    } else {
+        // Stockham stage at stride s: natural side x[q + s(p + m k)], scattered side y[q + s(R p + k)], twiddle w^{k p s}
+        const uint32_t s = st.span, per_blk = base_n / R, lpb = lg2(per_blk), ls = lg2(s);
+        auto nat = [=](int j, int k) {
+            const uint32_t b = t + NT * j;
+            return (b >> lpb) * base_n + (b & (per_blk - 1)) + per_blk * uint32_t(k);
+        };
+        auto sca = [=](int j, int k) {
+            const uint32_t b = t + NT * j, rem = b & (per_blk - 1);
+            return (b >> lpb) * base_n + (rem & (s - 1)) + (((rem >> ls) * R + uint32_t(k)) << ls);
+        };
+        auto twi = [=](int j, int k) { // planar half: w[p s + k base_n / R]
+            const uint32_t rem = (t + NT * j) & (per_blk - 1);
+            return (rem & ~(s - 1)) + per_blk * uint32_t(k);
+        };
+        const c64 *w = tw_ref + st.tw_off - base_n;
+        if (st.kind == ST_CORE_DIF) stage_body<R, FWD, false, true>(io, w, nat, sca, twi, v);
+        else stage_body<R, FWD, true, false>(io, w, sca, nat, twi, v);
+    }
+}
+
+// (A ping-pong variant -- two copies of the tile, one barrier per stage, 168 registers without spills, three
+// CTAs per SM -- measured 10-25 % slower than this in-place form with four: more CTAs matter more.)
+template <bool FWD, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT)
+c64_regs_kernel(c64 *__restrict__ data, uint64_t total, uint32_t base_n, StageProgram prog, const c64 *__restrict__ tw_ref,
+                const c64 *__restrict__ tw_top)
+{
+    constexpr uint32_t TILE = 16 * NT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileIo io;
+    io.s = reinterpret_cast<c64 *>(smem_raw);
+    const uint64_t start = uint64_t(blockIdx.x) * TILE;
+    io.g = data + start;
+    io.valid = total - start < TILE ? uint32_t(total - start) : TILE;
+    c64 v[16];
+    for (int si = 0; si < prog.count; si++) {
+        const Stage st = prog.st[si];
+        io.in_g = si == 0;
+        io.out_g = si == prog.count - 1;
+        if (!io.in_g) __syncthreads(); // the previous stage's shared-memory writes
+        if (st.radix == 16) run_stage<16, FWD, NT>(st, base_n, tw_ref, tw_top, io, v);
+        else if (st.radix == 8) run_stage<8, FWD, NT>(st, base_n, tw_ref, tw_top, io, v);
+        else if (st.radix == 4) run_stage<4, FWD, NT>(st, base_n, tw_ref, tw_top, io, v);
+        else run_stage<2, FWD, NT>(st, base_n, tw_ref, tw_top, io, v);
+    }
+}
+
+template <bool FWD, int NT>
+cudaError_t launch_regs_t(const StageProgram &prog, c64 *data, uint64_t total, uint32_t base_n, const c64 *tw_ref,
+                          const c64 *tw_top, cudaStream_t stream)
+{
+    constexpr uint32_t TILE = 16 * NT;
+    const size_t smem = size_t(TILE) * sizeof(c64);
+    if (smem > 48 * 1024) {
+        static thread_local int configured_device = -1;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (configured_device != dev) {
+            cudaError_t e = cudaFuncSetAttribute(c64_regs_kernel<FWD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            if (e != cudaSuccess) return e;
+            configured_device = dev;
+        }
+    }
+    const uint64_t tiles = (total + TILE - 1) / TILE;
+    c64_regs_kernel<FWD, NT><<<unsigned(tiles), NT, smem, stream>>>(data, total, base_n, prog, tw_ref, tw_top);
+    count_launch();
+    return cudaGetLastError();
+}
+
+} // namespace
+
+// tile: 1024 (64 threads), 2048 (128 threads) or 4096 (256 threads) elements; prog: the stages whose span fits the tile
+cudaError_t launch_c64_regs(bool inverse, uint32_t tile, const StageProgram &prog, double2 *data, uint64_t total,
+                            uint32_t base_n, const double2 *tw_ref, const double2 *tw_top, cudaStream_t stream)
+{
+    if (prog.count == 0 || total == 0) return cudaSuccess;
+    if (tile == 4096)
+        return inverse ? launch_regs_t<false, 256>(prog, data, total, base_n, tw_ref, tw_top, stream)
+                       : launch_regs_t<true, 256>(prog, data, total, base_n, tw_ref, tw_top, stream);
+    if (tile == 1024)
+        return inverse ? launch_regs_t<false, 64>(prog, data, total, base_n, tw_ref, tw_top, stream)
+                       : launch_regs_t<true, 64>(prog, data, total, base_n, tw_ref, tw_top, stream);
+    return inverse ? launch_regs_t<false, 128>(prog, data, total, base_n, tw_ref, tw_top, stream)
+                   : launch_regs_t<true, 128>(prog, data, total, base_n, tw_ref, tw_top, stream);
+}
+
+} // namespace cfft

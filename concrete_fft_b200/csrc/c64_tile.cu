@@ -12,6 +12,8 @@
 //
 // HBM traffic of the tile kernel is the algorithmic minimum (read N, write N c64 per transform);
 // twiddles come from the plan's tables through L1/L2.
+#include <cstdlib>
+
 #include "c64_math.cuh"
 #include "plan.h"
 
@@ -289,7 +291,9 @@ cudaError_t launch_c64_exact(const cfft_plan *plan, bool inverse, double2 *data,
 
     // tile = whole transforms when they fit, else a 4096-element sub-block of one transform
     uint32_t tile;
+    const bool regs = plan->exact_regs && !getenv("CFFT_B200_EXACT_TILE"); // register kernel (c64_regs.cu), the default
     if (n >= kTileMax) tile = kTileMax;
+    else if (regs) tile = (n <= 1024 && !getenv("CFFT_B200_REGS_TILE2048")) ? 1024 : 2048; // whole transforms; smaller tiles = more CTAs per SM
     else {
         uint64_t rows = (plan->tile_elems ? plan->tile_elems : 2048u) / n;
         if (rows < 1) rows = 1;
@@ -307,10 +311,12 @@ cudaError_t launch_c64_exact(const cfft_plan *plan, bool inverse, double2 *data,
         for (int i = 0; i < full.count; i++)
             if (full.st[i].kind == ST_TOP && full.st[i].span > tile)
                 if ((e = launch_global_stage<true>(full.st[i], data, total, tw, stream)) != cudaSuccess) return e;
+        if (regs) return launch_c64_regs(false, tile, in_tile, data, total, uint32_t(plan->base_n), tw, plan->d_top_tw[0], stream);
         return launch_tile<true>(in_tile, data, total, tile, uint32_t(plan->base_n), tw, stream);
     }
-    if ((e = launch_tile<false>(in_tile, data, total, tile, uint32_t(plan->base_n), tw, stream)) != cudaSuccess)
-        return e;
+    e = regs ? launch_c64_regs(true, tile, in_tile, data, total, uint32_t(plan->base_n), tw, plan->d_top_tw[1], stream)
+             : launch_tile<false>(in_tile, data, total, tile, uint32_t(plan->base_n), tw, stream);
+    if (e != cudaSuccess) return e;
     for (int i = 0; i < full.count; i++)
         if (full.st[i].kind == ST_TOP && full.st[i].span > tile)
             if ((e = launch_global_stage<false>(full.st[i], data, total, tw, stream)) != cudaSuccess) return e;

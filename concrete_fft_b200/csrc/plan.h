@@ -25,6 +25,7 @@ struct Stage {
     int radix;
     uint32_t span;   // ST_TOP: n_cur; cores: stride s; END: unused
     uint32_t tw_off; // offset (in c64) of this stage's twiddles inside the direction's table
+    uint32_t tw2;    // ST_TOP: offset of the planar copy w_k[p] (k-major) inside d_top_tw (c64_regs.cu)
 };
 
 constexpr int kMaxStages = 24;
@@ -60,6 +61,8 @@ struct cfft_plan {
     double2 *d_tw[2] = {nullptr, nullptr};
     double2 *d_monomial_tw = nullptr; // n entries, e^{-2 pi i k / n} (src/unordered.rs:714-720)
     cfft::StageProgram prog[2];       // [0] fwd, [1] inv: every stage in execution order
+    double2 *d_top_tw[2] = {nullptr, nullptr}; // planar copies of the unordered level tables (same values)
+    bool exact_regs = true;           // plans without a specialised kernel: register kernel (c64_regs.cu) or tile kernel
     int fast_variant = 0;             // 0 exact tile kernel; 1 fused register kernel; 2 column passes + rows;
                                       // 3 ordered (standard order in/out) above 2^10: column passes + transposing rows
                                       // 4 one transform per thread-block cluster (n = 8192, 16384), DSMEM exchange
@@ -86,6 +89,9 @@ cudaError_t launch_c64_exact(const cfft_plan *plan, bool inverse, double2 *data,
 cudaError_t launch_monomial(const cfft_plan *plan, uint64_t degree, double2 *data, cudaStream_t st);
 cudaError_t launch_permute(const cfft_plan *plan, bool to_standard, const double2 *src, double2 *dst,
                            uint64_t batch, cudaStream_t st);
+// kernels (c64_regs.cu): any stage program on a tile of 2048 / 4096 elements
+cudaError_t launch_c64_regs(bool inverse, uint32_t tile, const StageProgram &prog, double2 *data, uint64_t total,
+                            uint32_t base_n, const double2 *tw_ref, const double2 *tw_top, cudaStream_t st);
 // kernels (c64_fast.cu)
 bool fast_b256_supported(uint64_t n, int base_algo, uint64_t base_n);
 cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *data, uint64_t batch, cudaStream_t st);

@@ -353,7 +353,7 @@ def test_fast_register_kernel_bit_exact(C, torch, n):
         exact = C.unordered.Plan(n, C.unordered.Method.UserProvided(C.ordered.FftAlgo.Dif16, 256))
     finally:
         del os.environ["CFFT_B200_FORCE_EXACT"]
-    assert exact.kernel_name() == "exact-tile"
+    assert exact.kernel_name() == "exact-regs"
     assert bits_equal(dev_run(torch, exact.fwd, x), y)
 
 
@@ -447,7 +447,7 @@ def test_ord16_register_kernel_bit_exact(C, torch, n):
     po = C.ordered.Plan(n, C.ordered.Method.UserProvided(A.Dif16))
     pu = C.unordered.Plan(n, C.unordered.Method.UserProvided(A.Dif16, n))
     assert po.kernel_name() == "ord16-regs" and pu.kernel_name() == "ord16-regs"
-    assert C.ordered.Plan(n, C.ordered.Method.UserProvided(A.Dit16)).kernel_name() == "exact-tile"
+    assert C.ordered.Plan(n, C.ordered.Method.UserProvided(A.Dit16)).kernel_name() == "exact-regs"
     assert np.array_equal(pu.permutation(), np.arange(n))
     ref = O.OrderedPlan(n, O.DIF16)
     uref = O.UnorderedPlan(n, O.DIF16, n)
@@ -469,11 +469,41 @@ def test_ord16_register_kernel_bit_exact(C, torch, n):
         exact = C.ordered.Plan(n, C.ordered.Method.UserProvided(A.Dif16))
     finally:
         del os.environ["CFFT_B200_FORCE_EXACT"]
-    assert exact.kernel_name() == "exact-tile"
+    assert exact.kernel_name() == "exact-regs"
     assert bits_equal(dev_run(torch, exact.fwd, x), y)
     h = x.copy()
     po.fwd(h)  # host-memory entry
     assert bits_equal(h, y)
+
+
+@pytest.mark.parametrize("algo", range(8))
+def test_generic_register_kernel_matches_tile_kernel_and_oracle(C, torch, algo):
+    """c64_regs.cu (any plan, 16 c64 per thread, planar twiddles) against the oracle AND against the
+    shared-memory tile kernel it replaces (CFFT_B200_EXACT_TILE=1), ragged batches that leave partial
+    tiles, n below / at / above the tile, ordered and unordered."""
+    rng = np.random.default_rng(1700 + algo)
+    A = C.ordered.FftAlgo
+    cases = [(64, 64), (256, 32), (1024, 1024), (2048, 512), (4096, 128), (8192, 1024), (32768, 64)]
+    for n, base_n in cases:
+        plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(A(algo), base_n))
+        if not (algo == O.DIF16 and (base_n == 256 or base_n == n)):
+            assert plan.kernel_name() == "exact-regs", (algo, n, base_n, plan.kernel_name())
+        ref = O.UnorderedPlan(n, algo, base_n)
+        for batch in (1, 3, 2048 // min(n, 2048) + 1):
+            x = rand_c(rng, batch, n)
+            y = dev_run(torch, plan.fwd, x)
+            want = ref.fwd(x, threads=8)
+            assert bits_equal(y, want), (algo, n, base_n, batch)
+            assert bits_equal(dev_run(torch, plan.inv, y), ref.inv(want, threads=8)), (algo, n, base_n, batch)
+            os.environ["CFFT_B200_EXACT_TILE"] = "1"
+            try:
+                assert bits_equal(dev_run(torch, plan.fwd, x), y)
+            finally:
+                del os.environ["CFFT_B200_EXACT_TILE"]
+    for n in (2, 4, 8, 16, 32, 512, 1024):
+        plan = C.ordered.Plan(n, C.ordered.Method.UserProvided(A(algo)))
+        x = rand_c(rng, 131, n)
+        assert bits_equal(dev_run(torch, plan.fwd, x), O.OrderedPlan(n, algo).fwd(x)), (algo, n)
 
 
 def test_autotune_keeps_bits_and_order(C, torch):
@@ -501,7 +531,7 @@ def test_autotune_keeps_bits_and_order(C, torch):
         assert twin.kernel_name() == multi.kernel_name()
     # tile-size variants of the exact kernel and of fft128
     p = C.unordered.Plan(128, C.unordered.Method.Measure())
-    assert "exact-tile/" in p.tuning_report() and "selected:" in p.tuning_report()
+    assert "exact-tile/" in p.tuning_report() and "exact-regs" in p.tuning_report() and "selected:" in p.tuning_report()
     x = rand_c(rng, 300, 128)
     assert bits_equal(dev_run(torch, p.fwd, x), O.UnorderedPlan(128, O.DIF16, 128).fwd(x))
     fp = C.fft128.Plan(256)
