@@ -12,7 +12,9 @@
 //
 // HBM traffic of the tile kernel is the algorithmic minimum (read N, write N c64 per transform);
 // twiddles come from the plan's tables through L1/L2.
+#include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 #include "c64_math.cuh"
 #include "plan.h"
@@ -307,16 +309,44 @@ cudaError_t launch_c64_exact(const cfft_plan *plan, bool inverse, double2 *data,
         if (!(full.st[i].kind == ST_TOP && full.st[i].span > tile)) in_tile.st[in_tile.count++] = full.st[i];
 
     cudaError_t e;
+    if (regs) {
+        // Levels wider than the tile (all radix 8: a radix-2 / 4 level spans <= 4 base_n <= 4096) run as
+        // column passes over HBM, two levels per pass (c64_column.cu, planar twiddles), outermost pair first.
+        std::vector<Stage> wide; // outermost level first
+        for (int i = 0; i < full.count; i++)
+            if (full.st[i].kind == ST_TOP && full.st[i].span > tile) wide.push_back(full.st[i]);
+        if (inverse) std::reverse(wide.begin(), wide.end()); // prog[1] lists them innermost first
+        struct Pass { int radices[3]; const double2 *tw[3]; uint32_t span0; };
+        std::vector<Pass> passes;
+        const double2 *top = plan->d_top_tw[inverse ? 1 : 0];
+        for (size_t i = 0; i < wide.size(); i += 2) {
+            Pass ps = {{wide[i].radix, 1, 1}, {top + wide[i].tw2, top, top}, wide[i].span};
+            if (i + 1 < wide.size()) {
+                ps.radices[1] = wide[i + 1].radix;
+                ps.tw[1] = top + wide[i + 1].tw2;
+            }
+            passes.push_back(ps);
+        }
+        auto column = [&](const Pass &ps) {
+            return launch_c64_column_group(inverse, data, data, batch, uint32_t(n), ps.span0, ps.radices, ps.tw, stream);
+        };
+        if (!inverse) {
+            for (const Pass &ps : passes)
+                if ((e = column(ps)) != cudaSuccess) return e;
+            return launch_c64_regs(false, tile, in_tile, data, total, uint32_t(plan->base_n), tw, top, stream);
+        }
+        if ((e = launch_c64_regs(true, tile, in_tile, data, total, uint32_t(plan->base_n), tw, top, stream)) != cudaSuccess) return e;
+        for (size_t i = passes.size(); i-- > 0;)
+            if ((e = column(passes[i])) != cudaSuccess) return e;
+        return cudaSuccess;
+    }
     if (!inverse) {
         for (int i = 0; i < full.count; i++)
             if (full.st[i].kind == ST_TOP && full.st[i].span > tile)
                 if ((e = launch_global_stage<true>(full.st[i], data, total, tw, stream)) != cudaSuccess) return e;
-        if (regs) return launch_c64_regs(false, tile, in_tile, data, total, uint32_t(plan->base_n), tw, plan->d_top_tw[0], stream);
         return launch_tile<true>(in_tile, data, total, tile, uint32_t(plan->base_n), tw, stream);
     }
-    e = regs ? launch_c64_regs(true, tile, in_tile, data, total, uint32_t(plan->base_n), tw, plan->d_top_tw[1], stream)
-             : launch_tile<false>(in_tile, data, total, tile, uint32_t(plan->base_n), tw, stream);
-    if (e != cudaSuccess) return e;
+    if ((e = launch_tile<false>(in_tile, data, total, tile, uint32_t(plan->base_n), tw, stream)) != cudaSuccess) return e;
     for (int i = 0; i < full.count; i++)
         if (full.st[i].kind == ST_TOP && full.st[i].span > tile)
             if ((e = launch_global_stage<false>(full.st[i], data, total, tw, stream)) != cudaSuccess) return e;
