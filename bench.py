@@ -436,12 +436,14 @@ def main():
         return
 
     peak, peak_src, _ = measured_peaks()
-    traffic, traffic_src = None, None
+    traffic, traffic_src, ncu_fp64 = None, None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         rec = tj.get("%s:%d:%d" % (args.workload, n, batch))
         if rec:
             traffic, traffic_src = rec["traffic_bytes"], "profiles/traffic.json (ncu dram__bytes_read+write, %s)" % rec["kernel"]
+            if "sm__pipe_fp64_cycles_active_pct" in rec:
+                ncu_fp64 = dict(rec["sm__pipe_fp64_cycles_active_pct"], source=rec.get("source", "profiles/traffic.json"))
     except Exception:
         pass
     dom_ms = fwd_ms  # fwd and inv launches are the same kernel family; the fwd launch is reported
@@ -463,7 +465,7 @@ def main():
                     "unit": "T FP64 instr/s", "frac": rate / fp64_peak, "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": "64 FP64 lanes x 148 SMs x sampled SM clock (%.0f MHz); MEASURED_PEAKS.json has no FP64 entry" % sm_mhz,
                     "fp64_instr_per_transform": instr, "frac_at_max_clock": rate / (64 * 148 * 1965e6),
-                    "ncu_sm__pipe_fp64_cycles_active_pct": {"fwd": 76.38, "inv": 79.39, "source": "profiles/r1h_traffic_f128.csv"},
+                    "ncu_sm__pipe_fp64_cycles_active_pct": ncu_fp64,
                     "flop_frac_of_37.2TF": 106.0 / 94.0 * rate / (2 * 64 * 148 * 1965e6),
                     "algorithmic_bytes_per_launch": bytes_per_launch, "hbm_achieved_gbs": achieved, "hbm_frac": achieved / peak,
                     "fwd_ms": fwd_ms, "inv_ms": inv_ms}

@@ -261,8 +261,8 @@ c64_twopass_kernel(TwoPassParams prm)
                 if (threadIdx.x == 0) {
                     uint32_t spins = 0;
                     while (ld_acquire_u32(prm.sync + 1 + j) < uint32_t(F_ITEMS)) {
-                        __nanosleep(100);
-                        if (++spins > (1u << 24)) __trap(); // never hang the GPU on a lost signal
+                        __nanosleep(200);
+                        if (++spins > (1u << 25)) __trap(); // ~7 s: never hang the GPU on a lost signal
                     }
                 }
                 __syncthreads();
