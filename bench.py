@@ -114,6 +114,28 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(index):
+    """One process per GPU: run on (and first-touch the pinned host buffers from) the CPUs NVML reports as
+    local to this GPU, so the e2e copies do not all cross one socket's memory controller.  No-op when NVML
+    or the cpuset does not allow it."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        ideal = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        both = ideal & allowed
+        if both and both != allowed:
+            os.sched_setaffinity(0, both)
+            return "bound to %d of %d allowed CPUs (NVML ideal set for GPU %d)" % (len(both), len(allowed), index)
+        return "not bound: NVML ideal CPUs %s the allowed set (%d CPUs)" % ("cover" if both else "do not intersect", len(allowed))
+    except Exception as e:  # noqa: BLE001
+        return "not bound: %s" % type(e).__name__
+
+
 def workload_defaults(args):
     if args.workload == "ordered":
         # BASELINE.json configs[2]: standard-order N = 2^16, batch 4096 in total, sharded across the GPUs
@@ -295,6 +317,7 @@ def main():
     if not torch.cuda.is_available():
         sys.exit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
+    numa_note = bind_to_gpu_numa_node(local) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -429,6 +452,8 @@ def main():
                "ms_per_step": 1e3 * el / args.e2e_steps,
                "api": "Plan.fwd_inv_host -> cfft_c64_fwd_inv_host (pinned host buffers)" if args.workload in ("c64", "ordered")
                       else "fft128.Plan.fwd_inv_host on pinned host planes -> cfft_f128_fwd_inv_host"}
+        if numa_note:
+            e2e["host_placement"] = numa_note
 
     if rank != 0:
         if dist is not None:
