@@ -166,6 +166,7 @@ const char *variant_name(const cfft_plan *p)
     case 5: return "ordered-b256-regs-std";
     case 6: return "ord16-regs";
     case 8: return "fast-b256-persistent-2pass";
+    case 9: return "fast-b256-column+fused-rows";
     default: return p->exact_regs ? "exact-regs" : "exact-tile";
     }
 }
@@ -239,13 +240,42 @@ cfft_status build_fast_tables(cfft_plan *p)
         for (int i = it->first; i <= it->second; i++) g.radices[i - it->first] = p->fast_levels[size_t(i)].radix;
         p->fast_groups.push_back(g);
     }
+    // Variant 9: peel the largest tail of levels that a fused kernel covers (256 x tail radices <= 4096) and
+    // group only the levels above it, three radix-8 levels (512 rows) per column pass at most.
+    if (p->n >= 16384 && !ordered_large) {
+        int t = 1;
+        uint32_t tail = 256u * uint32_t(p->fast_levels[size_t(nl - 1)].radix);
+        if (nl >= 2 && tail * uint32_t(p->fast_levels[size_t(nl - 2)].radix) <= 4096) {
+            t = 2;
+            tail *= uint32_t(p->fast_levels[size_t(nl - 2)].radix);
+        }
+        p->tail_n = tail;
+        p->tail_first_level = nl - t;
+        const int k = nl - t; // upper levels, all radix 8
+        bool ok = k >= 1;
+        for (int i = 0; i < k; i++) ok = ok && p->fast_levels[size_t(i)].radix == 8;
+        if (ok) {
+            const int ngroups = (k + 2) / 3;
+            int first = 0;
+            for (int gi = 0; gi < ngroups; gi++) {
+                const int len = (k - first + (ngroups - gi) - 1) / (ngroups - gi); // spread evenly, larger groups first
+                cfft_plan::FastGroup g{{1, 1, 1}, p->fast_levels[size_t(first)].span, first};
+                for (int i = 0; i < len; i++) g.radices[i] = 8;
+                p->tail_groups.push_back(g);
+                first += len;
+            }
+        } else {
+            p->tail_n = 0;
+        }
+    }
     // n <= 8192 also has the fused single-kernel variant, the default there (autotune may switch)
-    p->fast_variant = ordered_large ? (p->n <= 8192 ? 5 : 3) : (p->n <= 8192 ? 1 : 2);
+    p->fast_variant = ordered_large ? (p->n <= 8192 ? 5 : 3) : (p->n <= 8192 ? 1 : (p->n >= 131072 && p->tail_n ? 9 : 2));
     if (const char *fv = getenv("CFFT_B200_FAST_VARIANT")) { // testing hook: force a variant
         if (ordered_large && atoi(fv) == 3) p->fast_variant = 3;
         if (!ordered_large && atoi(fv) == 2) p->fast_variant = 2;
         if (!ordered_large && atoi(fv) == 4 && (p->n == 8192 || p->n == 16384)) p->fast_variant = 4;
         if (!ordered_large && atoi(fv) == 8 && p->n >= 16384 && p->n <= 65536) p->fast_variant = 8;
+        if (!ordered_large && atoi(fv) == 9 && p->tail_n) p->fast_variant = 9;
     }
     p->kernel_name = variant_name(p);
     return CFFT_OK;
@@ -558,7 +588,12 @@ cfft_status cfft_plan_autotune(cfft_plan *p, uint64_t batch_hint)
         cands.push_back({"ordered-b256-column+rows-std", 3, 0});
         cands.push_back({"ordered-b256-column+rows-std/L2-16MBx4", 3, 0, 16, 4});
         cands.push_back({"ordered-b256-column+rows-std/L2-32MBx2", 3, 0, 32, 2});
-    } else if (p->fast_variant == 1 || p->fast_variant == 2 || p->fast_variant == 4 || p->fast_variant == 8) {
+    } else if (p->fast_variant == 1 || p->fast_variant == 2 || p->fast_variant == 4 || p->fast_variant == 8 || p->fast_variant == 9) {
+        if (p->tail_n) {
+            cands.push_back({"fast-b256-column+fused-rows", 9, 0});
+            cands.push_back({"fast-b256-column+fused-rows/L2-16MBx4", 9, 0, 16, 4});
+            cands.push_back({"fast-b256-column+fused-rows/L2-32MBx2", 9, 0, 32, 2});
+        }
         if (p->n >= 16384 && p->n <= 65536) cands.push_back({"fast-b256-persistent-2pass", 8, 0});
         if (p->n > 256 && p->n <= 8192) cands.push_back({"fast-b256-regs", 1, 0});
         if (p->n > 256 && p->n <= 16384) cands.push_back({"fast-b256-column+rows", 2, 0});

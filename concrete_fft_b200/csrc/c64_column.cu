@@ -355,6 +355,7 @@ cudaError_t launch_c64_column_group(bool inverse, const double2 *src, double2 *d
     case 881: return launch_group<8, 8, 1>(inverse, src, dst, prm, batch, stream);
     case 882: return launch_group<8, 8, 2>(inverse, src, dst, prm, batch, stream);
     case 884: return launch_group<8, 8, 4>(inverse, src, dst, prm, batch, stream);
+    case 888: return launch_group<8, 8, 8>(inverse, src, dst, prm, batch, stream);
     default: return cudaErrorInvalidValue;
     }
 }

@@ -475,7 +475,7 @@ cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *d
     tb.top1 = plan->fast_levels.size() > 0 ? base + plan->fast_levels[0].off : base;
     tb.top2 = plan->fast_levels.size() > 1 ? base + plan->fast_levels[1].off : base;
     tb.base = base + plan->fast_base_off;
-    if (plan->fast_variant == 2 || plan->fast_variant == 3) {
+    if (plan->fast_variant == 2 || plan->fast_variant == 3 || plan->fast_variant == 9) {
         // Multi-pass variants: unordered (2, in place) and ordered (3: the last column pass goes out of
         // place into a workspace and the base-FFT pass writes standard order back).
         //
@@ -494,7 +494,27 @@ cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *d
         uint64_t rows_per_chunk = chunk_bytes / (plan->n * sizeof(c64));
         if (rows_per_chunk < 1) rows_per_chunk = 1;
         const uint32_t n32 = uint32_t(plan->n);
-        const size_t ng = plan->fast_groups.size();
+        // variant 9: fewer column passes, then the fused kernel of tail_n points on contiguous blocks
+        const bool fused_tail = plan->fast_variant == 9;
+        const std::vector<cfft_plan::FastGroup> &groups = fused_tail ? plan->tail_groups : plan->fast_groups;
+        const size_t ng = groups.size();
+        FastTables tbt = tb;
+        if (fused_tail) {
+            const size_t l0 = size_t(plan->tail_first_level);
+            tbt.top1 = base + plan->fast_levels[l0].off;
+            tbt.top2 = l0 + 1 < plan->fast_levels.size() ? base + plan->fast_levels[l0 + 1].off : base;
+        }
+        auto tail_pass = [&](c64 *d0, uint64_t nrows, cudaStream_t st) -> cudaError_t {
+            if (!fused_tail) return launch_cfg<256, 1, 1>(inverse, d0, nrows * (n32 / 256), tb, st);
+            const uint64_t blocks = nrows * (n32 / plan->tail_n);
+            switch (plan->tail_n) {
+            case 512: return launch_cfg<512, 2, 1>(inverse, d0, blocks, tbt, st);
+            case 1024: return launch_cfg<1024, 4, 1>(inverse, d0, blocks, tbt, st);
+            case 2048: return launch_cfg<2048, 8, 1>(inverse, d0, blocks, tbt, st);
+            case 4096: return launch_cfg<4096, 8, 2>(inverse, d0, blocks, tbt, st);
+            default: return cudaErrorInvalidValue;
+            }
+        };
         cudaMemPool_t pool = nullptr;
         if (ordered) {
             cudaError_t e = workspace_pool(plan->device, &pool);
@@ -512,11 +532,11 @@ cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *d
             cudaError_t e = cudaSuccess;
             if (!ordered) {
                 if (!inverse) {
-                    for (size_t i = 0; i < ng && e == cudaSuccess; i++) e = group(plan->fast_groups[i], d0, d0);
-                    if (e == cudaSuccess) e = launch_cfg<256, 1, 1>(false, d0, rows * (n32 / 256), tb, st);
+                    for (size_t i = 0; i < ng && e == cudaSuccess; i++) e = group(groups[i], d0, d0);
+                    if (e == cudaSuccess) e = tail_pass(d0, rows, st);
                 } else {
-                    e = launch_cfg<256, 1, 1>(true, d0, rows * (n32 / 256), tb, st);
-                    for (size_t i = ng; i-- > 0 && e == cudaSuccess;) e = group(plan->fast_groups[i], d0, d0);
+                    e = tail_pass(d0, rows, st);
+                    for (size_t i = ng; i-- > 0 && e == cudaSuccess;) e = group(groups[i], d0, d0);
                 }
                 return e;
             }

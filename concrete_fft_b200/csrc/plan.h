@@ -67,6 +67,7 @@ struct cfft_plan {
                                       // 3 ordered (standard order in/out) above 2^10: column passes + transposing rows
                                       // 4 one transform per thread-block cluster (n = 8192, 16384), DSMEM exchange
                                       // 5 ordered above 2^10, n <= 8192: fused register kernel with standard-order in / out
+                                      // 9 n >= 2^14: column passes for the upper levels + fused kernel of 512 .. 4096 points for the rest
                                       // 8 n = 2^14 .. 2^16: both HBM passes in one persistent kernel, intermediate kept in L2
                                       // 6 whole-transform Dif16 plans, n = 32..128, 512, 1024 (c64_ord16.cu)
     double2 *d_fast_tw[2] = {nullptr, nullptr}; // planar re-layout of the same twiddle values
@@ -75,6 +76,11 @@ struct cfft_plan {
     uint32_t fast_base_off = 0;                 // planar half of the base init_wt table
     struct FastGroup { int radices[3]; uint32_t span0; int first_level; };
     std::vector<FastGroup> fast_groups;         // fast_variant == 2: levels grouped per HBM pass
+    // fast_variant == 9: the last one or two levels + the base FFTs run as the fused kernel of size tail_n
+    // (512 .. 4096) on contiguous blocks; only the levels above it are column passes (one HBM pass fewer for n >= 2^17)
+    std::vector<FastGroup> tail_groups;
+    uint32_t tail_n = 0;
+    int tail_first_level = 0;
 
     // fft128
     std::vector<double> h_f128_tw[4];

@@ -357,21 +357,33 @@ def test_fast_register_kernel_bit_exact(C, torch, n):
     assert bits_equal(dev_run(torch, exact.fwd, x), y)
 
 
-@pytest.mark.parametrize("logn", [14, 15, 16, 17, 18, 19, 20])
+@pytest.mark.parametrize("logn", [14, 15, 16, 17, 18, 19, 20, 21, 22])
 def test_fast_large_n_column_passes_bit_exact(C, torch, logn):
     """n = 2^14 .. 2^20 with base (Dif16, 256): levels as column passes (c64_column.cu) + base FFTs on
     rows; same bits and same permuted order as the reference plan."""
     n = 1 << logn
     rng = np.random.default_rng(logn)
     plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(C.ordered.FftAlgo.Dif16, 256))
-    assert plan.kernel_name() == "fast-b256-column+rows"
+    # default: base FFTs on rows of 256 up to 2^16; from 2^17 the last levels + base FFTs run as the fused
+    # kernel of 512 .. 4096 points, which saves one HBM pass
+    assert plan.kernel_name() == ("fast-b256-column+rows" if logn <= 16 else "fast-b256-column+fused-rows")
+    plans = [plan]
+    for var, name in (("2", "fast-b256-column+rows"), ("9", "fast-b256-column+fused-rows")):
+        os.environ["CFFT_B200_FAST_VARIANT"] = var
+        try:
+            plans.append(C.unordered.Plan(n, C.unordered.Method.UserProvided(C.ordered.FftAlgo.Dif16, 256)))
+        finally:
+            del os.environ["CFFT_B200_FAST_VARIANT"]
+        assert plans[-1].kernel_name() == name
     ref = O.UnorderedPlan(n, O.DIF16, 256)
     for batch in ([1, 3] if logn <= 17 else [2]):
         x = rand_c(rng, batch, n)
-        y = dev_run(torch, plan.fwd, x)
         want = ref.fwd(x, threads=8)
-        assert bits_equal(y, want), (n, batch)
-        assert bits_equal(dev_run(torch, plan.inv, y), ref.inv(want, threads=8)), (n, batch)
+        back = ref.inv(want, threads=8)
+        for pl in plans:
+            y = dev_run(torch, pl.fwd, x)
+            assert bits_equal(y, want), (n, batch, pl.kernel_name())
+            assert bits_equal(dev_run(torch, pl.inv, y), back), (n, batch, pl.kernel_name())
     pi = plan.permutation().astype(np.int64)
     f = np.fft.fft(x[0])
     assert np.linalg.norm(y[0][pi] - f) / np.linalg.norm(f) <= 1e-13 * logn
