@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dd-full", action="store_true",
+                    help="fft128: full-width double-double inputs (lo ~ U(-1/2, 1/2) ulp(hi)) instead of lo = 0 (SURVEY 8d config 4, second run)")
     return ap.parse_args()
 
 
@@ -351,6 +353,9 @@ def main():
         plan = C.fft128.Plan(n, device=local)
         planes = [torch.rand(batch, n, dtype=torch.float64, device=dev, generator=g), torch.zeros(batch, n, dtype=torch.float64, device=dev),
                   torch.rand(batch, n, dtype=torch.float64, device=dev, generator=g), torch.zeros(batch, n, dtype=torch.float64, device=dev)]
+        if args.dd_full:  # lo = (u - 1/2) * 2^-53 * hi: below half an ulp of hi, so (hi, lo) is a normalised double-double
+            for hi_i in (0, 2):
+                planes[hi_i + 1] = (torch.rand(batch, n, dtype=torch.float64, device=dev, generator=g) - 0.5) * planes[hi_i] * 2.0 ** -53
         bytes_per_launch = 2 * 32 * n * batch
         inv_scale = 1.0 / n
 
@@ -510,7 +515,8 @@ def main():
         "value": value, "unit": "transforms/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / K, "higher_is_better": True,
         "scaling": "strong" if args.workload == "ordered" else "weak", "vs_baseline": None,
-        "dtype": "f64x2 (double-double)" if args.workload == "f128" else "f64", "data": "synthetic",
+        "dtype": "f64x2 (double-double)" if args.workload == "f128" else "f64",
+        "data": "synthetic (full-width double-double: lo ~ U(-1/2, 1/2) ulp(hi))" if args.workload == "f128" and args.dd_full else "synthetic",
         "config": config_dict(args.workload, n, batch, base_n, algo, world),
         "hbm_gbs_whole_step": 2 * bytes_per_launch * world * K / (total_ms * 1e-3) / 1e9,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

@@ -652,6 +652,53 @@ def test_persistent_two_phase_kernel_bit_exact(C, torch, logn):
     assert "fast-b256-persistent-2pass" in plan.autotune()
 
 
+def test_persistent_kernels_share_the_gpu_without_deadlock(C, torch):
+    """Several persistent two-phase kernels (each sized to fill the GPU, each with spin-waits on its own
+    counters) launched back to back on different streams, on ONE shared plan, together with ordinary kernels:
+    items only wait for items handed out earlier to CTAs that are already running, so co-scheduling cannot
+    deadlock; results stay bit-exact."""
+    n = 1 << 15
+    rng = np.random.default_rng(77)
+    os.environ["CFFT_B200_FAST_VARIANT"] = "8"
+    try:
+        plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(C.ordered.FftAlgo.Dif16, 256))
+    finally:
+        del os.environ["CFFT_B200_FAST_VARIANT"]
+    small = C.unordered.Plan(2048, C.unordered.Method.UserProvided(C.ordered.FftAlgo.Dif16, 256))
+    x = rand_c(rng, 96, n)
+    ref = O.UnorderedPlan(n, O.DIF16, 256)
+    want = ref.fwd(x, threads=8)
+    back = ref.inv(want, threads=8)
+    streams = [torch.cuda.Stream() for _ in range(4)]
+    bufs = [torch.from_numpy(x.copy()).cuda() for _ in streams]
+    filler = torch.view_as_complex(torch.rand(4096, 2048, 2, dtype=torch.float64, device="cuda")).contiguous()
+    torch.cuda.synchronize()
+    for _ in range(3):  # stress rounds: three persistent launches per stream, an ordinary kernel in between
+        for s, b in zip(streams, bufs):
+            with torch.cuda.stream(s):
+                plan.fwd(b)
+                if s is streams[0]:
+                    small.fwd(filler)
+                plan.inv(b)
+                plan.fwd(b)
+        torch.cuda.synchronize()
+        for b in bufs:
+            b.copy_(torch.from_numpy(x))
+    # one checked round
+    for s, b in zip(streams, bufs):
+        with torch.cuda.stream(s):
+            plan.fwd(b)
+    torch.cuda.synchronize()
+    for b in bufs:
+        assert bits_equal(b.cpu().numpy(), want)
+    for s, b in zip(streams, bufs):
+        with torch.cuda.stream(s):
+            plan.inv(b)
+    torch.cuda.synchronize()
+    for b in bufs:
+        assert bits_equal(b.cpu().numpy(), back)
+
+
 def test_random_plans_fuzz(C, torch):
     """Seeded fuzz over everything Plan::new accepts: random n, algo, base_n, batch and entry point
     (device / host-pageable), bit-exact against the oracle in both directions."""
