@@ -217,28 +217,19 @@ cfft_status build_fast_tables(cfft_plan *p)
         p->kernel_name = variant_name(p);
         return CFFT_OK;
     }
-    // n > 8192: group the levels (8, 8, ..., 8, [4|2]) into HBM passes of combined radix <= 256:
-    // the last group takes the tail level plus up to two radix-8 levels, the rest pair up.
+    // n > 8192: group the levels (8, 8, ..., 8, [4|2]) into as few HBM passes as possible, up to three
+    // levels (combined radix <= 512) per pass, the levels spread evenly over the passes (inner passes larger).
     const int nl = int(p->fast_levels.size());
-    std::vector<std::pair<int, int>> spans; // [first, last] level index per group, built back to front
-    int hi = nl - 1;
     {
-        int lo = hi;
-        const bool tail = p->fast_levels[size_t(hi)].radix != 8;
-        const int want = tail ? 3 : 2;
-        while (lo > 0 && hi - lo + 1 < want) lo--;
-        spans.push_back({lo, hi});
-        hi = lo - 1;
-    }
-    while (hi >= 0) {
-        const int lo = hi >= 1 ? hi - 1 : hi;
-        spans.push_back({lo, hi});
-        hi = lo - 1;
-    }
-    for (auto it = spans.rbegin(); it != spans.rend(); ++it) {
-        cfft_plan::FastGroup g{{1, 1, 1}, p->fast_levels[size_t(it->first)].span, it->first};
-        for (int i = it->first; i <= it->second; i++) g.radices[i - it->first] = p->fast_levels[size_t(i)].radix;
-        p->fast_groups.push_back(g);
+        const int ngroups = (nl + 2) / 3, small = nl / ngroups, extra = nl % ngroups;
+        int first = 0;
+        for (int gi = 0; gi < ngroups; gi++) {
+            const int len = small + (gi >= ngroups - extra ? 1 : 0);
+            cfft_plan::FastGroup g{{1, 1, 1}, p->fast_levels[size_t(first)].span, first};
+            for (int i = 0; i < len; i++) g.radices[i] = p->fast_levels[size_t(first + i)].radix;
+            p->fast_groups.push_back(g);
+            first += len;
+        }
     }
     // Variant 9: peel the largest tail of levels that a fused kernel covers (256 x tail radices <= 4096) and
     // group only the levels above it, three radix-8 levels (512 rows) per column pass at most.
