@@ -37,22 +37,27 @@ struct TileIo {
 
 // One stage on the 16 register values of a thread.  in_idx / out_idx: tile positions of element k of
 // butterfly j; tw_idx: twiddle index of (j, k >= 1) or nullptr-equivalent when the stage has none.
+// A partial tile (the last CTA of a ragged batch) is handled without per-butterfly liveness: loads from
+// HBM clamp the index into the valid range, butterflies past the end compute on garbage that only ever lands
+// in shared memory, and only the HBM stores of the last stage are guarded.
 template <int R, bool FWD, bool TW_IN, bool TW_OUT, class FIn, class FOut, class FTw>
 __device__ __forceinline__ void stage_body(const TileIo &io, const c64 *__restrict__ tw, FIn in_idx, FOut out_idx, FTw tw_idx,
                                            c64 (&v)[16])
 {
     constexpr int B = 16 / R;
-    bool live[B];
+    if (io.in_g) {
+        const uint32_t last = io.valid - 1;
 #pragma unroll
-    for (int j = 0; j < B; j++) {
-        live[j] = in_idx(j, 0) < io.valid;
+        for (int j = 0; j < B; j++)
 #pragma unroll
-        for (int k = 0; k < R; k++) {
-            const uint32_t i = in_idx(j, k);
-            v[j * R + k] = !live[j] ? mk(0.0, 0.0) : (io.in_g ? ld_stream(io.g + i) : io.s[swz(i)]);
-        }
+            for (int k = 0; k < R; k++) v[j * R + k] = ld_stream(io.g + min(in_idx(j, k), last));
+    } else {
+#pragma unroll
+        for (int j = 0; j < B; j++)
+#pragma unroll
+            for (int k = 0; k < R; k++) v[j * R + k] = io.s[swz(in_idx(j, k))];
+        if (!io.out_g) __syncthreads(); // in place: every read before any write
     }
-    if (!io.in_g && !io.out_g) __syncthreads(); // in place: every read before any write
 #pragma unroll
     for (int j = 0; j < B; j++) {
         c64 *x = &v[j * R];
@@ -66,16 +71,20 @@ __device__ __forceinline__ void stage_body(const TileIo &io, const c64 *__restri
             for (int k = 1; k < R; k++) x[k] = cmul(ld_tw(tw + tw_idx(j, k)), x[k]);
         }
     }
+    if (io.out_g) {
 #pragma unroll
-    for (int j = 0; j < B; j++)
+        for (int j = 0; j < B; j++)
 #pragma unroll
-        for (int k = 0; k < R; k++) {
-            const uint32_t i = out_idx(j, k);
-            if (live[j]) {
-                if (io.out_g) st_stream(io.g + i, v[j * R + k]);
-                else io.s[swz(i)] = v[j * R + k];
+            for (int k = 0; k < R; k++) {
+                const uint32_t i = out_idx(j, k);
+                if (i < io.valid) st_stream(io.g + i, v[j * R + k]);
             }
-        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < B; j++)
+#pragma unroll
+            for (int k = 0; k < R; k++) io.s[swz(out_idx(j, k))] = v[j * R + k];
+    }
 }
 
 __device__ __forceinline__ uint32_t lg2(uint32_t x) { return 31u - uint32_t(__clz(int(x))); }
@@ -122,10 +131,10 @@ __device__ __forceinline__ void run_stage(const Stage &st, uint32_t base_n, cons
     }
 }
 
-// (A ping-pong variant -- two copies of the tile, one barrier per stage, 168 registers without spills, three
-// CTAs per SM -- measured 10-25 % slower than this in-place form with four: more CTAs matter more.)
-template <bool FWD, int NT>
-__global__ void __launch_bounds__(NT, 512 / NT)
+// (Measured and rejected: a ping-pong variant -- two copies of the tile, one barrier per stage, three CTAs per
+// SM -- 10-25 % slower; 168 registers / 12 warps per SM to avoid the ~270 B of spills -- no better on balance.)
+template <bool FWD, int NT, int WPS = 16>
+__global__ void __launch_bounds__(NT, WPS * 32 / NT)
 c64_regs_kernel(c64 *__restrict__ data, uint64_t total, uint32_t base_n, StageProgram prog, const c64 *__restrict__ tw_ref,
                 const c64 *__restrict__ tw_top)
 {
@@ -149,7 +158,7 @@ c64_regs_kernel(c64 *__restrict__ data, uint64_t total, uint32_t base_n, StagePr
     }
 }
 
-template <bool FWD, int NT>
+template <bool FWD, int NT, int WPS = 16>
 cudaError_t launch_regs_t(const StageProgram &prog, c64 *data, uint64_t total, uint32_t base_n, const c64 *tw_ref,
                           const c64 *tw_top, cudaStream_t stream)
 {
@@ -160,13 +169,13 @@ cudaError_t launch_regs_t(const StageProgram &prog, c64 *data, uint64_t total, u
         int dev = 0;
         cudaGetDevice(&dev);
         if (configured_device != dev) {
-            cudaError_t e = cudaFuncSetAttribute(c64_regs_kernel<FWD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            cudaError_t e = cudaFuncSetAttribute(c64_regs_kernel<FWD, NT, WPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
             if (e != cudaSuccess) return e;
             configured_device = dev;
         }
     }
     const uint64_t tiles = (total + TILE - 1) / TILE;
-    c64_regs_kernel<FWD, NT><<<unsigned(tiles), NT, smem, stream>>>(data, total, base_n, prog, tw_ref, tw_top);
+    c64_regs_kernel<FWD, NT, WPS><<<unsigned(tiles), NT, smem, stream>>>(data, total, base_n, prog, tw_ref, tw_top);
     count_launch();
     return cudaGetLastError();
 }
