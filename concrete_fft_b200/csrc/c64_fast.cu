@@ -396,9 +396,12 @@ c64_rows256_std_kernel(const c64 *__restrict__ src, c64 *__restrict__ dst, uint3
             st_stream(dst + row_base + size_t(hi) * m + lo0 + dd, s[dd * PITCH + hi]);
     } else {
         const int dd = threadIdx.x % TW, h0 = threadIdx.x / TW;
-#pragma unroll 4
-        for (int hi = h0; hi < 256; hi += 16 * TW / TW)
-            s[dd * PITCH + hi] = ld_stream(src + row_base + size_t(hi) * m + lo0 + dd);
+        // all 16 gathers of a thread in flight before the first shared-memory store (these are 256-byte
+        // segments m c64 apart: latency, not bandwidth, is what a shorter batch would expose)
+#pragma unroll
+        for (int i = 0; i < 16; i++) v[i] = ld_stream(src + row_base + size_t(h0 + 16 * i) * m + lo0 + dd);
+#pragma unroll
+        for (int i = 0; i < 16; i++) s[dd * PITCH + h0 + 16 * i] = v[i];
         __syncthreads();
         base256<false, false, true>(s + d * PITCH, s + d * PITCH, dst + row_base + size_t(c) * 256, tw_base, lane16, v);
     }
