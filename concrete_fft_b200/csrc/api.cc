@@ -761,6 +761,32 @@ cfft_status cfft_f128_cplx_mul_scale(int device, double *l_re0, double *l_re1, d
     return CFFT_OK;
 }
 
+static cfft_status run_pointwise(int device, void *acc, void *a, const void *b, uint64_t len, void *stream)
+{
+    if (len && (!a || !b)) return fail(CFFT_EINVAL, "null buffer");
+    if ((reinterpret_cast<uintptr_t>(acc) | reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15)
+        return fail(CFFT_EINVAL, "device buffers must be 16-byte aligned");
+    cfft_status st = check_device(device);
+    if (st != CFFT_OK) return st;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
+    cudaError_t e = launch_c64_pointwise(static_cast<double2 *>(acc), static_cast<double2 *>(a), static_cast<const double2 *>(b), len,
+                                         static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "c64 pointwise product launch");
+    return CFFT_OK;
+}
+
+cfft_status cfft_c64_mul_assign(int device, void *lhs_dev, const void *rhs_dev, uint64_t len, void *stream)
+{
+    return run_pointwise(device, nullptr, lhs_dev, rhs_dev, len, stream);
+}
+
+cfft_status cfft_c64_mul_add_assign(int device, void *acc_dev, const void *a_dev, const void *b_dev, uint64_t len, void *stream)
+{
+    if (len && !acc_dev) return fail(CFFT_EINVAL, "null buffer");
+    return run_pointwise(device, acc_dev, const_cast<void *>(a_dev), b_dev, len, stream);
+}
+
 cfft_status cfft_unordered_fwd_monomial(const cfft_plan *p, uint64_t degree, void *dev_buf, void *stream)
 {
     if (!p || p->kind != KIND_UNORDERED) return fail(CFFT_EINVAL, "not an unordered plan");

@@ -245,6 +245,19 @@ __global__ void permute_kernel(const c64 *__restrict__ src, c64 *__restrict__ ds
     }
 }
 
+// ---- element-wise Fourier-domain products (num_complex `*`, `+`: no FMA) ---------------------------
+template <bool ACC>
+__global__ void __launch_bounds__(256)
+c64_pointwise_kernel(c64 *out, const c64 *a, const c64 *__restrict__ b, uint64_t len) // out may be a
+{
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += uint64_t(gridDim.x) * blockDim.x) {
+        const c64 x = a[i], y = b[i];
+        c64 r = mk(__dsub_rn(__dmul_rn(x.x, y.x), __dmul_rn(x.y, y.y)), __dadd_rn(__dmul_rn(x.x, y.y), __dmul_rn(x.y, y.x)));
+        if (ACC) r = cadd(out[i], r);
+        out[i] = r;
+    }
+}
+
 template <bool FWD>
 cudaError_t launch_global_stage(const Stage &st, c64 *data, uint64_t total, const c64 *tw, cudaStream_t stream)
 {
@@ -351,6 +364,18 @@ cudaError_t launch_c64_exact(const cfft_plan *plan, bool inverse, double2 *data,
         if (full.st[i].kind == ST_TOP && full.st[i].span > tile)
             if ((e = launch_global_stage<false>(full.st[i], data, total, tw, stream)) != cudaSuccess) return e;
     return cudaSuccess;
+}
+
+// acc == nullptr: a <- a * b (a is `out`); else acc <- acc + a * b
+cudaError_t launch_c64_pointwise(double2 *acc, double2 *a, const double2 *b, uint64_t len, cudaStream_t stream)
+{
+    if (len == 0) return cudaSuccess;
+    uint64_t blocks = (len + 255) / 256;
+    if (blocks > 148ull * 32) blocks = 148ull * 32;
+    if (acc) c64_pointwise_kernel<true><<<unsigned(blocks), 256, 0, stream>>>(acc, a, b, len);
+    else c64_pointwise_kernel<false><<<unsigned(blocks), 256, 0, stream>>>(a, a, b, len);
+    count_launch();
+    return cudaGetLastError();
 }
 
 cudaError_t launch_monomial(const cfft_plan *plan, uint64_t degree, double2 *data, cudaStream_t stream)

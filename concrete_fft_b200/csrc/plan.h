@@ -93,6 +93,7 @@ namespace cfft {
 // kernels (c64_tile.cu)
 cudaError_t launch_c64_exact(const cfft_plan *plan, bool inverse, double2 *data, uint64_t batch, cudaStream_t st);
 cudaError_t launch_monomial(const cfft_plan *plan, uint64_t degree, double2 *data, cudaStream_t st);
+cudaError_t launch_c64_pointwise(double2 *acc, double2 *a, const double2 *b, uint64_t len, cudaStream_t st);
 cudaError_t launch_permute(const cfft_plan *plan, bool to_standard, const double2 *src, double2 *dst,
                            uint64_t batch, cudaStream_t st);
 // kernels (c64_regs.cu): any stage program on a tile of 2048 / 4096 elements

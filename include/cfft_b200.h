@@ -201,6 +201,18 @@ cfft_status cfft_f128_cplx_mul_scale(int device, double *l_re0, double *l_re1, d
                                      const double *r_im0, const double *r_im1, double factor,
                                      uint64_t len, void *stream);
 
+/* ---- c64 element-wise products in the Fourier domain ------------------------------------
+ * "The only operations that are performed in the Fourier domain are elementwise" (README.md:10-17,
+ * src/lib.rs:9-16): what a caller does between fwd and inv of a convolution / external product.  The
+ * reference leaves it to the caller's `c64` arithmetic, so the semantics are those of num_complex's
+ * `*` and `+` on Complex64 (the type src/lib.rs:84 re-exports): re = a.re*b.re - a.im*b.im,
+ * im = a.re*b.im + a.im*b.re, every operation individually rounded (no FMA); bit-exact.  Element order is
+ * irrelevant as long as both operands come from the same plan.  Device pointers, stream ordered. */
+cfft_status cfft_c64_mul_assign(int device, void *lhs_dev, const void *rhs_dev, uint64_t len, void *stream);
+/* acc[i] += a[i] * b[i]  (product as above, then a component-wise add) */
+cfft_status cfft_c64_mul_add_assign(int device, void *acc_dev, const void *a_dev, const void *b_dev, uint64_t len,
+                                    void *stream);
+
 /* ---- diagnostics ------------------------------------------------------------------- */
 
 const char *cfft_status_string(cfft_status st);

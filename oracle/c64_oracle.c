@@ -726,3 +726,20 @@ size_t orc_bit_rev_twice_inv(unsigned nbits, unsigned base_nbits, size_t i)
     size_t i_rev = (i & ~bottom_mask) | bottom_bits;
     return orc_bit_rev(nbits, i_rev);
 }
+
+/* Fourier-domain element-wise product as a Rust caller writes it on `c64` values (num_complex Mul / Add:
+ * each operation individually rounded; this file is built with -ffp-contract=off). */
+void orc_c64_pointwise(double *acc, double *a, const double *b, size_t len)
+{
+    for (size_t i = 0; i < len; i++) {
+        const double ar = a[2 * i], ai = a[2 * i + 1], br = b[2 * i], bi = b[2 * i + 1];
+        const double re = ar * br - ai * bi, im = ar * bi + ai * br;
+        if (acc) {
+            acc[2 * i] = acc[2 * i] + re;
+            acc[2 * i + 1] = acc[2 * i + 1] + im;
+        } else {
+            a[2 * i] = re;
+            a[2 * i + 1] = im;
+        }
+    }
+}

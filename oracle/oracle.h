@@ -88,6 +88,9 @@ void orc_f128_binary_op(int op, const double *a_hi, const double *a_lo, const do
                         double *out_hi, double *out_lo, size_t len);
 /* lhs <- (lhs * rhs) * factor on planar double-double complex arrays, scalar cplx_mul
  * (src/fft128/mod.rs:310-326) then four f64 scalings, exactly the loop at src/fft128/mod.rs:2033-2047 */
+/* element-wise c64 products with num_complex's `*` / `+` semantics (no FMA): lhs <- lhs * rhs, or
+ * acc <- acc + a * b when acc != NULL (the caller-side Fourier-domain step, README.md:10-17) */
+void orc_c64_pointwise(double *acc, double *a, const double *b, size_t len);
 void orc_f128_cplx_mul_scale(double *l_re0, double *l_re1, double *l_im0, double *l_im1, const double *r_re0,
                              const double *r_re1, const double *r_im0, const double *r_im1, double factor, size_t len);
 

@@ -352,4 +352,17 @@ pub mod device {
     pub unsafe fn c64_inv(plan: *const ffi::cfft_plan, dev_buf: *mut c_void, batch: u64, stream: *mut c_void) {
         ffi::check(ffi::cfft_c64_inv(plan, dev_buf, batch, stream));
     }
+    /// `lhs[i] *= rhs[i]` on `len` device c64 (the Fourier-domain step between `fwd` and `inv`; the bits of
+    /// `num_complex`'s `*`).
+    /// # Safety
+    /// Both pointers must address `len` c64 on `device`; `stream` is a `cudaStream_t`.
+    pub unsafe fn c64_mul_assign(device: i32, lhs: *mut c_void, rhs: *const c_void, len: u64, stream: *mut c_void) {
+        ffi::check(ffi::cfft_c64_mul_assign(device, lhs, rhs, len, stream));
+    }
+    /// `acc[i] += a[i] * b[i]`.
+    /// # Safety
+    /// See [`c64_mul_assign`].
+    pub unsafe fn c64_mul_add_assign(device: i32, acc: *mut c_void, a: *const c_void, b: *const c_void, len: u64, stream: *mut c_void) {
+        ffi::check(ffi::cfft_c64_mul_add_assign(device, acc, a, b, len, stream));
+    }
 }

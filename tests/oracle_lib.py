@@ -59,6 +59,7 @@ def lib(fast=False):
         "orc_f128_twiddles": (vp, [vp, ci]),
         "orc_f128_binary_op": (None, [ci, vp, vp, vp, vp, vp, vp, sz]),
         "orc_f128_cplx_mul_scale": (None, [vp, vp, vp, vp, vp, vp, vp, vp, dbl, sz]),
+        "orc_c64_pointwise": (None, [vp, vp, vp, sz]),
     }
     for k, (res, args) in sig.items():
         f = getattr(L, k)
@@ -205,3 +206,15 @@ def f128_cplx_mul_scale(lhs, rhs, factor):
     R = [np.ascontiguousarray(x, dtype=np.float64) for x in rhs]
     lib().orc_f128_cplx_mul_scale(*[_ptr(x) for x in L], *[_ptr(x) for x in R], float(factor), L[0].size)
     return L
+
+
+def c64_pointwise(a, b, acc=None):
+    """a * b (acc is None) or acc + a * b, element-wise, num_complex semantics (no FMA)."""
+    A = np.ascontiguousarray(a, dtype=np.complex128).copy()
+    B = np.ascontiguousarray(b, dtype=np.complex128)
+    if acc is None:
+        lib().orc_c64_pointwise(None, _ptr(A), _ptr(B), A.size)
+        return A
+    C = np.ascontiguousarray(acc, dtype=np.complex128).copy()
+    lib().orc_c64_pointwise(_ptr(C), _ptr(A), _ptr(B), A.size)
+    return C

@@ -325,13 +325,40 @@ def test_negacyclic_product_through_unordered_plan(C, torch, npoly, base_n):
     fb = torch.from_numpy(fold(b)).cuda()
     plan.fwd(fa)
     plan.fwd(fb)
-    fa.mul_(fb)  # same permutation on both operands: the order never has to be undone
+    C.pointwise.mul_assign(fa, fb)  # same permutation on both operands: the order never has to be undone
     plan.inv(fa)
     torch.cuda.synchronize()
     z = fa.cpu().numpy() / n * np.conj(twist)
     got = np.concatenate([z.real, z.imag], axis=1)
     assert np.array_equal(np.rint(got).astype(np.int64), want.astype(np.int64))
     assert np.abs(got - want.astype(np.float64)).max() < 0.05  # |c| < 2^42: far inside f64
+
+
+def test_pointwise_products_bit_exact(C, torch):
+    """cfft_c64_mul_assign / cfft_c64_mul_add_assign against the oracle's restatement of num_complex's `*`
+    and `+` (no FMA), on random data of ragged lengths plus signed zeros, infinities and NaN."""
+    rng = np.random.default_rng(31)
+    for length in (1, 7, 4096, 1000003):
+        a = rand_c(rng, length) - (0.5 + 0.5j)
+        b = rand_c(rng, length) * 1e3
+        acc = rand_c(rng, length)
+        if length >= 7:
+            a[:6] = [0.0, -0.0, complex(np.inf, 1.0), complex(1.0, -np.inf), complex(np.nan, 0.0), 1e308 + 1e308j]
+            b[:6] = [-1.0 + 0.0j, complex(0.0, -0.0), 0.0j, 2.0 + 3.0j, 1.0 + 1.0j, 10.0 + 10.0j]
+        da, db, dc = (torch.from_numpy(v.copy()).cuda() for v in (a, b, acc))
+        C.pointwise.mul_add_assign(dc, da, db)
+        C.pointwise.mul_assign(da, db)
+        torch.cuda.synchronize()
+        def same(got, want):  # bit-exact, except that NaN payloads / signs are not IEEE-specified (x86 vs GPU differ)
+            g, w = got.view(np.float64), want.view(np.float64)
+            nan = np.isnan(w)
+            return np.array_equal(np.isnan(g), nan) and np.array_equal(g[~nan].view(np.uint64), w[~nan].view(np.uint64))
+
+        with np.errstate(all="ignore"):
+            assert same(da.cpu().numpy(), O.c64_pointwise(a, b)), length
+            assert same(dc.cpu().numpy(), O.c64_pointwise(a, b, acc)), length
+    with pytest.raises(C.PanicError):
+        C.pointwise.mul_assign(da, db[:5])
 
 
 @pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096, 8192])
