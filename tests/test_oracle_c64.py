@@ -193,3 +193,17 @@ def test_avx2_build_same_bits_as_scalar(algo):
         x = rand_c(rng, 2, n)
         assert np.array_equal(O.OrderedPlan(n, algo).fwd(x).view(np.uint64), O.OrderedPlan(n, algo, fast=True).fwd(x).view(np.uint64))
         assert np.array_equal(O.OrderedPlan(n, algo).inv(x).view(np.uint64), O.OrderedPlan(n, algo, fast=True).inv(x).view(np.uint64))
+
+
+def test_pointwise_product_is_num_complex_arithmetic():
+    """orc_c64_pointwise restates what a Rust caller's `a * b` / `acc + a * b` on Complex64 computes
+    (num_complex: re = a.re*b.re - a.im*b.im, im = a.re*b.im + a.im*b.re, each operation rounded, no FMA):
+    checked against the same expression in Python floats, element by element."""
+    rng = np.random.default_rng(12)
+    a, b, acc = rand_c(rng, 257) - 0.5, rand_c(rng, 257) * 3.0, rand_c(rng, 257)
+    prod, fused = O.c64_pointwise(a, b), O.c64_pointwise(a, b, acc)
+    for i in range(a.size):
+        ar, ai, br, bi = float(a[i].real), float(a[i].imag), float(b[i].real), float(b[i].imag)
+        re, im = ar * br - ai * bi, ar * bi + ai * br
+        assert (prod[i].real, prod[i].imag) == (re, im)
+        assert (fused[i].real, fused[i].imag) == (float(acc[i].real) + re, float(acc[i].imag) + im)
