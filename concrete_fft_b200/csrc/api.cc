@@ -389,8 +389,8 @@ cfft_status cfft_ordered_plan_create(cfft_plan **out, int device, uint64_t n, in
         init_unordered_twiddles(n, 256, 16, p->h_tw[0], p->h_tw[1]);
         build_c64_programs(p);
         st = upload_c64(p);
-        if (st == CFFT_OK) st = build_top_planar(p);
         if (st == CFFT_OK) st = build_fast_tables(p);
+        if (st == CFFT_OK && p->fast_variant == 0) st = build_top_planar(p); // only the generic kernels read these copies
         if (st == CFFT_OK && method == CFFT_METHOD_MEASURE && !getenv("CFFT_B200_NO_AUTOTUNE")) st = cfft_plan_autotune(p, 0);
         if (st != CFFT_OK) { cfft_plan_destroy(p); return st; }
         *out = p;
@@ -406,8 +406,8 @@ cfft_status cfft_ordered_plan_create(cfft_plan **out, int device, uint64_t n, in
     append_base_stages(f, algo, n, uint32_t(n));
     append_base_stages(v, algo, n, uint32_t(n));
     st = upload_c64(p);
-    if (st == CFFT_OK) st = build_top_planar(p);
     if (st == CFFT_OK) st = build_fast_tables(p);
+    if (st == CFFT_OK && p->fast_variant == 0) st = build_top_planar(p); // only the generic kernels read these copies
     if (st != CFFT_OK) { cfft_plan_destroy(p); return st; }
     *out = p;
     return CFFT_OK;
@@ -445,8 +445,8 @@ cfft_status cfft_unordered_plan_create(cfft_plan **out, int device, uint64_t n, 
     init_unordered_twiddles(n, base_n, size_t(algo_radix(base_algo)), p->h_tw[0], p->h_tw[1]);
     build_c64_programs(p);
     st = upload_c64(p);
-    if (st == CFFT_OK) st = build_top_planar(p);
     if (st == CFFT_OK) st = build_fast_tables(p);
+    if (st == CFFT_OK && p->fast_variant == 0) st = build_top_planar(p); // only the generic kernels read these copies
     if (st == CFFT_OK && method == CFFT_METHOD_MEASURE && !getenv("CFFT_B200_NO_AUTOTUNE")) st = cfft_plan_autotune(p, 0);
     if (st != CFFT_OK) { cfft_plan_destroy(p); return st; }
     *out = p;
