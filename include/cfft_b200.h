@@ -98,7 +98,10 @@ cfft_status cfft_plan_scratch_req(const cfft_plan *plan, uint64_t *bytes, uint64
 int cfft_plan_kind(const cfft_plan *plan);
 int cfft_plan_device(const cfft_plan *plan);
 
-/* Which kernel family serves this plan: "exact-tile", "fast-..." (see DESIGN.md). */
+/* Which kernel family serves this plan: "fast-b256-regs", "fast-b256-cluster", "fast-b256-column+rows",
+ * "fast-b256-column+fused-rows", "fast-b256-persistent-2pass", "ordered-b256-regs-std",
+ * "ordered-b256-column+rows-std", "ord16-regs", "exact-regs", "exact-tile", "f128-radix8-tile", with
+ * "/L2-chunked" appended when the passes run chunk by chunk. */
 const char *cfft_plan_kernel_name(const cfft_plan *plan);
 
 /* ---- on-device autotune ------------------------------------------------------------ */
