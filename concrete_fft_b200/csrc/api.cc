@@ -787,6 +787,27 @@ cfft_status cfft_c64_mul_add_assign(int device, void *acc_dev, const void *a_dev
     return run_pointwise(device, acc_dev, const_cast<void *>(a_dev), b_dev, len, stream);
 }
 
+cfft_status cfft_c64_fwd_mul_inv(const cfft_plan *p, const void *a_dev, uint64_t k_terms, const void *b_dev,
+                                 uint64_t b_row_stride, void *out_dev, uint64_t batch, void *stream)
+{
+    if (!p || p->kind == KIND_F128) return fail(CFFT_EINVAL, "not a c64 plan");
+    if (k_terms == 0) return fail(CFFT_EINVAL, "k_terms must be >= 1");
+    if (batch && (!a_dev || !b_dev || !out_dev)) return fail(CFFT_EINVAL, "null buffer");
+    if ((reinterpret_cast<uintptr_t>(a_dev) | reinterpret_cast<uintptr_t>(b_dev) | reinterpret_cast<uintptr_t>(out_dev)) & 15)
+        return fail(CFFT_EINVAL, "device buffers must be 16-byte aligned (128-bit accesses)");
+    if (b_row_stride != 0 && b_row_stride < k_terms * p->n) return fail(CFFT_EINVAL, "b_row_stride must be 0 (b shared by every row) or >= k_terms * n");
+    if (out_dev == a_dev && k_terms != 1) return fail(CFFT_EINVAL, "out may alias a only when k_terms == 1");
+    if (out_dev == b_dev) return fail(CFFT_EINVAL, "out must not alias b");
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
+    cudaError_t e = launch_c64_fwd_mul_inv(p, static_cast<const double2 *>(a_dev), k_terms, static_cast<const double2 *>(b_dev),
+                                           b_row_stride, static_cast<double2 *>(out_dev), batch, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "c64 fwd-mul-inv launch");
+    return CFFT_OK;
+}
+
+int cfft_plan_has_fused_mul_kernel(const cfft_plan *p) { return p && p->kind != KIND_F128 && fused_mul_kernel_available(p) ? 1 : 0; }
+
 cfft_status cfft_unordered_fwd_monomial(const cfft_plan *p, uint64_t degree, void *dev_buf, void *stream)
 {
     if (!p || p->kind != KIND_UNORDERED) return fail(CFFT_EINVAL, "not an unordered plan");

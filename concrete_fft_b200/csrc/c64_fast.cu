@@ -363,6 +363,185 @@ cudaError_t launch_cfg(bool inverse, c64 *data, uint64_t batch, const FastTables
     return cudaGetLastError();
 }
 
+// ---- fwd -> point-wise multiply-accumulate -> inv in ONE kernel ----------
+// out[r] = inv( sum_k fwd(a[r][k]) (.) b[k] ): the external-product / convolution step of a caller that keeps
+// its data on the GPU.  As three library calls per term (cfft_c64_fwd, cfft_c64_mul_[add_]assign, cfft_c64_inv)
+// a K = 1 product moves 7 x 16 n bytes through HBM; here it moves 3 x 16 n (2 x 16 n when b is shared by the
+// batch and therefore L2-resident), and K terms cost (2K + 1) x 16 n instead of (5K + 2) x 16 n.  The forward
+// transform of a term ends with every thread holding 16 Fourier coefficients in registers at exactly the
+// positions the inverse base FFT starts from (blk * 256 + lane16 + 16 j), so the product and the running sum
+// never leave the SM: the sum of K > 1 terms lives in 16 more c64 registers per thread.  Butterflies, twiddles
+// and the order of every rounded operation are those of the separate kernels, the product is num_complex's (no FMA), terms are added in the order k = 0, 1, ... =>
+// bit-identical to the composition of the library calls (tests/test_gpu_c64.py).
+template <bool FWD>
+__device__ __forceinline__ void base256_core(c64 *__restrict__ sm_blk, const c64 *__restrict__ tw_planar, int lane16, c64 (&v)[16])
+{
+    const unsigned hmask = 0xFFFFu << (threadIdx.x & 16);
+    bf16<FWD>(v);
+#pragma unroll
+    for (int k = 1; k < 16; k++) v[k] = cmul(ld_tw(tw_planar + lane16 + 16 * k), v[k]);
+    __syncwarp(hmask);
+#pragma unroll
+    for (int k = 0; k < 16; k++) sm_blk[16 * lane16 + (k ^ lane16)] = v[k];
+    __syncwarp(hmask);
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = sm_blk[16 * k + (lane16 ^ k)];
+    bf16<FWD>(v);
+}
+
+// num_complex `*` (src/lib.rs:84 re-exports the type): four products, one subtraction, one addition, no FMA
+__device__ __forceinline__ c64 cmul_nc(c64 x, c64 y)
+{
+    return mk(__dsub_rn(__dmul_rn(x.x, y.x), __dmul_rn(x.y, y.y)), __dadd_rn(__dmul_rn(x.x, y.y), __dmul_rn(x.y, y.x)));
+}
+
+// MULTI = false: exactly one term, nothing to accumulate: the register budget and occupancy of the plain kernel.
+// MULTI = true: the running sum of the terms lives in 16 more c64 registers per thread (168 registers, three CTAs
+// of 128 threads per SM); a shared-memory accumulator was measured first and lost (the L1 / shared-memory pipe is
+// already the busiest unit of the plain kernel, and a second tile per CTA leaves too little L1 for the twiddles).
+template <int N, bool MULTI> struct FusedMulCfg {
+    static constexpr int NT = FastCfg<N>::NT;
+    static constexpr int MINB = !MULTI ? FastCfg<N>::MINB : (NT <= 128 ? 3 : 1);
+};
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <int N, int R1, int R2, bool MULTI>
+__global__ void __launch_bounds__(FusedMulCfg<N, MULTI>::NT, FusedMulCfg<N, MULTI>::MINB)
+c64_fwd_mul_inv_kernel(const c64 *__restrict__ a, const c64 *__restrict__ b, c64 *__restrict__ out, uint64_t batch,
+                       uint32_t kterms, uint64_t b_row_stride, FastTables tf, FastTables ti, uint32_t flags)
+{
+    static_assert(N == 256 * R1 * R2, "n = 256 * R1 * R2");
+    using Cfg = FastCfg<N>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int row = threadIdx.x / Cfg::TPR, t = threadIdx.x % Cfg::TPR;
+    const uint64_t grow = uint64_t(blockIdx.x) * Cfg::ROWS + row;
+    const bool active = grow < batch; // inactive rows compute on row 0's data and store nothing
+    const uint64_t r = active ? grow : 0;
+    const c64 *ga = a + r * kterms * N;
+    const c64 *gb = b + r * b_row_stride;
+    c64 *go = out + r * N;
+    c64 *s = reinterpret_cast<c64 *>(smem_raw) + row * N;
+    c64 v[16];
+    c64 acc[MULTI ? 16 : 1];
+    constexpr int N2 = N / R1;
+    constexpr bool FUSED = (R1 == 8 && R2 == 2);
+    const int blk = t / 16, lane16 = t % 16;
+    c64 *sb = s + blk * 256;
+
+    // the 16 n bytes of b this row's first term needs: request them now, they are consumed last
+    // (a row's threads cover its n c64 = n / 8 lines of 128 bytes with 2 requests each)
+    if (flags & 1) {
+#pragma unroll
+        for (int i = 0; i < 2; i++) prefetch_l2(gb + (t + Cfg::TPR * i) * 8);
+    }
+
+    const uint32_t kt = MULTI ? kterms : 1;
+    for (uint32_t k = 0; k < kt; k++) {
+        const c64 *g = ga + uint64_t(k) * N;
+        if (MULTI && k + 1 < kt && (flags & 2)) { // next term's input and multiplier on their way to L2 while this term computes
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                prefetch_l2(g + N + (t + Cfg::TPR * i) * 8);
+                prefetch_l2(gb + uint64_t(k + 1) * N + (t + Cfg::TPR * i) * 8);
+            }
+        }
+        if (MULTI && k > 0 && R1 > 1) __syncthreads(); // the previous term's base FFTs have consumed the tile
+        if (FUSED) {
+            level_8x2<N, Cfg::TPR, true>(g, nullptr, s, tf.top1, tf.top2, t, v);
+            __syncthreads();
+        } else if (R1 > 1) {
+            level<R1, N, Cfg::TPR, true, true, false>(g, s, tf.top1, t, v);
+            __syncthreads();
+        }
+        if (R2 > 1 && !FUSED) {
+            level<R2, N2, Cfg::TPR, true, false, false>(s, s, tf.top2, t, v);
+            __syncthreads();
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = R1 > 1 ? sb[lane16 + 16 * j] : ld_stream(g + blk * 256 + lane16 + 16 * j);
+        base256_core<true>(sb, tf.base, lane16, v);
+        const c64 *bk = gb + uint64_t(k) * N + blk * 256 + lane16;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const c64 p = cmul_nc(v[j], ld_stream(bk + 16 * j));
+            if (!MULTI) v[j] = p;
+            else acc[j] = k == 0 ? p : cadd(acc[j], p);
+        }
+    }
+    if (MULTI) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = acc[j];
+    }
+
+    base256_core<false>(sb, ti.base, lane16, v);
+    if (R1 == 1) {
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) st_stream(go + blk * 256 + lane16 + 16 * j, v[j]);
+        }
+        return;
+    }
+    __syncwarp(0xFFFFu << (threadIdx.x & 16));
+#pragma unroll
+    for (int j = 0; j < 16; j++) sb[lane16 + 16 * j] = v[j];
+    if (FUSED) {
+        __syncthreads();
+        if (active) level_8x2<N, Cfg::TPR, false>(nullptr, go, s, ti.top1, ti.top2, t, v);
+    } else {
+        if (R2 > 1) {
+            __syncthreads();
+            level<R2, N2, Cfg::TPR, false, false, false>(s, s, ti.top2, t, v);
+        }
+        __syncthreads();
+        if (active) level<R1, N, Cfg::TPR, false, false, true>(s, go, ti.top1, t, v);
+    }
+}
+
+template <int N, int R1, int R2>
+cudaError_t launch_fused_mul(const c64 *a, const c64 *b, c64 *out, uint64_t batch, uint32_t kterms, uint64_t b_row_stride,
+                             const FastTables &tf, const FastTables &ti, cudaStream_t stream)
+{
+    using Cfg = FastCfg<N>;
+    const size_t smem = size_t(Cfg::ROWS) * N * sizeof(c64);
+    const uint64_t ctas = (batch + Cfg::ROWS - 1) / Cfg::ROWS;
+    auto k1 = c64_fwd_mul_inv_kernel<N, R1, R2, false>;
+    auto km = c64_fwd_mul_inv_kernel<N, R1, R2, true>;
+    if (smem > 48 * 1024) {
+        static thread_local int configured_device = -1;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (configured_device != dev) {
+            cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(km, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            if (e != cudaSuccess) return e;
+            configured_device = dev;
+        }
+    }
+    static const int env_flags = [] { const char *e = getenv("CFFT_B200_FUSED_MUL_FLAGS"); return e ? atoi(e) : 3; }();
+    const uint32_t flags = uint32_t(env_flags) & 3;
+    if (kterms == 1 && !(env_flags & 4)) k1<<<unsigned(ctas), Cfg::NT, smem, stream>>>(a, b, out, batch, kterms, b_row_stride, tf, ti, flags);
+    else km<<<unsigned(ctas), Cfg::NT, smem, stream>>>(a, b, out, batch, kterms, b_row_stride, tf, ti, flags);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// out[r][i] = a[r * a_row_stride + i] * b[r * b_row_stride + i] (+ out[r][i] when ACC): the point-wise step of the
+// composed path below, with the operand b optionally shared by every row (stride 0).
+template <bool ACC>
+__global__ void __launch_bounds__(256)
+c64_pointwise_rows_kernel(c64 *__restrict__ out, const c64 *__restrict__ a, const c64 *__restrict__ b, uint32_t n, uint64_t rows,
+                          uint64_t b_row_stride)
+{
+    const uint64_t total = rows * n;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint64_t rr = i / n;
+        const uint32_t c = uint32_t(i - rr * n);
+        c64 p = cmul_nc(a[i], b[rr * b_row_stride + c]);
+        if (ACC) p = cadd(out[i], p);
+        out[i] = p;
+    }
+}
 
 // ---- standard-order ("ordered") transforms above the reference's 2^10 cap ---------------------
 // X_i of an n = 256 M transform sits, in the unordered layout, at row c = bitrev_L(i mod M),
@@ -467,6 +646,73 @@ cudaError_t workspace_pool(int device, cudaMemPool_t *out)
 bool fast_b256_supported(uint64_t n, int base_algo, uint64_t base_n)
 {
     return base_algo == 6 /* Dif16 */ && base_n == 256 && n >= 256 && n <= (uint64_t{1} << 26);
+}
+
+// out[r] = inv( sum_k fwd(a[r][k]) (.) b[r * b_row_stride + k n ..] ), r < batch, k < kterms.
+//   * plans of the (Dif16, 256) family with n <= 4096: one launch of c64_fwd_mul_inv_kernel;
+//   * every other c64 plan: the same arithmetic composed from the plan's own kernels through a stream-ordered
+//     workspace (strided copy of term k -> fwd -> point-wise into out, then inv on out), batch in chunks of
+//     <= 256 MiB.  Same bits either way.
+bool fused_mul_kernel_available(const cfft_plan *plan)
+{
+    return plan->d_fast_tw[0] && plan->n >= 256 && plan->n <= 4096 &&
+           (plan->fast_variant == 1 || plan->fast_variant == 2 || plan->fast_variant == 4);
+}
+
+cudaError_t launch_c64_fwd_mul_inv(const cfft_plan *plan, const double2 *a, uint64_t kterms, const double2 *b,
+                                   uint64_t b_row_stride, double2 *out, uint64_t batch, cudaStream_t stream)
+{
+    if (batch == 0 || kterms == 0) return cudaSuccess;
+    const bool force_composed = getenv("CFFT_B200_FUSED_MUL_COMPOSED") != nullptr; // testing hook, read per call
+    if (fused_mul_kernel_available(plan) && !force_composed && kterms <= 0xFFFFFFFFull) {
+        FastTables tf, ti;
+        const c64 *bf = plan->d_fast_tw[0], *bi = plan->d_fast_tw[1];
+        tf.top1 = plan->fast_levels.size() > 0 ? bf + plan->fast_levels[0].off : bf;
+        tf.top2 = plan->fast_levels.size() > 1 ? bf + plan->fast_levels[1].off : bf;
+        tf.base = bf + plan->fast_base_off;
+        ti.top1 = plan->fast_levels.size() > 0 ? bi + plan->fast_levels[0].off : bi;
+        ti.top2 = plan->fast_levels.size() > 1 ? bi + plan->fast_levels[1].off : bi;
+        ti.base = bi + plan->fast_base_off;
+        const uint32_t kt = uint32_t(kterms);
+        switch (plan->n) {
+        case 256: return launch_fused_mul<256, 1, 1>(a, b, out, batch, kt, b_row_stride, tf, ti, stream);
+        case 512: return launch_fused_mul<512, 2, 1>(a, b, out, batch, kt, b_row_stride, tf, ti, stream);
+        case 1024: return launch_fused_mul<1024, 4, 1>(a, b, out, batch, kt, b_row_stride, tf, ti, stream);
+        case 2048: return launch_fused_mul<2048, 8, 1>(a, b, out, batch, kt, b_row_stride, tf, ti, stream);
+        case 4096: return launch_fused_mul<4096, 8, 2>(a, b, out, batch, kt, b_row_stride, tf, ti, stream);
+        default: return cudaErrorInvalidValue;
+        }
+    }
+    const uint64_t n = plan->n, row_bytes = n * sizeof(c64);
+    uint64_t chunk_rows = (uint64_t{256} << 20) / row_bytes;
+    if (chunk_rows < 1) chunk_rows = 1;
+    if (chunk_rows > batch) chunk_rows = batch;
+    cudaMemPool_t pool = nullptr;
+    cudaError_t e = workspace_pool(plan->device, &pool);
+    if (e != cudaSuccess) return e;
+    c64 *ws = nullptr;
+    e = cudaMallocFromPoolAsync(reinterpret_cast<void **>(&ws), chunk_rows * row_bytes, pool, stream);
+    if (e != cudaSuccess) return e;
+    for (uint64_t r0 = 0; r0 < batch && e == cudaSuccess; r0 += chunk_rows) {
+        const uint64_t rows = batch - r0 < chunk_rows ? batch - r0 : chunk_rows;
+        c64 *o = out + r0 * n;
+        const c64 *bb = b + r0 * b_row_stride;
+        for (uint64_t k = 0; k < kterms && e == cudaSuccess; k++) {
+            e = cudaMemcpy2DAsync(ws, row_bytes, a + (r0 * kterms + k) * n, kterms * row_bytes, row_bytes, rows,
+                                  cudaMemcpyDeviceToDevice, stream);
+            if (e == cudaSuccess) e = launch_c64(plan, false, ws, rows, stream);
+            if (e != cudaSuccess) break;
+            uint64_t blocks = (rows * n + 255) / 256;
+            if (blocks > 148ull * 32) blocks = 148ull * 32;
+            if (k == 0) c64_pointwise_rows_kernel<false><<<unsigned(blocks), 256, 0, stream>>>(o, ws, bb, uint32_t(n), rows, b_row_stride);
+            else c64_pointwise_rows_kernel<true><<<unsigned(blocks), 256, 0, stream>>>(o, ws, bb + k * n, uint32_t(n), rows, b_row_stride);
+            count_launch();
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = launch_c64(plan, true, o, rows, stream);
+    }
+    const cudaError_t e2 = cudaFreeAsync(ws, stream);
+    return e != cudaSuccess ? e : e2;
 }
 
 cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *data, uint64_t batch, cudaStream_t stream)

@@ -102,6 +102,11 @@ cudaError_t launch_c64_regs(bool inverse, uint32_t tile, const StageProgram &pro
 // kernels (c64_fast.cu)
 bool fast_b256_supported(uint64_t n, int base_algo, uint64_t base_n);
 cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *data, uint64_t batch, cudaStream_t st);
+// fwd -> point-wise multiply-accumulate over k terms -> inv (c64_fast.cu): one fused kernel for (Dif16, 256) plans
+// with n <= 4096, the same arithmetic composed from the plan's kernels otherwise
+bool fused_mul_kernel_available(const cfft_plan *plan);
+cudaError_t launch_c64_fwd_mul_inv(const cfft_plan *plan, const double2 *a, uint64_t kterms, const double2 *b,
+                                   uint64_t b_row_stride, double2 *out, uint64_t batch, cudaStream_t st);
 // kernels (c64_ord16.cu)
 bool ord16_supported(uint64_t n, int algo);
 cudaError_t launch_c64_ord16(const cfft_plan *plan, bool inverse, double2 *data, uint64_t batch, cudaStream_t st);

@@ -131,6 +131,43 @@ class _PlanBase:
             raise N.PanicError("fwd_inv_host needs a host buffer of batch * n elements")
         N.check(N.lib.cfft_c64_fwd_inv_host(self._h, ptr, length, batch))
 
+    def fwd_mul_inv(self, a, b, out=None):
+        """out[r] = inv(sum_k fwd(a[r, k]) * b[r, k])  (cfft_c64_fwd_mul_inv): a convolution / external-product step in
+        one call, bit-identical to fwd + pointwise.mul_assign / mul_add_assign + inv.  CUDA complex128 tensors:
+        `a` [batch, k, n] (or [batch, n] for k = 1), `b` [k, n] shared by every row or [batch, k, n], `out`
+        [batch, n] (allocated when omitted; may be `a` itself when k = 1).  Returns out."""
+        import torch
+
+        n = self.fft_size()
+        for name, t in (("a", a), ("b", b)):
+            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.complex128 and t.is_contiguous()):
+                raise TypeError("%s must be a contiguous CUDA complex128 tensor" % name)
+        if a.dim() == 2:
+            a = a.unsqueeze(1)
+        if a.dim() != 3 or a.shape[2] != n or a.shape[1] < 1:
+            raise N.PanicError("assertion failed: a has shape [batch, k, fft_size]")
+        batch, k = int(a.shape[0]), int(a.shape[1])
+        if tuple(b.shape) in ((k, n), (n,) if k == 1 else None):
+            stride = 0
+        elif tuple(b.shape) in ((batch, k, n), (batch, n) if k == 1 else None):
+            stride = k * n
+        else:
+            raise N.PanicError("assertion failed: b has shape [k, fft_size] or [batch, k, fft_size]")
+        if out is None:
+            out = torch.empty((batch, n), dtype=torch.complex128, device=a.device)
+        if not (isinstance(out, torch.Tensor) and out.is_cuda and out.dtype == torch.complex128 and out.is_contiguous()
+                and out.numel() == batch * n):
+            raise N.PanicError("assertion failed: out holds batch * fft_size elements")
+        dev = a.device.index
+        if dev != self.device() or b.device.index != dev or out.device.index != dev:
+            raise ValueError("operands must live on the plan's device cuda:%d" % self.device())
+        N.check(N.lib.cfft_c64_fwd_mul_inv(self._h, a.data_ptr(), k, b.data_ptr(), stride, out.data_ptr(), batch,
+                                           current_stream_ptr(dev)))
+        return out
+
+    def has_fused_mul_kernel(self):
+        return bool(N.lib.cfft_plan_has_fused_mul_kernel(self._h))
+
     def twiddles(self, inverse=False):
         """Device twiddle table copied back to the host (tests)."""
         import numpy as np

@@ -216,6 +216,26 @@ cfft_status cfft_c64_mul_assign(int device, void *lhs_dev, const void *rhs_dev, 
 cfft_status cfft_c64_mul_add_assign(int device, void *acc_dev, const void *a_dev, const void *b_dev, uint64_t len,
                                     void *stream);
 
+/* out[r] = inv( sum_{k < k_terms} fwd(a[r][k]) (.) b[r][k] ),  r < batch: a whole convolution / external-product
+ * step (README.md:10-17 of the reference: forward transforms, element-wise products, one inverse transform) in
+ * ONE call on device memory, defined as -- and bit-identical to -- the composition
+ *     cfft_c64_fwd on every a[r][k];  acc = a[r][0] * b[r][0]  (cfft_c64_mul_assign);
+ *     acc += a[r][k] * b[r][k] for k = 1, 2, ... in that order  (cfft_c64_mul_add_assign);  cfft_c64_inv(acc)
+ * so the result is unnormalised exactly like fwd followed by inv (n x the convolution, src/unordered.rs:902-940).
+ *   a    [batch][k_terms][n] c64, read only;
+ *   b    Fourier-domain operand in THIS plan's order: [k_terms][n] shared by every row when b_row_stride == 0
+ *        (e.g. one bootstrapping-key GGSW against a batch of ciphertexts), else row r starts at b + r * b_row_stride
+ *        (in c64 elements, >= k_terms * n);
+ *   out  [batch][n]; may be the same pointer as a only when k_terms == 1 (in place), never b.
+ * Plans of the (Dif16, 256) family with 256 <= n <= 4096 (what Method::Measure selects on this library) run it as
+ * one kernel that keeps the products and the running sum on the SM: (2 k_terms + 1) x 16 n bytes of HBM traffic
+ * per row instead of (5 k_terms + 2) x 16 n for the separate calls; cfft_plan_has_fused_mul_kernel tells.  Every
+ * other c64 plan (ordered plans included) runs the same arithmetic from its own kernels through a stream-ordered
+ * workspace.  Stream ordered on the plan's device. */
+cfft_status cfft_c64_fwd_mul_inv(const cfft_plan *plan, const void *a_dev, uint64_t k_terms, const void *b_dev,
+                                 uint64_t b_row_stride, void *out_dev, uint64_t batch, void *stream);
+int cfft_plan_has_fused_mul_kernel(const cfft_plan *plan);
+
 /* ---- diagnostics ------------------------------------------------------------------- */
 
 const char *cfft_status_string(cfft_status st);

@@ -365,4 +365,15 @@ pub mod device {
     pub unsafe fn c64_mul_add_assign(device: i32, acc: *mut c_void, a: *const c_void, b: *const c_void, len: u64, stream: *mut c_void) {
         ffi::check(ffi::cfft_c64_mul_add_assign(device, acc, a, b, len, stream));
     }
+    /// `out[r] = inv(sum_k fwd(a[r][k]) * b[r][k])` for `batch` rows of `k_terms` polynomials: forward transforms,
+    /// element-wise multiply-accumulate and the inverse transform in one call (one kernel for plans of the
+    /// `(Dif16, 256)` family with `n <= 4096`), bit-identical to the separate calls.  `b_row_stride == 0` shares
+    /// `b` (`[k_terms][n]`) between all rows.
+    /// # Safety
+    /// `a`: `batch * k_terms * n` c64, `b`: `k_terms * n` (shared) or `batch` rows `b_row_stride` apart, `out`:
+    /// `batch * n` c64, all on the plan's device; `out` may equal `a` only when `k_terms == 1`.
+    #[allow(clippy::too_many_arguments)]
+    pub unsafe fn c64_fwd_mul_inv(plan: *const ffi::cfft_plan, a: *const c_void, k_terms: u64, b: *const c_void, b_row_stride: u64, out: *mut c_void, batch: u64, stream: *mut c_void) {
+        ffi::check(ffi::cfft_c64_fwd_mul_inv(plan, a, k_terms, b, b_row_stride, out, batch, stream));
+    }
 }

@@ -361,6 +361,152 @@ def test_pointwise_products_bit_exact(C, torch):
         C.pointwise.mul_assign(da, db[:5])
 
 
+def _oracle_fwd_mul_inv(ref, a, b):
+    """inv(sum_k fwd(a[r, k]) * b[r or shared, k]) composed from the oracle's pieces, terms added in order."""
+    batch, k, n = a.shape
+    out = np.empty((batch, n), np.complex128)
+    for r in range(batch):
+        br = b if b.ndim == 2 else b[r]
+        acc = O.c64_pointwise(ref.fwd(a[r, 0]), br[0])
+        for j in range(1, k):
+            acc = O.c64_pointwise(ref.fwd(a[r, j]), br[j], acc)
+        out[r] = ref.inv(acc)
+    return out
+
+
+@pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096])
+def test_fwd_mul_inv_fused_kernel_bit_exact(C, torch, n):
+    """cfft_c64_fwd_mul_inv on plans with the one-kernel path (c64_fwd_mul_inv_kernel): bit-identical to the oracle's
+    fwd -> num_complex product / sum -> inv, to the composition of the library's own calls and to the composed
+    device path, for 1..5 terms, whole and ragged CTA tiles, b shared by the batch or per row, and in place."""
+    rng = np.random.default_rng(900 + n)
+    plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(C.ordered.FftAlgo.Dif16, 256))
+    assert plan.has_fused_mul_kernel()
+    ref = O.UnorderedPlan(n, O.DIF16, 256)
+    for batch, k, shared in [(1, 1, True), (7, 1, False), (8, 2, True), (5, 3, False), (33, 2, True), (3, 5, True)]:
+        a = rand_c(rng, batch, k, n) - (0.5 + 0.5j)
+        b = (rand_c(rng, k, n) if shared else rand_c(rng, batch, k, n)) - (0.5 + 0.5j)
+        want = _oracle_fwd_mul_inv(ref, a, b)
+        da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+        launches = C._native.launch_count()
+        got = plan.fwd_mul_inv(da, db)
+        assert C._native.launch_count() - launches == 1  # one kernel
+        torch.cuda.synchronize()
+        assert bits_equal(got.cpu().numpy(), want), (n, batch, k, shared)
+        assert bits_equal(da.cpu().numpy(), a)  # inputs untouched
+        # the library's separate calls
+        fa = da.clone()
+        plan.fwd(fa)
+        bb = db if not shared else db.unsqueeze(0).expand(batch, k, n).contiguous()
+        acc = fa[:, 0].contiguous()
+        C.pointwise.mul_assign(acc, bb[:, 0].contiguous())
+        for j in range(1, k):
+            C.pointwise.mul_add_assign(acc, fa[:, j].contiguous(), bb[:, j].contiguous())
+        plan.inv(acc)
+        torch.cuda.synchronize()
+        assert bits_equal(acc.cpu().numpy(), want), (n, batch, k, shared)
+        # the composed device path (what plans without the fused kernel run)
+        os.environ["CFFT_B200_FUSED_MUL_COMPOSED"] = "1"
+        try:
+            got2 = plan.fwd_mul_inv(da, db)
+        finally:
+            del os.environ["CFFT_B200_FUSED_MUL_COMPOSED"]
+        torch.cuda.synchronize()
+        assert bits_equal(got2.cpu().numpy(), want), (n, batch, k, shared)
+        if k == 1:  # in place
+            inplace = da.clone().reshape(batch, n)
+            assert plan.fwd_mul_inv(inplace, db, out=inplace) is inplace
+            torch.cuda.synchronize()
+            assert bits_equal(inplace.cpu().numpy(), want), (n, batch)
+
+
+@pytest.mark.parametrize("kind,n,algo,base_n", [("unordered", 2048, "Dif4", 32), ("unordered", 8192, "Dif16", 256),
+                                                ("unordered", 16384, "Dif16", 256), ("unordered", 64, "Dit8", 64),
+                                                ("ordered", 512, "Dif8", 0), ("ordered", 256, "Dif16", 0)])
+def test_fwd_mul_inv_any_plan_bit_exact(C, torch, kind, n, algo, base_n):
+    """cfft_c64_fwd_mul_inv on plans without the one-kernel path (and the ordered 256-point plan, which has it):
+    the same bits as the oracle composition."""
+    rng = np.random.default_rng(n + base_n)
+    A = getattr(C.ordered.FftAlgo, algo)
+    oa = getattr(O, algo.upper())
+    if kind == "unordered":
+        plan, ref = C.unordered.Plan(n, C.unordered.Method.UserProvided(A, base_n)), O.UnorderedPlan(n, oa, base_n)
+    else:
+        plan, ref = C.ordered.Plan(n, C.ordered.Method.UserProvided(A)), O.OrderedPlan(n, oa)
+    assert plan.has_fused_mul_kernel() == (n == 256)
+    for batch, k, shared in [(3, 1, True), (5, 3, False), (2, 2, True)]:
+        a = rand_c(rng, batch, k, n) - (0.5 + 0.5j)
+        b = (rand_c(rng, k, n) if shared else rand_c(rng, batch, k, n)) - (0.5 + 0.5j)
+        got = plan.fwd_mul_inv(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda())
+        torch.cuda.synchronize()
+        assert bits_equal(got.cpu().numpy(), _oracle_fwd_mul_inv(ref, a, b)), (kind, n, batch, k, shared)
+
+
+def test_fwd_mul_inv_negacyclic_external_product(C, torch):
+    """The shape the call exists for: out = sum_k a_k * b_k modulo X^N + 1 (N = 4096, fft size 2048, k = 4 terms, b
+    shared by the batch like a bootstrapping-key GGSW row), one call on the device, against the exact integer
+    schoolbook product."""
+    npoly, n, k, batch = 4096, 2048, 4, 5
+    rng = np.random.default_rng(77)
+    a = rng.integers(-(1 << 16), 1 << 16, size=(batch, k, npoly))
+    b = rng.integers(-(1 << 10), 1 << 10, size=(k, npoly))
+    want = np.zeros((batch, npoly), dtype=object)
+    for r in range(batch):
+        for j in range(k):
+            full = np.convolve(a[r, j].astype(object), b[j].astype(object))
+            want[r] += full[:npoly]
+            want[r][: npoly - 1] -= full[npoly:]
+    twist = np.exp(1j * np.pi * np.arange(n) / npoly)
+    fold = lambda p: (p[..., :n] + 1j * p[..., n:]) * twist
+    plan = C.unordered.Plan(n, C.unordered.Method.Measure())
+    assert plan.has_fused_mul_kernel()
+    fb = torch.from_numpy(fold(b)).cuda()
+    plan.fwd(fb)  # the key is kept in the Fourier domain, in this plan's order
+    out = plan.fwd_mul_inv(torch.from_numpy(fold(a)).cuda(), fb)
+    torch.cuda.synchronize()
+    z = out.cpu().numpy() / n * np.conj(twist)
+    got = np.concatenate([z.real, z.imag], axis=1)
+    assert np.array_equal(np.rint(got).astype(np.int64), want.astype(np.int64))
+
+
+def test_fwd_mul_inv_full_size_matches_separate_calls(C, torch):
+    """BASELINE.json configs[1] shape through the fused call: 16384 rows of N = 2048 with 2 terms each against the
+    library's separate fwd / product / inv launches, bit for bit (the oracle pins those at small sizes)."""
+    n, k, batch = 2048, 2, 16384
+    plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(C.ordered.FftAlgo.Dif16, 256))
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.view_as_complex(torch.rand((batch, k, n, 2), generator=g, device="cuda", dtype=torch.float64) - 0.5)
+    b = torch.view_as_complex(torch.rand((k, n, 2), generator=g, device="cuda", dtype=torch.float64) - 0.5)
+    got = plan.fwd_mul_inv(a, b)
+    fa = a.clone()
+    plan.fwd(fa)
+    acc = fa[:, 0].contiguous()
+    C.pointwise.mul_assign(acc, b[0].expand(batch, n).contiguous())
+    C.pointwise.mul_add_assign(acc, fa[:, 1].contiguous(), b[1].expand(batch, n).contiguous())
+    plan.inv(acc)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.view_as_real(got).view(torch.int64), torch.view_as_real(acc).view(torch.int64))
+
+
+def test_fwd_mul_inv_argument_checks(C, torch):
+    plan = C.unordered.Plan(512, C.unordered.Method.UserProvided(C.ordered.FftAlgo.Dif16, 256))
+    a = torch.zeros((4, 2, 512), dtype=torch.complex128, device="cuda")
+    b = torch.zeros((2, 512), dtype=torch.complex128, device="cuda")
+    with pytest.raises(C.PanicError):
+        plan.fwd_mul_inv(a, b[:1].contiguous())  # wrong number of terms
+    with pytest.raises(C.PanicError):
+        plan.fwd_mul_inv(a[:, :, :256].contiguous(), b)  # wrong fft size
+    with pytest.raises(C.PanicError):
+        plan.fwd_mul_inv(a, b, out=torch.zeros((3, 512), dtype=torch.complex128, device="cuda"))
+    with pytest.raises(C.PanicError):  # aliasing a with more than one term
+        C._native.check(C._native.lib.cfft_c64_fwd_mul_inv(plan._h, a.data_ptr(), 2, b.data_ptr(), 0, a.data_ptr(), 4, 0))
+    with pytest.raises(C.PanicError):  # zero terms
+        C._native.check(C._native.lib.cfft_c64_fwd_mul_inv(plan._h, a.data_ptr(), 0, b.data_ptr(), 0, a.data_ptr(), 4, 0))
+    f128 = C.fft128.Plan(64)
+    with pytest.raises(C.PanicError):
+        C._native.check(C._native.lib.cfft_c64_fwd_mul_inv(f128._h, a.data_ptr(), 1, b.data_ptr(), 0, a.data_ptr(), 1, 0))
+
+
 @pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096, 8192])
 def test_fast_register_kernel_bit_exact(C, torch, n):
     """c64_fast.cu (plans with base (Dif16, 256)): same bits and order as the reference plan, for

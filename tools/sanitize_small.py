@@ -14,6 +14,26 @@ A = C.ordered.FftAlgo
 rng = np.random.default_rng(0)
 
 
+def run_fused_mul():
+    """cfft_c64_fwd_mul_inv: the one-kernel path at every size (1 and 3 terms, ragged tile), the composed path once"""
+    for n in [256, 512, 1024, 2048, 4096]:
+        plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(A.Dif16, 256))
+        for k in (1, 3):
+            a = torch.from_numpy(rng.random((5, k, n)) + 1j * rng.random((5, k, n))).cuda()
+            b = torch.from_numpy(rng.random((k, n)) + 1j * rng.random((k, n))).cuda()
+            plan.fwd_mul_inv(a, b)
+    plan = C.unordered.Plan(2048, C.unordered.Method.UserProvided(A.Dif4, 32))
+    a = torch.from_numpy(rng.random((3, 2, 2048)) + 1j * rng.random((3, 2, 2048))).cuda()
+    plan.fwd_mul_inv(a, a.clone())
+    torch.cuda.synchronize()
+
+
+if "--only-fused-mul" in sys.argv:
+    run_fused_mul()
+    print("sanitize_small (fused mul only) done, launches =", C.launch_count())
+    sys.exit(0)
+
+
 def run_c64(plan, n, batch):
     x = torch.from_numpy(rng.random((batch, n)) + 1j * rng.random((batch, n))).cuda()
     plan.fwd(x)
@@ -57,4 +77,5 @@ p.deserialize_fourier_buffer(std, buf)
 h = rng.random((7, 1024)) + 0j
 p.fwd(h)
 torch.cuda.synchronize()
+run_fused_mul()
 print("sanitize_small done, launches =", C.launch_count())
