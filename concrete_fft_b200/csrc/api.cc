@@ -761,6 +761,21 @@ cfft_status cfft_f128_cplx_mul_scale(int device, double *l_re0, double *l_re1, d
     return CFFT_OK;
 }
 
+cfft_status cfft_f128_fwd_mul_inv(const cfft_plan *p, double *l_re0, double *l_re1, double *l_im0, double *l_im1,
+                                  const double *r_re0, const double *r_re1, const double *r_im0, const double *r_im1,
+                                  uint64_t rhs_row_stride, double factor, uint64_t batch, void *stream)
+{
+    if (!p || p->kind != KIND_F128) return fail(CFFT_EINVAL, "not an fft128 plan");
+    if (batch && (!l_re0 || !l_re1 || !l_im0 || !l_im1 || !r_re0 || !r_re1 || !r_im0 || !r_im1)) return fail(CFFT_EINVAL, "null buffer");
+    if (rhs_row_stride != 0 && rhs_row_stride != p->n) return fail(CFFT_EINVAL, "rhs_row_stride must be 0 (rhs shared by every row) or n");
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
+    cudaError_t e = launch_f128_fwd_mul_inv(p, l_re0, l_re1, l_im0, l_im1, r_re0, r_re1, r_im0, r_im1, rhs_row_stride == 0, factor,
+                                            batch, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "f128 fwd-mul-inv launch");
+    return CFFT_OK;
+}
+
 static cfft_status run_pointwise(int device, void *acc, void *a, const void *b, uint64_t len, void *stream)
 {
     if (len && (!a || !b)) return fail(CFFT_EINVAL, "null buffer");
@@ -806,7 +821,11 @@ cfft_status cfft_c64_fwd_mul_inv(const cfft_plan *p, const void *a_dev, uint64_t
     return CFFT_OK;
 }
 
-int cfft_plan_has_fused_mul_kernel(const cfft_plan *p) { return p && p->kind != KIND_F128 && fused_mul_kernel_available(p) ? 1 : 0; }
+int cfft_plan_has_fused_mul_kernel(const cfft_plan *p)
+{
+    if (!p) return 0;
+    return (p->kind == KIND_F128 ? f128_fused_mul_kernel_available(p) : fused_mul_kernel_available(p)) ? 1 : 0;
+}
 
 cfft_status cfft_unordered_fwd_monomial(const cfft_plan *p, uint64_t degree, void *dev_buf, void *stream)
 {

@@ -292,6 +292,69 @@ f128_tile_kernel(Planes data, uint64_t total, uint32_t tile, uint32_t n, uint32_
     dispatch_pass<FWD, false, true, NT, SMAX>(ls, g, sre, sim, valid, tile, row_off, n, logn, ld, tw, vec);
 }
 
+// ---- fwd -> point-wise product with a Fourier-domain operand -> inv in ONE kernel ------
+// The negacyclic polynomial product as the reference's own test runs it (src/fft128/mod.rs:2018-2053): Plan::fwd on
+// the left operand, lhs <- cplx_mul(lhs, rhs) * factor with the SCALAR double-double product (Scalar::cplx_mul
+// :310-326 over mul_f128_f128, f128_ops.rs:395-400 -- not the FMA form the butterflies use), Plan::inv.  As three
+// launches the product is a streaming kernel moving 96 B per point; here the tile stays in shared memory between
+// the last forward pass and the first inverse pass, so only the right operand is read (32 B per point, from L2 when
+// it is shared by the batch).  Same operations in the same order => the bits of the three separate calls.
+F128_DEV dd dd_mul_scalar(dd a, dd b)
+{
+    const double p = __dmul_rn(a.hi, b.hi);
+    const double e = __fma_rn(a.hi, b.hi, -p);
+    return quick_two_sum(p, __dadd_rn(e, __dadd_rn(__dmul_rn(a.hi, b.lo), __dmul_rn(a.lo, b.hi))));
+}
+
+template <int NT, int MINB = 512 / NT>
+__global__ void __launch_bounds__(NT, MINB)
+f128_fwd_mul_inv_kernel(Planes lhs, Planes rhs, bool rhs_shared, double factor, uint64_t total, uint32_t tile, uint32_t n,
+                        uint32_t logn, PassList passes, const Tw4 *__restrict__ tw, bool vec)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2 *sre = reinterpret_cast<double2 *>(smem_raw);
+    double2 *sim = sre + tile;
+    const uint64_t start = uint64_t(blockIdx.x) * tile;
+    const uint32_t valid = (total - start < tile) ? uint32_t(total - start) : tile;
+    const uint32_t row_off = uint32_t(start & (n - 1));
+    Planes g;
+#pragma unroll
+    for (int i = 0; i < 4; i++) g.p[i] = lhs.p[i] + start;
+    const int count = passes.count;
+
+    // forward: every pass ends in shared memory
+    dispatch_pass<true, true, false, NT, 3>(passes.s[0], g, sre, sim, valid, tile, row_off, n, logn, passes.d0[0], tw, vec);
+#pragma unroll 1
+    for (int pi = 1; pi < count; pi++) {
+        pass_barrier<NT>(n, passes.d0[pi - 1], passes.d0[pi], tile);
+        dispatch_pass<true, false, false, NT, 3>(passes.s[pi], g, sre, sim, valid, tile, row_off, n, logn, passes.d0[pi], tw, vec);
+    }
+    __syncthreads();
+    // lhs <- (lhs * rhs) * factor on the tile; element i of the tile is point (row_off + i) mod n of its transform
+    {
+        const uint64_t roff = rhs_shared ? 0 : start;
+        for (uint32_t i = threadIdx.x; i < valid; i += NT) {
+            const uint32_t si = swz(i);
+            const uint64_t ri = roff + (rhs_shared ? ((row_off + i) & (n - 1)) : i);
+            const double2 lre = sre[si], lim = sim[si];
+            const dd ar = {lre.x, lre.y}, ai = {lim.x, lim.y};
+            const dd br = {__ldg(rhs.p[0] + ri), __ldg(rhs.p[1] + ri)}, bi = {__ldg(rhs.p[2] + ri), __ldg(rhs.p[3] + ri)};
+            const dd rr = dd_mul_scalar(ar, br), rim = dd_mul_scalar(ar, bi), ir = dd_mul_scalar(ai, br), ii = dd_mul_scalar(ai, bi);
+            const dd pr = dd_sub(rr, ii), pim = dd_add(ir, rim);
+            sre[si] = make_double2(__dmul_rn(pr.hi, factor), __dmul_rn(pr.lo, factor));
+            sim[si] = make_double2(__dmul_rn(pim.hi, factor), __dmul_rn(pim.lo, factor));
+        }
+    }
+    __syncthreads();
+    // inverse: the forward passes in reverse order, the last one writes HBM
+#pragma unroll 1
+    for (int pi = count - 1; pi >= 1; pi--) {
+        dispatch_pass<false, false, false, NT, 3>(passes.s[pi], g, sre, sim, valid, tile, row_off, n, logn, passes.d0[pi], tw, vec);
+        pass_barrier<NT>(n, passes.d0[pi], passes.d0[pi - 1], tile);
+    }
+    dispatch_pass<false, false, true, NT, 3>(passes.s[0], g, sre, sim, valid, tile, row_off, n, logn, passes.d0[0], tw, vec);
+}
+
 // stages whose span exceeds a tile: one in-place pass through HBM
 template <int S, bool FWD>
 __global__ void __launch_bounds__(kThreads, 2)
@@ -453,6 +516,70 @@ cudaError_t launch_f128(const cfft_plan *plan, bool inverse, double *re0, double
     for (int i = gcount - 1; i >= 0; i--)
         if ((e = launch_global<false>(gs[i], data, total, n, logn, gd0[i], tw, stream)) != cudaSuccess) return e;
     return cudaSuccess;
+}
+
+bool f128_fused_mul_kernel_available(const cfft_plan *plan) { return plan->n >= 32 && plan->n <= kF128TileMax; }
+
+// lhs <- inv( (fwd(lhs) * rhs) * factor ) on `batch` rows; rhs is in the Fourier domain (this plan's bit-reversed
+// order), one row shared by the batch or one row per transform.  n <= 4096: one kernel; larger n: the three launches.
+cudaError_t launch_f128_fwd_mul_inv(const cfft_plan *plan, double *l_re0, double *l_re1, double *l_im0, double *l_im1,
+                                    const double *r_re0, const double *r_re1, const double *r_im0, const double *r_im1,
+                                    bool rhs_shared, double factor, uint64_t batch, cudaStream_t stream)
+{
+    if (batch == 0) return cudaSuccess;
+    const uint32_t n = uint32_t(plan->n), logn = ilog2(plan->n);
+    const bool composed = !f128_fused_mul_kernel_available(plan) || getenv("CFFT_B200_FUSED_MUL_COMPOSED") != nullptr;
+    if (composed) {
+        cudaError_t e = launch_f128(plan, false, l_re0, l_re1, l_im0, l_im1, batch, stream);
+        if (e == cudaSuccess)
+            e = launch_f128_cplx_mul_scale_rows(l_re0, l_re1, l_im0, l_im1, r_re0, r_re1, r_im0, r_im1, rhs_shared ? n : 0, factor,
+                                                uint64_t(n) * batch, stream);
+        if (e == cudaSuccess) e = launch_f128(plan, true, l_re0, l_re1, l_im0, l_im1, batch, stream);
+        return e;
+    }
+    const uint64_t total = uint64_t(n) * batch;
+    uint32_t tile = n;
+    if (n < 2048) {
+        uint64_t rows = 2048u / n;
+        if (rows > batch) rows = batch;
+        tile = uint32_t(rows * n);
+    }
+    PassList passes;
+    passes.count = 0;
+    {
+        const int k = int(logn), np = (k + 2) / 3, lo = k / np, extra = k % np;
+        for (int i = 0, d = 0; i < np; i++) {
+            const int sz = lo + (i < extra ? 1 : 0);
+            passes.d0[passes.count] = d;
+            passes.s[passes.count++] = sz;
+            d += sz;
+        }
+    }
+    const size_t smem = size_t(tile) * 4 * sizeof(double);
+    const bool vec = ((reinterpret_cast<uintptr_t>(l_re0) | reinterpret_cast<uintptr_t>(l_re1) | reinterpret_cast<uintptr_t>(l_im0) |
+                       reinterpret_cast<uintptr_t>(l_im1)) & 15) == 0;
+    Planes lhs = {{l_re0, l_re1, l_im0, l_im1}};
+    Planes rhs = {{const_cast<double *>(r_re0), const_cast<double *>(r_re1), const_cast<double *>(r_im0), const_cast<double *>(r_im1)}};
+    const Tw4 *tw = reinterpret_cast<const Tw4 *>(plan->d_f128_tw4);
+    const unsigned tiles = unsigned((total + tile - 1) / tile);
+    static thread_local int configured_device = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured_device != dev) {
+        cudaError_t e = cudaFuncSetAttribute(f128_fwd_mul_inv_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             int(kF128TileMax * 4 * sizeof(double)));
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(f128_fwd_mul_inv_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     int(kF128TileMax * 4 * sizeof(double)));
+        if (e != cudaSuccess) return e;
+        configured_device = dev;
+    }
+    if (tile > 2048)
+        f128_fwd_mul_inv_kernel<512><<<tiles, 512, smem, stream>>>(lhs, rhs, rhs_shared, factor, total, tile, n, logn, passes, tw, vec);
+    else
+        f128_fwd_mul_inv_kernel<256><<<tiles, 256, smem, stream>>>(lhs, rhs, rhs_shared, factor, total, tile, n, logn, passes, tw, vec);
+    count_launch();
+    return cudaGetLastError();
 }
 
 } // namespace cfft

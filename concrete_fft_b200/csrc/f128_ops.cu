@@ -107,14 +107,16 @@ __global__ void f128_binary_kernel(const double *__restrict__ a_hi, const double
     }
 }
 
+// rhs_period != 0: the right operand holds rhs_period points shared by every row (index i mod rhs_period, a power of two)
 __global__ void f128_cplx_mul_scale_kernel(double *l_re0, double *l_re1, double *l_im0, double *l_im1,
                                            const double *__restrict__ r_re0, const double *__restrict__ r_re1,
                                            const double *__restrict__ r_im0, const double *__restrict__ r_im1,
-                                           double factor, uint64_t len)
+                                           double factor, uint64_t len, uint64_t rhs_period = 0)
 {
     for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint64_t j = rhs_period ? (i & (rhs_period - 1)) : i;
         const dd ar = {l_re0[i], l_re1[i]}, ai = {l_im0[i], l_im1[i]};
-        const dd br = {r_re0[i], r_re1[i]}, bi = {r_im0[i], r_im1[i]};
+        const dd br = {r_re0[j], r_re1[j]}, bi = {r_im0[j], r_im1[j]};
         const dd rr = mul(ar, br), ri = mul(ar, bi), ir = mul(ai, br), ii = mul(ai, bi);
         const dd pr = sub_est(rr, ii), pi = add_est(ir, ri);
         l_re0[i] = __dmul_rn(pr.hi, factor);
@@ -159,6 +161,17 @@ cudaError_t launch_f128_cplx_mul_scale(double *l_re0, double *l_re1, double *l_i
     if (len == 0) return cudaSuccess;
     f128_cplx_mul_scale_kernel<<<grid_for(len), 256, 0, st>>>(l_re0, l_re1, l_im0, l_im1, r_re0, r_re1, r_im0, r_im1,
                                                                factor, len);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_f128_cplx_mul_scale_rows(double *l_re0, double *l_re1, double *l_im0, double *l_im1, const double *r_re0,
+                                            const double *r_re1, const double *r_im0, const double *r_im1, uint64_t rhs_period,
+                                            double factor, uint64_t len, cudaStream_t st)
+{
+    if (len == 0) return cudaSuccess;
+    f128_cplx_mul_scale_kernel<<<grid_for(len), 256, 0, st>>>(l_re0, l_re1, l_im0, l_im1, r_re0, r_re1, r_im0, r_im1,
+                                                               factor, len, rhs_period);
     count_launch();
     return cudaGetLastError();
 }

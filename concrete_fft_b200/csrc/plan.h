@@ -131,6 +131,15 @@ cudaError_t launch_f128_cplx_mul_scale(double *l_re0, double *l_re1, double *l_i
                                        const double *r_re1, const double *r_im0, const double *r_im1, double factor,
                                        uint64_t len, cudaStream_t st);
 
+cudaError_t launch_f128_cplx_mul_scale_rows(double *l_re0, double *l_re1, double *l_im0, double *l_im1, const double *r_re0,
+                                            const double *r_re1, const double *r_im0, const double *r_im1, uint64_t rhs_period,
+                                            double factor, uint64_t len, cudaStream_t st);
+// fft128 fwd -> point-wise product * factor -> inv, one kernel for n <= 4096 (f128.cu)
+bool f128_fused_mul_kernel_available(const cfft_plan *plan);
+cudaError_t launch_f128_fwd_mul_inv(const cfft_plan *plan, double *l_re0, double *l_re1, double *l_im0, double *l_im1,
+                                    const double *r_re0, const double *r_re1, const double *r_im0, const double *r_im1,
+                                    bool rhs_shared, double factor, uint64_t batch, cudaStream_t st);
+
 void count_launch(uint64_t k = 1);
 
 } // namespace cfft

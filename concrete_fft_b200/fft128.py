@@ -89,6 +89,28 @@ class Plan:
             raise N.PanicError("fwd_inv_host needs four host planes of batch * n doubles")
         N.check(N.lib.cfft_f128_fwd_inv_host(self._h, *[v[1] for v in views], views[0][2], views[0][2] // n))
 
+    def fwd_mul_inv(self, lhs, rhs, factor):
+        """lhs <- inv((fwd(lhs) * rhs) * factor)  (cfft_f128_fwd_mul_inv): the negacyclic product of the reference's
+        tests (src/fft128/mod.rs:2018-2053) in one call.  `lhs`: four CUDA float64 planes of batch * n, in place; `rhs`:
+        four Fourier-domain planes of n (shared by every row) or batch * n doubles."""
+        n = self.fft_size()
+        lv = [f64_view(t) for t in lhs]
+        rv = [f64_view(t) for t in rhs]
+        if any(v[0] != "device" for v in lv + rv) or len({v[2] for v in lv}) != 1 or len({v[2] for v in rv}) != 1:
+            raise TypeError("fwd_mul_inv takes two sets of four CUDA float64 planes of equal length")
+        length = lv[0][2]
+        if length == 0 or length % n:
+            raise N.PanicError("assertion failed: buf.len() == fft_size")
+        if rv[0][2] not in (n, length):
+            raise N.PanicError("assertion failed: rhs holds fft_size or batch * fft_size points")
+        stride = 0 if rv[0][2] == n else n
+        dev = lv[0][3]
+        N.check(N.lib.cfft_f128_fwd_mul_inv(self._h, *[v[1] for v in lv], *[v[1] for v in rv], stride, float(factor),
+                                            length // n, current_stream_ptr(dev)))
+
+    def has_fused_mul_kernel(self):
+        return bool(N.lib.cfft_plan_has_fused_mul_kernel(self._h))
+
     def twiddles(self):
         import numpy as np
 

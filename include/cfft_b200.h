@@ -204,6 +204,19 @@ cfft_status cfft_f128_cplx_mul_scale(int device, double *l_re0, double *l_re1, d
                                      const double *r_im0, const double *r_im1, double factor,
                                      uint64_t len, void *stream);
 
+/* lhs <- inv( (fwd(lhs) * rhs) * factor ) for `batch` transforms in ONE call: the negacyclic polynomial product
+ * exactly as the reference's own tests run it (src/fft128/mod.rs:2018-2053: Plan::fwd on the left operand, the loop
+ * of scalar cplx_mul + scale at :2033-2047, Plan::inv), defined as -- and bit-identical to -- cfft_f128_fwd,
+ * cfft_f128_cplx_mul_scale, cfft_f128_inv in sequence.  lhs: four planes of batch * n doubles, standard order in,
+ * standard order out, in place.  rhs: Fourier-domain operand (already through cfft_f128_fwd, bit-reversed order), n
+ * doubles per plane shared by every row when rhs_row_stride == 0, or batch * n per plane when rhs_row_stride == n.
+ * n <= 4096 runs as one kernel (the tile never leaves shared memory between the last forward and the first inverse
+ * pass); larger n as the three launches. */
+cfft_status cfft_f128_fwd_mul_inv(const cfft_plan *plan, double *l_re0, double *l_re1, double *l_im0, double *l_im1,
+                                  const double *r_re0, const double *r_re1, const double *r_im0,
+                                  const double *r_im1, uint64_t rhs_row_stride, double factor, uint64_t batch,
+                                  void *stream);
+
 /* ---- c64 element-wise products in the Fourier domain ------------------------------------
  * "The only operations that are performed in the Fourier domain are elementwise" (README.md:10-17,
  * src/lib.rs:9-16): what a caller does between fwd and inv of a convolution / external product.  The
@@ -229,7 +242,8 @@ cfft_status cfft_c64_mul_add_assign(int device, void *acc_dev, const void *a_dev
  *   out  [batch][n]; may be the same pointer as a only when k_terms == 1 (in place), never b.
  * Plans of the (Dif16, 256) family with 256 <= n <= 4096 (what Method::Measure selects on this library) run it as
  * one kernel that keeps the products and the running sum on the SM: (2 k_terms + 1) x 16 n bytes of HBM traffic
- * per row instead of (5 k_terms + 2) x 16 n for the separate calls; cfft_plan_has_fused_mul_kernel tells.  Every
+ * per row instead of (6 k_terms + 1) x 16 n for the separate calls; cfft_plan_has_fused_mul_kernel tells
+ * (also for fft128 plans and cfft_f128_fwd_mul_inv).  Every
  * other c64 plan (ordered plans included) runs the same arithmetic from its own kernels through a stream-ordered
  * workspace.  Stream ordered on the plan's device. */
 cfft_status cfft_c64_fwd_mul_inv(const cfft_plan *plan, const void *a_dev, uint64_t k_terms, const void *b_dev,

@@ -365,6 +365,15 @@ pub mod device {
     pub unsafe fn c64_mul_add_assign(device: i32, acc: *mut c_void, a: *const c_void, b: *const c_void, len: u64, stream: *mut c_void) {
         ffi::check(ffi::cfft_c64_mul_add_assign(device, acc, a, b, len, stream));
     }
+    /// fft128: `lhs <- inv((fwd(lhs) * rhs) * factor)` on `batch` transforms in one call (one kernel for
+    /// `n <= 4096`): the negacyclic product of the reference's tests, bit-identical to `fwd`, the scalar
+    /// `cplx_mul` loop and `inv`.  `rhs_row_stride` is 0 (one Fourier-domain `rhs` row shared by the batch) or `n`.
+    /// # Safety
+    /// The `l_*` planes hold `batch * n` doubles, the `r_*` planes `n` or `batch * n`, all on the plan's device.
+    #[allow(clippy::too_many_arguments)]
+    pub unsafe fn f128_fwd_mul_inv(plan: *const ffi::cfft_plan, l: [*mut f64; 4], r: [*const f64; 4], rhs_row_stride: u64, factor: f64, batch: u64, stream: *mut c_void) {
+        ffi::check(ffi::cfft_f128_fwd_mul_inv(plan, l[0], l[1], l[2], l[3], r[0], r[1], r[2], r[3], rhs_row_stride, factor, batch, stream));
+    }
     /// `out[r] = inv(sum_k fwd(a[r][k]) * b[r][k])` for `batch` rows of `k_terms` polynomials: forward transforms,
     /// element-wise multiply-accumulate and the inverse transform in one call (one kernel for plans of the
     /// `(Dif16, 256)` family with `n <= 4096`), bit-identical to the separate calls.  `b_row_stride == 0` shares

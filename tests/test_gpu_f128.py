@@ -210,6 +210,86 @@ def test_pointwise_product_bit_exact_and_full_size_convolution(C, torch):
         assert float(err) < 1e-30 * npoly  # src/fft128/mod.rs:2062
 
 
+@pytest.mark.parametrize("n,batch", [(32, 1), (32, 70), (64, 33), (256, 9), (1024, 3), (2048, 3), (4096, 2), (8192, 2)])
+def test_fwd_mul_inv_bit_exact(C, torch, n, batch):
+    """cfft_f128_fwd_mul_inv (one kernel for n <= 4096, the three launches above): the bits of the oracle's fwd (FMA
+    butterflies) -> scalar cplx_mul * factor (src/fft128/mod.rs:2033-2047) -> inv, of the library's three separate
+    calls and of the composed path; rhs shared by the batch or one row per transform; ragged last tiles."""
+    import os
+
+    rng = np.random.default_rng(7 * n + batch)
+    plan = C.fft128.Plan(n)
+    assert plan.has_fused_mul_kernel() == (n <= 4096)
+    ref = O.F128Plan(n)
+    factor = 2.0 / (2 * n)
+    for shared in (True, False):
+        lhs = planes_random(rng, batch, n)
+        rhs = [p - 0.5 * (i % 2 == 0) for i, p in enumerate(planes_random(rng, 1 if shared else batch, n))]  # Fourier-domain operand
+        F = ref.fwd(*lhs, variant=O.F128_FMA)
+        R = [np.broadcast_to(p, (batch, n)).copy() for p in rhs]
+        want = ref.inv(*O.f128_cplx_mul_scale(F, R, factor), variant=O.F128_FMA)
+        dl = [torch.from_numpy(p.copy()).cuda() for p in lhs]
+        dr = [torch.from_numpy(np.ascontiguousarray(p if not shared else p[0]).copy()).cuda() for p in rhs]
+        launches = C.launch_count()
+        plan.fwd_mul_inv(dl, dr, factor)
+        torch.cuda.synchronize()
+        if n <= 4096:
+            assert C.launch_count() - launches == 1
+        assert bits_equal([t.cpu().numpy() for t in dl], want), (n, batch, shared)
+        # the library's three calls
+        d2 = [torch.from_numpy(p.copy()).cuda() for p in lhs]
+        plan.fwd(*d2)
+        C.fft128.cplx_mul_scale(d2, [torch.from_numpy(p).cuda() for p in R], factor)
+        plan.inv(*d2)
+        torch.cuda.synchronize()
+        assert bits_equal([t.cpu().numpy() for t in d2], want), (n, batch, shared)
+        os.environ["CFFT_B200_FUSED_MUL_COMPOSED"] = "1"
+        try:
+            d3 = [torch.from_numpy(p.copy()).cuda() for p in lhs]
+            plan.fwd_mul_inv(d3, dr, factor)
+        finally:
+            del os.environ["CFFT_B200_FUSED_MUL_COMPOSED"]
+        torch.cuda.synchronize()
+        assert bits_equal([t.cpu().numpy() for t in d3], want), (n, batch, shared)
+    with pytest.raises(C.PanicError):
+        plan.fwd_mul_inv(dl, [t[..., : n // 4].contiguous() for t in dr], factor)
+
+
+def test_fwd_mul_inv_negacyclic_product_full_size(C, torch):
+    """BASELINE configs[3] size (n = 2048, batch 16384) through the one-kernel product: equals the three separate
+    launches bit for bit on every row, and sampled rows meet the reference's bound 1e-30 * N against the exact
+    schoolbook negacyclic convolution (src/fft128/mod.rs:2062)."""
+    n, batch = 2048, 16384
+    npoly = 2 * n
+    g = torch.Generator(device="cuda").manual_seed(123)
+    def operand():
+        t = [torch.rand(batch, n, dtype=torch.float64, device="cuda", generator=g), torch.zeros(batch, n, dtype=torch.float64, device="cuda"),
+             torch.rand(batch, n, dtype=torch.float64, device="cuda", generator=g), torch.zeros(batch, n, dtype=torch.float64, device="cuda")]
+        for x in (t[0], t[2]):
+            x.mul_(2.0 ** 40).floor_().mul_(2.0 ** -40)
+        return t
+    L, R = operand(), operand()
+    rows = [0, 777, 16383]
+    lhs = [np.concatenate([L[0][r].cpu().numpy(), L[2][r].cpu().numpy()]) for r in rows]
+    rhs = [np.concatenate([R[0][r].cpu().numpy(), R[2][r].cpu().numpy()]) for r in rows]
+    plan = C.fft128.Plan(n)
+    plan.fwd(*R)
+    L2 = [t.clone() for t in L]
+    plan.fwd_mul_inv(L, R, 2.0 / npoly)
+    plan.fwd(*L2)
+    C.fft128.cplx_mul_scale(L2, R, 2.0 / npoly)
+    plan.inv(*L2)
+    torch.cuda.synchronize()
+    for a, b in zip(L, L2):
+        assert torch.equal(a.view(torch.int64), b.view(torch.int64))
+    for k, r in enumerate(rows):
+        exact = negacyclic_schoolbook_exact(lhs[k], rhs[k])
+        hi = np.concatenate([L[0][r].cpu().numpy(), L[2][r].cpu().numpy()])
+        lo = np.concatenate([L[1][r].cpu().numpy(), L[3][r].cpu().numpy()])
+        err = max(abs(dd_to_fraction(h, l) - e) for h, l, e in zip(hi, lo, exact))
+        assert float(err) < 1e-30 * npoly
+
+
 def test_random_sizes_fuzz(C, torch):
     rng = np.random.default_rng(424242)
     for trial in range(16):

@@ -12,7 +12,6 @@ import torch
 
 import concrete_fft_b200 as C
 
-sizes = [int(s) for s in sys.argv[1:]] or [512, 1024, 2048, 4096]
 A = C.ordered.FftAlgo
 
 
@@ -29,6 +28,36 @@ def timed(fn, reps):
     return ts[len(ts) // 2]
 
 
+if len(sys.argv) > 1 and sys.argv[1] == "f128":
+    # cfft_f128_fwd_mul_inv against cfft_f128_fwd + cfft_f128_cplx_mul_scale + cfft_f128_inv
+    for n in [int(s) for s in sys.argv[2:]] or [1024, 2048, 4096]:
+        plan = C.fft128.Plan(n)
+        rows = (1 << 30) // (32 * n)
+        for shared in (True, False):
+            L = [torch.rand(rows, n, dtype=torch.float64, device="cuda") * (1.0 if i % 2 == 0 else 1e-17) for i in range(4)]
+            R = [torch.rand(*((n,) if shared else (rows, n)), dtype=torch.float64, device="cuda") * (1.0 if i % 2 == 0 else 1e-17) for i in range(4)]
+            Rfull = R if not shared else [r.expand(rows, n).contiguous() for r in R]
+            f = 0.5 / n  # keeps |lhs| bounded over repetitions (operands in [0, 1): product of n terms < n)
+
+            def separate():
+                plan.fwd(*L)
+                C.fft128.cplx_mul_scale(L, Rfull, f)
+                plan.inv(*L)
+
+            t_fused = timed(lambda: plan.fwd_mul_inv(L, R, f), 10)
+            for t in L:
+                t.uniform_(0, 1)
+            t_sep = timed(separate, 10)
+            print(json.dumps({"kind": "f128", "n": n, "rows": rows, "rhs": "shared" if shared else "per-row",
+                              "fused_ms": round(t_fused, 4), "separate_ms": round(t_sep, 4), "speedup": round(t_sep / t_fused, 3),
+                              "fused_products_per_s": round(rows / t_fused * 1e3),
+                              "fp64_issue_frac": round(rows * (n // 2) * (n.bit_length() - 1) * 94 * 2 / (t_fused * 1e-3) / (64 * 148 * 1.965e9), 3)}),
+                  flush=True)
+            del L, R, Rfull
+            torch.cuda.empty_cache()
+    sys.exit(0)
+
+sizes = [int(s) for s in sys.argv[1:]] or [512, 1024, 2048, 4096]
 for n in sizes:
     plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(A.Dif16, 256))
     for k, shared in [(1, False), (1, True), (2, True), (4, True), (6, True), (4, False)]:
