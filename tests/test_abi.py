@@ -63,6 +63,17 @@ def test_argument_checks_match_reference_panics(C):
             F.Plan(n)  # src/fft128/mod.rs:1865-1866
 
 
+def test_fused_product_entry_points_reject_bad_plans_before_cuda(C):
+    """cfft_c64_fwd_mul_inv / cfft_f128_fwd_mul_inv: a null plan is CFFT_EINVAL (no CUDA call is made), and the capability
+    query answers 0 for it."""
+    lib = C._native.lib
+    assert lib.cfft_c64_fwd_mul_inv(None, None, 1, None, 0, None, 0, None) == C._native.EINVAL
+    assert b"c64 plan" in lib.cfft_last_error()
+    assert lib.cfft_f128_fwd_mul_inv(None, None, None, None, None, None, None, None, None, 0, 1.0, 0, None) == C._native.EINVAL
+    assert b"fft128 plan" in lib.cfft_last_error()
+    assert lib.cfft_plan_has_fused_mul_kernel(None) == 0
+
+
 def test_no_cpu_fallback(C):
     import torch
 
