@@ -25,6 +25,12 @@ def run_fused_mul():
     plan = C.unordered.Plan(2048, C.unordered.Method.UserProvided(A.Dif4, 32))
     a = torch.from_numpy(rng.random((3, 2, 2048)) + 1j * rng.random((3, 2, 2048))).cuda()
     plan.fwd_mul_inv(a, a.clone())
+    # cfft_f128_fwd_mul_inv: one kernel (ragged multi-row tile, 2048- and 4096-point tiles), then the three launches
+    for n, batch in [(64, 70), (2048, 3), (4096, 2), (8192, 2)]:
+        p128 = C.fft128.Plan(n)
+        lhs = [torch.rand(batch, n, dtype=torch.float64, device="cuda") for _ in range(4)]
+        p128.fwd_mul_inv(lhs, [torch.rand(n, dtype=torch.float64, device="cuda") for _ in range(4)], 1.0 / n)
+        p128.fwd_mul_inv(lhs, [torch.rand(batch, n, dtype=torch.float64, device="cuda") for _ in range(4)], 1.0 / n)
     torch.cuda.synchronize()
 
 
