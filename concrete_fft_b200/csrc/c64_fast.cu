@@ -698,8 +698,9 @@ cudaError_t launch_c64_fwd_mul_inv(const cfft_plan *plan, const double2 *a, uint
         c64 *o = out + r0 * n;
         const c64 *bb = b + r0 * b_row_stride;
         for (uint64_t k = 0; k < kterms && e == cudaSuccess; k++) {
-            e = cudaMemcpy2DAsync(ws, row_bytes, a + (r0 * kterms + k) * n, kterms * row_bytes, row_bytes, rows,
-                                  cudaMemcpyDeviceToDevice, stream);
+            if (kterms == 1) e = cudaMemcpyAsync(ws, a + r0 * n, rows * row_bytes, cudaMemcpyDeviceToDevice, stream);
+            else e = cudaMemcpy2DAsync(ws, row_bytes, a + (r0 * kterms + k) * n, kterms * row_bytes, row_bytes, rows,
+                                       cudaMemcpyDeviceToDevice, stream);
             if (e == cudaSuccess) e = launch_c64(plan, false, ws, rows, stream);
             if (e != cudaSuccess) break;
             uint64_t blocks = (rows * n + 255) / 256;

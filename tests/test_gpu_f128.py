@@ -210,7 +210,7 @@ def test_pointwise_product_bit_exact_and_full_size_convolution(C, torch):
         assert float(err) < 1e-30 * npoly  # src/fft128/mod.rs:2062
 
 
-@pytest.mark.parametrize("n,batch", [(32, 1), (32, 70), (64, 33), (256, 9), (1024, 3), (2048, 3), (4096, 2), (8192, 2)])
+@pytest.mark.parametrize("n,batch", [(32, 1), (32, 70), (64, 33), (256, 3), (256, 9), (1024, 3), (2048, 1), (2048, 3), (4096, 2), (8192, 2)])
 def test_fwd_mul_inv_bit_exact(C, torch, n, batch):
     """cfft_f128_fwd_mul_inv (one kernel for n <= 4096, the three launches above): the bits of the oracle's fwd (FMA
     butterflies) -> scalar cplx_mul * factor (src/fft128/mod.rs:2033-2047) -> inv, of the library's three separate
