@@ -207,3 +207,32 @@ def test_pointwise_product_is_num_complex_arithmetic():
         re, im = ar * br - ai * bi, ar * bi + ai * br
         assert (prod[i].real, prod[i].imag) == (re, im)
         assert (fused[i].real, fused[i].imag) == (float(acc[i].real) + re, float(acc[i].imag) + im)
+
+
+def test_oracle_external_product_composition_is_exact_negacyclic_sum():
+    """The checker the GPU tests hold cfft_c64_fwd_mul_inv against -- oracle fwd per term, num_complex product and sum
+    in term order, oracle inv -- computes sum_k a_k * b_k modulo X^N + 1: equal to the exact integer schoolbook
+    result after rounding (what the crate exists for, README.md:10-17), and independent of the plan's base size."""
+    npoly, n, k = 512, 256, 3
+    rng = np.random.default_rng(5)
+    a = rng.integers(-(1 << 16), 1 << 16, size=(k, npoly))
+    b = rng.integers(-(1 << 10), 1 << 10, size=(k, npoly))
+    want = np.zeros(npoly, dtype=object)
+    for j in range(k):
+        full = np.convolve(a[j].astype(object), b[j].astype(object))
+        want += full[:npoly]
+        want[: npoly - 1] -= full[npoly:]
+    twist = np.exp(1j * np.pi * np.arange(n) / npoly)
+    fold = lambda p: (p[..., :n] + 1j * p[..., n:]) * twist
+    results = []
+    for algo, base in [(O.DIF16, 256), (O.DIF4, 32), (O.DIT8, 64)]:
+        plan = O.UnorderedPlan(n, algo, base)
+        fa, fb = fold(a), fold(b)
+        acc = O.c64_pointwise(plan.fwd(fa[0]), plan.fwd(fb[0]))
+        for j in range(1, k):
+            acc = O.c64_pointwise(plan.fwd(fa[j]), plan.fwd(fb[j]), acc)
+        z = plan.inv(acc) / n * np.conj(twist)
+        got = np.concatenate([z.real, z.imag])
+        assert np.array_equal(np.rint(got).astype(np.int64), want.astype(np.int64)), (algo, base)
+        results.append(got)
+    assert np.abs(results[0] - results[1]).max() < 1e-3 and np.abs(results[0] - results[2]).max() < 1e-3
