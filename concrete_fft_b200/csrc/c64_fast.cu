@@ -498,15 +498,17 @@ c64_fwd_mul_inv_kernel(const c64 *__restrict__ a, const c64 *__restrict__ b, c64
     }
 }
 
-template <int N, int R1, int R2>
+// ALLOW_MULTI = false (n = 8192: 512 threads fill the register file at 128 registers each): one term only
+template <int N, int R1, int R2, bool ALLOW_MULTI = true>
 cudaError_t launch_fused_mul(const c64 *a, const c64 *b, c64 *out, uint64_t batch, uint32_t kterms, uint64_t b_row_stride,
                              const FastTables &tf, const FastTables &ti, cudaStream_t stream)
 {
     using Cfg = FastCfg<N>;
     const size_t smem = size_t(Cfg::ROWS) * N * sizeof(c64);
     const uint64_t ctas = (batch + Cfg::ROWS - 1) / Cfg::ROWS;
+    if (!ALLOW_MULTI && kterms != 1) return cudaErrorInvalidValue;
     auto k1 = c64_fwd_mul_inv_kernel<N, R1, R2, false>;
-    auto km = c64_fwd_mul_inv_kernel<N, R1, R2, true>;
+    auto km = c64_fwd_mul_inv_kernel<N, R1, R2, ALLOW_MULTI>;
     if (smem > 48 * 1024) {
         static thread_local int configured_device = -1;
         int dev = 0;
@@ -664,7 +666,9 @@ cudaError_t launch_c64_fwd_mul_inv(const cfft_plan *plan, const double2 *a, uint
 {
     if (batch == 0 || kterms == 0) return cudaSuccess;
     const bool force_composed = getenv("CFFT_B200_FUSED_MUL_COMPOSED") != nullptr; // testing hook, read per call
-    if (fused_mul_kernel_available(plan) && !force_composed && kterms <= 0xFFFFFFFFull) {
+    // n = 8192 has the one-term kernel only (cfft_plan_has_fused_mul_kernel stays 0 for it: it promises every k)
+    const bool one_term_8192 = plan->d_fast_tw[0] && plan->n == 8192 && kterms == 1 && (plan->fast_variant == 1 || plan->fast_variant == 2 || plan->fast_variant == 4);
+    if ((fused_mul_kernel_available(plan) || one_term_8192) && !force_composed && kterms <= 0xFFFFFFFFull) {
         FastTables tf, ti;
         const c64 *bf = plan->d_fast_tw[0], *bi = plan->d_fast_tw[1];
         tf.top1 = plan->fast_levels.size() > 0 ? bf + plan->fast_levels[0].off : bf;
@@ -680,6 +684,7 @@ cudaError_t launch_c64_fwd_mul_inv(const cfft_plan *plan, const double2 *a, uint
         case 1024: return launch_fused_mul<1024, 4, 1>(a, b, out, batch, kt, b_row_stride, tf, ti, stream);
         case 2048: return launch_fused_mul<2048, 8, 1>(a, b, out, batch, kt, b_row_stride, tf, ti, stream);
         case 4096: return launch_fused_mul<4096, 8, 2>(a, b, out, batch, kt, b_row_stride, tf, ti, stream);
+        case 8192: return launch_fused_mul<8192, 8, 4, false>(a, b, out, batch, kt, b_row_stride, tf, ti, stream);
         default: return cudaErrorInvalidValue;
         }
     }
