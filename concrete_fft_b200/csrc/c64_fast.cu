@@ -469,6 +469,22 @@ c64_fwd_mul_inv_kernel(const c64 *__restrict__ a, const c64 *__restrict__ b, c64
             else acc[j] = k == 0 ? p : cadd(acc[j], p);
         }
     }
+    if (!MULTI) {
+        // chained launches (one term each, for sizes without the accumulating kernel): bit 3 adds the Fourier-domain
+        // partial sum the previous launch left in `out`, bit 4 stores the new partial sum instead of inverting it
+        c64 *gs = go + blk * 256 + lane16;
+        if (flags & 8) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) v[j] = cadd(ld_stream(gs + 16 * j), v[j]);
+        }
+        if (flags & 16) {
+            if (active) {
+#pragma unroll
+                for (int j = 0; j < 16; j++) st_stream(gs + 16 * j, v[j]);
+            }
+            return;
+        }
+    }
     if (MULTI) {
 #pragma unroll
         for (int j = 0; j < 16; j++) v[j] = acc[j];
@@ -498,7 +514,7 @@ c64_fwd_mul_inv_kernel(const c64 *__restrict__ a, const c64 *__restrict__ b, c64
     }
 }
 
-// ALLOW_MULTI = false (n = 8192: 512 threads fill the register file at 128 registers each): one term only
+// ALLOW_MULTI = false (n = 8192: 512 threads fill the register file at 128 registers each): one term per launch
 template <int N, int R1, int R2, bool ALLOW_MULTI = true>
 cudaError_t launch_fused_mul(const c64 *a, const c64 *b, c64 *out, uint64_t batch, uint32_t kterms, uint64_t b_row_stride,
                              const FastTables &tf, const FastTables &ti, cudaStream_t stream)
@@ -506,7 +522,6 @@ cudaError_t launch_fused_mul(const c64 *a, const c64 *b, c64 *out, uint64_t batc
     using Cfg = FastCfg<N>;
     const size_t smem = size_t(Cfg::ROWS) * N * sizeof(c64);
     const uint64_t ctas = (batch + Cfg::ROWS - 1) / Cfg::ROWS;
-    if (!ALLOW_MULTI && kterms != 1) return cudaErrorInvalidValue;
     auto k1 = c64_fwd_mul_inv_kernel<N, R1, R2, false>;
     auto km = c64_fwd_mul_inv_kernel<N, R1, R2, ALLOW_MULTI>;
     if (smem > 48 * 1024) {
@@ -521,7 +536,16 @@ cudaError_t launch_fused_mul(const c64 *a, const c64 *b, c64 *out, uint64_t batc
         }
     }
     static const int env_flags = [] { const char *e = getenv("CFFT_B200_FUSED_MUL_FLAGS"); return e ? atoi(e) : 3; }();
-    const uint32_t flags = uint32_t(env_flags) & 3;
+    uint32_t flags = uint32_t(env_flags) & 3;
+    if (!ALLOW_MULTI && kterms > 1) {
+        // one launch per term: out holds the Fourier-domain partial sum between launches, the last launch inverts it
+        for (uint32_t k = 0; k < kterms; k++) {
+            const uint32_t f = (flags & 1) | (k > 0 ? 8u : 0u) | (k + 1 < kterms ? 16u : 0u);
+            k1<<<unsigned(ctas), Cfg::NT, smem, stream>>>(a + uint64_t(k) * N, b + uint64_t(k) * N, out, batch, kterms, b_row_stride, tf, ti, f);
+            count_launch();
+        }
+        return cudaGetLastError();
+    }
     if (kterms == 1 && !(env_flags & 4)) k1<<<unsigned(ctas), Cfg::NT, smem, stream>>>(a, b, out, batch, kterms, b_row_stride, tf, ti, flags);
     else km<<<unsigned(ctas), Cfg::NT, smem, stream>>>(a, b, out, batch, kterms, b_row_stride, tf, ti, flags);
     count_launch();
@@ -657,7 +681,8 @@ bool fast_b256_supported(uint64_t n, int base_algo, uint64_t base_n)
 //     <= 256 MiB.  Same bits either way.
 bool fused_mul_kernel_available(const cfft_plan *plan)
 {
-    return plan->d_fast_tw[0] && plan->n >= 256 && plan->n <= 4096 &&
+    // n = 8192: one kernel per term (512 threads x 128 registers leave no room for a running sum), chained through `out`
+    return plan->d_fast_tw[0] && plan->n >= 256 && plan->n <= 8192 &&
            (plan->fast_variant == 1 || plan->fast_variant == 2 || plan->fast_variant == 4);
 }
 
@@ -666,9 +691,7 @@ cudaError_t launch_c64_fwd_mul_inv(const cfft_plan *plan, const double2 *a, uint
 {
     if (batch == 0 || kterms == 0) return cudaSuccess;
     const bool force_composed = getenv("CFFT_B200_FUSED_MUL_COMPOSED") != nullptr; // testing hook, read per call
-    // n = 8192 has the one-term kernel only (cfft_plan_has_fused_mul_kernel stays 0 for it: it promises every k)
-    const bool one_term_8192 = plan->d_fast_tw[0] && plan->n == 8192 && kterms == 1 && (plan->fast_variant == 1 || plan->fast_variant == 2 || plan->fast_variant == 4);
-    if ((fused_mul_kernel_available(plan) || one_term_8192) && !force_composed && kterms <= 0xFFFFFFFFull) {
+    if (fused_mul_kernel_available(plan) && !force_composed && kterms <= 0xFFFFFFFFull) {
         FastTables tf, ti;
         const c64 *bf = plan->d_fast_tw[0], *bi = plan->d_fast_tw[1];
         tf.top1 = plan->fast_levels.size() > 0 ? bf + plan->fast_levels[0].off : bf;
