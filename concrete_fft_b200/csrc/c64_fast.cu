@@ -367,7 +367,7 @@ cudaError_t launch_cfg(bool inverse, c64 *data, uint64_t batch, const FastTables
 // out[r] = inv( sum_k fwd(a[r][k]) (.) b[k] ): the external-product / convolution step of a caller that keeps
 // its data on the GPU.  As three library calls per term (cfft_c64_fwd, cfft_c64_mul_[add_]assign, cfft_c64_inv)
 // a K = 1 product moves 7 x 16 n bytes through HBM; here it moves 3 x 16 n (2 x 16 n when b is shared by the
-// batch and therefore L2-resident), and K terms cost (2K + 1) x 16 n instead of (5K + 2) x 16 n.  The forward
+// batch and therefore L2-resident), and K terms cost (2K + 1) x 16 n instead of (6K + 1) x 16 n.  The forward
 // transform of a term ends with every thread holding 16 Fourier coefficients in registers at exactly the
 // positions the inverse base FFT starts from (blk * 256 + lane16 + 16 j), so the product and the running sum
 // never leave the SM: the sum of K > 1 terms lives in 16 more c64 registers per thread.  Butterflies, twiddles

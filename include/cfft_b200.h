@@ -242,10 +242,10 @@ cfft_status cfft_c64_mul_add_assign(int device, void *acc_dev, const void *a_dev
  *   out  [batch][n]; may be the same pointer as a only when k_terms == 1 (in place), never b.
  * Plans of the (Dif16, 256) family with 256 <= n <= 8192 (what Method::Measure selects on this library) run it as
  * one kernel that keeps the products and the running sum on the SM: (2 k_terms + 1) x 16 n bytes of HBM traffic
- * per row instead of (6 k_terms + 1) x 16 n for the separate calls (n = 8192: one launch per term, 3 x 16 n per term); cfft_plan_has_fused_mul_kernel tells
- * (also for fft128 plans and cfft_f128_fwd_mul_inv).  Every
- * other c64 plan (ordered plans included) runs the same arithmetic from its own kernels through a stream-ordered
- * workspace.  Stream ordered on the plan's device. */
+ * per row instead of (6 k_terms + 1) x 16 n for the separate calls (n = 8192: one launch per term with the partial
+ * sum kept in out, 3 x 16 n per term); cfft_plan_has_fused_mul_kernel tells (also for fft128 plans and
+ * cfft_f128_fwd_mul_inv).  Every other c64 plan (ordered plans included) runs the same arithmetic from its own
+ * kernels through a stream-ordered workspace.  Stream ordered on the plan's device. */
 cfft_status cfft_c64_fwd_mul_inv(const cfft_plan *plan, const void *a_dev, uint64_t k_terms, const void *b_dev,
                                  uint64_t b_row_stride, void *out_dev, uint64_t batch, void *stream);
 int cfft_plan_has_fused_mul_kernel(const cfft_plan *plan);
