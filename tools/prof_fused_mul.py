@@ -11,6 +11,16 @@ import torch
 
 import concrete_fft_b200 as C
 
+if sys.argv[1] == "f128":  # python tools/prof_fused_mul.py f128 <n> <rows>   (-k regex:f128_fwd_mul_inv)
+    n, rows = int(sys.argv[2]), int(sys.argv[3])
+    plan = C.fft128.Plan(n)
+    L = [torch.rand(rows, n, dtype=torch.float64, device="cuda") * (1.0 if i % 2 == 0 else 1e-17) for i in range(4)]
+    R = [torch.rand(n, dtype=torch.float64, device="cuda") * (1.0 if i % 2 == 0 else 1e-17) for i in range(4)]
+    for _ in range(3):
+        plan.fwd_mul_inv(L, R, 0.5 / n)
+    torch.cuda.synchronize()
+    print("fused kernel:", plan.has_fused_mul_kernel())
+    sys.exit(0)
 n, k, rows = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 per_row = len(sys.argv) > 4
 plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(C.ordered.FftAlgo.Dif16, 256))
