@@ -821,6 +821,25 @@ cfft_status cfft_c64_fwd_mul_inv(const cfft_plan *p, const void *a_dev, uint64_t
     return CFFT_OK;
 }
 
+cfft_status cfft_c64_fwd_mul_add(const cfft_plan *p, const void *a_dev, uint64_t a_row_stride, const void *b_dev,
+                                 uint64_t b_row_stride, void *acc_dev, int accumulate, uint64_t batch, void *stream)
+{
+    if (!p || p->kind == KIND_F128) return fail(CFFT_EINVAL, "not a c64 plan");
+    if (batch && (!a_dev || !b_dev || !acc_dev)) return fail(CFFT_EINVAL, "null buffer");
+    if ((reinterpret_cast<uintptr_t>(a_dev) | reinterpret_cast<uintptr_t>(b_dev) | reinterpret_cast<uintptr_t>(acc_dev)) & 15)
+        return fail(CFFT_EINVAL, "device buffers must be 16-byte aligned (128-bit accesses)");
+    if (a_row_stride == 0 || a_row_stride % p->n) return fail(CFFT_EINVAL, "a_row_stride must be a positive multiple of n");
+    if (b_row_stride != 0 && b_row_stride < p->n) return fail(CFFT_EINVAL, "b_row_stride must be 0 (b shared by every row) or >= n");
+    if (acc_dev == a_dev || acc_dev == b_dev) return fail(CFFT_EINVAL, "acc must not alias a or b");
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
+    cudaError_t e = launch_c64_fwd_mul_add(p, static_cast<const double2 *>(a_dev), a_row_stride / p->n, static_cast<const double2 *>(b_dev),
+                                           b_row_stride, static_cast<double2 *>(acc_dev), accumulate != 0, batch,
+                                           static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "c64 fwd-mul-add launch");
+    return CFFT_OK;
+}
+
 int cfft_plan_has_fused_mul_kernel(const cfft_plan *p)
 {
     if (!p) return 0;

@@ -517,7 +517,7 @@ c64_fwd_mul_inv_kernel(const c64 *__restrict__ a, const c64 *__restrict__ b, c64
 // ALLOW_MULTI = false (n = 8192: 512 threads fill the register file at 128 registers each): one term per launch
 template <int N, int R1, int R2, bool ALLOW_MULTI = true>
 cudaError_t launch_fused_mul(const c64 *a, const c64 *b, c64 *out, uint64_t batch, uint32_t kterms, uint64_t b_row_stride,
-                             const FastTables &tf, const FastTables &ti, cudaStream_t stream)
+                             const FastTables &tf, const FastTables &ti, cudaStream_t stream, uint32_t chain = 0)
 {
     using Cfg = FastCfg<N>;
     const size_t smem = size_t(Cfg::ROWS) * N * sizeof(c64);
@@ -537,6 +537,13 @@ cudaError_t launch_fused_mul(const c64 *a, const c64 *b, c64 *out, uint64_t batc
     }
     static const int env_flags = [] { const char *e = getenv("CFFT_B200_FUSED_MUL_FLAGS"); return e ? atoi(e) : 3; }();
     uint32_t flags = uint32_t(env_flags) & 3;
+    if (chain) {
+        // cfft_c64_fwd_mul_add: ONE term per row (rows kterms * N apart), Fourier-domain result stored (bit 4) on top of
+        // what `out` holds (bit 3) -- no inverse
+        k1<<<unsigned(ctas), Cfg::NT, smem, stream>>>(a, b, out, batch, kterms, b_row_stride, tf, ti, (flags & 1) | chain);
+        count_launch();
+        return cudaGetLastError();
+    }
     if (!ALLOW_MULTI && kterms > 1) {
         // one launch per term: out holds the Fourier-domain partial sum between launches, the last launch inverts it
         for (uint32_t k = 0; k < kterms; k++) {
@@ -686,31 +693,73 @@ bool fused_mul_kernel_available(const cfft_plan *plan)
            (plan->fast_variant == 1 || plan->fast_variant == 2 || plan->fast_variant == 4);
 }
 
+static cudaError_t dispatch_fused_mul(const cfft_plan *plan, const c64 *a, const c64 *b, c64 *out, uint64_t batch, uint32_t kt,
+                                      uint64_t b_row_stride, cudaStream_t stream, uint32_t chain)
+{
+    FastTables tf, ti;
+    const c64 *bf = plan->d_fast_tw[0], *bi = plan->d_fast_tw[1];
+    tf.top1 = plan->fast_levels.size() > 0 ? bf + plan->fast_levels[0].off : bf;
+    tf.top2 = plan->fast_levels.size() > 1 ? bf + plan->fast_levels[1].off : bf;
+    tf.base = bf + plan->fast_base_off;
+    ti.top1 = plan->fast_levels.size() > 0 ? bi + plan->fast_levels[0].off : bi;
+    ti.top2 = plan->fast_levels.size() > 1 ? bi + plan->fast_levels[1].off : bi;
+    ti.base = bi + plan->fast_base_off;
+    switch (plan->n) {
+    case 256: return launch_fused_mul<256, 1, 1>(a, b, out, batch, kt, b_row_stride, tf, ti, stream, chain);
+    case 512: return launch_fused_mul<512, 2, 1>(a, b, out, batch, kt, b_row_stride, tf, ti, stream, chain);
+    case 1024: return launch_fused_mul<1024, 4, 1>(a, b, out, batch, kt, b_row_stride, tf, ti, stream, chain);
+    case 2048: return launch_fused_mul<2048, 8, 1>(a, b, out, batch, kt, b_row_stride, tf, ti, stream, chain);
+    case 4096: return launch_fused_mul<4096, 8, 2>(a, b, out, batch, kt, b_row_stride, tf, ti, stream, chain);
+    case 8192: return launch_fused_mul<8192, 8, 4, false>(a, b, out, batch, kt, b_row_stride, tf, ti, stream, chain);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+// acc[r] <- [acc[r] +] fwd(a[r * a_row_terms * n ..]) (.) b[r * b_row_stride ..], all in the Fourier domain (no inverse): the
+// building block of loops that produce their terms one at a time, or that feed several accumulators from the same input.
+// Plans with the fused kernel: one launch (a read once, acc read + written once); others: copy -> fwd -> point-wise.
+cudaError_t launch_c64_fwd_mul_add(const cfft_plan *plan, const double2 *a, uint64_t a_row_terms, const double2 *b,
+                                   uint64_t b_row_stride, double2 *acc, bool accumulate, uint64_t batch, cudaStream_t stream)
+{
+    if (batch == 0) return cudaSuccess;
+    const bool force_composed = getenv("CFFT_B200_FUSED_MUL_COMPOSED") != nullptr;
+    if (fused_mul_kernel_available(plan) && !force_composed && a_row_terms <= 0xFFFFFFFFull)
+        return dispatch_fused_mul(plan, a, b, acc, batch, uint32_t(a_row_terms), b_row_stride, stream, 16u | (accumulate ? 8u : 0u));
+    const uint64_t n = plan->n, row_bytes = n * sizeof(c64);
+    uint64_t chunk_rows = (uint64_t{256} << 20) / row_bytes;
+    if (chunk_rows < 1) chunk_rows = 1;
+    if (chunk_rows > batch) chunk_rows = batch;
+    cudaMemPool_t pool = nullptr;
+    cudaError_t e = workspace_pool(plan->device, &pool);
+    if (e != cudaSuccess) return e;
+    c64 *ws = nullptr;
+    e = cudaMallocFromPoolAsync(reinterpret_cast<void **>(&ws), chunk_rows * row_bytes, pool, stream);
+    if (e != cudaSuccess) return e;
+    for (uint64_t r0 = 0; r0 < batch && e == cudaSuccess; r0 += chunk_rows) {
+        const uint64_t rows = batch - r0 < chunk_rows ? batch - r0 : chunk_rows;
+        if (a_row_terms == 1) e = cudaMemcpyAsync(ws, a + r0 * n, rows * row_bytes, cudaMemcpyDeviceToDevice, stream);
+        else e = cudaMemcpy2DAsync(ws, row_bytes, a + r0 * a_row_terms * n, a_row_terms * row_bytes, row_bytes, rows,
+                                   cudaMemcpyDeviceToDevice, stream);
+        if (e == cudaSuccess) e = launch_c64(plan, false, ws, rows, stream);
+        if (e != cudaSuccess) break;
+        uint64_t blocks = (rows * n + 255) / 256;
+        if (blocks > 148ull * 32) blocks = 148ull * 32;
+        if (accumulate) c64_pointwise_rows_kernel<true><<<unsigned(blocks), 256, 0, stream>>>(acc + r0 * n, ws, b + r0 * b_row_stride, uint32_t(n), rows, b_row_stride);
+        else c64_pointwise_rows_kernel<false><<<unsigned(blocks), 256, 0, stream>>>(acc + r0 * n, ws, b + r0 * b_row_stride, uint32_t(n), rows, b_row_stride);
+        count_launch();
+        e = cudaGetLastError();
+    }
+    const cudaError_t e2 = cudaFreeAsync(ws, stream);
+    return e != cudaSuccess ? e : e2;
+}
+
 cudaError_t launch_c64_fwd_mul_inv(const cfft_plan *plan, const double2 *a, uint64_t kterms, const double2 *b,
                                    uint64_t b_row_stride, double2 *out, uint64_t batch, cudaStream_t stream)
 {
     if (batch == 0 || kterms == 0) return cudaSuccess;
     const bool force_composed = getenv("CFFT_B200_FUSED_MUL_COMPOSED") != nullptr; // testing hook, read per call
-    if (fused_mul_kernel_available(plan) && !force_composed && kterms <= 0xFFFFFFFFull) {
-        FastTables tf, ti;
-        const c64 *bf = plan->d_fast_tw[0], *bi = plan->d_fast_tw[1];
-        tf.top1 = plan->fast_levels.size() > 0 ? bf + plan->fast_levels[0].off : bf;
-        tf.top2 = plan->fast_levels.size() > 1 ? bf + plan->fast_levels[1].off : bf;
-        tf.base = bf + plan->fast_base_off;
-        ti.top1 = plan->fast_levels.size() > 0 ? bi + plan->fast_levels[0].off : bi;
-        ti.top2 = plan->fast_levels.size() > 1 ? bi + plan->fast_levels[1].off : bi;
-        ti.base = bi + plan->fast_base_off;
-        const uint32_t kt = uint32_t(kterms);
-        switch (plan->n) {
-        case 256: return launch_fused_mul<256, 1, 1>(a, b, out, batch, kt, b_row_stride, tf, ti, stream);
-        case 512: return launch_fused_mul<512, 2, 1>(a, b, out, batch, kt, b_row_stride, tf, ti, stream);
-        case 1024: return launch_fused_mul<1024, 4, 1>(a, b, out, batch, kt, b_row_stride, tf, ti, stream);
-        case 2048: return launch_fused_mul<2048, 8, 1>(a, b, out, batch, kt, b_row_stride, tf, ti, stream);
-        case 4096: return launch_fused_mul<4096, 8, 2>(a, b, out, batch, kt, b_row_stride, tf, ti, stream);
-        case 8192: return launch_fused_mul<8192, 8, 4, false>(a, b, out, batch, kt, b_row_stride, tf, ti, stream);
-        default: return cudaErrorInvalidValue;
-        }
-    }
+    if (fused_mul_kernel_available(plan) && !force_composed && kterms <= 0xFFFFFFFFull)
+        return dispatch_fused_mul(plan, a, b, out, batch, uint32_t(kterms), b_row_stride, stream, 0);
     const uint64_t n = plan->n, row_bytes = n * sizeof(c64);
     uint64_t chunk_rows = (uint64_t{256} << 20) / row_bytes;
     if (chunk_rows < 1) chunk_rows = 1;

@@ -107,6 +107,8 @@ cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *d
 bool fused_mul_kernel_available(const cfft_plan *plan);
 cudaError_t launch_c64_fwd_mul_inv(const cfft_plan *plan, const double2 *a, uint64_t kterms, const double2 *b,
                                    uint64_t b_row_stride, double2 *out, uint64_t batch, cudaStream_t st);
+cudaError_t launch_c64_fwd_mul_add(const cfft_plan *plan, const double2 *a, uint64_t a_row_terms, const double2 *b,
+                                   uint64_t b_row_stride, double2 *acc, bool accumulate, uint64_t batch, cudaStream_t st);
 // kernels (c64_ord16.cu)
 bool ord16_supported(uint64_t n, int algo);
 cudaError_t launch_c64_ord16(const cfft_plan *plan, bool inverse, double2 *data, uint64_t batch, cudaStream_t st);

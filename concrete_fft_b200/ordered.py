@@ -165,6 +165,35 @@ class _PlanBase:
                                            current_stream_ptr(dev)))
         return out
 
+    def fwd_mul_add(self, a, b, acc, accumulate=True):
+        """acc[r] (Fourier domain) <- [acc[r] +] fwd(a[r]) * b[r]  (cfft_c64_fwd_mul_add), no inverse.  `a`: [batch, n] CUDA
+        complex128, possibly a strided view a3[:, j] of a contiguous [batch, k, n] tensor; `b`: [n] / [batch, n] (or such a
+        view of [batch, k, n]); `acc`: contiguous [batch, n]."""
+        import torch
+
+        n = self.fft_size()
+        if not (isinstance(acc, torch.Tensor) and acc.is_cuda and acc.dtype == torch.complex128 and acc.is_contiguous()
+                and acc.dim() == 2 and acc.shape[1] == n):
+            raise N.PanicError("assertion failed: acc is a contiguous [batch, fft_size] complex128 CUDA tensor")
+        batch = int(acc.shape[0])
+
+        def rows(t, name, may_share):
+            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.complex128):
+                raise TypeError("%s must be a CUDA complex128 tensor" % name)
+            if may_share and t.dim() == 1 and t.shape[0] == n and t.stride(0) == 1:
+                return 0
+            if t.dim() != 2 or tuple(t.shape) != (batch, n) or t.stride(1) != 1 or (batch > 1 and t.stride(0) < n):
+                raise N.PanicError("assertion failed: %s has shape [batch, fft_size] with unit inner stride" % name)
+            return int(t.stride(0)) if batch > 1 else n
+
+        sa, sb = rows(a, "a", False), rows(b, "b", True)
+        dev = acc.device.index
+        if dev != self.device() or a.device.index != dev or b.device.index != dev:
+            raise ValueError("operands must live on the plan's device cuda:%d" % self.device())
+        N.check(N.lib.cfft_c64_fwd_mul_add(self._h, a.data_ptr(), sa, b.data_ptr(), sb, acc.data_ptr(), int(bool(accumulate)),
+                                           batch, current_stream_ptr(dev)))
+        return acc
+
     def has_fused_mul_kernel(self):
         return bool(N.lib.cfft_plan_has_fused_mul_kernel(self._h))
 

@@ -248,6 +248,16 @@ cfft_status cfft_c64_mul_add_assign(int device, void *acc_dev, const void *a_dev
  * kernels through a stream-ordered workspace.  Stream ordered on the plan's device. */
 cfft_status cfft_c64_fwd_mul_inv(const cfft_plan *plan, const void *a_dev, uint64_t k_terms, const void *b_dev,
                                  uint64_t b_row_stride, void *out_dev, uint64_t batch, void *stream);
+/* acc[r] <- fwd(a[r]) (.) b[r]  (accumulate == 0)   or   acc[r] <- acc[r] + fwd(a[r]) (.) b[r]  (accumulate != 0), r < batch:
+ * the forward transform and the element-wise multiply[-accumulate] into a FOURIER-DOMAIN accumulator (this plan's order)
+ * in one call, without the inverse -- for loops that produce their terms one at a time or feed several accumulators
+ * from one input (out_j += fwd(a_i) (.) B[i][j]), finished by cfft_c64_inv(acc).  Bit-identical to cfft_c64_fwd on a
+ * copy of a followed by cfft_c64_mul_assign / cfft_c64_mul_add_assign.  Row r of a starts at a + r * a_row_stride
+ * (c64 elements, a positive multiple of n: picks one term out of a [batch][k][n] array), row r of b at
+ * b + r * b_row_stride (0 = shared), acc is [batch][n] and must not alias a or b.  One kernel on plans for which
+ * cfft_plan_has_fused_mul_kernel answers 1 (a read once, acc read and written once), else copy + fwd + product. */
+cfft_status cfft_c64_fwd_mul_add(const cfft_plan *plan, const void *a_dev, uint64_t a_row_stride, const void *b_dev,
+                                 uint64_t b_row_stride, void *acc_dev, int accumulate, uint64_t batch, void *stream);
 int cfft_plan_has_fused_mul_kernel(const cfft_plan *plan);
 
 /* ---- diagnostics ------------------------------------------------------------------- */

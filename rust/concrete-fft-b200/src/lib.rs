@@ -365,6 +365,15 @@ pub mod device {
     pub unsafe fn c64_mul_add_assign(device: i32, acc: *mut c_void, a: *const c_void, b: *const c_void, len: u64, stream: *mut c_void) {
         ffi::check(ffi::cfft_c64_mul_add_assign(device, acc, a, b, len, stream));
     }
+    /// `acc[r] <- [acc[r] +] fwd(a[r]) * b[r]` in the Fourier domain (no inverse): forward transform and multiply[-accumulate]
+    /// in one call, for loops that produce terms one at a time or feed several accumulators from one input; finish with
+    /// [`c64_inv`].  Strides in c64 elements; `a_row_stride` a positive multiple of `n`, `b_row_stride == 0` shares `b`.
+    /// # Safety
+    /// `a`, `b`, `acc` address `batch` rows of `n` c64 at those strides on the plan's device; `acc` aliases neither input.
+    #[allow(clippy::too_many_arguments)]
+    pub unsafe fn c64_fwd_mul_add(plan: *const ffi::cfft_plan, a: *const c_void, a_row_stride: u64, b: *const c_void, b_row_stride: u64, acc: *mut c_void, accumulate: bool, batch: u64, stream: *mut c_void) {
+        ffi::check(ffi::cfft_c64_fwd_mul_add(plan, a, a_row_stride, b, b_row_stride, acc, accumulate as i32, batch, stream));
+    }
     /// fft128: `lhs <- inv((fwd(lhs) * rhs) * factor)` on `batch` transforms in one call (one kernel for
     /// `n <= 4096`): the negacyclic product of the reference's tests, bit-identical to `fwd`, the scalar
     /// `cplx_mul` loop and `inv`.  `rhs_row_stride` is 0 (one Fourier-domain `rhs` row shared by the batch) or `n`.

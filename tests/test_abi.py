@@ -71,6 +71,7 @@ def test_fused_product_entry_points_reject_bad_plans_before_cuda(C):
     assert b"c64 plan" in lib.cfft_last_error()
     assert lib.cfft_f128_fwd_mul_inv(None, None, None, None, None, None, None, None, None, 0, 1.0, 0, None) == C._native.EINVAL
     assert b"fft128 plan" in lib.cfft_last_error()
+    assert lib.cfft_c64_fwd_mul_add(None, None, 0, None, 0, None, 0, 0, None) == C._native.EINVAL
     assert lib.cfft_plan_has_fused_mul_kernel(None) == 0
 
 

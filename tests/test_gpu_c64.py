@@ -442,6 +442,45 @@ def test_fwd_mul_inv_any_plan_bit_exact(C, torch, kind, n, algo, base_n):
         assert bits_equal(got.cpu().numpy(), _oracle_fwd_mul_inv(ref, a, b)), (kind, n, batch, k, shared)
 
 
+@pytest.mark.parametrize("n,algo,base_n", [(256, "Dif16", 256), (1024, "Dif16", 256), (2048, "Dif16", 256), (4096, "Dif16", 256),
+                                           (8192, "Dif16", 256), (2048, "Dif4", 32), (16384, "Dif16", 256)])
+def test_fwd_mul_add_bit_exact(C, torch, n, algo, base_n):
+    """cfft_c64_fwd_mul_add (forward transform + multiply[-accumulate] into a Fourier-domain accumulator, no inverse): term by
+    term it builds exactly the oracle's sum, and cfft_c64_inv of it equals cfft_c64_fwd_mul_inv; strided views of a
+    [batch, k, n] array as inputs, b shared or per row, one kernel per call where the plan has the fused kernel."""
+    rng = np.random.default_rng(31 * n + base_n)
+    plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(getattr(C.ordered.FftAlgo, algo), base_n))
+    ref = O.UnorderedPlan(n, getattr(O, algo.upper()), base_n)
+    for batch, k, shared in [(5, 3, True), (2, 2, False), (1, 1, True)]:
+        a = rand_c(rng, batch, k, n) - (0.5 + 0.5j)
+        b = (rand_c(rng, k, n) if shared else rand_c(rng, batch, k, n)) - (0.5 + 0.5j)
+        want = np.empty((batch, n), np.complex128)
+        for r in range(batch):
+            br = b if shared else b[r]
+            acc = O.c64_pointwise(ref.fwd(a[r, 0]), br[0])
+            for j in range(1, k):
+                acc = O.c64_pointwise(ref.fwd(a[r, j]), br[j], acc)
+            want[r] = acc
+        da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+        dacc = torch.full((batch, n), float("nan"), dtype=torch.complex128, device="cuda")
+        launches = C._native.launch_count()
+        for j in range(k):
+            plan.fwd_mul_add(da[:, j], db[j] if shared else db[:, j], dacc, accumulate=j > 0)
+        if plan.has_fused_mul_kernel():
+            assert C._native.launch_count() - launches == k
+        torch.cuda.synchronize()
+        assert bits_equal(dacc.cpu().numpy(), want), (n, batch, k, shared)
+        assert bits_equal(da.cpu().numpy(), a)
+        plan.inv(dacc)
+        full = plan.fwd_mul_inv(da, db)
+        torch.cuda.synchronize()
+        assert bits_equal(dacc.cpu().numpy(), full.cpu().numpy()), (n, batch, k, shared)
+    with pytest.raises(C.PanicError):
+        plan.fwd_mul_add(da[:, 0], db[0], dacc[:, : n // 2].contiguous())
+    with pytest.raises(C.PanicError):  # acc aliasing an input
+        C._native.check(C._native.lib.cfft_c64_fwd_mul_add(plan._h, dacc.data_ptr(), n, db.data_ptr(), 0, dacc.data_ptr(), 0, 1, 0))
+
+
 def test_fwd_mul_inv_negacyclic_external_product(C, torch):
     """The shape the call exists for: out = sum_k a_k * b_k modulo X^N + 1 (N = 4096, fft size 2048, k = 4 terms, b
     shared by the batch like a bootstrapping-key GGSW row), one call on the device, against the exact integer
