@@ -14,7 +14,7 @@ import numpy as _np
 
 from . import _native  # noqa: F401  (raises ImportError if libcfft_b200.so is missing)
 from . import fft128, ordered, pointwise, unordered  # noqa: F401
-from ._native import CfftError, InvalidLength, PanicError, launch_count, version  # noqa: F401
+from ._native import CfftError, InvalidLength, PanicError, launch_count, probe_fp64_issue_rate, version  # noqa: F401
 
 c64 = _np.complex128  # src/lib.rs:84
-__all__ = ["ordered", "unordered", "fft128", "pointwise", "c64", "CfftError", "PanicError", "InvalidLength", "launch_count", "version"]
+__all__ = ["ordered", "unordered", "fft128", "pointwise", "c64", "CfftError", "PanicError", "InvalidLength", "launch_count", "version", "probe_fp64_issue_rate"]

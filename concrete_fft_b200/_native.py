@@ -81,6 +81,7 @@ _SIGNATURES = {
     "cfft_launch_count": (_u64, []),
     "cfft_version": (ctypes.c_char_p, []),
     "cfft_plan_copy_twiddles": (ctypes.c_int32, [_vp, _int, _vp, _u64]),
+    "cfft_probe_fp64_issue_rate": (ctypes.c_int32, [_int] + [ctypes.POINTER(ctypes.c_double)] * 4 + [ctypes.POINTER(_int)]),
 }
 EXPORTED_SYMBOLS = sorted(_SIGNATURES)
 for _name, (_res, _args) in _SIGNATURES.items():
@@ -100,6 +101,15 @@ def check(status, panic_on=(EINVAL, ELENGTH)):
 
 def launch_count():
     return int(lib.cfft_launch_count())
+
+
+def probe_fp64_issue_rate(device=0):
+    """Measured FP64 issue rate of `device`: {"dfma_per_s", "dadd_per_s", "mix_per_s", "sm_mhz", "sm_count"}."""
+    vals = [ctypes.c_double() for _ in range(4)]
+    sms = _int()
+    check(lib.cfft_probe_fp64_issue_rate(device, *[ctypes.byref(v) for v in vals], ctypes.byref(sms)))
+    return {"dfma_per_s": vals[0].value, "dadd_per_s": vals[1].value, "mix_per_s": vals[2].value, "sm_mhz": vals[3].value,
+            "sm_count": sms.value}
 
 
 def version():

@@ -38,6 +38,13 @@ cfft_status cuda_fail(cudaError_t e, const char *what)
         if (e__ != cudaSuccess) return cuda_fail(e__, #call);           \
     } while (0)
 
+// do the byte ranges [a, a + na) and [b, b + nb) intersect?
+bool ranges_overlap(const void *a, uint64_t na, const void *b, uint64_t nb)
+{
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(a), b0 = reinterpret_cast<uintptr_t>(b);
+    return na && nb && a0 < b0 + nb && b0 < a0 + na;
+}
+
 struct DeviceGuard {
     int prev = -1;
     bool ok = false;
@@ -585,7 +592,8 @@ cfft_status cfft_plan_autotune(cfft_plan *p, uint64_t batch_hint)
             cands.push_back({"fast-b256-column+fused-rows/L2-16MBx4", 9, 0, 16, 4});
             cands.push_back({"fast-b256-column+fused-rows/L2-32MBx2", 9, 0, 32, 2});
         }
-        if (p->n >= 16384 && p->n <= 65536) cands.push_back({"fast-b256-persistent-2pass", 8, 0});
+        // the persistent two-phase kernel spin-waits on other CTAs: opt-in, never picked silently
+        if (p->n >= 16384 && p->n <= 65536 && getenv("CFFT_B200_ALLOW_PERSISTENT")) cands.push_back({"fast-b256-persistent-2pass", 8, 0});
         if (p->n > 256 && p->n <= 8192) cands.push_back({"fast-b256-regs", 1, 0});
         if (p->n > 256 && p->n <= 16384) cands.push_back({"fast-b256-column+rows", 2, 0});
         if (p->n == 8192 || p->n == 16384) cands.push_back({"fast-b256-cluster", 4, 0});
@@ -641,6 +649,11 @@ cfft_status cfft_plan_autotune(cfft_plan *p, uint64_t batch_hint)
         if (ms < best_ms) { best_ms = ms; best = i; }
     }
     cleanup();
+    {   // give back what the timed candidates left in the stream-ordered workspace pool (a Measure plan must
+        // not keep hundreds of MiB of device memory for the life of the process)
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceSynchronize() == cudaSuccess && workspace_pool(p->device, &pool) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    }
     if (rc != CFFT_OK) {
         p->fast_variant = keep_variant;
         p->tile_elems = keep_tile;
@@ -811,8 +824,18 @@ cfft_status cfft_c64_fwd_mul_inv(const cfft_plan *p, const void *a_dev, uint64_t
     if ((reinterpret_cast<uintptr_t>(a_dev) | reinterpret_cast<uintptr_t>(b_dev) | reinterpret_cast<uintptr_t>(out_dev)) & 15)
         return fail(CFFT_EINVAL, "device buffers must be 16-byte aligned (128-bit accesses)");
     if (b_row_stride != 0 && b_row_stride < k_terms * p->n) return fail(CFFT_EINVAL, "b_row_stride must be 0 (b shared by every row) or >= k_terms * n");
-    if (out_dev == a_dev && k_terms != 1) return fail(CFFT_EINVAL, "out may alias a only when k_terms == 1");
-    if (out_dev == b_dev) return fail(CFFT_EINVAL, "out must not alias b");
+    {   // the kernels read a and b through __restrict__ pointers while other rows of out are being written: only the exact
+        // in-place case (out == a, one term) is allowed, any other intersection of the extents is rejected
+        const uint64_t row = p->n * sizeof(cplx);
+        const uint64_t a_bytes = batch * k_terms * row, out_bytes = batch * row;
+        const uint64_t b_bytes = batch == 0 ? 0 : (b_row_stride == 0 ? k_terms * row : ((batch - 1) * b_row_stride + k_terms * p->n) * sizeof(cplx));
+        if (out_dev == a_dev) {
+            if (k_terms != 1) return fail(CFFT_EINVAL, "out may alias a only when k_terms == 1");
+        } else if (ranges_overlap(out_dev, out_bytes, a_dev, a_bytes)) {
+            return fail(CFFT_EINVAL, "out overlaps a without being the same buffer");
+        }
+        if (ranges_overlap(out_dev, out_bytes, b_dev, b_bytes)) return fail(CFFT_EINVAL, "out must not overlap b");
+    }
     DeviceGuard guard(p->device);
     if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
     cudaError_t e = launch_c64_fwd_mul_inv(p, static_cast<const double2 *>(a_dev), k_terms, static_cast<const double2 *>(b_dev),
@@ -830,7 +853,13 @@ cfft_status cfft_c64_fwd_mul_add(const cfft_plan *p, const void *a_dev, uint64_t
         return fail(CFFT_EINVAL, "device buffers must be 16-byte aligned (128-bit accesses)");
     if (a_row_stride == 0 || a_row_stride % p->n) return fail(CFFT_EINVAL, "a_row_stride must be a positive multiple of n");
     if (b_row_stride != 0 && b_row_stride < p->n) return fail(CFFT_EINVAL, "b_row_stride must be 0 (b shared by every row) or >= n");
-    if (acc_dev == a_dev || acc_dev == b_dev) return fail(CFFT_EINVAL, "acc must not alias a or b");
+    {
+        const uint64_t row = p->n * sizeof(cplx);
+        const uint64_t a_bytes = batch == 0 ? 0 : ((batch - 1) * a_row_stride + p->n) * sizeof(cplx);
+        const uint64_t b_bytes = batch == 0 ? 0 : (b_row_stride == 0 ? row : ((batch - 1) * b_row_stride + p->n) * sizeof(cplx));
+        if (ranges_overlap(acc_dev, batch * row, a_dev, a_bytes) || ranges_overlap(acc_dev, batch * row, b_dev, b_bytes))
+            return fail(CFFT_EINVAL, "acc must not overlap a or b");
+    }
     DeviceGuard guard(p->device);
     if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
     cudaError_t e = launch_c64_fwd_mul_add(p, static_cast<const double2 *>(a_dev), a_row_stride / p->n, static_cast<const double2 *>(b_dev),
@@ -869,7 +898,7 @@ static cfft_status run_permute(const cfft_plan *p, bool to_std, const void *src,
 {
     if (!p || p->kind == KIND_F128) return fail(CFFT_EINVAL, "not a c64 plan");
     if (batch && (!src || !dst)) return fail(CFFT_EINVAL, "null buffer");
-    if (src == dst) return fail(CFFT_EINVAL, "src and dst must not overlap");
+    if (ranges_overlap(src, batch * p->n * sizeof(cplx), dst, batch * p->n * sizeof(cplx))) return fail(CFFT_EINVAL, "src and dst must not overlap");
     DeviceGuard guard(p->device);
     cudaError_t e = launch_permute(p, to_std, static_cast<const double2 *>(src), static_cast<double2 *>(dst), batch,
                                    static_cast<cudaStream_t>(stream));

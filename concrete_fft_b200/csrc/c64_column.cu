@@ -11,6 +11,8 @@
 //
 // Same butterflies and twiddle values as the reference => bit-identical results; the element
 // order produced is the reference's (bit-reversed slotting per level).
+#include <cstdlib>
+
 #include "c64_dev.cuh"
 #include "plan.h"
 
@@ -209,6 +211,8 @@ struct TwoPassParams {
     uint32_t *sync;     // [0] queue head; [1 + j] finished first-phase items of transform j
 };
 
+__device__ unsigned int g_twopass_timeouts = 0; // second-phase items that gave up waiting for their first phase
+
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p)
 {
     uint32_t v;
@@ -262,7 +266,13 @@ c64_twopass_kernel(TwoPassParams prm)
                     uint32_t spins = 0;
                     while (ld_acquire_u32(prm.sync + 1 + j) < uint32_t(F_ITEMS)) {
                         __nanosleep(200);
-                        if (++spins > (1u << 25)) __trap(); // ~7 s: never hang the GPU on a lost signal
+                        // ~7 s without the signal (producers descheduled by MPS / a debugger / preemption): never hang and
+                        // never trap the context -- give up waiting, count it, and let the host see the count
+                        // (cfft_twopass_timeouts); the variant is opt-in for exactly this reason
+                        if (++spins > (1u << 25)) {
+                            atomicAdd(&g_twopass_timeouts, 1u);
+                            break;
+                        }
                     }
                 }
                 __syncthreads();
@@ -346,6 +356,12 @@ cudaError_t launch_c64_column_group(bool inverse, const double2 *src, double2 *d
     prm.total_tiles = 0;
     for (int i = 0; i < 3; i++) prm.tw[i] = tw[i];
     const int key = ra * 100 + rb * 10 + rc;
+    // two radix-8 levels: one thread per column with tensor memory between the levels (c64_tmem.cu), bit-identical.
+    // Measured slower than the shared-memory tiles on B200 (profiles/r2a_tmem_columns.txt: n = 2^16 3.0 vs 3.3 TB/s:
+    // eight warps per SM with one serial chain each do not keep HBM busy), so it is opt-in: CFFT_B200_TMEM_COLUMNS=1
+    static const bool use_tmem = [] { const char *e = getenv("CFFT_B200_TMEM_COLUMNS"); return e && atoi(e) != 0; }();
+    if (key == 881 && use_tmem && tmem_column88_supported(n, span0))
+        return launch_c64_tmem_column88(inverse, src, dst, batch, n, span0, tw[0], tw[1], stream);
     switch (key) {
     case 811: return launch_group<8, 1, 1>(inverse, src, dst, prm, batch, stream);
     case 411: return launch_group<4, 1, 1>(inverse, src, dst, prm, batch, stream);
@@ -363,6 +379,13 @@ cudaError_t launch_c64_column_group(bool inverse, const double2 *src, double2 *d
 } // namespace cfft
 
 namespace cfft {
+
+// number of second-phase work items of the persistent kernel that timed out waiting on this device since load (0 in a
+// healthy process; a non-zero count means results of those calls are invalid and variant 2 should be used instead)
+cudaError_t twopass_timeouts(unsigned int *out)
+{
+    return cudaMemcpyFromSymbol(out, g_twopass_timeouts, sizeof(unsigned int));
+}
 
 // n = 2^14, 2^15, 2^16 (one column group + base FFTs): the persistent two-phase kernel.  lag = 0: automatic.
 cudaError_t launch_c64_twopass(bool inverse, double2 *data, uint64_t batch, uint32_t n, const int radices[3],

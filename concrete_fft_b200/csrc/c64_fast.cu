@@ -28,6 +28,7 @@
 
 namespace cfft {
 using namespace dev;
+constexpr uint64_t kWorkspaceChunkBytes = uint64_t{256} << 20;
 namespace {
 
 // One unordered level of span NCUR on the 16 register values of a thread: B = 16/R butterflies,
@@ -649,8 +650,8 @@ cudaError_t launch_rows_std(bool inverse, const c64 *src, c64 *dst, uint64_t bat
 
 } // namespace
 
-// Stream-ordered workspace for the out-of-place (ordered) path: one private pool per device that keeps
-// its memory between calls (release threshold = max), so steady-state calls never touch the OS allocator.
+// Stream-ordered workspace for the out-of-place (ordered) path and the composed fused-product path: one private
+// pool per device with a bounded release threshold; every user allocates at most kWorkspaceChunkBytes per call.
 cudaError_t workspace_pool(int device, cudaMemPool_t *out)
 {
     static std::mutex mu;
@@ -665,7 +666,9 @@ cudaError_t workspace_pool(int device, cudaMemPool_t *out)
         props.location.id = device;
         cudaError_t e = cudaMemPoolCreate(&pools[device], &props);
         if (e != cudaSuccess) return e;
-        uint64_t keep = ~uint64_t{0};
+        // keep at most kWorkspaceChunkBytes between calls (steady-state calls of the chunked paths never touch the
+        // OS allocator); anything above that goes back to the driver at the next synchronisation point
+        uint64_t keep = kWorkspaceChunkBytes;
         e = cudaMemPoolSetAttribute(pools[device], cudaMemPoolAttrReleaseThreshold, &keep);
         if (e != cudaSuccess) return e;
     }
@@ -867,21 +870,36 @@ cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *d
                 }
                 return e;
             }
+            // the out-of-place workspace is bounded (kWorkspaceChunkBytes): a larger call runs slice by slice on the
+            // same stream, so the pool never holds more than that on behalf of one call
+            uint64_t ws_rows = kWorkspaceChunkBytes / (plan->n * sizeof(c64));
+            if (ws_rows < 1) ws_rows = 1;
+            if (ws_rows > rows) ws_rows = rows;
             c64 *ws = nullptr;
-            e = cudaMallocFromPoolAsync(reinterpret_cast<void **>(&ws), rows * plan->n * sizeof(c64), pool, st);
+            e = cudaMallocFromPoolAsync(reinterpret_cast<void **>(&ws), ws_rows * plan->n * sizeof(c64), pool, st);
             if (e != cudaSuccess) return e;
-            auto rows_pass = [&](const c64 *src, c64 *dst) {
-                return n32 / 256 >= 16 ? launch_rows_std<16>(inverse, src, dst, rows, n32, tb.base, st)
-                                       : launch_rows_std<8>(inverse, src, dst, rows, n32, tb.base, st);
-            };
-            if (!inverse) {
-                for (size_t i = 0; i < ng && e == cudaSuccess; i++)
-                    e = group(plan->fast_groups[i], d0, i + 1 == ng ? ws : d0);
-                if (e == cudaSuccess) e = rows_pass(ws, d0);
-            } else {
-                e = rows_pass(d0, ws);
-                for (size_t i = ng; i-- > 0 && e == cudaSuccess;)
-                    e = group(plan->fast_groups[i], i + 1 == ng ? ws : d0, d0);
+            for (uint64_t r0 = 0; r0 < rows && e == cudaSuccess; r0 += ws_rows) {
+                const uint64_t nr = rows - r0 < ws_rows ? rows - r0 : ws_rows;
+                c64 *dd = d0 + r0 * plan->n;
+                auto group_n = [&](const cfft_plan::FastGroup &g, const c64 *src, c64 *dst) {
+                    const double2 *tw[3] = {base, base, base};
+                    for (int i = 0; i < 3; i++)
+                        if (g.radices[i] > 1) tw[i] = base + plan->fast_levels[size_t(g.first_level + i)].off;
+                    return launch_c64_column_group(inverse, src, dst, nr, n32, g.span0, g.radices, tw, st);
+                };
+                auto rows_pass = [&](const c64 *src, c64 *dst) {
+                    return n32 / 256 >= 16 ? launch_rows_std<16>(inverse, src, dst, nr, n32, tb.base, st)
+                                           : launch_rows_std<8>(inverse, src, dst, nr, n32, tb.base, st);
+                };
+                if (!inverse) {
+                    for (size_t i = 0; i < ng && e == cudaSuccess; i++)
+                        e = group_n(plan->fast_groups[i], dd, i + 1 == ng ? ws : dd);
+                    if (e == cudaSuccess) e = rows_pass(ws, dd);
+                } else {
+                    e = rows_pass(dd, ws);
+                    for (size_t i = ng; i-- > 0 && e == cudaSuccess;)
+                        e = group_n(plan->fast_groups[i], i + 1 == ng ? ws : dd, dd);
+                }
             }
             const cudaError_t e2 = cudaFreeAsync(ws, st);
             return e != cudaSuccess ? e : e2;
@@ -889,31 +907,46 @@ cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *d
 
         if (rows_per_chunk >= batch) return process(data, batch, stream);
 
-        struct Aux { int device = -1; cudaStream_t st[4] = {}; cudaEvent_t done[4] = {}; cudaEvent_t start = nullptr; };
-        static thread_local Aux aux;
+        // auxiliary streams / events of the fork-join: one set per (host thread, device), created once and kept
+        struct Aux { bool ready = false; cudaStream_t st[4] = {}; cudaEvent_t done[4] = {}; cudaEvent_t start = nullptr; };
+        static thread_local Aux aux_by_device[64];
         const bool fork = nstreams > 1;
-        if (fork && aux.device != plan->device) {
-            for (int i = 0; i < 4; i++) {
-                if (cudaStreamCreateWithFlags(&aux.st[i], cudaStreamNonBlocking) != cudaSuccess) return cudaGetLastError();
-                if (cudaEventCreateWithFlags(&aux.done[i], cudaEventDisableTiming) != cudaSuccess) return cudaGetLastError();
+        if (fork && (plan->device < 0 || plan->device >= 64)) return cudaErrorInvalidDevice;
+        Aux &aux = aux_by_device[fork ? plan->device : 0];
+        if (fork && !aux.ready) {
+            cudaError_t ce = cudaSuccess;
+            for (int i = 0; i < 4 && ce == cudaSuccess; i++) {
+                ce = cudaStreamCreateWithFlags(&aux.st[i], cudaStreamNonBlocking);
+                if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&aux.done[i], cudaEventDisableTiming);
             }
-            if (cudaEventCreateWithFlags(&aux.start, cudaEventDisableTiming) != cudaSuccess) return cudaGetLastError();
-            aux.device = plan->device;
-        }
-        if (fork) {
-            cudaEventRecord(aux.start, stream);
-            for (int i = 0; i < nstreams; i++) cudaStreamWaitEvent(aux.st[i], aux.start, 0);
+            if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&aux.start, cudaEventDisableTiming);
+            if (ce != cudaSuccess) { // nothing half-built is kept
+                for (int i = 0; i < 4; i++) {
+                    if (aux.st[i]) cudaStreamDestroy(aux.st[i]);
+                    if (aux.done[i]) cudaEventDestroy(aux.done[i]);
+                }
+                if (aux.start) cudaEventDestroy(aux.start);
+                aux = Aux{};
+                return ce;
+            }
+            aux.ready = true;
         }
         cudaError_t e = cudaSuccess;
+        if (fork) {
+            e = cudaEventRecord(aux.start, stream);
+            for (int i = 0; i < nstreams && e == cudaSuccess; i++) e = cudaStreamWaitEvent(aux.st[i], aux.start, 0);
+            if (e != cudaSuccess) return e;
+        }
         uint64_t chunk_index = 0;
         for (uint64_t r0 = 0; r0 < batch && e == cudaSuccess; r0 += rows_per_chunk, chunk_index++) {
             const uint64_t rows = (batch - r0 < rows_per_chunk) ? batch - r0 : rows_per_chunk;
             e = process(data + r0 * plan->n, rows, fork ? aux.st[chunk_index % uint64_t(nstreams)] : stream);
         }
-        if (fork) {
+        if (fork) { // always join, even after a failed launch: the caller's stream must stay ordered after the side streams
             for (int i = 0; i < nstreams; i++) {
-                cudaEventRecord(aux.done[i], aux.st[i]);
-                cudaStreamWaitEvent(stream, aux.done[i], 0);
+                cudaError_t je = cudaEventRecord(aux.done[i], aux.st[i]);
+                if (je == cudaSuccess) je = cudaStreamWaitEvent(stream, aux.done[i], 0);
+                if (e == cudaSuccess) e = je;
             }
         }
         return e != cudaSuccess ? e : cudaGetLastError();

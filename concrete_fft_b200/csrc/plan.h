@@ -115,9 +115,15 @@ cudaError_t launch_c64_ord16(const cfft_plan *plan, bool inverse, double2 *data,
 // kernels (c64_column.cu): one group of <= 3 unordered levels in one HBM pass
 cudaError_t launch_c64_column_group(bool inverse, const double2 *src, double2 *dst, uint64_t batch, uint32_t n, uint32_t span0,
                                     const int radices[3], const double2 *const tw[3], cudaStream_t st);
+// kernels (c64_tmem.cu): two radix-8 levels in one HBM pass, one thread per 64-element column, tensor memory as the
+// parking space between the levels (no shared memory, no block barrier)
+bool tmem_column88_supported(uint32_t n, uint32_t span0);
+cudaError_t launch_c64_tmem_column88(bool inverse, const double2 *src, double2 *dst, uint64_t batch, uint32_t n, uint32_t span0,
+                                     const double2 *tw0, const double2 *tw1, cudaStream_t st);
 // n = 2^14 .. 2^16: column group + base FFTs in one persistent kernel (c64_column.cu)
 cudaError_t launch_c64_twopass(bool inverse, double2 *data, uint64_t batch, uint32_t n, const int radices[3],
                                const double2 *const tw[3], const double2 *tw_base, uint32_t lag, int device, cudaStream_t st);
+cudaError_t twopass_timeouts(unsigned int *out);
 // stream-ordered scratch pool, one per device, keeps its memory between calls (c64_fast.cu)
 cudaError_t workspace_pool(int device, cudaMemPool_t *out);
 // dispatcher (api.cc): fast kernel when the plan has one, else the exact tile kernel

@@ -70,6 +70,8 @@ class Plan:
             N.check(fn(self._h, *ptrs, length, batch))
         else:
             dev = views[0][3]
+            if any(v[3] != self.device() for v in views):
+                raise ValueError("planes must live on the plan's device cuda:%d" % self.device())
             fn = N.lib.cfft_f128_inv if inverse else N.lib.cfft_f128_fwd
             N.check(fn(self._h, *ptrs, batch, current_stream_ptr(dev)))
 
@@ -105,6 +107,8 @@ class Plan:
             raise N.PanicError("assertion failed: rhs holds fft_size or batch * fft_size points")
         stride = 0 if rv[0][2] == n else n
         dev = lv[0][3]
+        if any(v[3] != self.device() for v in lv + rv):
+            raise ValueError("planes must live on the plan's device cuda:%d" % self.device())
         N.check(N.lib.cfft_f128_fwd_mul_inv(self._h, *[v[1] for v in lv], *[v[1] for v in rv], stride, float(factor),
                                             length // n, current_stream_ptr(dev)))
 

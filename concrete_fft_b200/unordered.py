@@ -69,7 +69,12 @@ class Plan(_PlanBase):
         if kind == "host":
             N.check(N.lib.cfft_unordered_fwd_monomial_host(self._h, degree, ptr, length))
         else:
+            self._check_device(dev)
             N.check(N.lib.cfft_unordered_fwd_monomial(self._h, degree, ptr, current_stream_ptr(dev)))
+
+    def _check_device(self, dev):
+        if dev != self.device():
+            raise ValueError("buffer is on cuda:%d but the plan lives on cuda:%d" % (dev, self.device()))
 
     def permutation(self):
         """perm[i] = index in the plan's buffer of Fourier coefficient i (bit_rev_twice)."""
@@ -94,6 +99,7 @@ class Plan(_PlanBase):
             return out
         import torch
 
+        self._check_device(dev)
         out = torch.empty_like(buf)
         N.check(N.lib.cfft_unordered_to_standard(self._h, ptr, out.data_ptr(), batch, current_stream_ptr(dev)))
         return out
@@ -104,11 +110,19 @@ class Plan(_PlanBase):
         n = self.fft_size()
         kind, ptr, length, batch, dev = c64_view(buf, n)
         if kind == "device":
-            if not is_torch(seq) or seq.numel() != length or length % n:
-                raise N.InvalidLength("invalid length %d, expected a sequence of %d 64-bit complex numbers"
-                                      % (seq.numel() if is_torch(seq) else len(seq), n))
-            N.check(N.lib.cfft_unordered_from_standard(self._h, seq.contiguous().data_ptr(), ptr, batch,
-                                                       current_stream_ptr(dev)))
+            self._check_device(dev)
+            if not is_torch(seq):
+                raise TypeError("a CUDA buffer needs its sequence as a CUDA complex128 tensor on the same device")
+            # the sequence is validated exactly like the buffer: a host tensor, another dtype or another GPU would hand the
+            # kernel a pointer it cannot read (a sticky illegal-address error that poisons the CUDA context)
+            skind, sptr, slen, _, sdev = c64_view(seq.contiguous(), n)
+            if sdev != dev:
+                raise ValueError("sequence is on cuda:%d but the buffer is on cuda:%d" % (sdev, dev))
+            if slen != length or length % n:
+                raise N.InvalidLength("invalid length %d, expected a sequence of %d 64-bit complex numbers" % (slen, n))
+            if sptr == ptr:
+                raise N.PanicError("sequence and buffer must not be the same memory")
+            N.check(N.lib.cfft_unordered_from_standard(self._h, sptr, ptr, batch, current_stream_ptr(dev)))
             return
         if length != n:
             raise N.PanicError("assertion failed: n == buf.len()")
@@ -121,7 +135,10 @@ class Plan(_PlanBase):
     def serialize_bincode(self, buf):
         """bincode 1.3 framing of serialize_fourier_buffer (u64 LE length, then re, im f64 LE per
         element), the format the reference's serde test round-trips (src/unordered.rs:9447-9454)."""
-        std = self.serialize_fourier_buffer(np.ascontiguousarray(buf))
+        if is_torch(buf):  # CUDA tensor: gather on the device, frame the host copy
+            std = self.serialize_fourier_buffer(buf.contiguous()).cpu().numpy()
+        else:
+            std = self.serialize_fourier_buffer(np.ascontiguousarray(buf))
         return struct.pack("<Q", std.size) + std.astype("<c16").tobytes()
 
     def deserialize_bincode(self, blob, buf):

@@ -269,6 +269,13 @@ const char *cfft_last_error(void);
 uint64_t cfft_launch_count(void);
 /* "cfft_b200 <version> sm_100a" */
 const char *cfft_version(void);
+/* Measured FP64 issue rate of `device` (thread-level FP64 instructions per second over the whole GPU): chains of
+ * DFMA, of DADD, and a 1 : 7 DFMA : DADD mix like the fft128 butterfly's (94 instructions = 78 DADD + 12 DFMA + 4 DMUL,
+ * src/fft128/mod.rs:310-346), 16 warps per SM, timed with CUDA events; plus the SM clock observed inside the kernel
+ * (clock64 / globaltimer) and the SM count.  bench.py uses it as the measured peak of the fft128 roofline
+ * ("measure it with a DFMA microbenchmark").  Any out pointer may be NULL. */
+cfft_status cfft_probe_fp64_issue_rate(int device, double *dfma_per_s, double *dadd_per_s, double *mix_per_s,
+                                       double *sm_mhz, int *sm_count);
 /* copy of a plan's device twiddle table to host (tests: table parity with the reference's
  * init_wt / init_twiddles / init_negacyclic_twiddles).  which: c64 0 = fwd, 1 = inv table
  * (n + base_n c64 each; 2n for ordered); fft128 0..3 = re0, re1, im0, im1 (n doubles). */
