@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libcfft_b200.so")
 
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED, ELENGTH = 0, -1, -2, -3, -4, -5
 METHOD_USER, METHOD_MEASURE = 0, 1
+POLY_INTEGER, POLY_TORUS, POLY_ACCUMULATE = 0, 1, 2
 
 
 class CfftError(RuntimeError):
@@ -81,6 +82,13 @@ _SIGNATURES = {
     "cfft_launch_count": (_u64, []),
     "cfft_version": (ctypes.c_char_p, []),
     "cfft_plan_copy_twiddles": (ctypes.c_int32, [_vp, _int, _vp, _u64]),
+    "cfft_c64_poly_fwd": (ctypes.c_int32, [_vp, _vp, _vp, _u64, ctypes.c_uint32, _vp]),
+    "cfft_c64_poly_inv": (ctypes.c_int32, [_vp, _vp, _vp, _u64, ctypes.c_uint32, _vp]),
+    "cfft_c64_poly_mul": (ctypes.c_int32, [_vp, _vp, _u64, _vp, _u64, _vp, _u64, ctypes.c_uint32, _vp]),
+    "cfft_c64_poly_mul_host": (ctypes.c_int32, [_vp, _vp, _u64, _vp, _u64, _vp, _u64, ctypes.c_uint32]),
+    "cfft_plan_has_fused_poly_kernel": (_int, [_vp, _u64]),
+    "cfft_plan_copy_twist": (ctypes.c_int32, [_vp, _vp, _u64]),
+    "cfft_twopass_timeouts": (ctypes.c_int32, [_int, ctypes.POINTER(ctypes.c_uint32)]),
     "cfft_probe_fp64_issue_rate": (ctypes.c_int32, [_int] + [ctypes.POINTER(ctypes.c_double)] * 4 + [ctypes.POINTER(_int)]),
 }
 EXPORTED_SYMBOLS = sorted(_SIGNATURES)

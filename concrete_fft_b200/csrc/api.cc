@@ -134,6 +134,20 @@ cfft_status upload_c64(cfft_plan *p)
         CU(cudaMalloc(reinterpret_cast<void **>(&p->d_monomial_tw), p->n * sizeof(cplx)));
         CU(cudaMemcpy(p->d_monomial_tw, mono.data(), p->n * sizeof(cplx), cudaMemcpyHostToDevice));
     }
+    {
+        // negacyclic twist of the polynomial entry points (cfft_c64_poly_*): twist[j] = e^{+i pi j / (2n)} through the
+        // reference's sincospi64 (src/fft_simd.rs:237-296; j / 2n is exact), untwist[j] = conj(twist[j]) / n (exact, n = 2^k)
+        std::vector<cplx> tw(2 * p->n);
+        const double inv_n = 1.0 / double(p->n);
+        for (uint64_t j = 0; j < p->n; j++) {
+            double s, c;
+            sincospi64(double(j) / double(2 * p->n), s, c);
+            tw[j] = cplx{c, s};
+            tw[p->n + j] = cplx{c * inv_n, -s * inv_n};
+        }
+        CU(cudaMalloc(reinterpret_cast<void **>(&p->d_twist), 2 * p->n * sizeof(cplx)));
+        CU(cudaMemcpy(p->d_twist, tw.data(), 2 * p->n * sizeof(cplx), cudaMemcpyHostToDevice));
+    }
     return CFFT_OK;
 }
 
@@ -508,6 +522,7 @@ void cfft_plan_destroy(cfft_plan *p)
     for (int d = 0; d < 2; d++) if (p->d_fast_tw[d]) cudaFree(p->d_fast_tw[d]);
     for (int d = 0; d < 2; d++) if (p->d_top_tw[d]) cudaFree(p->d_top_tw[d]);
     if (p->d_monomial_tw) cudaFree(p->d_monomial_tw);
+    if (p->d_twist) cudaFree(p->d_twist);
     for (int i = 0; i < 4; i++) if (p->d_f128_tw[i]) cudaFree(p->d_f128_tw[i]);
     if (p->d_f128_tw4) cudaFree(p->d_f128_tw4);
     delete p;
@@ -866,6 +881,99 @@ cfft_status cfft_c64_fwd_mul_add(const cfft_plan *p, const void *a_dev, uint64_t
                                            b_row_stride, static_cast<double2 *>(acc_dev), accumulate != 0, batch,
                                            static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "c64 fwd-mul-add launch");
+    return CFFT_OK;
+}
+
+// ---- integer polynomials <-> Fourier domain -------------------------------------------------------------------------
+static cfft_status poly_args(const cfft_plan *p, const void *poly, const void *fourier, uint64_t batch, uint32_t flags, bool allow_acc)
+{
+    if (!p || p->kind == KIND_F128) return fail(CFFT_EINVAL, "not a c64 plan");
+    if (flags & ~3u) return fail(CFFT_EINVAL, "unknown flag bits");
+    if (!allow_acc && (flags & 2u)) return fail(CFFT_EINVAL, "CFFT_POLY_ACCUMULATE applies to polynomial outputs only");
+    if (batch && (!poly || !fourier)) return fail(CFFT_EINVAL, "null buffer");
+    if (reinterpret_cast<uintptr_t>(fourier) & 15) return fail(CFFT_EINVAL, "Fourier-domain buffers must be 16-byte aligned (128-bit accesses)");
+    if (reinterpret_cast<uintptr_t>(poly) & 7) return fail(CFFT_EINVAL, "polynomials must be 8-byte aligned");
+    return CFFT_OK;
+}
+
+cfft_status cfft_c64_poly_fwd(const cfft_plan *p, const int64_t *poly_dev, void *fourier_dev, uint64_t batch, uint32_t flags, void *stream)
+{
+    cfft_status st = poly_args(p, poly_dev, fourier_dev, batch, flags, false);
+    if (st != CFFT_OK) return st;
+    const uint64_t bytes = batch * p->n * sizeof(cplx);
+    if (ranges_overlap(poly_dev, bytes, fourier_dev, bytes)) return fail(CFFT_EINVAL, "poly and fourier must not overlap");
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
+    cudaError_t e = launch_c64_poly_fwd(p, reinterpret_cast<const long long *>(poly_dev), static_cast<double2 *>(fourier_dev), batch, flags,
+                                        static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "c64 poly fwd launch");
+    return CFFT_OK;
+}
+
+cfft_status cfft_c64_poly_inv(const cfft_plan *p, const void *fourier_dev, int64_t *poly_dev, uint64_t batch, uint32_t flags, void *stream)
+{
+    cfft_status st = poly_args(p, poly_dev, fourier_dev, batch, flags, true);
+    if (st != CFFT_OK) return st;
+    const uint64_t bytes = batch * p->n * sizeof(cplx);
+    if (ranges_overlap(poly_dev, bytes, fourier_dev, bytes)) return fail(CFFT_EINVAL, "poly and fourier must not overlap");
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
+    cudaError_t e = launch_c64_poly_inv(p, static_cast<const double2 *>(fourier_dev), reinterpret_cast<long long *>(poly_dev), batch, flags,
+                                        static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "c64 poly inv launch");
+    return CFFT_OK;
+}
+
+cfft_status cfft_c64_poly_mul(const cfft_plan *p, const int64_t *a_dev, uint64_t k_terms, const void *b_dev, uint64_t b_row_stride,
+                              int64_t *out_dev, uint64_t batch, uint32_t flags, void *stream)
+{
+    cfft_status st = poly_args(p, a_dev, b_dev, batch, flags, true);
+    if (st != CFFT_OK) return st;
+    if (k_terms == 0) return fail(CFFT_EINVAL, "k_terms must be >= 1");
+    if (batch && !out_dev) return fail(CFFT_EINVAL, "null buffer");
+    if (reinterpret_cast<uintptr_t>(out_dev) & 7) return fail(CFFT_EINVAL, "polynomials must be 8-byte aligned");
+    if (b_row_stride != 0 && b_row_stride < k_terms * p->n) return fail(CFFT_EINVAL, "b_row_stride must be 0 (b shared by every row) or >= k_terms * n");
+    {
+        const uint64_t row = p->n * sizeof(cplx); // a polynomial of 2n coefficients is as large as n c64
+        const uint64_t b_bytes = batch == 0 ? 0 : (b_row_stride == 0 ? k_terms * row : ((batch - 1) * b_row_stride + k_terms * p->n) * sizeof(cplx));
+        if (out_dev == a_dev) {
+            if (k_terms != 1 || (flags & 2u)) return fail(CFFT_EINVAL, "out may alias a only when k_terms == 1 and not accumulating");
+        } else if (ranges_overlap(out_dev, batch * row, a_dev, batch * k_terms * row)) {
+            return fail(CFFT_EINVAL, "out overlaps a without being the same buffer");
+        }
+        if (ranges_overlap(out_dev, batch * row, b_dev, b_bytes)) return fail(CFFT_EINVAL, "out must not overlap b");
+    }
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
+    cudaError_t e = launch_c64_poly_mul(p, reinterpret_cast<const long long *>(a_dev), k_terms, static_cast<const double2 *>(b_dev), b_row_stride,
+                                        reinterpret_cast<long long *>(out_dev), batch, flags, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "c64 poly mul launch");
+    return CFFT_OK;
+}
+
+int cfft_plan_has_fused_poly_kernel(const cfft_plan *p, uint64_t k_terms)
+{
+    return (p && p->kind != KIND_F128 && poly_fused_available(p, k_terms)) ? 1 : 0;
+}
+
+cfft_status cfft_plan_copy_twist(const cfft_plan *p, void *host_out, uint64_t bytes)
+{
+    if (!p || p->kind == KIND_F128 || !host_out) return fail(CFFT_EINVAL, "not a c64 plan / null out");
+    if (bytes != 2 * p->n * sizeof(cplx)) return fail(CFFT_EINVAL, "twist tables hold 2 n c64");
+    DeviceGuard guard(p->device);
+    CU(cudaMemcpy(host_out, p->d_twist, bytes, cudaMemcpyDeviceToHost));
+    return CFFT_OK;
+}
+
+cfft_status cfft_twopass_timeouts(int device, uint32_t *out)
+{
+    if (!out) return fail(CFFT_EINVAL, "null out");
+    cfft_status st = check_device(device);
+    if (st != CFFT_OK) return st;
+    DeviceGuard guard(device);
+    unsigned int v = 0;
+    CU(twopass_timeouts(&v));
+    *out = v;
     return CFFT_OK;
 }
 

@@ -11,7 +11,7 @@ HOSTFLAGS="-Xcompiler -fPIC,-ffp-contract=off,-O2,-Wall"
 CUFLAGS="-std=c++17 -O3 -lineinfo --fmad=false $ARCH $HOSTFLAGS"
 mkdir -p _obj
 pids=()
-for f in c64_tile.cu c64_regs.cu c64_fast.cu c64_ord16.cu c64_column.cu c64_tmem.cu f128.cu f128_ops.cu probe.cu; do
+for f in c64_tile.cu c64_regs.cu c64_fast.cu c64_poly.cu c64_ord16.cu c64_column.cu c64_colpipe.cu c64_tmem.cu f128.cu f128_ops.cu probe.cu; do
   $NVCC $CUFLAGS ${PTXAS_V:+-Xptxas -v} -c $f -o _obj/${f%.cu}.o &
   pids+=($!)
 done

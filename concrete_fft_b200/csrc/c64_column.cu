@@ -362,6 +362,16 @@ cudaError_t launch_c64_column_group(bool inverse, const double2 *src, double2 *d
     static const bool use_tmem = [] { const char *e = getenv("CFFT_B200_TMEM_COLUMNS"); return e && atoi(e) != 0; }();
     if (key == 881 && use_tmem && tmem_column88_supported(n, span0))
         return launch_c64_tmem_column88(inverse, src, dst, batch, n, span0, tw[0], tw[1], stream);
+    // groups of two or three levels: the persistent kernel of c64_colpipe.cu (CFFT_B200_COLPIPE=0: the one-shot tiles
+    // below; CFFT_B200_COLPIPE_MIN_BATCH: smallest batch per launch that takes it; same bits either way)
+    static const bool use_pipe = [] { const char *e = getenv("CFFT_B200_COLPIPE"); return !e || atoi(e) != 0; }();
+    static const long pipe_min_batch = [] { const char *e = getenv("CFFT_B200_COLPIPE_MIN_BATCH"); return e ? atol(e) : 1; }();
+    if (use_pipe && colpipe_supported(radices) && long(batch) >= pipe_min_batch) {
+        int dev = 0;
+        cudaError_t ce = cudaGetDevice(&dev);
+        if (ce != cudaSuccess) return ce;
+        return launch_c64_colpipe_group(inverse, src, dst, batch, n, span0, radices, tw, dev, stream);
+    }
     switch (key) {
     case 811: return launch_group<8, 1, 1>(inverse, src, dst, prm, batch, stream);
     case 411: return launch_group<4, 1, 1>(inverse, src, dst, prm, batch, stream);

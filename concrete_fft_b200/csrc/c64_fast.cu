@@ -23,211 +23,13 @@
 #include <cstdlib>
 #include <mutex>
 
-#include "c64_dev.cuh"
-#include "plan.h"
+#include "c64_fast_kernels.cuh"
 
 namespace cfft {
 using namespace dev;
+using namespace fastk;
 constexpr uint64_t kWorkspaceChunkBytes = uint64_t{256} << 20;
 namespace {
-
-// One unordered level of span NCUR on the 16 register values of a thread: B = 16/R butterflies,
-// butterfly j covers positions base_j + m*k.  Twiddles planar: tw[(k-1)*m + p].
-template <int R, int NCUR, int TPR, bool FWD, bool G_IN, bool G_OUT>
-__device__ __forceinline__ void level(const c64 *__restrict__ src, c64 *__restrict__ dst,
-                                      const c64 *__restrict__ tw, int t, c64 (&v)[16])
-{
-    constexpr int B = 16 / R, m = NCUR / R;
-    int base[B], p[B];
-#pragma unroll
-    for (int j = 0; j < B; j++) {
-        const int b = t + TPR * j;
-        const int blk = b / m;
-        p[j] = b - blk * m;
-        base[j] = blk * NCUR + p[j];
-    }
-#pragma unroll
-    for (int j = 0; j < B; j++)
-#pragma unroll
-        for (int k = 0; k < R; k++) {
-            const int pos = base[j] + m * (FWD ? k : brev_c<R>(k));
-            v[j * R + k] = G_IN ? ld_stream(src + pos) : src[pos];
-        }
-    if (!G_IN && !G_OUT) __syncthreads(); // everyone has read before anyone overwrites (in place)
-#pragma unroll
-    for (int j = 0; j < B; j++) {
-        c64 *x = &v[j * R];
-        if (!FWD) {
-#pragma unroll
-            for (int k = 1; k < R; k++) x[k] = cmul(ld_tw(tw + (k - 1) * m + p[j]), x[k]);
-        }
-        bfR<R, FWD>(x);
-        if (FWD) {
-#pragma unroll
-            for (int k = 1; k < R; k++) x[k] = cmul(ld_tw(tw + (k - 1) * m + p[j]), x[k]);
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < B; j++)
-#pragma unroll
-        for (int k = 0; k < R; k++) {
-            const int pos = base[j] + m * (FWD ? brev_c<R>(k) : k);
-            if (G_OUT) st_stream(dst + pos, v[j * R + k]);
-            else dst[pos] = v[j * R + k];
-        }
-}
-
-// Two consecutive unordered levels (radix 8 on span NCUR, then radix 2 on span NCUR/8) fused in
-// registers: a thread's two radix-8 butterflies sit at p = t and t + NCUR/16, which is exactly the
-// pair the radix-2 level combines inside every chunk, so no exchange is needed between them.
-// Arithmetic per butterfly is unchanged (src/unordered.rs:24-43, 98-219).
-template <int NCUR, int TPR, bool FWD>
-__device__ __forceinline__ void level_8x2(const c64 *__restrict__ gsrc, c64 *__restrict__ gdst, c64 *__restrict__ s,
-                                          const c64 *__restrict__ tw8, const c64 *__restrict__ tw2, int t, c64 (&v)[16])
-{
-    static_assert(TPR * 16 == NCUR, "thread t owns p = t and p = t + NCUR/16");
-    constexpr int m = NCUR / 8;  // 8 chunks of m after the radix-8 level
-    constexpr int h = NCUR / 16; // half a chunk = span of the radix-2 level's butterflies
-    if (FWD) {
-#pragma unroll
-        for (int j = 0; j < 2; j++)
-#pragma unroll
-            for (int k = 0; k < 8; k++) v[j * 8 + k] = ld_stream(gsrc + t + h * j + m * k);
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            c64 *x = &v[j * 8];
-            bf8<true>(x);
-#pragma unroll
-            for (int k = 1; k < 8; k++) x[k] = cmul(ld_tw(tw8 + (k - 1) * m + t + h * j), x[k]);
-        }
-        const c64 w = ld_tw(tw2 + t);
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const c64 a = v[k], b = v[8 + k];
-            const int chunk = m * brev_c<8>(k);
-            s[chunk + t] = cadd(a, b);              // fwd_butterfly_x2
-            s[chunk + h + t] = cmul(w, csub(a, b));
-        }
-    } else {
-        const c64 w = ld_tw(tw2 + t);
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int chunk = m * brev_c<8>(k);
-            const c64 a = s[chunk + t], b = cmul(w, s[chunk + h + t]); // inv_butterfly_x2
-            v[k] = cadd(a, b);
-            v[8 + k] = csub(a, b);
-        }
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            c64 *x = &v[j * 8];
-#pragma unroll
-            for (int k = 1; k < 8; k++) x[k] = cmul(ld_tw(tw8 + (k - 1) * m + t + h * j), x[k]);
-            bf8<false>(x);
-#pragma unroll
-            for (int k = 0; k < 8; k++) st_stream(gdst + t + h * j + m * k, x[k]);
-        }
-    }
-}
-
-struct FastTables {
-    const c64 *top1; // planar (R1-1) x n/R1
-    const c64 *top2; // planar (R2-1) x n/(R1 R2)
-    const c64 *base; // planar half of init_wt(16, 256): w[p + 16 k]
-};
-
-template <int N> struct FastCfg {
-    static constexpr int TPR = N / 16;                  // threads per transform
-    static constexpr int NT = TPR < 128 ? 128 : TPR;    // threads per CTA
-    static constexpr int ROWS = NT / TPR;               // transforms per CTA
-    static constexpr int MINB = (NT <= 128) ? 4 : (NT <= 256 ? 2 : 1);
-};
-
-// STD = true: standard-order ("ordered") in / out.  X_i sits in the unordered layout at chunk
-// c = bitrev_L(i mod M), offset i / M (M = N / 256 chunks, src/unordered.rs:1046-1051), so the kernel
-// adds one more shared-memory exchange: chunk c keeps offset hi at (hi ^ (lo & 7)), lo = bitrev_L(c),
-// which makes both the base FFT's 16-consecutive accesses and the transposing pass (lanes on
-// consecutive i, i.e. on consecutive lo first) conflict-free; HBM sees consecutive i only.
-template <int N, int R1, int R2, bool FWD, bool STD = false>
-__global__ void __launch_bounds__(FastCfg<N>::NT, FastCfg<N>::MINB)
-c64_fast_b256_kernel(c64 *__restrict__ data, uint64_t batch, FastTables tb)
-{
-    static_assert(N == 256 * R1 * R2, "n = 256 * R1 * R2");
-    static_assert(!STD || N >= 2048, "standard-order variant: M = N / 256 >= 8 chunks");
-    using Cfg = FastCfg<N>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int row = threadIdx.x / Cfg::TPR, t = threadIdx.x % Cfg::TPR;
-    const uint64_t grow = uint64_t(blockIdx.x) * Cfg::ROWS + row;
-    // rows are whole-warp aligned (TPR >= 16 and ROWS * TPR = NT), but a CTA may own fewer rows at
-    // the tail; inactive rows still take part in the block barriers below.
-    const bool active = grow < batch;
-    c64 *g = data + (active ? grow : 0) * N;
-    c64 *s = reinterpret_cast<c64 *>(smem_raw) + row * N;
-    c64 v[16];
-    constexpr int N2 = N / R1;      // span of the second level
-    const int blk = t / 16, lane16 = t % 16;
-
-    constexpr int M = N / 256, LOGM = (M == 8 ? 3 : (M == 16 ? 4 : 5));
-    const int sw = STD ? int(__brev(unsigned(blk)) >> (32 - LOGM)) & 7 : 0; // (lo & 7) of this thread's chunk
-    auto std_pos = [](int i) { // shared-memory position of standard index i
-        const int lo = i & (M - 1), hi = i / M;
-        return int(__brev(unsigned(lo)) >> (32 - LOGM)) * 256 + (hi ^ (lo & 7));
-    };
-
-    constexpr bool FUSED = (R1 == 8 && R2 == 2); // both levels in registers, see level_8x2
-    if (FWD) {
-        if (FUSED) {
-            if (active) level_8x2<N, Cfg::TPR, true>(g, g, s, tb.top1, tb.top2, t, v);
-            __syncthreads();
-        } else if (R1 > 1) {
-            if (active) level<R1, N, Cfg::TPR, true, true, false>(g, s, tb.top1, t, v);
-            __syncthreads();
-        }
-        if (R2 > 1 && !FUSED) {
-            level<R2, N2, Cfg::TPR, true, false, false>(s, s, tb.top2, t, v);
-            __syncthreads();
-        }
-        if (STD) {
-            base256<true, false, false>(s + blk * 256, s + blk * 256, s + blk * 256, tb.base, lane16, v, 0, sw);
-            __syncthreads();
-            if (active) {
-#pragma unroll
-                for (int j = 0; j < 16; j++) v[j] = s[std_pos(t + Cfg::TPR * j)];
-#pragma unroll
-                for (int j = 0; j < 16; j++) st_stream(g + t + Cfg::TPR * j, v[j]);
-            }
-        } else if (active) {
-            if (R1 > 1) base256<true, false, true>(s + blk * 256, s + blk * 256, g + blk * 256, tb.base, lane16, v);
-            else base256<true, true, true>(g + blk * 256, s + blk * 256, g + blk * 256, tb.base, lane16, v);
-        }
-    } else {
-        if (STD) {
-            if (active) {
-#pragma unroll
-                for (int j = 0; j < 16; j++) v[j] = ld_stream(g + t + Cfg::TPR * j);
-#pragma unroll
-                for (int j = 0; j < 16; j++) s[std_pos(t + Cfg::TPR * j)] = v[j];
-            }
-            __syncthreads();
-            base256<false, false, false>(s + blk * 256, s + blk * 256, s + blk * 256, tb.base, lane16, v, sw, 0);
-        } else if (active) {
-            if (R1 > 1) base256<false, true, false>(g + blk * 256, s + blk * 256, s + blk * 256, tb.base, lane16, v);
-            else base256<false, true, true>(g + blk * 256, s + blk * 256, g + blk * 256, tb.base, lane16, v);
-        }
-        if (FUSED) {
-            __syncthreads();
-            if (active) level_8x2<N, Cfg::TPR, false>(g, g, s, tb.top1, tb.top2, t, v);
-        } else {
-            if (R2 > 1) {
-                __syncthreads();
-                level<R2, N2, Cfg::TPR, false, false, false>(s, s, tb.top2, t, v);
-            }
-            if (R1 > 1) {
-                __syncthreads();
-                if (active) level<R1, N, Cfg::TPR, false, false, true>(s, g, tb.top1, t, v);
-            }
-        }
-    }
-}
 
 // ---- n = 8192 / 16384: one transform per thread-block CLUSTER --------------------------------
 // A 128 / 256 KiB transform does not fit one SM with room for a second CTA, so the fused kernel above
@@ -358,161 +160,11 @@ cudaError_t launch_cfg(bool inverse, c64 *data, uint64_t batch, const FastTables
             configured_device = dev;
         }
     }
-    if (inverse) inv_k<<<unsigned(ctas), Cfg::NT, smem, stream>>>(data, batch, tb);
-    else fwd_k<<<unsigned(ctas), Cfg::NT, smem, stream>>>(data, batch, tb);
+    const BatchIo<false, false> bio = plain_batch(data, data, N, N);
+    if (inverse) inv_k<<<unsigned(ctas), Cfg::NT, smem, stream>>>(bio, batch, tb);
+    else fwd_k<<<unsigned(ctas), Cfg::NT, smem, stream>>>(bio, batch, tb);
     count_launch();
     return cudaGetLastError();
-}
-
-// ---- fwd -> point-wise multiply-accumulate -> inv in ONE kernel ----------
-// out[r] = inv( sum_k fwd(a[r][k]) (.) b[k] ): the external-product / convolution step of a caller that keeps
-// its data on the GPU.  As three library calls per term (cfft_c64_fwd, cfft_c64_mul_[add_]assign, cfft_c64_inv)
-// a K = 1 product moves 7 x 16 n bytes through HBM; here it moves 3 x 16 n (2 x 16 n when b is shared by the
-// batch and therefore L2-resident), and K terms cost (2K + 1) x 16 n instead of (6K + 1) x 16 n.  The forward
-// transform of a term ends with every thread holding 16 Fourier coefficients in registers at exactly the
-// positions the inverse base FFT starts from (blk * 256 + lane16 + 16 j), so the product and the running sum
-// never leave the SM: the sum of K > 1 terms lives in 16 more c64 registers per thread.  Butterflies, twiddles
-// and the order of every rounded operation are those of the separate kernels, the product is num_complex's (no FMA), terms are added in the order k = 0, 1, ... =>
-// bit-identical to the composition of the library calls (tests/test_gpu_c64.py).
-template <bool FWD>
-__device__ __forceinline__ void base256_core(c64 *__restrict__ sm_blk, const c64 *__restrict__ tw_planar, int lane16, c64 (&v)[16])
-{
-    const unsigned hmask = 0xFFFFu << (threadIdx.x & 16);
-    bf16<FWD>(v);
-#pragma unroll
-    for (int k = 1; k < 16; k++) v[k] = cmul(ld_tw(tw_planar + lane16 + 16 * k), v[k]);
-    __syncwarp(hmask);
-#pragma unroll
-    for (int k = 0; k < 16; k++) sm_blk[16 * lane16 + (k ^ lane16)] = v[k];
-    __syncwarp(hmask);
-#pragma unroll
-    for (int k = 0; k < 16; k++) v[k] = sm_blk[16 * k + (lane16 ^ k)];
-    bf16<FWD>(v);
-}
-
-// num_complex `*` (src/lib.rs:84 re-exports the type): four products, one subtraction, one addition, no FMA
-__device__ __forceinline__ c64 cmul_nc(c64 x, c64 y)
-{
-    return mk(__dsub_rn(__dmul_rn(x.x, y.x), __dmul_rn(x.y, y.y)), __dadd_rn(__dmul_rn(x.x, y.y), __dmul_rn(x.y, y.x)));
-}
-
-// MULTI = false: exactly one term, nothing to accumulate: the register budget and occupancy of the plain kernel.
-// MULTI = true: the running sum of the terms lives in 16 more c64 registers per thread (168 registers, three CTAs
-// of 128 threads per SM); a shared-memory accumulator was measured first and lost (the L1 / shared-memory pipe is
-// already the busiest unit of the plain kernel, and a second tile per CTA leaves too little L1 for the twiddles).
-template <int N, bool MULTI> struct FusedMulCfg {
-    static constexpr int NT = FastCfg<N>::NT;
-    static constexpr int MINB = !MULTI ? FastCfg<N>::MINB : (NT <= 128 ? 3 : 1);
-};
-
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-template <int N, int R1, int R2, bool MULTI>
-__global__ void __launch_bounds__(FusedMulCfg<N, MULTI>::NT, FusedMulCfg<N, MULTI>::MINB)
-c64_fwd_mul_inv_kernel(const c64 *__restrict__ a, const c64 *__restrict__ b, c64 *__restrict__ out, uint64_t batch,
-                       uint32_t kterms, uint64_t b_row_stride, FastTables tf, FastTables ti, uint32_t flags)
-{
-    static_assert(N == 256 * R1 * R2, "n = 256 * R1 * R2");
-    using Cfg = FastCfg<N>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int row = threadIdx.x / Cfg::TPR, t = threadIdx.x % Cfg::TPR;
-    const uint64_t grow = uint64_t(blockIdx.x) * Cfg::ROWS + row;
-    const bool active = grow < batch; // inactive rows compute on row 0's data and store nothing
-    const uint64_t r = active ? grow : 0;
-    const c64 *ga = a + r * kterms * N;
-    const c64 *gb = b + r * b_row_stride;
-    c64 *go = out + r * N;
-    c64 *s = reinterpret_cast<c64 *>(smem_raw) + row * N;
-    c64 v[16];
-    c64 acc[MULTI ? 16 : 1];
-    constexpr int N2 = N / R1;
-    constexpr bool FUSED = (R1 == 8 && R2 == 2);
-    const int blk = t / 16, lane16 = t % 16;
-    c64 *sb = s + blk * 256;
-
-    // the 16 n bytes of b this row's first term needs: request them now, they are consumed last
-    // (a row's threads cover its n c64 = n / 8 lines of 128 bytes with 2 requests each)
-    if (flags & 1) {
-#pragma unroll
-        for (int i = 0; i < 2; i++) prefetch_l2(gb + (t + Cfg::TPR * i) * 8);
-    }
-
-    const uint32_t kt = MULTI ? kterms : 1;
-    for (uint32_t k = 0; k < kt; k++) {
-        const c64 *g = ga + uint64_t(k) * N;
-        if (MULTI && k + 1 < kt && (flags & 2)) { // next term's input and multiplier on their way to L2 while this term computes
-#pragma unroll
-            for (int i = 0; i < 2; i++) {
-                prefetch_l2(g + N + (t + Cfg::TPR * i) * 8);
-                prefetch_l2(gb + uint64_t(k + 1) * N + (t + Cfg::TPR * i) * 8);
-            }
-        }
-        if (MULTI && k > 0 && R1 > 1) __syncthreads(); // the previous term's base FFTs have consumed the tile
-        if (FUSED) {
-            level_8x2<N, Cfg::TPR, true>(g, nullptr, s, tf.top1, tf.top2, t, v);
-            __syncthreads();
-        } else if (R1 > 1) {
-            level<R1, N, Cfg::TPR, true, true, false>(g, s, tf.top1, t, v);
-            __syncthreads();
-        }
-        if (R2 > 1 && !FUSED) {
-            level<R2, N2, Cfg::TPR, true, false, false>(s, s, tf.top2, t, v);
-            __syncthreads();
-        }
-#pragma unroll
-        for (int j = 0; j < 16; j++) v[j] = R1 > 1 ? sb[lane16 + 16 * j] : ld_stream(g + blk * 256 + lane16 + 16 * j);
-        base256_core<true>(sb, tf.base, lane16, v);
-        const c64 *bk = gb + uint64_t(k) * N + blk * 256 + lane16;
-#pragma unroll
-        for (int j = 0; j < 16; j++) {
-            const c64 p = cmul_nc(v[j], ld_stream(bk + 16 * j));
-            if (!MULTI) v[j] = p;
-            else acc[j] = k == 0 ? p : cadd(acc[j], p);
-        }
-    }
-    if (!MULTI) {
-        // chained launches (one term each, for sizes without the accumulating kernel): bit 3 adds the Fourier-domain
-        // partial sum the previous launch left in `out`, bit 4 stores the new partial sum instead of inverting it
-        c64 *gs = go + blk * 256 + lane16;
-        if (flags & 8) {
-#pragma unroll
-            for (int j = 0; j < 16; j++) v[j] = cadd(ld_stream(gs + 16 * j), v[j]);
-        }
-        if (flags & 16) {
-            if (active) {
-#pragma unroll
-                for (int j = 0; j < 16; j++) st_stream(gs + 16 * j, v[j]);
-            }
-            return;
-        }
-    }
-    if (MULTI) {
-#pragma unroll
-        for (int j = 0; j < 16; j++) v[j] = acc[j];
-    }
-
-    base256_core<false>(sb, ti.base, lane16, v);
-    if (R1 == 1) {
-        if (active) {
-#pragma unroll
-            for (int j = 0; j < 16; j++) st_stream(go + blk * 256 + lane16 + 16 * j, v[j]);
-        }
-        return;
-    }
-    __syncwarp(0xFFFFu << (threadIdx.x & 16));
-#pragma unroll
-    for (int j = 0; j < 16; j++) sb[lane16 + 16 * j] = v[j];
-    if (FUSED) {
-        __syncthreads();
-        if (active) level_8x2<N, Cfg::TPR, false>(nullptr, go, s, ti.top1, ti.top2, t, v);
-    } else {
-        if (R2 > 1) {
-            __syncthreads();
-            level<R2, N2, Cfg::TPR, false, false, false>(s, s, ti.top2, t, v);
-        }
-        __syncthreads();
-        if (active) level<R1, N, Cfg::TPR, false, false, true>(s, go, ti.top1, t, v);
-    }
 }
 
 // ALLOW_MULTI = false (n = 8192: 512 threads fill the register file at 128 registers each): one term per launch
@@ -541,7 +193,7 @@ cudaError_t launch_fused_mul(const c64 *a, const c64 *b, c64 *out, uint64_t batc
     if (chain) {
         // cfft_c64_fwd_mul_add: ONE term per row (rows kterms * N apart), Fourier-domain result stored (bit 4) on top of
         // what `out` holds (bit 3) -- no inverse
-        k1<<<unsigned(ctas), Cfg::NT, smem, stream>>>(a, b, out, batch, kterms, b_row_stride, tf, ti, (flags & 1) | chain);
+        k1<<<unsigned(ctas), Cfg::NT, smem, stream>>>(plain_batch(a, nullptr, N, 0), b, plain_batch(nullptr, out, 0, N), batch, kterms, b_row_stride, tf, ti, (flags & 1) | chain);
         count_launch();
         return cudaGetLastError();
     }
@@ -549,13 +201,14 @@ cudaError_t launch_fused_mul(const c64 *a, const c64 *b, c64 *out, uint64_t batc
         // one launch per term: out holds the Fourier-domain partial sum between launches, the last launch inverts it
         for (uint32_t k = 0; k < kterms; k++) {
             const uint32_t f = (flags & 1) | (k > 0 ? 8u : 0u) | (k + 1 < kterms ? 16u : 0u);
-            k1<<<unsigned(ctas), Cfg::NT, smem, stream>>>(a + uint64_t(k) * N, b + uint64_t(k) * N, out, batch, kterms, b_row_stride, tf, ti, f);
+            k1<<<unsigned(ctas), Cfg::NT, smem, stream>>>(plain_batch(a + uint64_t(k) * N, nullptr, N, 0), b + uint64_t(k) * N, plain_batch(nullptr, out, 0, N), batch, kterms, b_row_stride, tf, ti, f);
             count_launch();
         }
         return cudaGetLastError();
     }
-    if (kterms == 1 && !(env_flags & 4)) k1<<<unsigned(ctas), Cfg::NT, smem, stream>>>(a, b, out, batch, kterms, b_row_stride, tf, ti, flags);
-    else km<<<unsigned(ctas), Cfg::NT, smem, stream>>>(a, b, out, batch, kterms, b_row_stride, tf, ti, flags);
+    const BatchIo<false, false> ain = plain_batch(a, nullptr, N, 0), oout = plain_batch(nullptr, out, 0, N);
+    if (kterms == 1 && !(env_flags & 4)) k1<<<unsigned(ctas), Cfg::NT, smem, stream>>>(ain, b, oout, batch, kterms, b_row_stride, tf, ti, flags);
+    else km<<<unsigned(ctas), Cfg::NT, smem, stream>>>(ain, b, oout, batch, kterms, b_row_stride, tf, ti, flags);
     count_launch();
     return cudaGetLastError();
 }

@@ -276,6 +276,94 @@ cfft_status run_pipeline(const cfft_plan *plan, void *const *planes, int nplanes
     return CFFT_OK;
 }
 
+// out_host[r] (+)= the negacyclic product step of launch_c64_poly_mul for host-resident polynomials: per chunk, the k terms of
+// its rows go up (k * 16 n bytes per row), one fused kernel runs against the device-resident Fourier-domain operand b, and
+// the result polynomials come back (16 n bytes per row) -- k + 1 row-sizes over PCIe for k transforms forward and one back,
+// where the plain host entry points move 2 per transform.  Same three-slot overlap as run_pipeline.
+cfft_status run_poly_pipeline(const cfft_plan *plan, const long long *a_host, uint64_t kterms, const double2 *b_dev, uint64_t b_row_stride,
+                              long long *out_host, uint64_t batch, uint32_t flags, std::string &err)
+{
+    if (batch == 0) return CFFT_OK;
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
+    if (prev_dev != plan->device && cudaSetDevice(plan->device) != cudaSuccess) {
+        err = "cudaSetDevice failed";
+        return CFFT_ECUDA;
+    }
+    const size_t in_row = size_t(kterms) * 2 * plan->n * sizeof(long long), out_row = size_t(2) * plan->n * sizeof(long long);
+    const bool pinned = is_pinned(a_host) && is_pinned(out_host);
+    const bool accumulate = (flags & 2u) != 0; // the device needs the old output polynomials too
+    const int nslots = pipe_slots();
+    size_t rows_per_chunk = pipe_chunk_bytes() / (in_row + out_row);
+    if (rows_per_chunk < 1) rows_per_chunk = 1;
+    if (rows_per_chunk > batch) rows_per_chunk = size_t(batch);
+    const size_t in_bytes = rows_per_chunk * in_row, out_bytes = rows_per_chunk * out_row;
+
+    PipeCtx *ctx = acquire_ctx(plan->device);
+    cudaError_t e = cudaSuccess;
+    const char *what = "";
+    auto flush_pending = [&](Slot &s) {
+        if (!s.pending) return;
+        std::memcpy(reinterpret_cast<char *>(out_host) + s.pend_row0 * out_row, static_cast<char *>(s.pinned) + in_bytes, s.pend_rows * out_row);
+        s.pending = false;
+    };
+    const size_t nchunks = (size_t(batch) + rows_per_chunk - 1) / rows_per_chunk;
+    for (size_t c = 0; c < nchunks && e == cudaSuccess; c++) {
+        Slot &s = ctx->slot[c % size_t(nslots)];
+        what = "poly pipeline slot setup";
+        if ((e = ensure_slot(s, in_bytes + out_bytes, pinned ? 0 : in_bytes + out_bytes)) != cudaSuccess) break;
+        const size_t row0 = c * rows_per_chunk;
+        const size_t rows = (row0 + rows_per_chunk <= batch) ? rows_per_chunk : size_t(batch) - row0;
+        const char *src_a = reinterpret_cast<const char *>(a_host) + row0 * in_row;
+        char *dst_o = reinterpret_cast<char *>(out_host) + row0 * out_row;
+        char *d_in = static_cast<char *>(s.dev), *d_out = d_in + in_bytes;
+        if (!pinned) {
+            what = "poly pipeline event sync";
+            if (c >= size_t(nslots) && (e = cudaEventSynchronize(s.done)) != cudaSuccess) break;
+            flush_pending(s);
+            std::memcpy(s.pinned, src_a, rows * in_row);
+            if (accumulate) std::memcpy(static_cast<char *>(s.pinned) + in_bytes, dst_o, rows * out_row);
+        }
+        what = "poly pipeline H2D";
+        e = cudaMemcpyAsync(d_in, pinned ? src_a : static_cast<const char *>(s.pinned), rows * in_row, cudaMemcpyHostToDevice, s.stream);
+        if (e == cudaSuccess && accumulate)
+            e = cudaMemcpyAsync(d_out, pinned ? dst_o : static_cast<char *>(s.pinned) + in_bytes, rows * out_row, cudaMemcpyHostToDevice, s.stream);
+        if (e != cudaSuccess) break;
+        what = "poly pipeline kernel launch";
+        e = launch_c64_poly_mul(plan, reinterpret_cast<const long long *>(d_in), kterms, b_dev + row0 * b_row_stride, b_row_stride,
+                                reinterpret_cast<long long *>(d_out), rows, flags, s.stream);
+        if (e != cudaSuccess) break;
+        what = "poly pipeline D2H";
+        e = cudaMemcpyAsync(pinned ? dst_o : static_cast<char *>(s.pinned) + in_bytes, d_out, rows * out_row, cudaMemcpyDeviceToHost, s.stream);
+        if (e != cudaSuccess) break;
+        if (!pinned) {
+            s.pending = true;
+            s.pend_row0 = row0;
+            s.pend_rows = rows;
+            e = cudaEventRecord(s.done, s.stream);
+        }
+    }
+    const int used = int(nchunks < size_t(nslots) ? nchunks : size_t(nslots));
+    for (int i = 0; i < used; i++) {
+        Slot &s = ctx->slot[i];
+        if (!s.stream) continue;
+        cudaError_t e2 = cudaStreamSynchronize(s.stream);
+        if (e == cudaSuccess && e2 != cudaSuccess) {
+            e = e2;
+            what = "poly pipeline drain";
+        }
+        if (e == cudaSuccess) flush_pending(s);
+        s.pending = false;
+    }
+    release_ctx(ctx);
+    if (prev_dev >= 0 && prev_dev != plan->device) cudaSetDevice(prev_dev);
+    if (e != cudaSuccess) {
+        err = std::string(what) + ": " + cudaGetErrorString(e);
+        return CFFT_ECUDA;
+    }
+    return CFFT_OK;
+}
+
 } // namespace
 
 // defined in api.cc
@@ -335,6 +423,22 @@ cfft_status cfft_f128_fwd_inv_host(const cfft_plan *p, double *re0, double *re1,
                                    uint64_t batch)
 {
     return f128_host(p, re0, re1, im0, im1, len, batch, 2);
+}
+
+cfft_status cfft_c64_poly_mul_host(const cfft_plan *p, const int64_t *a_host, uint64_t k_terms, const void *b_dev, uint64_t b_row_stride,
+                                   int64_t *out_host, uint64_t batch, uint32_t flags)
+{
+    if (!p || p->kind == KIND_F128) return set_last_error(CFFT_EINVAL, "not a c64 plan");
+    if (k_terms == 0) return set_last_error(CFFT_EINVAL, "k_terms must be >= 1");
+    if (flags & ~3u) return set_last_error(CFFT_EINVAL, "unknown flag bits");
+    if (batch && (!a_host || !b_dev || !out_host)) return set_last_error(CFFT_EINVAL, "null buffer");
+    if (reinterpret_cast<uintptr_t>(b_dev) & 15) return set_last_error(CFFT_EINVAL, "b must be 16-byte aligned device memory");
+    if ((reinterpret_cast<uintptr_t>(a_host) | reinterpret_cast<uintptr_t>(out_host)) & 7) return set_last_error(CFFT_EINVAL, "polynomials must be 8-byte aligned");
+    if (b_row_stride != 0 && b_row_stride < k_terms * p->n) return set_last_error(CFFT_EINVAL, "b_row_stride must be 0 (b shared by every row) or >= k_terms * n");
+    std::string err;
+    cfft_status st = run_poly_pipeline(p, reinterpret_cast<const long long *>(a_host), k_terms, static_cast<const double2 *>(b_dev), b_row_stride,
+                                       reinterpret_cast<long long *>(out_host), batch, flags, err);
+    return st == CFFT_OK ? st : set_last_error(st, err);
 }
 
 cfft_status cfft_unordered_fwd_monomial_host(const cfft_plan *p, uint64_t degree, void *host_buf, uint64_t len)

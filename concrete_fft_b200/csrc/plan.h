@@ -60,6 +60,7 @@ struct cfft_plan {
     std::vector<cfft::cplx> h_tw[2]; // [0] fwd, [1] inv (host copies, kept for clone / tests)
     double2 *d_tw[2] = {nullptr, nullptr};
     double2 *d_monomial_tw = nullptr; // n entries, e^{-2 pi i k / n} (src/unordered.rs:714-720)
+    double2 *d_twist = nullptr;       // 2n entries: twist e^{+i pi j / 2n}, then untwist conj(twist) / n (cfft_c64_poly_*)
     cfft::StageProgram prog[2];       // [0] fwd, [1] inv: every stage in execution order
     double2 *d_top_tw[2] = {nullptr, nullptr}; // planar copies of the unordered level tables (same values)
     bool exact_regs = true;           // plans without a specialised kernel: register kernel (c64_regs.cu) or tile kernel
@@ -109,12 +110,25 @@ cudaError_t launch_c64_fwd_mul_inv(const cfft_plan *plan, const double2 *a, uint
                                    uint64_t b_row_stride, double2 *out, uint64_t batch, cudaStream_t st);
 cudaError_t launch_c64_fwd_mul_add(const cfft_plan *plan, const double2 *a, uint64_t a_row_terms, const double2 *b,
                                    uint64_t b_row_stride, double2 *acc, bool accumulate, uint64_t batch, cudaStream_t st);
+// kernels (c64_poly.cu): integer polynomials (2n signed 64-bit coefficients per row) <-> the Fourier domain with the fold,
+// the conversion, the negacyclic twist and the rounding fused into the transform's first / last pass; flags: bit 0 torus
+// (x 2^-64 in, fractional part x 2^64 out), bit 1 accumulate into the output polynomial (modulo 2^64)
+bool poly_fused_available(const cfft_plan *plan, uint64_t kterms);
+cudaError_t launch_c64_poly_fwd(const cfft_plan *plan, const long long *poly, double2 *fourier, uint64_t batch, uint32_t flags, cudaStream_t st);
+cudaError_t launch_c64_poly_inv(const cfft_plan *plan, const double2 *fourier, long long *poly, uint64_t batch, uint32_t flags, cudaStream_t st);
+cudaError_t launch_c64_poly_mul(const cfft_plan *plan, const long long *a, uint64_t kterms, const double2 *b, uint64_t b_row_stride,
+                                long long *out, uint64_t batch, uint32_t flags, cudaStream_t st);
 // kernels (c64_ord16.cu)
 bool ord16_supported(uint64_t n, int algo);
 cudaError_t launch_c64_ord16(const cfft_plan *plan, bool inverse, double2 *data, uint64_t batch, cudaStream_t st);
 // kernels (c64_column.cu): one group of <= 3 unordered levels in one HBM pass
 cudaError_t launch_c64_column_group(bool inverse, const double2 *src, double2 *dst, uint64_t batch, uint32_t n, uint32_t span0,
                                     const int radices[3], const double2 *const tw[3], cudaStream_t st);
+// kernels (c64_colpipe.cu): the same groups as a persistent kernel -- a CTA keeps one tile position and walks through the
+// batch with the position's twiddles in registers and the next tile's loads in flight
+bool colpipe_supported(const int radices[3]);
+cudaError_t launch_c64_colpipe_group(bool inverse, const double2 *src, double2 *dst, uint64_t batch, uint32_t n, uint32_t span0,
+                                     const int radices[3], const double2 *const tw[3], int device, cudaStream_t st);
 // kernels (c64_tmem.cu): two radix-8 levels in one HBM pass, one thread per 64-element column, tensor memory as the
 // parking space between the levels (no shared memory, no block barrier)
 bool tmem_column88_supported(uint32_t n, uint32_t span0);

@@ -197,6 +197,127 @@ class _PlanBase:
     def has_fused_mul_kernel(self):
         return bool(N.lib.cfft_plan_has_fused_mul_kernel(self._h))
 
+    # ---- integer polynomials <-> the Fourier domain (cfft_c64_poly_*, include/cfft_b200.h) --------------------------
+    @staticmethod
+    def _poly_flags(torus, accumulate=False):
+        return (N.POLY_TORUS if torus else 0) | (N.POLY_ACCUMULATE if accumulate else 0)
+
+    def _poly_tensor(self, t, name, inner):
+        import torch
+
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.int64 and t.is_contiguous()):
+            raise TypeError("%s must be a contiguous CUDA int64 tensor" % name)
+        if t.numel() == 0 or t.numel() % inner:
+            raise N.PanicError("assertion failed: %s holds whole polynomials of %d coefficients" % (name, inner))
+        if t.device.index != self.device():
+            raise ValueError("%s is on cuda:%d but the plan lives on cuda:%d" % (name, t.device.index, self.device()))
+        return t
+
+    def _fourier_tensor(self, t, name):
+        import torch
+
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.complex128 and t.is_contiguous()):
+            raise TypeError("%s must be a contiguous CUDA complex128 tensor" % name)
+        if t.device.index != self.device():
+            raise ValueError("%s is on cuda:%d but the plan lives on cuda:%d" % (name, t.device.index, self.device()))
+        return t
+
+    def fwd_poly(self, poly, out=None, torus=False):
+        """fourier[r] = fwd(twist(fold(poly[r])))  (cfft_c64_poly_fwd).  `poly`: CUDA int64 [batch, 2 n] (torus: the u64
+        torus elements viewed as int64); returns complex128 [batch, n] in this plan's order."""
+        import torch
+
+        n = self.fft_size()
+        poly = self._poly_tensor(poly, "poly", 2 * n)
+        batch = poly.numel() // (2 * n)
+        if out is None:
+            out = torch.empty((batch, n), dtype=torch.complex128, device=poly.device)
+        out = self._fourier_tensor(out, "out")
+        if out.numel() != batch * n:
+            raise N.PanicError("assertion failed: out holds batch * fft_size elements")
+        N.check(N.lib.cfft_c64_poly_fwd(self._h, poly.data_ptr(), out.data_ptr(), batch, self._poly_flags(torus), current_stream_ptr(self.device())))
+        return out
+
+    def inv_poly(self, fourier, out=None, torus=False, accumulate=False):
+        """poly[r] (+)= round(untwist(inv(fourier[r])))  (cfft_c64_poly_inv); `fourier` is left untouched."""
+        import torch
+
+        n = self.fft_size()
+        fourier = self._fourier_tensor(fourier, "fourier")
+        if fourier.numel() == 0 or fourier.numel() % n:
+            raise N.PanicError("assertion failed: fourier holds batch * fft_size elements")
+        batch = fourier.numel() // n
+        if out is None:
+            if accumulate:
+                raise N.PanicError("accumulate needs an output polynomial to add to")
+            out = torch.empty((batch, 2 * n), dtype=torch.int64, device=fourier.device)
+        out = self._poly_tensor(out, "out", 2 * n)
+        if out.numel() != batch * 2 * n:
+            raise N.PanicError("assertion failed: out holds batch polynomials")
+        N.check(N.lib.cfft_c64_poly_inv(self._h, fourier.data_ptr(), out.data_ptr(), batch, self._poly_flags(torus, accumulate),
+                                        current_stream_ptr(self.device())))
+        return out
+
+    def poly_mul(self, a, b, out=None, torus=False, accumulate=False):
+        """out[r] (+)= round(untwist(inv(sum_k fwd(twist(fold(a[r, k]))) * b[r, k])))  (cfft_c64_poly_mul[_host]): a negacyclic
+        product / external-product step with integer polynomials in and out.  `a`: int64 [batch, k, 2 n] (or [batch, 2 n]) --
+        a CUDA tensor, or a numpy array in host memory (then `out` is a numpy array too and the call streams the batch
+        through the GPU); `b`: CUDA complex128 Fourier-domain operand [k, n] (shared) or [batch, k, n]."""
+        import numpy as np
+        import torch
+
+        n = self.fft_size()
+        b = self._fourier_tensor(b, "b")
+        host = isinstance(a, np.ndarray)
+        if host:
+            if a.dtype != np.int64 or not a.flags["C_CONTIGUOUS"]:
+                raise TypeError("a must be a C-contiguous numpy int64 array")
+        else:
+            a = self._poly_tensor(a, "a", 2 * n)
+        if a.ndim == 2:
+            a = a.reshape(a.shape[0], 1, a.shape[1])
+        if a.ndim != 3 or a.shape[2] != 2 * n or a.shape[1] < 1:
+            raise N.PanicError("assertion failed: a has shape [batch, k, 2 * fft_size]")
+        batch, k = int(a.shape[0]), int(a.shape[1])
+        if tuple(b.shape) in ((k, n), (n,) if k == 1 else None):
+            stride = 0
+        elif tuple(b.shape) in ((batch, k, n), (batch, n) if k == 1 else None):
+            stride = k * n
+        else:
+            raise N.PanicError("assertion failed: b has shape [k, fft_size] or [batch, k, fft_size]")
+        flags = self._poly_flags(torus, accumulate)
+        if host:
+            if out is None:
+                if accumulate:
+                    raise N.PanicError("accumulate needs an output polynomial to add to")
+                out = np.empty((batch, 2 * n), np.int64)
+            if not (isinstance(out, np.ndarray) and out.dtype == np.int64 and out.flags["C_CONTIGUOUS"] and out.size == batch * 2 * n):
+                raise N.PanicError("assertion failed: out is a C-contiguous numpy int64 array of batch polynomials")
+            N.check(N.lib.cfft_c64_poly_mul_host(self._h, a.ctypes.data, k, b.data_ptr(), stride, out.ctypes.data, batch, flags))
+            return out
+        if out is None:
+            if accumulate:
+                raise N.PanicError("accumulate needs an output polynomial to add to")
+            out = torch.empty((batch, 2 * n), dtype=torch.int64, device=a.device)
+        out = self._poly_tensor(out, "out", 2 * n)
+        if out.numel() != batch * 2 * n:
+            raise N.PanicError("assertion failed: out holds batch polynomials")
+        N.check(N.lib.cfft_c64_poly_mul(self._h, a.data_ptr(), k, b.data_ptr(), stride, out.data_ptr(), batch, flags,
+                                        current_stream_ptr(self.device())))
+        return out
+
+    def has_fused_poly_kernel(self, k_terms=1):
+        return bool(N.lib.cfft_plan_has_fused_poly_kernel(self._h, k_terms))
+
+    def twist_tables(self):
+        """(twist, untwist): e^{+i pi j / 2n} and conj / n, copied back from the device (tests)."""
+        import numpy as np
+
+        n = self.fft_size()
+        out = np.empty(2 * n, np.complex128)
+        N.check(N.lib.cfft_plan_copy_twist(self._h, out.ctypes.data, out.nbytes))
+        return out[:n].copy(), out[n:].copy()
+
     def twiddles(self, inverse=False):
         """Device twiddle table copied back to the host (tests)."""
         import numpy as np

@@ -260,6 +260,48 @@ cfft_status cfft_c64_fwd_mul_add(const cfft_plan *plan, const void *a_dev, uint6
                                  uint64_t b_row_stride, void *acc_dev, int accumulate, uint64_t batch, void *stream);
 int cfft_plan_has_fused_mul_kernel(const cfft_plan *plan);
 
+/* ---- integer polynomials <-> the Fourier domain --------------------------------
+ * What a caller does on either side of the transforms of a negacyclic polynomial product modulo X^N + 1 (N = 2 n), fused
+ * into the transform's first / last pass so that the conversions cost no HBM traffic of their own:
+ *   in :  fold       z_j = coeff[j] + i coeff[j + n], j < n            (the fold of src/fft128/mod.rs:2006-2016)
+ *         convert    signed 64-bit -> f64, round to nearest; CFFT_POLY_TORUS: the u64 torus element reinterpreted as i64, x 2^-64
+ *         twist      z_j <- z_j * e^{+i pi j / N}, table entries (cos, sin) from sincospi64 (src/fft_simd.rs:237-296),
+ *                    product with num_complex semantics (no FMA, src/lib.rs:84)
+ *         then Plan::fwd
+ *   out:  Plan::inv, then untwist + scale  t_j = z_j * (conj(twist_j) / n), then
+ *         integer mode: coeff = f64::round(t) (half away from zero) as i64 (saturating, NaN -> 0)
+ *         torus mode:   coeff = round((t - round(t)) * 2^64) modulo 2^64
+ *         coeff[j] <- re, coeff[j + n] <- im; CFFT_POLY_ACCUMULATE adds to the existing coefficients modulo 2^64 instead.
+ * The reference crate stops at the transform (README.md:10-17): these steps live in its caller, so the choices above are this
+ * library's (documented here, restated on the CPU by the test oracle, and checked end to end against exact integer
+ * schoolbook products); the transforms in between are the reference's, bit for bit.
+ * Polynomials: 2 n int64 per row, 8-byte aligned; Fourier-domain buffers: n c64 per row, 16-byte aligned, in THIS plan's
+ * order.  Plans of the (Dif16, 256) family with 256 <= n <= 8192 run each call as ONE kernel; every other c64 plan runs
+ * stand-alone conversion kernels around its own transform (same bits).  Device pointers, stream ordered. */
+enum { CFFT_POLY_INTEGER = 0, CFFT_POLY_TORUS = 1, CFFT_POLY_ACCUMULATE = 2 };
+/* fourier[r] = fwd(twist(fold(poly[r]))), r < batch.  flags: CFFT_POLY_TORUS or 0. */
+cfft_status cfft_c64_poly_fwd(const cfft_plan *plan, const int64_t *poly_dev, void *fourier_dev, uint64_t batch,
+                              uint32_t flags, void *stream);
+/* poly[r] (+)= round(untwist(inv(fourier[r]))); fourier is not modified. */
+cfft_status cfft_c64_poly_inv(const cfft_plan *plan, const void *fourier_dev, int64_t *poly_dev, uint64_t batch,
+                              uint32_t flags, void *stream);
+/* out[r] (+)= round(untwist(inv( sum_{k < k_terms} fwd(twist(fold(a[r][k]))) (.) b[r][k] ))): a whole negacyclic
+ * product / external-product step, integers in, integers out, one kernel for n <= 4096 (n = 8192: k_terms == 1).
+ * a: [batch][k_terms][2n] int64; b: Fourier-domain operand as in cfft_c64_fwd_mul_inv (b_row_stride 0 = shared by every
+ * row); out: [batch][2n] int64, may be a itself when k_terms == 1 and not accumulating.  Defined as -- and bit-identical
+ * to -- cfft_c64_poly_fwd on every term, cfft_c64_mul_assign / cfft_c64_mul_add_assign in term order, cfft_c64_poly_inv. */
+cfft_status cfft_c64_poly_mul(const cfft_plan *plan, const int64_t *a_dev, uint64_t k_terms, const void *b_dev,
+                              uint64_t b_row_stride, int64_t *out_dev, uint64_t batch, uint32_t flags, void *stream);
+/* Same with the polynomials in HOST memory (pinned or pageable) and b resident on the device (a bootstrapping / key-switching
+ * key stays in the Fourier domain on the GPU): per row k_terms * 16 n bytes go up and 16 n come back, against
+ * 2 * 16 n each way per TRANSFORM for the plain host entry points.  Synchronous. */
+cfft_status cfft_c64_poly_mul_host(const cfft_plan *plan, const int64_t *a_host, uint64_t k_terms, const void *b_dev,
+                                   uint64_t b_row_stride, int64_t *out_host, uint64_t batch, uint32_t flags);
+/* 1 when the three calls above run as single fused kernels for this plan and term count */
+int cfft_plan_has_fused_poly_kernel(const cfft_plan *plan, uint64_t k_terms);
+/* the plan's twist tables: n entries e^{+i pi j / 2n}, then n entries conj / n (tests) */
+cfft_status cfft_plan_copy_twist(const cfft_plan *plan, void *host_out, uint64_t bytes);
+
 /* ---- diagnostics ------------------------------------------------------------------- */
 
 const char *cfft_status_string(cfft_status st);
@@ -269,6 +311,10 @@ const char *cfft_last_error(void);
 uint64_t cfft_launch_count(void);
 /* "cfft_b200 <version> sm_100a" */
 const char *cfft_version(void);
+/* The opt-in persistent two-phase kernel (CFFT_B200_FAST_VARIANT=8 / CFFT_B200_ALLOW_PERSISTENT) waits on other CTAs with
+ * a bounded spin; if a wait ever expires (producers descheduled by MPS, a debugger, preemption) the kernel gives up waiting
+ * instead of hanging or trapping and counts it here: a non-zero value means such calls returned invalid data. */
+cfft_status cfft_twopass_timeouts(int device, uint32_t *out);
 /* Measured FP64 issue rate of `device` (thread-level FP64 instructions per second over the whole GPU): chains of
  * DFMA, of DADD, and a 1 : 7 DFMA : DADD mix like the fft128 butterfly's (94 instructions = 78 DADD + 12 DFMA + 4 DMUL,
  * src/fft128/mod.rs:310-346), 16 warps per SM, timed with CUDA events; plus the SM clock observed inside the kernel

@@ -60,6 +60,13 @@ void orc_parallel_rows(int threads, size_t total, void (*fn)(void *ctx, size_t l
 void orc_unordered_fwd_batch(const orc_unordered_plan *, oc64 *buf, size_t batch, int threads);
 void orc_unordered_inv_batch(const orc_unordered_plan *, oc64 *buf, size_t batch, int threads);
 
+/* ---- caller-side steps around the c64 transform (poly_oracle.c; semantics fixed by this library, see its header) ---- */
+void orc_poly_twist_tables(size_t n, oc64 *twist, oc64 *untwist);
+void orc_poly_fold_twist(size_t n, int torus, const int64_t *poly, const oc64 *twist, oc64 *out);
+void orc_poly_untwist_round(size_t n, int torus, int accumulate, const oc64 *z, const oc64 *untwist, int64_t *out);
+void orc_poly_mul_batch(const orc_unordered_plan *plan, size_t n, size_t base_n, const int64_t *a, size_t k_terms, const oc64 *b,
+                        size_t b_row_stride, int64_t *out, size_t batch, int torus, int accumulate, int threads);
+
 /* src/unordered.rs:1039-1059 */
 size_t orc_bit_rev(unsigned nbits, size_t i);
 size_t orc_bit_rev_twice(unsigned nbits, unsigned base_nbits, size_t i);

@@ -60,6 +60,10 @@ def lib(fast=False):
         "orc_f128_binary_op": (None, [ci, vp, vp, vp, vp, vp, vp, sz]),
         "orc_f128_cplx_mul_scale": (None, [vp, vp, vp, vp, vp, vp, vp, vp, dbl, sz]),
         "orc_c64_pointwise": (None, [vp, vp, vp, sz]),
+        "orc_poly_twist_tables": (None, [sz, vp, vp]),
+        "orc_poly_fold_twist": (None, [sz, ci, vp, vp, vp]),
+        "orc_poly_untwist_round": (None, [sz, ci, ci, vp, vp, vp]),
+        "orc_poly_mul_batch": (None, [vp, sz, sz, vp, sz, vp, sz, vp, sz, ci, ci, ci]),
     }
     for k, (res, args) in sig.items():
         f = getattr(L, k)
@@ -218,3 +222,47 @@ def c64_pointwise(a, b, acc=None):
     C = np.ascontiguousarray(acc, dtype=np.complex128).copy()
     lib().orc_c64_pointwise(_ptr(C), _ptr(A), _ptr(B), A.size)
     return C
+
+
+# ---- caller-side steps around the c64 transform (oracle/poly_oracle.c) ----------------------------------------
+
+def poly_twist_tables(n):
+    tw, un = np.empty(n, np.complex128), np.empty(n, np.complex128)
+    lib().orc_poly_twist_tables(n, _ptr(tw), _ptr(un))
+    return tw, un
+
+
+def poly_fold_twist(poly, torus=False):
+    """[rows, 2n] int64 -> [rows, n] complex128: fold, convert (torus: x 2^-64), twist."""
+    poly = np.ascontiguousarray(poly, dtype=np.int64)
+    rows, n = poly.reshape(-1, poly.shape[-1]).shape[0], poly.shape[-1] // 2
+    tw, _ = poly_twist_tables(n)
+    out = np.empty((rows, n), np.complex128)
+    flat = poly.reshape(rows, 2 * n)
+    for r in range(rows):
+        lib().orc_poly_fold_twist(n, int(torus), _ptr(flat[r]), _ptr(tw), _ptr(out[r]))
+    return out.reshape(poly.shape[:-1] + (n,))
+
+
+def poly_untwist_round(z, torus=False, acc=None):
+    """[rows, n] complex128 (output of the unnormalised inverse) -> [rows, 2n] int64."""
+    z = np.ascontiguousarray(z, dtype=np.complex128)
+    n = z.shape[-1]
+    flat = z.reshape(-1, n)
+    _, un = poly_twist_tables(n)
+    out = np.zeros((flat.shape[0], 2 * n), np.int64) if acc is None else np.ascontiguousarray(acc, dtype=np.int64).reshape(-1, 2 * n).copy()
+    for r in range(flat.shape[0]):
+        lib().orc_poly_untwist_round(n, int(torus), int(acc is not None), _ptr(flat[r]), _ptr(un), _ptr(out[r]))
+    return out
+
+
+def poly_mul(plan, a, b, torus=False, acc=None, threads=1):
+    """The whole product step through the oracle: a [batch, k, 2n] int64, b [k, n] (shared) or [batch, k, n] complex128
+    in `plan`'s order (an UnorderedPlan) -> [batch, 2n] int64."""
+    a = np.ascontiguousarray(a, dtype=np.int64)
+    b = np.ascontiguousarray(b, dtype=np.complex128)
+    batch, k, n = a.shape[0], a.shape[1], a.shape[2] // 2
+    stride = 0 if b.ndim == 2 else k * n
+    out = np.zeros((batch, 2 * n), np.int64) if acc is None else np.ascontiguousarray(acc, dtype=np.int64).copy()
+    plan.L.orc_poly_mul_batch(plan.h, n, plan.base_n, _ptr(a), k, _ptr(b), stride, _ptr(out), batch, int(torus), int(acc is not None), threads)
+    return out

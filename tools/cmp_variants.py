@@ -12,11 +12,11 @@ import concrete_fft_b200 as C
 
 logn = int(sys.argv[1])
 n = 1 << logn
-batch = (1 << 31) // (16 * n)
+batch = int(os.environ.get("CMP_BATCH", 0)) or (1 << 31) // (16 * n)
 data = torch.view_as_complex(torch.rand(batch, n, 2, dtype=torch.float64, device="cuda")).contiguous()
 
 
-def timeit(fn, reps=10):
+def timeit(fn, reps=int(os.environ.get("CMP_REPS", 10))):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
     ev[0].record()
     for i in range(reps):

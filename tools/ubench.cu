@@ -132,13 +132,14 @@ __device__ __forceinline__ void st_na(double2 *p, double2 v)
     asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
 
-// MODE 0 read, 1 write, 2 copy a -> b.  One sweep = every thread touches elements i, i + n/4, i + n/2, i + 3n/4 (grid = n / 4 / 256 blocks),
-// so each sweep covers the buffer exactly once
+// MODE 0 read, 1 write, 2 copy a -> b, 3 read-modify-write in place (the access pattern of an in-place transform pass).
+// One sweep = every thread touches elements i, i + n/4, i + n/2, i + 3n/4 (grid = n / 4 / 256 blocks), so each sweep covers
+// the buffer exactly once; the start index rotates with the sweep so that no load can be hoisted out of the loop.
 template <int MODE> __global__ void __launch_bounds__(256) l2_rate(double2 *a, double2 *b, size_t n, int reps, double *out)
 {
     double acc = 0;
     const size_t q = n / 4;
-    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     for (int r = 0; r < reps; r++) {
         if (MODE == 1) {
 #pragma unroll
@@ -150,9 +151,12 @@ template <int MODE> __global__ void __launch_bounds__(256) l2_rate(double2 *a, d
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 if (MODE == 2) st_na(b + i + u * q, v[u]);
+                else if (MODE == 3) st_na(a + i + u * q, make_double2(v[u].x + 1.0, v[u].y));
                 else acc += v[u].x + v[u].y;
             }
         }
+        i += 256 * 37; // another block's slice next sweep
+        if (i >= q) i -= q;
     }
     if (acc == 123.456) out[0] = acc;
 }
@@ -246,19 +250,20 @@ int main()
         for (size_t mb : sizes_mb) {
             const size_t n = (mb << 20) / 16;
             const int reps = int((size_t(8) << 30) / (mb << 20));
-            for (int mode = 0; mode < 3; mode++) {
+            for (int mode = 0; mode < 4; mode++) {
                 for (int w = 0; w < 2; w++) {
                     CK(cudaEventRecord(e0));
                     if (mode == 0) l2_rate<0><<<unsigned(n / 4 / 256), 256>>>(a, b, n, w ? reps : 1, out);
                     if (mode == 1) l2_rate<1><<<unsigned(n / 4 / 256), 256>>>(a, b, n, w ? reps : 1, out);
                     if (mode == 2) l2_rate<2><<<unsigned(n / 4 / 256), 256>>>(a, b, n, w ? reps : 1, out);
+                    if (mode == 3) l2_rate<3><<<unsigned(n / 4 / 256), 256>>>(a, b, n, w ? reps : 1, out);
                     CK(cudaEventRecord(e1));
                     CK(cudaEventSynchronize(e1));
                 }
                 CK(cudaEventElapsedTime(&ms, e0, e1));
-                const double bytes = double(mb << 20) * reps * (mode == 2 ? 2 : 1);
-                printf("%-5s buffer %4zu MiB%s x %4d sweeps: %6.0f GB/s (%s bytes)\n", mode == 0 ? "read" : (mode == 1 ? "write" : "copy"), mb,
-                       mode == 2 ? " x 2" : "    ", reps, bytes / ms / 1e6, mode == 2 ? "read + write" : "moved");
+                const double bytes = double(mb << 20) * reps * (mode >= 2 ? 2 : 1);
+                printf("%-5s buffer %4zu MiB%s x %4d sweeps: %6.0f GB/s (%s bytes)\n", mode == 0 ? "read" : (mode == 1 ? "write" : (mode == 2 ? "copy" : "rmw")), mb,
+                       mode == 2 ? " x 2" : "    ", reps, bytes / ms / 1e6, mode >= 2 ? "read + write" : "moved");
             }
         }
     }
