@@ -20,8 +20,9 @@ roofline    = achieved HBM GB/s of the dominant kernel (algorithmic bytes 2 * 16
 cpu_baseline= the oracle port of the reference algorithm (-O3 build, bit-identical results) on the host
               cores, bounded sample of the same workload (rank 0, N = 1 only).
 extra  = (default workload only) short legs for BASELINE.json configs[3] (fft128 n = 2048 x 16384) and
-         configs[2] (ordered N = 2^16 x 4096 in total), each with value / roofline / e2e / cpu_baseline, and
-         configs[0] (unordered N = 1024, one polynomial, one host thread, in cache: the `cargo bench` shape).
+         configs[2] (ordered N = 2^16 x 4096 in total), each with value / roofline / e2e / cpu_baseline;
+         configs[0] (unordered N = 1024, one polynomial, one host thread, in cache: the `cargo bench` shape);
+         poly_mul: the fused integer negacyclic product step, device-resident and from host memory.
 parity = every rank pushes the reference's golden vector through its own GPU (bit-exact against
          tests/golden, no oracle involved) and ranks compare a checksum of the headline plan's output on
          identical rows, outside the timed region.
@@ -355,6 +356,12 @@ def run_reference(args):
             en, eb, ebn, ealgo = workload_defaults(wl)
             sub = reference_leg(wl, en, eb, ebn, ealgo, args.gpus, 3, 1, 12.0)
             extra[wl] = {k: sub[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "cpu_baseline", "dtype")}
+        import numpy as np
+
+        key = np.random.default_rng(1).integers(-(1 << 10), 1 << 10, size=(4, 4096), dtype=np.int64)
+        extra["poly_mul"] = {"metric": "negacyclic integer polynomial products: transforms/s (k fwd + 1 inv per product)",
+                             "cpu_baseline": cpu_poly_mul(key, 4.0)}
+        extra["poly_mul"]["value"] = extra["poly_mul"]["cpu_baseline"]["value"]
         extra["cpu_n1024_1thread"] = cpu_single_polynomial()
         line["extra"] = extra
     print(json.dumps(line), flush=True)
@@ -647,6 +654,109 @@ def gpu_leg(ctx, workload, n, batch, base_n, algo, steps, warmup, e2e_steps, cpu
     return line
 
 
+def cpu_poly_mul(key_np, seconds):
+    """the same product step through the oracle port on all host threads (N = 4096, k terms, key shared)"""
+    import numpy as np
+    import oracle_lib as O
+
+    O.build()
+    k, npoly = key_np.shape
+    n = npoly // 2
+    threads = host_threads()
+    ref = O.UnorderedPlan(n, O.DIF16, 256, fast=True)
+    fb = ref.fwd(O.poly_fold_twist(key_np))
+    rows = 1024
+    rng = np.random.default_rng(0)
+    sample = rng.integers(-(1 << 20), 1 << 20, size=(rows, k, npoly), dtype=np.int64)
+    O.poly_mul(ref, sample[:64], fb, threads=threads)
+    w0, reps = time.perf_counter(), 0
+    while time.perf_counter() - w0 < seconds:
+        O.poly_mul(ref, sample, fb, threads=threads)
+        reps += 1
+    el = time.perf_counter() - w0
+    return {"value": rows * (k + 1) * reps / el, "unit": "transforms/s", "products_per_s": rows * reps / el, "cores": threads,
+            "kind": "port", "sample": "%d products x %d repetitions in %.1f s: fold + twist, %d reference forward transforms, "
+            "element-wise multiply-accumulate, inverse, untwist + round per product" % (rows, reps, el, k)}
+
+
+def poly_leg(ctx, steps, e2e_steps, cpu_seconds):
+    """SURVEY 8f rank 3 as a bench leg: the negacyclic product step on INTEGER polynomials -- out[r] = sum_k a[r][k] * key[k]
+    mod X^N + 1, N = 4096 (fft size 2048), k = 4 terms, key shared by the batch and resident in the Fourier domain on the GPU
+    (a GGSW row against a batch of decomposed ciphertexts) -- through cfft_c64_poly_mul (device-resident) and
+    cfft_c64_poly_mul_host (polynomials in host memory).  Counted in transforms (k forward + 1 inverse per row)."""
+    import numpy as np
+    import torch
+
+    C, rank, world, local, dist, dev = ctx.C, ctx.rank, ctx.world, ctx.local, ctx.dist, ctx.dev
+    from concrete_fft_b200.sharding import max_over_ranks
+
+    npoly, n, k, batch = 4096, 2048, 4, 16384
+    A = C.ordered.FftAlgo
+    plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(A.Dif16, 256), device=local)
+    g = torch.Generator(device=dev).manual_seed(0xB0B0 + rank)
+    a = torch.randint(-(1 << 20), 1 << 20, (batch, k, npoly), dtype=torch.int64, device=dev, generator=g)
+    key = torch.randint(-(1 << 10), 1 << 10, (k, npoly), dtype=torch.int64, device=dev, generator=g)
+    fkey = plan.fwd_poly(key)
+    out = torch.empty((batch, npoly), dtype=torch.int64, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(3):
+        plan.poly_mul(a, fkey, out=out)
+    launches0 = C.launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for _ in range(steps):
+        plan.poly_mul(a, fkey, out=out)
+    t1.record()
+    barrier()
+    launches = C.launch_count() - launches0
+    ms = max_over_ranks(t0.elapsed_time(t1), dist, dev) / steps
+    tr_per_step = batch * (k + 1)
+    value = tr_per_step * world / (ms * 1e-3)
+    e2e = None
+    if e2e_steps > 0:
+        ha = a.cpu().pin_memory()
+        ho = torch.empty((batch, npoly), dtype=torch.int64).pin_memory()
+        plan.poly_mul(ha.numpy(), fkey, out=ho.numpy())
+        assert torch.equal(ho, out.cpu())  # the host entry returns the device call's bits
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            plan.poly_mul(ha.numpy(), fkey, out=ho.numpy())
+        barrier()
+        el = max_over_ranks(time.perf_counter() - w0, dist, dev)
+        e2e = {"value": tr_per_step * world * e2e_steps / el, "unit": "transforms/s", "h2d_bytes_per_step": batch * k * npoly * 8,
+               "d2h_bytes_per_step": batch * npoly * 8, "steps": e2e_steps, "ms_per_step": 1e3 * el / e2e_steps,
+               "products_per_s": batch * world * e2e_steps / el,
+               "api": "Plan.poly_mul(numpy) -> cfft_c64_poly_mul_host (pinned host polynomials, Fourier-domain key resident on the GPU)"}
+        del ha, ho
+    fused = plan.has_fused_poly_kernel(k)
+    key_np = key.cpu().numpy()
+    del plan, a, out, fkey, key
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    peak, peak_src, _ = measured_peaks()
+    bytes_per_step = batch * (k + 1) * npoly * 8  # k polynomials in, one out per row; the shared key stays in L2
+    line = {"metric": "negacyclic integer polynomial products: transforms/s (k fwd + 1 inv per product)", "value": value, "unit": "transforms/s",
+            "products_per_s": batch * world / (ms * 1e-3), "n_gpus": world, "steps": steps, "ms_per_step": ms, "dtype": "i64 polynomials, f64 transforms",
+            "config": {"workload": "out[r] = sum_k a[r][k] * key[k] mod X^N + 1, integers in / out (SURVEY 8f rank 3)", "N_poly": npoly, "n": n,
+                       "k_terms": k, "batch_per_gpu": batch, "key": "shared by the batch, Fourier domain, device resident", "fused_kernel": bool(fused)},
+            "roofline": {"bound": "hbm", "kernel": "c64_fwd_mul_inv_kernel<2048, ..., PIN, POUT>", "achieved": bytes_per_step / (ms * 1e-3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": bytes_per_step / (ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_per_step, "traffic": None},
+            "e2e": e2e, "gpu_launches": int(launches), "cpu_baseline": None}
+    if cpu_seconds > 0 and world == 1:
+        line["cpu_baseline"] = cpu_poly_mul(key_np, cpu_seconds)
+    return line
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -689,6 +799,9 @@ def main():
             sub = gpu_leg(ctx, wl, en, eb, ebn, ealgo, st, 3, 0 if args.no_e2e else 2, 0.0 if args.no_cpu else 5.0, 0.0)
             if sub is not None:
                 extra[wl] = sub
+        sub = poly_leg(ctx, 10, 0 if args.no_e2e else 2, 0.0 if args.no_cpu else 4.0)
+        if sub is not None:
+            extra["poly_mul"] = sub
         if ctx.rank == 0 and not args.no_cpu:
             import oracle_lib  # noqa: F401
 

@@ -70,6 +70,8 @@ _SIGNATURES = {
     "cfft_f128_inv_host": (ctypes.c_int32, [_vp, _vp, _vp, _vp, _vp, _u64, _u64]),
     "cfft_f128_fwd_inv_host": (ctypes.c_int32, [_vp, _vp, _vp, _vp, _vp, _u64, _u64]),
     "cfft_f128_binary_op": (ctypes.c_int32, [_int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _vp]),
+    "cfft_f128_unary_op": (ctypes.c_int32, [_int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _vp]),
+    "cfft_f128_compare": (ctypes.c_int32, [_int, _vp, _vp, _vp, _vp, _vp, _u64, _vp]),
     "cfft_f128_cplx_mul_scale": (ctypes.c_int32, [_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_double, _u64, _vp]),
     "cfft_c64_mul_assign": (ctypes.c_int32, [_int, _vp, _vp, _u64, _vp]),
     "cfft_c64_mul_add_assign": (ctypes.c_int32, [_int, _vp, _vp, _vp, _u64, _vp]),

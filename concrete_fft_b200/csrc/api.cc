@@ -762,14 +762,64 @@ cfft_status cfft_f128_inv(const cfft_plan *p, double *re0, double *re1, double *
 cfft_status cfft_f128_binary_op(int device, int op, const double *a_hi, const double *a_lo, const double *b_hi,
                                 const double *b_lo, double *out_hi, double *out_lo, uint64_t len, void *stream)
 {
-    if (op < CFFT_F128_ADD || op > CFFT_F128_DIV_ESTIMATE) return fail(CFFT_EINVAL, "unknown f128 operator");
-    if (len && (!a_hi || !a_lo || !b_hi || !b_lo || !out_hi || !out_lo)) return fail(CFFT_EINVAL, "null buffer");
+    if (op < CFFT_F128_ADD || op > CFFT_F128_DIV_F64_F64) return fail(CFFT_EINVAL, "unknown f128 operator");
+    // which operands are f64 (their lo plane is ignored and may be NULL): a for 9, 12 and 13..16, b for 7, 8, 10, 11 and 13..16
+    const bool a_f64 = op == CFFT_F128_SUB_F64_F128 || op == CFFT_F128_DIV_F64_F128 || op >= CFFT_F128_ADD_F64_F64;
+    const bool b_f64 = op == CFFT_F128_ADD_F128_F64 || op == CFFT_F128_SUB_F128_F64 || op == CFFT_F128_MUL_F128_F64 ||
+                       op == CFFT_F128_DIV_F128_F64 || op >= CFFT_F128_ADD_F64_F64;
+    if (len && (!a_hi || (!a_lo && !a_f64) || !b_hi || (!b_lo && !b_f64) || !out_hi || !out_lo)) return fail(CFFT_EINVAL, "null buffer");
+    if (a_f64) a_lo = nullptr;
+    if (b_f64) b_lo = nullptr;
     cfft_status st = check_device(device);
     if (st != CFFT_OK) return st;
     DeviceGuard guard(device);
     if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
     cudaError_t e = launch_f128_binary(op, a_hi, a_lo, b_hi, b_lo, out_hi, out_lo, len, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "f128 binary op launch");
+    return CFFT_OK;
+}
+
+cfft_status cfft_f128_unary_op(int device, int op, const double *a_hi, const double *a_lo, double *out_hi, double *out_lo,
+                               double *out2_hi, double *out2_lo, uint64_t len, void *stream)
+{
+    if (op < CFFT_F128_SQR || op > CFFT_F128_IS_NAN) return fail(CFFT_EINVAL, "unknown f128 unary operator");
+    if (len && (!a_hi || !a_lo || !out_hi || !out_lo)) return fail(CFFT_EINVAL, "null buffer");
+    if (len && op == CFFT_F128_SINCOSPI && (!out2_hi || !out2_lo)) return fail(CFFT_EINVAL, "sincospi needs the second output (cos)");
+    cfft_status st = check_device(device);
+    if (st != CFFT_OK) return st;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    unsigned int *bad = nullptr;
+    if (op == CFFT_F128_SINCOSPI) {
+        CU(cudaMalloc(reinterpret_cast<void **>(&bad), sizeof(unsigned int)));
+        cudaError_t e0 = cudaMemsetAsync(bad, 0, sizeof(unsigned int), cs);
+        if (e0 != cudaSuccess) { cudaFree(bad); return cuda_fail(e0, "f128 sincospi setup"); }
+    }
+    cudaError_t e = launch_f128_unary(op, a_hi, a_lo, out_hi, out_lo, out2_hi, out2_lo, len, bad, cs);
+    if (op == CFFT_F128_SINCOSPI) {
+        // the reference panics on inputs outside [-1, 1] (f128_ops.rs:536-538): this one entry point is synchronous so
+        // that the same precondition comes back as a status instead of silently as NaNs
+        unsigned int h = 0;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&h, bad, sizeof(h), cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
+        cudaFree(bad);
+        if (e == cudaSuccess && h) return fail(CFFT_EINVAL, "only inputs in [-1, 1] are currently supported (f128_ops.rs:537)");
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "f128 unary op launch");
+    return CFFT_OK;
+}
+
+cfft_status cfft_f128_compare(int device, const double *a_hi, const double *a_lo, const double *b_hi, const double *b_lo, int8_t *out,
+                              uint64_t len, void *stream)
+{
+    if (len && (!a_hi || !a_lo || !b_hi || !out)) return fail(CFFT_EINVAL, "null buffer");
+    cfft_status st = check_device(device);
+    if (st != CFFT_OK) return st;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
+    cudaError_t e = launch_f128_compare(a_hi, a_lo, b_hi, b_lo, reinterpret_cast<signed char *>(out), len, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "f128 compare launch");
     return CFFT_OK;
 }
 

@@ -2,6 +2,10 @@
 // c64_fast.cu (plain c64 rows) and c64_poly.cu (integer polynomials in / out).  See c64_fast.cu for the
 // design notes; every kernel reads and writes global memory only through the row accessors of c64_dev.cuh.
 #pragma once
+#include <mutex>
+#include <set>
+#include <utility>
+
 #include "c64_dev.cuh"
 #include "plan.h"
 
@@ -138,20 +142,21 @@ inline FastTables fast_tables(const cfft_plan *plan, int dir)
     return tb;
 }
 
-// opt a kernel in to more than 48 KiB of dynamic shared memory, once per (kernel, host thread, device)
+// opt a kernel in to more than 48 KiB of dynamic shared memory, once per (kernel, device)
 template <class K> inline cudaError_t allow_smem(K kernel, size_t smem)
 {
     if (smem <= 48 * 1024) return cudaSuccess;
-    static thread_local int configured_device = -1;
+    static std::mutex mu;
+    static std::set<std::pair<const void *, int>> done; // K is only the TYPE of the kernel pointer: key on its value
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (configured_device != dev) {
-        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        if (e != cudaSuccess) return e;
-        configured_device = dev;
-    }
-    return cudaSuccess;
+    const std::pair<const void *, int> key(reinterpret_cast<const void *>(kernel), dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if (done.count(key)) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e == cudaSuccess) done.insert(key);
+    return e;
 }
 
 template <int N> struct FastCfg {

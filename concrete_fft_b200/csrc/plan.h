@@ -149,6 +149,10 @@ cudaError_t launch_f128(const cfft_plan *plan, bool inverse, double *re0, double
 // kernels (f128_ops.cu)
 cudaError_t launch_f128_binary(int op, const double *a_hi, const double *a_lo, const double *b_hi, const double *b_lo,
                                double *out_hi, double *out_lo, uint64_t len, cudaStream_t st);
+cudaError_t launch_f128_unary(int op, const double *a_hi, const double *a_lo, double *out_hi, double *out_lo, double *out2_hi,
+                              double *out2_lo, uint64_t len, unsigned int *bad, cudaStream_t st);
+cudaError_t launch_f128_compare(const double *a_hi, const double *a_lo, const double *b_hi, const double *b_lo, signed char *out,
+                                uint64_t len, cudaStream_t st);
 cudaError_t launch_f128_cplx_mul_scale(double *l_re0, double *l_re1, double *l_im0, double *l_im1, const double *r_re0,
                                        const double *r_re1, const double *r_im0, const double *r_im1, double factor,
                                        uint64_t len, cudaStream_t st);

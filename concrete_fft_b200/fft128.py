@@ -127,23 +127,81 @@ class Plan:
 
 
 # ---- the scalar f128 operators on device arrays (src/fft128/f128_ops.rs) ---------------------------
-_OPS = {"add": 0, "sub": 1, "mul": 2, "div": 3, "add_estimate": 4, "sub_estimate": 5, "div_estimate": 6}
+_OPS = {"add": 0, "sub": 1, "mul": 2, "div": 3, "add_estimate": 4, "sub_estimate": 5, "div_estimate": 6,
+        # mixed-operand forms (f128_ops.rs:279-455): the f64 operand is passed as its value plane, lo = None
+        "add_f128_f64": 7, "sub_f128_f64": 8, "sub_f64_f128": 9, "mul_f128_f64": 10, "div_f128_f64": 11, "div_f64_f128": 12,
+        "add_f64_f64": 13, "sub_f64_f64": 14, "mul_f64_f64": 15, "div_f64_f64": 16}
+_A_F64 = {9, 12, 13, 14, 15, 16}
+_B_F64 = {7, 8, 10, 11, 13, 14, 15, 16}
+_UNARY = {"sqr": 0, "abs": 1, "neg": 2, "sincospi": 3, "is_nan": 4}
+
+
+def _plane(t, name):
+    v = f64_view(t)
+    if v[0] != "device":
+        raise TypeError("%s must be a CUDA float64 tensor" % name)
+    return v
 
 
 def f128_op(op, a_hi, a_lo, b_hi, b_lo):
-    """Element-wise f128 operator on CUDA float64 tensors; returns (hi, lo).  `op` is one of
-    add, sub, mul, div (f128::add_f128_f128 ... div_f128_f128) or add_estimate, sub_estimate,
-    div_estimate; bit-exact with the reference's scalar functions."""
+    """Element-wise f128 operator on CUDA float64 tensors; returns (hi, lo), bit-exact with the reference's scalar functions.
+    `op`: add, sub, mul, div (f128::add_f128_f128 ... div_f128_f128), add_estimate, sub_estimate, div_estimate, or a
+    mixed-operand form add_f128_f64, sub_f128_f64, sub_f64_f128, mul_f128_f64, div_f128_f64, div_f64_f128, add_f64_f64,
+    sub_f64_f64, mul_f64_f64, div_f64_f64 -- pass None as the lo plane of an f64 operand (add_f64_f128 / mul_f64_f128 are the
+    f128_f64 forms with the operands swapped, f128_ops.rs:294-298, 388-391)."""
     import torch
 
-    views = [f64_view(t) for t in (a_hi, a_lo, b_hi, b_lo)]
-    if any(v[0] != "device" for v in views) or len({v[2] for v in views}) != 1:
-        raise TypeError("f128_op takes four CUDA float64 tensors of equal length")
-    dev = views[0][3]
+    code = _OPS[op]
+    planes = [("a_hi", a_hi, False), ("a_lo", a_lo, code in _A_F64), ("b_hi", b_hi, False), ("b_lo", b_lo, code in _B_F64)]
+    ptrs, length, dev = [], None, None
+    for name, t, optional in planes:
+        if t is None and optional:
+            ptrs.append(None)
+            continue
+        v = _plane(t, name)
+        if length is None:
+            length, dev = v[2], v[3]
+        if v[2] != length or v[3] != dev:
+            raise TypeError("f128_op operands must have equal length and live on one device")
+        ptrs.append(v[1])
     out_hi, out_lo = torch.empty_like(a_hi), torch.empty_like(a_hi)
-    N.check(N.lib.cfft_f128_binary_op(dev, _OPS[op], views[0][1], views[1][1], views[2][1], views[3][1],
-                                      out_hi.data_ptr(), out_lo.data_ptr(), views[0][2], current_stream_ptr(dev)))
+    N.check(N.lib.cfft_f128_binary_op(dev, code, *ptrs, out_hi.data_ptr(), out_lo.data_ptr(), length, current_stream_ptr(dev)))
     return out_hi, out_lo
+
+
+def f128_unary(op, a_hi, a_lo):
+    """sqr, abs, neg, is_nan -> (hi, lo); sincospi -> ((sin_hi, sin_lo), (cos_hi, cos_lo)) for inputs in [-1, 1] (raises
+    PanicError otherwise, like the reference's panic)  (f128_ops.rs:404-409, 494-575)."""
+    import torch
+
+    va, vb = _plane(a_hi, "a_hi"), _plane(a_lo, "a_lo")
+    if va[2] != vb[2] or va[3] != vb[3]:
+        raise TypeError("f128_unary operands must have equal length and live on one device")
+    dev = va[3]
+    code = _UNARY[op]
+    out_hi, out_lo = torch.empty_like(a_hi), torch.empty_like(a_hi)
+    o2h = torch.empty_like(a_hi) if code == 3 else None
+    o2l = torch.empty_like(a_hi) if code == 3 else None
+    N.check(N.lib.cfft_f128_unary_op(dev, code, va[1], vb[1], out_hi.data_ptr(), out_lo.data_ptr(), o2h.data_ptr() if code == 3 else None,
+                                     o2l.data_ptr() if code == 3 else None, va[2], current_stream_ptr(dev)))
+    if code == 3:
+        return (out_hi, out_lo), (o2h, o2l)
+    return out_hi, out_lo
+
+
+def f128_compare(a_hi, a_lo, b_hi, b_lo=None):
+    """PartialOrd of f128 element-wise: int8 tensor of -1 (Less), 0 (Equal), 1 (Greater), 2 (None / unordered); b_lo = None
+    compares with the f64 values b_hi (f128_ops.rs:240-274)."""
+    import torch
+
+    vs = [_plane(a_hi, "a_hi"), _plane(a_lo, "a_lo"), _plane(b_hi, "b_hi")] + ([_plane(b_lo, "b_lo")] if b_lo is not None else [])
+    if len({v[2] for v in vs}) != 1 or len({v[3] for v in vs}) != 1:
+        raise TypeError("f128_compare operands must have equal length and live on one device")
+    dev = vs[0][3]
+    out = torch.empty(a_hi.shape, dtype=torch.int8, device=a_hi.device)
+    N.check(N.lib.cfft_f128_compare(dev, vs[0][1], vs[1][1], vs[2][1], vs[3][1] if b_lo is not None else None, out.data_ptr(), vs[0][2],
+                                    current_stream_ptr(dev)))
+    return out
 
 
 def cplx_mul_scale(lhs, rhs, factor):

@@ -190,11 +190,36 @@ cfft_status cfft_f128_fwd_inv_host(const cfft_plan *plan, double *re0, double *r
  * out may alias an input.  Stream ordered on `device`. */
 enum {
     CFFT_F128_ADD = 0, CFFT_F128_SUB, CFFT_F128_MUL, CFFT_F128_DIV,
-    CFFT_F128_ADD_ESTIMATE, CFFT_F128_SUB_ESTIMATE, CFFT_F128_DIV_ESTIMATE
+    CFFT_F128_ADD_ESTIMATE, CFFT_F128_SUB_ESTIMATE, CFFT_F128_DIV_ESTIMATE,
+    /* mixed-operand forms (the Add/Sub/Mul/Div<f64> impls, f128_ops.rs:48-230): the f64 operand's lo plane is ignored and may
+     * be NULL.  add_f64_f128 / mul_f64_f128 are the f128_f64 forms with the operands swapped (:294-298, :388-391). */
+    CFFT_F128_ADD_F128_F64,  /* :286-291 */
+    CFFT_F128_SUB_F128_F64,  /* :331-336 */
+    CFFT_F128_SUB_F64_F128,  /* :339-345 */
+    CFFT_F128_MUL_F128_F64,  /* :380-385 */
+    CFFT_F128_DIV_F128_F64,  /* :431-448 */
+    CFFT_F128_DIV_F64_F128,  /* :451-454 */
+    CFFT_F128_ADD_F64_F64,   /* :279-283 */
+    CFFT_F128_SUB_F64_F64,   /* :324-328 */
+    CFFT_F128_MUL_F64_F64,   /* :373-377 */
+    CFFT_F128_DIV_F64_F64    /* :413-428 */
 };
 cfft_status cfft_f128_binary_op(int device, int op, const double *a_hi, const double *a_lo,
                                 const double *b_hi, const double *b_lo, double *out_hi,
                                 double *out_lo, uint64_t len, void *stream);
+
+/* Unary operators of `f128` on device arrays, bit-exact with the reference's scalar functions:
+ *   SQR sqr :404-409, ABS abs :506-511, NEG the Neg impl :232-238, IS_NAN is_nan :499-501 (out_hi = 1.0 / 0.0, out_lo = 0.0),
+ *   SINCOSPI sincospi :514-575 + tables :578-618: out = sin(pi a), out2 = cos(pi a); the reference panics on inputs outside
+ *   [-1, 1], here such elements become NaN and the call returns CFFT_EINVAL (this one operator synchronises the stream).
+ * out2_* is only used by SINCOSPI.  `to_f64` (:494-496) is the hi plane itself.  out may alias the input. */
+enum { CFFT_F128_SQR = 0, CFFT_F128_ABS, CFFT_F128_NEG, CFFT_F128_SINCOSPI, CFFT_F128_IS_NAN };
+cfft_status cfft_f128_unary_op(int device, int op, const double *a_hi, const double *a_lo, double *out_hi, double *out_lo,
+                               double *out2_hi, double *out2_lo, uint64_t len, void *stream);
+/* PartialOrd / PartialEq of `f128` (f128_ops.rs:240-274) element-wise: out[i] = -1 Less, 0 Equal (== is exactly this case),
+ * 1 Greater, 2 None (unordered: a NaN decided the comparison).  b_lo == NULL compares with the f64 values b_hi (:248-259, :267-274). */
+cfft_status cfft_f128_compare(int device, const double *a_hi, const double *a_lo, const double *b_hi, const double *b_lo,
+                              int8_t *out, uint64_t len, void *stream);
 
 /* lhs <- (lhs * rhs) * factor, point-wise on planar double-double complex arrays: the step between
  * fwd and inv of a negacyclic product exactly as the reference's tests do it (scalar cplx_mul,

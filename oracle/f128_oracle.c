@@ -154,11 +154,54 @@ of128 orc_f128_div_estimate(of128 a, of128 b)
     return q;
 }
 
+/* mixed-operand forms, f128_ops.rs:279-299, 324-347, 373-392, 413-455 */
+static of128 sub_f128_f64_(of128 a, double b) /* :331-336 */
+{
+    double s1, s2;
+    two_diff(a.hi, b, &s1, &s2);
+    s2 = s2 + a.lo;
+    of128 r;
+    quick_two_sum(s1, s2, &r.hi, &r.lo);
+    return r;
+}
+static of128 sub_f64_f128_(double a, of128 b) /* :339-345 */
+{
+    double s1, s2;
+    two_diff(a, b.hi, &s1, &s2);
+    s2 = s2 - b.lo;
+    of128 r;
+    quick_two_sum(s1, s2, &r.hi, &r.lo);
+    return r;
+}
+static of128 div_f64_f64_(double a, double b) /* :413-428 */
+{
+    double q1 = a / b, p1, p2, s, e;
+    two_prod(q1, b, &p1, &p2);
+    two_diff(a, p1, &s, &e);
+    e = e - p2;
+    double q2 = (s + e) / b;
+    of128 r;
+    quick_two_sum(q1, q2, &r.hi, &r.lo);
+    return r;
+}
+static of128 div_f128_f64_(of128 a, double b) /* :431-448 */
+{
+    double q1 = a.hi / b, p1, p2, s, e;
+    two_prod(q1, b, &p1, &p2);
+    two_diff(a.hi, p1, &s, &e);
+    e = e + a.lo;
+    e = e - p2;
+    double q2 = (s + e) / b;
+    of128 r;
+    quick_two_sum(q1, q2, &r.hi, &r.lo);
+    return r;
+}
+
 void orc_f128_binary_op(int op, const double *a_hi, const double *a_lo, const double *b_hi, const double *b_lo,
                         double *out_hi, double *out_lo, size_t len)
 {
     for (size_t i = 0; i < len; i++) {
-        of128 a = { a_hi[i], a_lo[i] }, b = { b_hi[i], b_lo[i] }, r;
+        of128 a = { a_hi[i], a_lo ? a_lo[i] : 0.0 }, b = { b_hi[i], b_lo ? b_lo[i] : 0.0 }, r;
         switch (op) {
         case 0: r = orc_f128_add(a, b); break;
         case 1: r = orc_f128_sub(a, b); break;
@@ -166,7 +209,17 @@ void orc_f128_binary_op(int op, const double *a_hi, const double *a_lo, const do
         case 3: r = orc_f128_div(a, b); break;
         case 4: r = orc_f128_add_estimate(a, b); break;
         case 5: r = orc_f128_sub_estimate(a, b); break;
-        default: r = orc_f128_div_estimate(a, b); break;
+        case 6: r = orc_f128_div_estimate(a, b); break;
+        case 7: r = add_f128_f64(a, b.hi); break;                        /* add_f128_f64 :286-291 (= add_f64_f128 swapped) */
+        case 8: r = sub_f128_f64_(a, b.hi); break;
+        case 9: r = sub_f64_f128_(a.hi, b); break;
+        case 10: r = mul_f128_f64(a, b.hi); break;                       /* :380-385 (= mul_f64_f128 swapped) */
+        case 11: r = div_f128_f64_(a, b.hi); break;
+        case 12: r = orc_f128_div(dd(a.hi, 0.0), b); break;              /* div_f64_f128 :451-454 */
+        case 13: two_sum(a.hi, b.hi, &r.hi, &r.lo); break;               /* add_f64_f64 :279-283 */
+        case 14: two_diff(a.hi, b.hi, &r.hi, &r.lo); break;              /* sub_f64_f64 :324-328 */
+        case 15: two_prod(a.hi, b.hi, &r.hi, &r.lo); break;              /* mul_f64_f64 :373-377 */
+        default: r = div_f64_f64_(a.hi, b.hi); break;                    /* div_f64_f64 :413-428 */
         }
         out_hi[i] = r.hi;
         out_lo[i] = r.lo;
@@ -504,3 +557,36 @@ void orc_f128_inv_batch(const orc_f128_plan *p, double *re0, double *re1, double
 }
 
 of128 orc_f128_sqr(of128 a) { return sqr_f128(a); }
+
+/* unary operators on arrays; op codes match include/cfft_b200.h: 0 sqr :404-409, 1 abs :506-511, 2 neg (Neg impl :232-238),
+ * 3 sincospi :534-575 (out = sin, out2 = cos; inputs must lie in [-1, 1]), 4 is_nan :499-501 (out_hi = 1.0 / 0.0, out_lo = 0) */
+void orc_f128_unary_op(int op, const double *a_hi, const double *a_lo, double *out_hi, double *out_lo, double *out2_hi,
+                       double *out2_lo, size_t len)
+{
+    for (size_t i = 0; i < len; i++) {
+        of128 a = { a_hi[i], a_lo[i] }, r = { 0.0, 0.0 }, r2 = { 0.0, 0.0 };
+        switch (op) {
+        case 0: r = sqr_f128(a); break;
+        case 1: r = a.hi < 0.0 ? neg_f128(a) : a; break;
+        case 2: r = neg_f128(a); break;
+        case 3: orc_f128_sincospi(a, &r, &r2); break;
+        default: r.hi = (a.hi != a.hi || a.lo != a.lo) ? 1.0 : 0.0; break;
+        }
+        out_hi[i] = r.hi;
+        out_lo[i] = r.lo;
+        if (op == 3) {
+            out2_hi[i] = r2.hi;
+            out2_lo[i] = r2.lo;
+        }
+    }
+}
+
+/* PartialOrd / PartialEq, f128_ops.rs:240-274: -1 Less, 0 Equal, 1 Greater, 2 None (unordered); b_lo == NULL: an f64 operand */
+static int cmp_f64(double x, double y) { return x < y ? -1 : (x > y ? 1 : (x == y ? 0 : 2)); }
+void orc_f128_compare(const double *a_hi, const double *a_lo, const double *b_hi, const double *b_lo, signed char *out, size_t len)
+{
+    for (size_t i = 0; i < len; i++) {
+        const int first = cmp_f64(a_hi[i], b_hi[i]);
+        out[i] = (signed char)(first == 0 ? cmp_f64(a_lo[i], b_lo ? b_lo[i] : 0.0) : first);
+    }
+}

@@ -93,6 +93,11 @@ of128 orc_f128_sqr(of128 a);                   /* f128_ops.rs:404-409 */
  * 0 add, 1 sub, 2 mul (scalar form :395-400), 3 div, 4 add_estimate, 5 sub_estimate, 6 div_estimate */
 void orc_f128_binary_op(int op, const double *a_hi, const double *a_lo, const double *b_hi, const double *b_lo,
                         double *out_hi, double *out_lo, size_t len);
+/* 7 add_f128_f64, 8 sub_f128_f64, 9 sub_f64_f128, 10 mul_f128_f64, 11 div_f128_f64, 12 div_f64_f128, 13 add_f64_f64,
+ * 14 sub_f64_f64, 15 mul_f64_f64, 16 div_f64_f64 (f64 operands: the lo pointer may be NULL) */
+void orc_f128_unary_op(int op, const double *a_hi, const double *a_lo, double *out_hi, double *out_lo, double *out2_hi,
+                       double *out2_lo, size_t len);
+void orc_f128_compare(const double *a_hi, const double *a_lo, const double *b_hi, const double *b_lo, signed char *out, size_t len);
 /* lhs <- (lhs * rhs) * factor on planar double-double complex arrays, scalar cplx_mul
  * (src/fft128/mod.rs:310-326) then four f64 scalings, exactly the loop at src/fft128/mod.rs:2033-2047 */
 /* element-wise c64 products with num_complex's `*` / `+` semantics (no FMA): lhs <- lhs * rhs, or

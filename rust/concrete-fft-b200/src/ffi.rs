@@ -57,6 +57,32 @@ extern "C" {
     pub fn cfft_launch_count() -> u64;
     pub fn cfft_version() -> *const c_char;
     pub fn cfft_plan_copy_twiddles(plan: *const cfft_plan, which: c_int, host_out: *mut c_void, bytes: u64) -> cfft_status;
+    pub fn cfft_f128_unary_op(device: c_int, op: c_int, a_hi: *const f64, a_lo: *const f64, out_hi: *mut f64, out_lo: *mut f64, out2_hi: *mut f64, out2_lo: *mut f64, len: u64, stream: *mut c_void) -> cfft_status;
+    pub fn cfft_f128_compare(device: c_int, a_hi: *const f64, a_lo: *const f64, b_hi: *const f64, b_lo: *const f64, out: *mut i8, len: u64, stream: *mut c_void) -> cfft_status;
+    pub fn cfft_c64_poly_fwd(plan: *const cfft_plan, poly_dev: *const i64, fourier_dev: *mut c_void, batch: u64, flags: u32, stream: *mut c_void) -> cfft_status;
+    pub fn cfft_c64_poly_inv(plan: *const cfft_plan, fourier_dev: *const c_void, poly_dev: *mut i64, batch: u64, flags: u32, stream: *mut c_void) -> cfft_status;
+    pub fn cfft_c64_poly_mul(plan: *const cfft_plan, a_dev: *const i64, k_terms: u64, b_dev: *const c_void, b_row_stride: u64, out_dev: *mut i64, batch: u64, flags: u32, stream: *mut c_void) -> cfft_status;
+    pub fn cfft_c64_poly_mul_host(plan: *const cfft_plan, a_host: *const i64, k_terms: u64, b_dev: *const c_void, b_row_stride: u64, out_host: *mut i64, batch: u64, flags: u32) -> cfft_status;
+    pub fn cfft_plan_has_fused_poly_kernel(plan: *const cfft_plan, k_terms: u64) -> c_int;
+    pub fn cfft_plan_copy_twist(plan: *const cfft_plan, host_out: *mut c_void, bytes: u64) -> cfft_status;
+    pub fn cfft_twopass_timeouts(device: c_int, out: *mut u32) -> cfft_status;
+    pub fn cfft_probe_fp64_issue_rate(device: c_int, dfma_per_s: *mut f64, dadd_per_s: *mut f64, mix_per_s: *mut f64, sm_mhz: *mut f64, sm_count: *mut c_int) -> cfft_status;
+}
+
+/// flags of the polynomial entry points (`cfft_c64_poly_*`)
+pub const CFFT_POLY_INTEGER: u32 = 0;
+pub const CFFT_POLY_TORUS: u32 = 1;
+pub const CFFT_POLY_ACCUMULATE: u32 = 2;
+
+/// Shared by the three `Plan` types: kernel family name, on-device autotune and its report.
+pub(crate) fn kernel_name(h: &Handle) -> String {
+    unsafe { core::ffi::CStr::from_ptr(cfft_plan_kernel_name(h.0)) }.to_string_lossy().into_owned()
+}
+pub(crate) fn autotune(h: &mut Handle, batch_hint: u64) -> String {
+    check(unsafe { cfft_plan_autotune(h.0, batch_hint) });
+    let mut buf = vec![0u8; 4096];
+    let n = unsafe { cfft_plan_tuning_report(h.0, buf.as_mut_ptr().cast(), buf.len() as u64) } as usize;
+    String::from_utf8_lossy(&buf[..n]).into_owned()
 }
 
 /// Turns a non-zero status into the panic the reference would have raised at the same place.

@@ -116,6 +116,30 @@ pub mod ordered {
             let b = (buf.len() / self.fft_size()) as u64;
             ffi::check(unsafe { ffi::cfft_c64_inv_host(self.h.0, buf.as_mut_ptr().cast(), buf.len() as u64, b) });
         }
+        /// Extension: standard-order plans above the reference's 2^10 cap (up to 2^20).
+        #[track_caller]
+        pub fn new_large(n: usize, method: Method) -> Self {
+            let (m, algo) = match method {
+                Method::UserProvided(a) => (ffi::CFFT_METHOD_USER, a as i32),
+                #[cfg(feature = "std")]
+                Method::Measure(_) => (ffi::CFFT_METHOD_MEASURE, 0),
+            };
+            let mut out = core::ptr::null_mut();
+            ffi::check(unsafe { ffi::cfft_ordered_plan_create(&mut out, ffi::default_device(), n as u64, m, algo, 1) });
+            Self { h: ffi::Handle(out) }
+        }
+        /// The raw plan handle for the [`crate::device`] entry points (valid as long as `self` lives).
+        pub fn as_raw(&self) -> *const ffi::cfft_plan {
+            self.h.0
+        }
+        /// Which kernel family serves this plan.
+        pub fn kernel_name(&self) -> String {
+            ffi::kernel_name(&self.h)
+        }
+        /// On-device kernel-variant autotune (what `Method::Measure` runs implicitly); returns the timing report.
+        pub fn autotune(&mut self, batch_hint: u64) -> String {
+            ffi::autotune(&mut self.h, batch_hint)
+        }
     }
 }
 
@@ -202,6 +226,38 @@ pub mod unordered {
             ffi::check(unsafe { ffi::cfft_c64_inv_host(self.h.0, buf.as_mut_ptr().cast(), buf.len() as u64, b) });
         }
 
+        /// The raw plan handle for the [`crate::device`] entry points (valid as long as `self` lives).
+        pub fn as_raw(&self) -> *const ffi::cfft_plan {
+            self.h.0
+        }
+        /// Which kernel family serves this plan.
+        pub fn kernel_name(&self) -> String {
+            ffi::kernel_name(&self.h)
+        }
+        /// On-device kernel-variant autotune (what `Method::Measure` runs implicitly); returns the timing report.
+        /// Never changes `(base_algo, base_n)`, the Fourier-domain order or any output bit.
+        pub fn autotune(&mut self, batch_hint: u64) -> String {
+            ffi::autotune(&mut self.h, batch_hint)
+        }
+        /// `perm[i]` = index in this plan's buffers of Fourier coefficient `i` (`bit_rev_twice`, src/unordered.rs:1046-1051).
+        pub fn permutation(&self) -> Vec<u64> {
+            let mut out = vec![0u64; self.fft_size()];
+            ffi::check(unsafe { ffi::cfft_unordered_permutation(self.h.0, out.as_mut_ptr()) });
+            out
+        }
+        /// Extension: a whole negacyclic product step on integer polynomials in host memory --
+        /// `out[r] (+)= round(untwist(inv(sum_k fwd(twist(fold(a[r][k]))) * b[r][k])))` with the Fourier-domain operand `b_dev`
+        /// resident on the GPU (`[k_terms][n]` c64 shared by every row when `b_row_stride == 0`).  `a`: `batch * k_terms`
+        /// polynomials of `2 * fft_size()` coefficients, `out`: `batch` polynomials.  `flags`: `ffi::CFFT_POLY_*`.
+        /// # Safety
+        /// `b_dev` must be a device pointer on this plan's GPU holding the operand described above.
+        #[track_caller]
+        pub unsafe fn poly_mul_host(&self, a: &[i64], k_terms: usize, b_dev: *const core::ffi::c_void, b_row_stride: u64, out: &mut [i64], flags: u32) {
+            let npoly = 2 * self.fft_size();
+            assert!(k_terms >= 1 && out.len() % npoly == 0 && a.len() == out.len() * k_terms);
+            ffi::check(ffi::cfft_c64_poly_mul_host(self.h.0, a.as_ptr(), k_terms as u64, b_dev, b_row_stride, out.as_mut_ptr(), (out.len() / npoly) as u64, flags));
+        }
+
         /// src/unordered.rs:951-972
         #[cfg(feature = "serde")]
         pub fn serialize_fourier_buffer<S: serde::Serializer>(&self, serializer: S, buf: &[c64]) -> Result<S::Ok, S::Error> {
@@ -224,7 +280,7 @@ pub mod unordered {
             let n = self.fft_size();
             assert_eq!(n, buf.len());
             struct SeqVisitor<'a> {
-                plan: &'a Plan,
+                perm: Vec<u64>,
                 buf: &'a mut [c64],
             }
             impl<'de, 'a> Visitor<'de> for SeqVisitor<'a> {
@@ -233,27 +289,24 @@ pub mod unordered {
                     write!(f, "a sequence of {} 64-bit complex numbers", self.buf.len())
                 }
                 fn visit_seq<S: SeqAccess<'de>>(self, mut seq: S) -> Result<(), S::Error> {
+                    // element i of the standard-order sequence lands at perm[i]; like the reference, the first n elements are
+                    // written even when the sequence turns out too short or too long, and the length is judged at the end
                     let n = self.buf.len();
-                    let mut std_order = Vec::with_capacity(n);
-                    let mut i = 0usize;
+                    let mut count = 0usize;
                     while let Some(v) = seq.next_element::<c64>()? {
-                        if i < n {
-                            std_order.push(v);
+                        if count < n {
+                            self.buf[self.perm[count] as usize] = v;
                         }
-                        i += 1;
+                        count += 1;
                     }
-                    let st = unsafe {
-                        ffi::cfft_unordered_from_standard_host(self.plan.h.0, std_order.as_ptr().cast(), i as u64, self.buf.as_mut_ptr().cast())
-                    };
-                    if st == ffi::CFFT_ELENGTH {
-                        Err(serde::de::Error::invalid_length(i, &self))
-                    } else {
-                        ffi::check(st);
+                    if count == n {
                         Ok(())
+                    } else {
+                        Err(serde::de::Error::invalid_length(count, &self))
                     }
                 }
             }
-            deserializer.deserialize_seq(SeqVisitor { plan: self, buf })
+            deserializer.deserialize_seq(SeqVisitor { perm: self.permutation(), buf })
         }
     }
 }
@@ -267,6 +320,10 @@ pub mod fft128 {
     #[derive(Copy, Clone, Debug)]
     #[repr(C)]
     pub struct f128(pub f64, pub f64);
+
+    /// the scalar operator surface of `f128` (src/fft128/f128_ops.rs:48-618): `+ - * /` with `f128` and `f64` operands,
+    /// `Neg`, `PartialEq`, `PartialOrd`, the named `*_f128_f64`-style functions, `sqr`, `abs`, `to_f64`, `is_nan`, `sincospi`
+    mod f128_ops; // src/fft128/f128_ops.rs
 
     /// src/fft128/mod.rs:1832-1838
     #[derive(Clone)]
@@ -316,6 +373,18 @@ pub mod fft128 {
                 ffi::cfft_f128_inv_host(self.h.0, buf_re0.as_mut_ptr(), buf_re1.as_mut_ptr(), buf_im0.as_mut_ptr(), buf_im1.as_mut_ptr(), n as u64, 1)
             });
         }
+        /// The raw plan handle for the [`crate::device`] entry points (valid as long as `self` lives).
+        pub fn as_raw(&self) -> *const ffi::cfft_plan {
+            self.h.0
+        }
+        /// Which kernel family serves this plan.
+        pub fn kernel_name(&self) -> String {
+            ffi::kernel_name(&self.h)
+        }
+        /// On-device autotune of the tile size / group shape; returns the timing report.
+        pub fn autotune(&mut self, batch_hint: u64) -> String {
+            ffi::autotune(&mut self.h, batch_hint)
+        }
         /// Extension: `len / fft_size()` transforms per call on planar arrays.
         #[track_caller]
         pub fn fwd_batch(&self, re0: &mut [f64], re1: &mut [f64], im0: &mut [f64], im1: &mut [f64]) {
@@ -344,6 +413,7 @@ pub mod device {
 
     /// # Safety
     /// `dev_buf` must point to `batch * fft_size` c64 on the plan's device; `stream` is a `cudaStream_t`.
+    /// `plan` comes from `Plan::as_raw()` of any of the three plan types.
     pub unsafe fn c64_fwd(plan: *const ffi::cfft_plan, dev_buf: *mut c_void, batch: u64, stream: *mut c_void) {
         ffi::check(ffi::cfft_c64_fwd(plan, dev_buf, batch, stream));
     }
@@ -382,6 +452,50 @@ pub mod device {
     #[allow(clippy::too_many_arguments)]
     pub unsafe fn f128_fwd_mul_inv(plan: *const ffi::cfft_plan, l: [*mut f64; 4], r: [*const f64; 4], rhs_row_stride: u64, factor: f64, batch: u64, stream: *mut c_void) {
         ffi::check(ffi::cfft_f128_fwd_mul_inv(plan, l[0], l[1], l[2], l[3], r[0], r[1], r[2], r[3], rhs_row_stride, factor, batch, stream));
+    }
+    /// Integer polynomials (2 n signed 64-bit coefficients per row) to the Fourier domain with the fold, the conversion and
+    /// the negacyclic twist fused into the forward transform (`cfft_c64_poly_fwd`); `flags`: `ffi::CFFT_POLY_TORUS` or 0.
+    /// # Safety
+    /// `poly`: `batch * 2 n` i64, `fourier`: `batch * n` c64 (16-byte aligned), both on the plan's device, not overlapping.
+    pub unsafe fn c64_poly_fwd(plan: *const ffi::cfft_plan, poly: *const i64, fourier: *mut c_void, batch: u64, flags: u32, stream: *mut c_void) {
+        ffi::check(ffi::cfft_c64_poly_fwd(plan, poly, fourier, batch, flags, stream));
+    }
+    /// The way back: inverse transform, untwist, 1 / n, rounding (`f64::round`; torus: fractional part x 2^64), optionally added
+    /// to `poly` modulo 2^64 (`cfft_c64_poly_inv`); `fourier` is not modified.
+    /// # Safety
+    /// See [`c64_poly_fwd`].
+    pub unsafe fn c64_poly_inv(plan: *const ffi::cfft_plan, fourier: *const c_void, poly: *mut i64, batch: u64, flags: u32, stream: *mut c_void) {
+        ffi::check(ffi::cfft_c64_poly_inv(plan, fourier, poly, batch, flags, stream));
+    }
+    /// `out[r] (+)= round(untwist(inv(sum_k fwd(twist(fold(a[r][k]))) * b[r][k])))`: a whole negacyclic product / external
+    /// product step, integers in, integers out, one kernel for `n <= 4096` (`cfft_c64_poly_mul`).
+    /// # Safety
+    /// `a`: `batch * k_terms * 2 n` i64, `b`: Fourier-domain c64 as in [`c64_fwd_mul_inv`], `out`: `batch * 2 n` i64, all on the
+    /// plan's device; `out` may equal `a` only when `k_terms == 1` and not accumulating.
+    #[allow(clippy::too_many_arguments)]
+    pub unsafe fn c64_poly_mul(plan: *const ffi::cfft_plan, a: *const i64, k_terms: u64, b: *const c_void, b_row_stride: u64, out: *mut i64, batch: u64, flags: u32, stream: *mut c_void) {
+        ffi::check(ffi::cfft_c64_poly_mul(plan, a, k_terms, b, b_row_stride, out, batch, flags, stream));
+    }
+    /// Element-wise `f128` operator on device planes, bit-identical to the host scalars of `fft128::f128`
+    /// (`op`: `CFFT_F128_*` of include/cfft_b200.h; the lo plane of an f64 operand may be null).
+    /// # Safety
+    /// Every non-null plane addresses `len` doubles on `device`.
+    #[allow(clippy::too_many_arguments)]
+    pub unsafe fn f128_binary_op(device: i32, op: i32, a: [*const f64; 2], b: [*const f64; 2], out: [*mut f64; 2], len: u64, stream: *mut c_void) {
+        ffi::check(ffi::cfft_f128_binary_op(device, op, a[0], a[1], b[0], b[1], out[0], out[1], len, stream));
+    }
+    /// `sqr`, `abs`, `neg`, `sincospi` (second output = cos), `is_nan` on device planes.
+    /// # Safety
+    /// See [`f128_binary_op`]; `out2` is only written by `sincospi`.
+    #[allow(clippy::too_many_arguments)]
+    pub unsafe fn f128_unary_op(device: i32, op: i32, a: [*const f64; 2], out: [*mut f64; 2], out2: [*mut f64; 2], len: u64, stream: *mut c_void) {
+        ffi::check(ffi::cfft_f128_unary_op(device, op, a[0], a[1], out[0], out[1], out2[0], out2[1], len, stream));
+    }
+    /// `PartialOrd` of `f128` element-wise: -1 / 0 / 1 / 2 (unordered) per element; null `b[1]` compares with f64 values.
+    /// # Safety
+    /// See [`f128_binary_op`]; `out` addresses `len` bytes.
+    pub unsafe fn f128_compare(device: i32, a: [*const f64; 2], b: [*const f64; 2], out: *mut i8, len: u64, stream: *mut c_void) {
+        ffi::check(ffi::cfft_f128_compare(device, a[0], a[1], b[0], b[1], out, len, stream));
     }
     /// `out[r] = inv(sum_k fwd(a[r][k]) * b[r][k])` for `batch` rows of `k_terms` polynomials: forward transforms,
     /// element-wise multiply-accumulate and the inverse transform in one call (one kernel for plans of the

@@ -59,6 +59,8 @@ def lib(fast=False):
         "orc_f128_twiddles": (vp, [vp, ci]),
         "orc_f128_binary_op": (None, [ci, vp, vp, vp, vp, vp, vp, sz]),
         "orc_f128_cplx_mul_scale": (None, [vp, vp, vp, vp, vp, vp, vp, vp, dbl, sz]),
+        "orc_f128_unary_op": (None, [ci, vp, vp, vp, vp, vp, vp, sz]),
+        "orc_f128_compare": (None, [vp, vp, vp, vp, vp, sz]),
         "orc_c64_pointwise": (None, [vp, vp, vp, sz]),
         "orc_poly_twist_tables": (None, [sz, vp, vp]),
         "orc_poly_fold_twist": (None, [sz, ci, vp, vp, vp]),
@@ -195,14 +197,33 @@ class F128Plan:
         return out
 
 
-F128_OPS = {"add": 0, "sub": 1, "mul": 2, "div": 3, "add_estimate": 4, "sub_estimate": 5, "div_estimate": 6}
+F128_OPS = {"add": 0, "sub": 1, "mul": 2, "div": 3, "add_estimate": 4, "sub_estimate": 5, "div_estimate": 6,
+            "add_f128_f64": 7, "sub_f128_f64": 8, "sub_f64_f128": 9, "mul_f128_f64": 10, "div_f128_f64": 11, "div_f64_f128": 12,
+            "add_f64_f64": 13, "sub_f64_f64": 14, "mul_f64_f64": 15, "div_f64_f64": 16}
+F128_UNARY = {"sqr": 0, "abs": 1, "neg": 2, "sincospi": 3, "is_nan": 4}
 
 
 def f128_binary_op(op, a_hi, a_lo, b_hi, b_lo):
-    arrs = [np.ascontiguousarray(x, dtype=np.float64) for x in (a_hi, a_lo, b_hi, b_lo)]
+    """a_lo / b_lo may be None for the f64 operands of the mixed forms"""
+    arrs = [None if x is None else np.ascontiguousarray(x, dtype=np.float64) for x in (a_hi, a_lo, b_hi, b_lo)]
     out_hi, out_lo = np.empty_like(arrs[0]), np.empty_like(arrs[0])
-    lib().orc_f128_binary_op(F128_OPS[op], *[_ptr(x) for x in arrs], _ptr(out_hi), _ptr(out_lo), arrs[0].size)
+    lib().orc_f128_binary_op(F128_OPS[op], *[None if x is None else _ptr(x) for x in arrs], _ptr(out_hi), _ptr(out_lo), arrs[0].size)
     return out_hi, out_lo
+
+
+def f128_unary_op(op, a_hi, a_lo):
+    a_hi, a_lo = np.ascontiguousarray(a_hi, dtype=np.float64), np.ascontiguousarray(a_lo, dtype=np.float64)
+    o = [np.empty_like(a_hi) for _ in range(4)]
+    lib().orc_f128_unary_op(F128_UNARY[op], _ptr(a_hi), _ptr(a_lo), *[_ptr(x) for x in o], a_hi.size)
+    return ((o[0], o[1]), (o[2], o[3])) if op == "sincospi" else (o[0], o[1])
+
+
+def f128_compare(a_hi, a_lo, b_hi, b_lo=None):
+    arrs = [np.ascontiguousarray(x, dtype=np.float64) for x in (a_hi, a_lo, b_hi)]
+    bl = None if b_lo is None else np.ascontiguousarray(b_lo, dtype=np.float64)
+    out = np.empty(arrs[0].shape, np.int8)
+    lib().orc_f128_compare(*[_ptr(x) for x in arrs], None if bl is None else _ptr(bl), _ptr(out), arrs[0].size)
+    return out
 
 
 def f128_cplx_mul_scale(lhs, rhs, factor):

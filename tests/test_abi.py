@@ -112,3 +112,48 @@ def test_header_is_plain_c_and_demo_links(C, tmp_path):
         assert rc.returncode == 0, rc.stdout + rc.stderr
     else:
         assert rc.returncode == 77, rc.stdout + rc.stderr  # fails loudly without a GPU: no CPU fallback
+
+
+def test_rust_call_sequences_replayed_in_c(C, tmp_path):
+    """The Rust crate (rust/concrete-fft-b200) cannot be compiled here (no rustc in the image), so every call sequence its
+    methods make -- panics as statuses, serde invalid_length paths, clone / drop, as_raw() + device entry points, the
+    polynomial host entry -- is replayed by a strict-C99 program against the same shared library."""
+    import subprocess
+
+    exe = tmp_path / "rust_call_sequences"
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "rust_call_sequences.c"), "-L", os.path.join(ROOT, "concrete_fft_b200"), "-lcfft_b200",
+           "-Wl,-rpath," + os.path.join(ROOT, "concrete_fft_b200"), "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath,/usr/local/cuda/lib64",
+           "-lm", "-o", str(exe)]
+    subprocess.run(cmd, check=True)
+    rc = subprocess.run([str(exe)], capture_output=True, text=True)
+    import torch
+
+    if torch.cuda.is_available():
+        assert rc.returncode == 0, rc.stdout + rc.stderr
+        assert "all sequences ok" in rc.stdout
+    else:
+        assert rc.returncode == 77, rc.stdout + rc.stderr
+
+
+def test_rust_crate_declares_every_symbol_of_the_header():
+    """rust/concrete-fft-b200/src/ffi.rs must bind exactly the functions include/cfft_b200.h declares (the crate is source only:
+    this is the closest thing to a link check), and the f128 operator surface of the reference must be present by name."""
+    import re
+
+    declared = set(header_functions())
+    ffi = open(os.path.join(ROOT, "rust", "concrete-fft-b200", "src", "ffi.rs")).read()
+    bound = set(re.findall(r"pub fn (cfft_[a-z0-9_]+)\s*\(", ffi))
+    assert declared == bound, (sorted(declared - bound), sorted(bound - declared))
+    ops = open(os.path.join(ROOT, "rust", "concrete-fft-b200", "src", "fft128", "f128_ops.rs")).read()
+    for name in ["add_f64_f64", "add_f128_f64", "add_f64_f128", "add_estimate_f128_f128", "add_f128_f128", "sub_f64_f64", "sub_f128_f64",
+                 "sub_f64_f128", "sub_estimate_f128_f128", "sub_f128_f128", "mul_f64_f64", "mul_f128_f64", "mul_f64_f128", "mul_f128_f128",
+                 "sqr", "div_f64_f64", "div_f128_f64", "div_f64_f128", "div_estimate_f128_f128", "div_f128_f128", "to_f64", "is_nan", "abs",
+                 "sincospi"]:
+        assert re.search(r"pub fn %s\b" % name, ops), name
+    for tr in ["Neg for f128", "PartialEq<f128> for f128", "PartialEq<f64> for f128", "PartialEq<f128> for f64", "PartialOrd<f128> for f128",
+               "PartialOrd<f64> for f128", "PartialOrd<f128> for f64", "From<f64> for f128"]:
+        assert tr in ops, tr
+    assert "binop!(Add, add, AddAssign" in ops and "binop!(Div, div, DivAssign" in ops
+    lib = open(os.path.join(ROOT, "rust", "concrete-fft-b200", "src", "lib.rs")).read()
+    assert lib.count("pub fn as_raw(&self)") == 3  # every plan type hands its handle to device::*

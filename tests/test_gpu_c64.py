@@ -853,7 +853,18 @@ def test_persistent_two_phase_kernel_bit_exact(C, torch, logn):
         want = ref.fwd(x, threads=8)
         assert bits_equal(y, want), (n, batch)
         assert bits_equal(dev_run(torch, plan.inv, y), ref.inv(want, threads=8)), (n, batch)
-    assert "fast-b256-persistent-2pass" in plan.autotune()
+    # opt-in only (it spin-waits on other CTAs): never an autotune candidate unless the caller allows it
+    assert "fast-b256-persistent-2pass" not in plan.autotune()
+    os.environ["CFFT_B200_ALLOW_PERSISTENT"] = "1"
+    try:
+        assert "fast-b256-persistent-2pass" in plan.autotune()
+    finally:
+        del os.environ["CFFT_B200_ALLOW_PERSISTENT"]
+    lib = C._native.lib
+    import ctypes
+    count = ctypes.c_uint32(123)
+    C._native.check(lib.cfft_twopass_timeouts(0, ctypes.byref(count)))
+    assert count.value == 0  # no wait ever expired
 
 
 def test_persistent_kernels_share_the_gpu_without_deadlock(C, torch):

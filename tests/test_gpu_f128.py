@@ -172,6 +172,57 @@ def test_f128_operator_set_bit_exact(C, torch):
         assert np.array_equal(lo.cpu().numpy().view(np.uint64), want_lo.view(np.uint64)), op
 
 
+def test_f128_mixed_unary_and_compare_operators_bit_exact(C, torch):
+    """the rest of the `f128` operator surface (f128_ops.rs:48-274 operator impls with f64 operands, :279-455 mixed forms,
+    :404 sqr, :494-511 to_f64 / is_nan / abs, :514-618 sincospi) on device arrays: bit-exact against the oracle"""
+    rng = np.random.default_rng(41)
+    n = 50021
+    a_hi = rng.uniform(-4, 4, n)
+    b_hi = rng.uniform(0.25, 4, n) * rng.choice([-1.0, 1.0], n)
+    a_lo = (rng.random(n) - 0.5) * np.spacing(a_hi)
+    b_lo = (rng.random(n) - 0.5) * np.spacing(b_hi)
+    d = {k: torch.from_numpy(v).cuda() for k, v in dict(a_hi=a_hi, a_lo=a_lo, b_hi=b_hi, b_lo=b_lo).items()}
+    eq = lambda t, w: np.array_equal(t.cpu().numpy().view(np.uint64), w.view(np.uint64))
+    for op in ["add_f128_f64", "sub_f128_f64", "mul_f128_f64", "div_f128_f64"]:
+        hi, lo = C.fft128.f128_op(op, d["a_hi"], d["a_lo"], d["b_hi"], None)
+        wh, wl = O.f128_binary_op(op, a_hi, a_lo, b_hi, None)
+        assert eq(hi, wh) and eq(lo, wl), op
+    for op in ["sub_f64_f128", "div_f64_f128"]:
+        hi, lo = C.fft128.f128_op(op, d["a_hi"], None, d["b_hi"], d["b_lo"])
+        wh, wl = O.f128_binary_op(op, a_hi, None, b_hi, b_lo)
+        assert eq(hi, wh) and eq(lo, wl), op
+    for op in ["add_f64_f64", "sub_f64_f64", "mul_f64_f64", "div_f64_f64"]:
+        hi, lo = C.fft128.f128_op(op, d["a_hi"], None, d["b_hi"], None)
+        wh, wl = O.f128_binary_op(op, a_hi, None, b_hi, None)
+        assert eq(hi, wh) and eq(lo, wl), op
+    for op in ["sqr", "abs", "neg", "is_nan"]:
+        hi, lo = C.fft128.f128_unary(op, d["a_hi"], d["a_lo"])
+        wh, wl = O.f128_unary_op(op, a_hi, a_lo)
+        assert eq(hi, wh) and eq(lo, wl), op
+    # sincospi on [-1, 1], including the quadrant / sixteenth boundaries and the end points
+    x_hi = np.concatenate([rng.uniform(-1, 1, 20000), np.arange(-32, 33) / 32.0, [1.0, -1.0, 0.0, 0.5, -0.5, 0.03125]])
+    x_lo = (rng.random(x_hi.size) - 0.5) * np.spacing(x_hi) * (np.abs(x_hi) < 1)
+    (sh, sl), (ch, cl) = C.fft128.f128_unary("sincospi", torch.from_numpy(x_hi).cuda(), torch.from_numpy(x_lo).cuda())
+    (wsh, wsl), (wch, wcl) = O.f128_unary_op("sincospi", x_hi, x_lo)
+    assert eq(sh, wsh) and eq(sl, wsl) and eq(ch, wch) and eq(cl, wcl)
+    with pytest.raises(C.PanicError):  # the reference panics outside [-1, 1]
+        C.fft128.f128_unary("sincospi", torch.tensor([0.5, 1.5], dtype=torch.float64, device="cuda"), torch.zeros(2, dtype=torch.float64, device="cuda"))
+    # comparisons, NaNs and equal-hi cases included
+    c_hi = a_hi.copy()
+    c_lo = a_lo.copy()
+    c_hi[::7] = b_hi[::7]
+    c_lo[::14] = b_lo[::14]
+    c_hi[5::1001] = np.nan
+    c_lo[9::1003] = np.nan
+    dc = [torch.from_numpy(v).cuda() for v in (c_hi, c_lo)]
+    got = C.fft128.f128_compare(dc[0], dc[1], d["b_hi"], d["b_lo"]).cpu().numpy()
+    assert np.array_equal(got, O.f128_compare(c_hi, c_lo, b_hi, b_lo)) and set(np.unique(got)) == {-1, 0, 1, 2}
+    got = C.fft128.f128_compare(dc[0], dc[1], d["b_hi"]).cpu().numpy()  # against f64 values
+    assert np.array_equal(got, O.f128_compare(c_hi, c_lo, b_hi))
+    hi, _ = C.fft128.f128_unary("is_nan", dc[0], dc[1])
+    assert np.array_equal(hi.cpu().numpy() != 0, np.isnan(c_hi) | np.isnan(c_lo))
+
+
 def test_pointwise_product_bit_exact_and_full_size_convolution(C, torch):
     """fwd -> point-wise product -> inv entirely on the device at BASELINE configs[3] size
     (n = 2048, batch 16384 = 1 GiB per operand): the product kernel is bit-exact against the oracle,

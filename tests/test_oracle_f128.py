@@ -132,6 +132,57 @@ def test_operator_set_error_bounds():
             assert abs(got - want) <= bound * scale, (op, i)
 
 
+def test_mixed_operand_and_unary_operators_error_bounds():
+    """the rest of the scalar operator surface (f128_ops.rs:279-455 mixed forms, :404 sqr, :506 abs, :232 neg, :514-618
+    sincospi) against mpmath at 1024 bits: exact ops <= 2^-104 relative (the reference's own bound, f128_ops.rs:1062-1070),
+    sincospi <= 2^-103 (:1189-1215); the f64-f64 forms are error-free transformations (exact) except div."""
+    mpmath.mp.prec = 1024
+    rng = np.random.default_rng(6)
+    n = 200
+    a_hi = rng.uniform(-4, 4, n)
+    b_hi = rng.uniform(0.25, 4, n) * rng.choice([-1.0, 1.0], n)
+    a_lo = (rng.random(n) - 0.5) * np.spacing(a_hi)
+    b_lo = (rng.random(n) - 0.5) * np.spacing(b_hi)
+    M = lambda h, l=0.0: mpmath.mpf(float(h)) + mpmath.mpf(float(l))
+    fns = {"add": lambda x, y: x + y, "sub": lambda x, y: x - y, "mul": lambda x, y: x * y, "div": lambda x, y: x / y}
+    for op in ["add_f128_f64", "sub_f128_f64", "sub_f64_f128", "mul_f128_f64", "div_f128_f64", "div_f64_f128", "add_f64_f64", "sub_f64_f64",
+               "mul_f64_f64", "div_f64_f64"]:
+        a_is_f64 = op.split("_")[1] == "f64"
+        b_is_f64 = op.split("_")[2] == "f64"
+        hi, lo = O.f128_binary_op(op, a_hi, None if a_is_f64 else a_lo, b_hi, None if b_is_f64 else b_lo)
+        exact = a_is_f64 and b_is_f64 and not op.startswith("div")
+        for i in range(n):
+            A = M(a_hi[i], 0.0 if a_is_f64 else a_lo[i])
+            B = M(b_hi[i], 0.0 if b_is_f64 else b_lo[i])
+            want, got = fns[op.split("_")[0]](A, B), M(hi[i], lo[i])
+            if exact:
+                assert got == want, (op, i)  # two_sum / two_diff / two_prod lose nothing
+            else:
+                scale = max(abs(want), abs(A) if op.startswith(("add", "sub")) else abs(want))
+                assert abs(got - want) <= mpmath.mpf(2) ** -104 * scale, (op, i)
+    hi, lo = O.f128_unary_op("sqr", a_hi, a_lo)
+    for i in range(n):
+        A = M(a_hi[i], a_lo[i])
+        assert abs(M(hi[i], lo[i]) - A * A) <= mpmath.mpf(2) ** -104 * A * A
+    hi, lo = O.f128_unary_op("abs", a_hi, a_lo)
+    assert all(M(hi[i], lo[i]) == abs(M(a_hi[i], a_lo[i])) for i in range(n))
+    hi, lo = O.f128_unary_op("neg", a_hi, a_lo)
+    assert np.array_equal(hi, -a_hi) and np.array_equal(lo, -a_lo)
+    x_hi = np.concatenate([rng.uniform(-1, 1, 150), np.arange(-16, 17) / 16.0])
+    x_lo = (rng.random(x_hi.size) - 0.5) * np.spacing(x_hi) * (np.abs(x_hi) < 1)
+    (sh, sl), (ch, cl) = O.f128_unary_op("sincospi", x_hi, x_lo)
+    for i in range(x_hi.size):
+        X = M(x_hi[i], x_lo[i])
+        assert abs(M(sh[i], sl[i]) - mpmath.sinpi(X)) <= mpmath.mpf(2) ** -103, i
+        assert abs(M(ch[i], cl[i]) - mpmath.cospi(X)) <= mpmath.mpf(2) ** -103, i
+    # PartialOrd / PartialEq (f128_ops.rs:240-274) on a handful of decided cases
+    ah, al = np.array([1.0, 1.0, 1.0, 2.0, np.nan, 1.0, 1.0]), np.array([0.0, 1e-20, -1e-20, 0.0, 0.0, np.nan, 0.0])
+    bh, bl = np.array([1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 2.0]), np.array([0.0, 0.0, 0.0, 5.0, 0.0, 0.0, -9.0])
+    assert list(O.f128_compare(ah, al, bh, bl)) == [0, 1, -1, 1, 2, 2, -1]
+    assert list(O.f128_compare(ah, al, bh)) == [0, 1, -1, 1, 2, 2, -1]
+    assert list(O.f128_unary_op("is_nan", ah, al)[0]) == [0, 0, 0, 0, 1, 1, 0]
+
+
 def test_vectorised_build_same_bits():
     rng = np.random.default_rng(77)
     for n in [32, 64, 256, 2048]:
