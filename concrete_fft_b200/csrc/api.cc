@@ -188,7 +188,11 @@ const char *variant_name(const cfft_plan *p)
     case 6: return "ord16-regs";
     case 8: return "fast-b256-persistent-2pass";
     case 9: return "fast-b256-column+fused-rows";
-    default: return p->exact_regs ? "exact-regs" : "exact-tile";
+    default:
+        if (p->exact_regs && p->kind == KIND_UNORDERED && !getenv("CFFT_B200_REGS_NO_SPEC") &&
+            regs_spec_supported(p->n, algo_radix(p->algo), algo_is_dit(p->algo), p->base_n))
+            return "exact-regs-spec"; // compile-time schedule (c64_regs.cu)
+        return p->exact_regs ? "exact-regs" : "exact-tile";
     }
 }
 

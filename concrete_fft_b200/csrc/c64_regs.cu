@@ -158,6 +158,141 @@ c64_regs_kernel(c64 *__restrict__ data, uint64_t total, uint32_t base_n, StagePr
     }
 }
 
+// ---- compile-time stage schedules --------------------------------------------------------------------------------
+// The interpreter above spends ~45 % of its instructions on index arithmetic for stage shapes it only learns at run time
+// (profiles/r1z_ncu_regs_*).  For the plans the reference's own Method::Measure tends to produce (base_n = 512 / 1024 with
+// the radix-8 / 16 algorithms, src/unordered.rs:568-630) and the golden-vector plan (Dif4, 32) the schedule is built at
+// COMPILE time by the same rules as build_c64_programs / build_top_planar (api.cc), the stage loop is unrolled and every
+// stride, mask and table offset folds into an immediate.  The launcher compares the compile-time schedule with the
+// plan's own stage by stage and only then takes this path, so the two can never diverge.  Same run_stage, same bits.
+struct CProg {
+    int count;
+    Stage st[12];
+};
+
+constexpr uint32_t c_ilog2(uint32_t x) { return x <= 1 ? 0 : 1 + c_ilog2(x >> 1); }
+
+constexpr void c_append_base(CProg &pg, int R, bool dit, uint32_t base_n, uint32_t tw_off)
+{
+    const uint32_t rho = c_ilog2(uint32_t(R));
+    uint32_t bits = c_ilog2(base_n), s = 1, strides[12] = {}, ns = 0;
+    while (bits > rho) {
+        strides[ns++] = s;
+        s *= uint32_t(R);
+        bits -= rho;
+    }
+    if (!dit) {
+        for (uint32_t i = 0; i < ns; i++) pg.st[pg.count++] = Stage{ST_CORE_DIF, R, strides[i], tw_off, 0};
+        pg.st[pg.count++] = Stage{ST_END, 1 << bits, 0, tw_off, 0};
+    } else {
+        pg.st[pg.count++] = Stage{ST_END, 1 << bits, 0, tw_off, 0};
+        for (uint32_t i = ns; i-- > 0;) pg.st[pg.count++] = Stage{ST_CORE_DIT, R, strides[i], tw_off, 0};
+    }
+}
+
+constexpr CProg make_cprog(uint32_t n, int R, bool dit, uint32_t base_n, bool inverse)
+{
+    CProg pg = {};
+    struct Lvl { int r; uint32_t span, off_f, off_i; } lv[8] = {};
+    int nl = 0;
+    uint32_t cur = n, head = 0, tail = n + base_n;
+    while (cur > base_n) {
+        const int r = cur == 2 * base_n ? 2 : (cur == 4 * base_n ? 4 : 8);
+        const uint32_t sz = uint32_t(r - 1) * (cur / uint32_t(r));
+        tail -= sz;
+        lv[nl++] = Lvl{r, cur, head, tail};
+        head += sz;
+        cur /= uint32_t(r);
+    }
+    uint32_t planar = 0;
+    if (!inverse) {
+        for (int i = 0; i < nl; i++) {
+            pg.st[pg.count++] = Stage{ST_TOP, lv[i].r, lv[i].span, lv[i].off_f, planar};
+            planar += uint32_t(lv[i].r - 1) * (lv[i].span / uint32_t(lv[i].r));
+        }
+        c_append_base(pg, R, dit, base_n, head + base_n);
+    } else {
+        c_append_base(pg, R, dit, base_n, base_n);
+        for (int i = nl; i-- > 0;) {
+            pg.st[pg.count++] = Stage{ST_TOP, lv[i].r, lv[i].span, lv[i].off_i, planar};
+            planar += uint32_t(lv[i].r - 1) * (lv[i].span / uint32_t(lv[i].r));
+        }
+    }
+    return pg;
+}
+
+template <bool FWD, uint32_t N, int R, bool DIT, uint32_t BASE_N> struct SpecProg {
+    static constexpr CProg P = make_cprog(N, R, DIT, BASE_N, !FWD);
+};
+
+template <class SP, int SI, bool FWD, int NT>
+__device__ __forceinline__ void run_spec_from(uint32_t base_n, const c64 *tw_ref, const c64 *tw_top, TileIo &io, c64 (&v)[16])
+{
+    constexpr Stage st = SP::P.st[SI];
+    io.in_g = SI == 0;
+    io.out_g = SI == SP::P.count - 1;
+    if (SI != 0) __syncthreads(); // the previous stage's shared-memory writes
+    run_stage<st.radix, FWD, NT>(st, base_n, tw_ref, tw_top, io, v);
+    if constexpr (SI + 1 < SP::P.count) run_spec_from<SP, SI + 1, FWD, NT>(base_n, tw_ref, tw_top, io, v);
+}
+
+template <bool FWD, uint32_t N, int R, bool DIT, uint32_t BASE_N>
+__global__ void __launch_bounds__((N < 1024 ? 1024 : N) / 16, 16 * 32 / ((N < 1024 ? 1024 : N) / 16))
+c64_regs_spec_kernel(c64 *__restrict__ data, uint64_t total, const c64 *__restrict__ tw_ref, const c64 *__restrict__ tw_top)
+{
+    constexpr int NT = (N < 1024 ? 1024 : N) / 16;
+    constexpr uint32_t TILE = 16 * NT;
+    using SP = SpecProg<FWD, N, R, DIT, BASE_N>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileIo io;
+    io.s = reinterpret_cast<c64 *>(smem_raw);
+    const uint64_t start = uint64_t(blockIdx.x) * TILE;
+    io.g = data + start;
+    io.valid = total - start < TILE ? uint32_t(total - start) : TILE;
+    c64 v[16];
+    run_spec_from<SP, 0, FWD, NT>(BASE_N, tw_ref, tw_top, io, v);
+}
+
+inline bool same_program(const CProg &c, const StageProgram &p)
+{
+    if (c.count != p.count) return false;
+    for (int i = 0; i < c.count; i++) {
+        const Stage &a = c.st[i], &b = p.st[i];
+        if (a.kind != b.kind || a.radix != b.radix || a.tw_off != b.tw_off) return false;
+        if (a.kind != ST_END && a.span != b.span) return false;
+        if (a.kind == ST_TOP && a.tw2 != b.tw2) return false;
+    }
+    return true;
+}
+
+template <bool FWD, uint32_t N, int R, bool DIT, uint32_t BASE_N>
+cudaError_t launch_spec_t(const StageProgram &prog, c64 *data, uint64_t total, const c64 *tw_ref, const c64 *tw_top, cudaStream_t stream,
+                          bool *taken)
+{
+    using SP = SpecProg<FWD, N, R, DIT, BASE_N>;
+    constexpr int NT = (N < 1024 ? 1024 : N) / 16;
+    constexpr uint32_t TILE = 16 * NT;
+    static const CProg cp = SP::P;
+    if (!same_program(cp, prog)) return cudaSuccess; // not this schedule after all: the interpreter runs it
+    *taken = true;
+    const size_t smem = size_t(TILE) * sizeof(c64);
+    auto k = c64_regs_spec_kernel<FWD, N, R, DIT, BASE_N>;
+    if (smem > 48 * 1024) {
+        static thread_local int configured_device = -1;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (configured_device != dev) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            if (e != cudaSuccess) return e;
+            configured_device = dev;
+        }
+    }
+    const uint64_t tiles = (total + TILE - 1) / TILE;
+    k<<<unsigned(tiles), NT, smem, stream>>>(data, total, tw_ref, tw_top);
+    count_launch();
+    return cudaGetLastError();
+}
+
 template <bool FWD, int NT, int WPS = 16>
 cudaError_t launch_regs_t(const StageProgram &prog, c64 *data, uint64_t total, uint32_t base_n, const c64 *tw_ref,
                           const c64 *tw_top, cudaStream_t stream)
@@ -181,6 +316,33 @@ cudaError_t launch_regs_t(const StageProgram &prog, c64 *data, uint64_t total, u
 }
 
 } // namespace
+
+// Unordered plans with a compile-time schedule (whole transforms per tile).  *taken tells whether the call was launched here.
+#define CFFT_SPEC_PLANS(X)                                                                                          \
+    X(2048, 16, false, 1024) X(2048, 16, false, 512) X(2048, 8, false, 512) X(2048, 4, false, 32) X(2048, 16, true, 1024) \
+    X(1024, 16, false, 512) X(1024, 8, false, 512) X(4096, 16, false, 1024) X(4096, 8, false, 512)
+
+bool regs_spec_supported(uint64_t n, int radix, bool dit, uint64_t base_n)
+{
+#define X(N, R, DIT, B) if (n == N && radix == R && dit == DIT && base_n == B) return true;
+    CFFT_SPEC_PLANS(X)
+#undef X
+    return false;
+}
+
+cudaError_t launch_c64_regs_spec(bool inverse, uint64_t n, int radix, bool dit, uint64_t base_n, const StageProgram &prog, double2 *data,
+                                 uint64_t total, const double2 *tw_ref, const double2 *tw_top, cudaStream_t stream, bool *taken)
+{
+    *taken = false;
+    if (total == 0) return cudaSuccess;
+#define X(N, R, DIT, B)                                                                                                          \
+    if (n == N && radix == R && dit == DIT && base_n == B)                                                                       \
+        return inverse ? launch_spec_t<false, N, R, DIT, B>(prog, data, total, tw_ref, tw_top, stream, taken)                     \
+                       : launch_spec_t<true, N, R, DIT, B>(prog, data, total, tw_ref, tw_top, stream, taken);
+    CFFT_SPEC_PLANS(X)
+#undef X
+    return cudaSuccess;
+}
 
 // tile: 1024 (64 threads), 2048 (128 threads) or 4096 (256 threads) elements; prog: the stages whose span fits the tile
 cudaError_t launch_c64_regs(bool inverse, uint32_t tile, const StageProgram &prog, double2 *data, uint64_t total,

@@ -322,6 +322,13 @@ cudaError_t launch_c64_exact(const cfft_plan *plan, bool inverse, double2 *data,
         if (!(full.st[i].kind == ST_TOP && full.st[i].span > tile)) in_tile.st[in_tile.count++] = full.st[i];
 
     cudaError_t e;
+    if (regs && plan->kind == KIND_UNORDERED && n <= kTileMax && !getenv("CFFT_B200_REGS_NO_SPEC")) {
+        // plans with a compile-time schedule (c64_regs.cu): same stages, same tables, index arithmetic folded away
+        bool taken = false;
+        e = launch_c64_regs_spec(inverse, n, algo_radix(plan->algo), algo_is_dit(plan->algo), plan->base_n, full, data, total, tw,
+                                 plan->d_top_tw[inverse ? 1 : 0], stream, &taken);
+        if (e != cudaSuccess || taken) return e;
+    }
     if (regs) {
         // Levels wider than the tile (all radix 8: a radix-2 / 4 level spans <= 4 base_n <= 4096) run as
         // column passes over HBM, two levels per pass (c64_column.cu, planar twiddles), outermost pair first.

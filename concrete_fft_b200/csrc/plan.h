@@ -100,6 +100,10 @@ cudaError_t launch_permute(const cfft_plan *plan, bool to_standard, const double
 // kernels (c64_regs.cu): any stage program on a tile of 2048 / 4096 elements
 cudaError_t launch_c64_regs(bool inverse, uint32_t tile, const StageProgram &prog, double2 *data, uint64_t total,
                             uint32_t base_n, const double2 *tw_ref, const double2 *tw_top, cudaStream_t st);
+// the same kernel with the schedule of a few common unordered plans built at compile time (no index arithmetic left)
+bool regs_spec_supported(uint64_t n, int radix, bool dit, uint64_t base_n);
+cudaError_t launch_c64_regs_spec(bool inverse, uint64_t n, int radix, bool dit, uint64_t base_n, const StageProgram &prog, double2 *data,
+                                 uint64_t total, const double2 *tw_ref, const double2 *tw_top, cudaStream_t st, bool *taken);
 // kernels (c64_fast.cu)
 bool fast_b256_supported(uint64_t n, int base_algo, uint64_t base_n);
 cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *data, uint64_t batch, cudaStream_t st);

@@ -703,7 +703,7 @@ def test_generic_register_kernel_matches_tile_kernel_and_oracle(C, torch, algo):
     for n, base_n in cases:
         plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(A(algo), base_n))
         if not (algo == O.DIF16 and (base_n == 256 or base_n == n)):
-            assert plan.kernel_name() == "exact-regs", (algo, n, base_n, plan.kernel_name())
+            assert plan.kernel_name() in ("exact-regs", "exact-regs-spec"), (algo, n, base_n, plan.kernel_name())
         ref = O.UnorderedPlan(n, algo, base_n)
         for batch in (1, 3, 2048 // min(n, 2048) + 1):
             x = rand_c(rng, batch, n)
@@ -720,6 +720,34 @@ def test_generic_register_kernel_matches_tile_kernel_and_oracle(C, torch, algo):
         plan = C.ordered.Plan(n, C.ordered.Method.UserProvided(A(algo)))
         x = rand_c(rng, 131, n)
         assert bits_equal(dev_run(torch, plan.fwd, x), O.OrderedPlan(n, algo).fwd(x)), (algo, n)
+
+
+SPEC_PLANS = [(2048, O.DIF16, 1024), (2048, O.DIF16, 512), (2048, O.DIF8, 512), (2048, O.DIF4, 32), (2048, O.DIT16, 1024),
+              (1024, O.DIF16, 512), (1024, O.DIF8, 512), (4096, O.DIF16, 1024), (4096, O.DIF8, 512)]
+
+
+@pytest.mark.parametrize("n,algo,base_n", SPEC_PLANS)
+def test_compile_time_schedule_kernels_bit_exact(C, torch, n, algo, base_n):
+    """c64_regs_spec_kernel: the plans the reference's own Method::Measure tends to produce (src/unordered.rs:568-630) and the
+    golden-vector plan with their stage schedule built at compile time -- against the oracle and against the interpreter
+    (CFFT_B200_REGS_NO_SPEC=1), whole and ragged batches, fwd and inv."""
+    rng = np.random.default_rng(4100 + n + algo + base_n)
+    A = C.ordered.FftAlgo
+    plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(A(algo), base_n))
+    assert plan.kernel_name() == "exact-regs-spec"
+    ref = O.UnorderedPlan(n, algo, base_n)
+    for batch in (1, 2, 37):
+        x = rand_c(rng, batch, n)
+        y = dev_run(torch, plan.fwd, x)
+        want = ref.fwd(x, threads=8)
+        assert bits_equal(y, want), (n, algo, base_n, batch)
+        back = dev_run(torch, plan.inv, y)
+        assert bits_equal(back, ref.inv(want, threads=8)), (n, algo, base_n, batch)
+        os.environ["CFFT_B200_REGS_NO_SPEC"] = "1"
+        try:
+            assert bits_equal(dev_run(torch, plan.fwd, x), y) and bits_equal(dev_run(torch, plan.inv, y), back)
+        finally:
+            del os.environ["CFFT_B200_REGS_NO_SPEC"]
 
 
 def test_autotune_keeps_bits_and_order(C, torch):
