@@ -54,6 +54,10 @@ _SIGNATURES = {
     "cfft_plan_tuning_report": (_u64, [_vp, ctypes.c_char_p, _u64]),
     "cfft_c64_fwd": (ctypes.c_int32, [_vp, _vp, _u64, _vp]),
     "cfft_c64_inv": (ctypes.c_int32, [_vp, _vp, _u64, _vp]),
+    "cfft_c64_fwd_strided": (ctypes.c_int32, [_vp, _vp, _u64, _u64, _vp]),
+    "cfft_c64_inv_strided": (ctypes.c_int32, [_vp, _vp, _u64, _u64, _vp]),
+    "cfft_f128_fwd_strided": (ctypes.c_int32, [_vp, _vp, _vp, _vp, _vp, _u64, _u64, _vp]),
+    "cfft_f128_inv_strided": (ctypes.c_int32, [_vp, _vp, _vp, _vp, _vp, _u64, _u64, _vp]),
     "cfft_c64_fwd_host": (ctypes.c_int32, [_vp, _vp, _u64, _u64]),
     "cfft_c64_inv_host": (ctypes.c_int32, [_vp, _vp, _u64, _u64]),
     "cfft_c64_fwd_inv_host": (ctypes.c_int32, [_vp, _vp, _u64, _u64]),

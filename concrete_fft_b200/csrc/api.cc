@@ -740,6 +740,56 @@ cfft_status cfft_c64_inv(const cfft_plan *p, void *dev_buf, uint64_t batch, void
     return run_c64(p, true, dev_buf, batch, stream);
 }
 
+// Rows row_stride >= n elements apart (the stride_elems of the ABI proposal -- a caller whose polynomials sit
+// inside larger records, e.g. one polynomial of every GLWE ciphertext).  Plans served by one fused register kernel take the
+// stride in the kernel's row accessor; every other plan packs <= 256 MiB of rows at a time into the stream-ordered
+// workspace, transforms them there and copies them back (two extra passes over the data: correct, not fast).
+static cfft_status run_c64_strided(const cfft_plan *p, bool inverse, void *dev_buf, uint64_t row_stride, uint64_t batch, void *stream)
+{
+    if (!p || p->kind == KIND_F128) return fail(CFFT_EINVAL, "not a c64 plan");
+    if (row_stride == p->n || batch <= 1) return run_c64(p, inverse, dev_buf, batch, stream);
+    if (row_stride < p->n) return fail(CFFT_EINVAL, "row stride smaller than the transform size (rows would overlap)");
+    if (!dev_buf) return fail(CFFT_EINVAL, "null buffer");
+    if (reinterpret_cast<uintptr_t>(dev_buf) & 15) return fail(CFFT_EINVAL, "device buffer must be 16-byte aligned (128-bit accesses)");
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double2 *data = static_cast<double2 *>(dev_buf);
+    if (fast_b256_strided_available(p)) {
+        cudaError_t e = launch_c64_fast_b256_strided(p, inverse, data, row_stride, batch, st);
+        if (e != cudaSuccess) return cuda_fail(e, "strided c64 launch");
+        return CFFT_OK;
+    }
+    const uint64_t row_bytes = p->n * sizeof(double2), pitch = row_stride * sizeof(double2);
+    uint64_t chunk_rows = std::max<uint64_t>(1, (uint64_t{256} << 20) / row_bytes);
+    chunk_rows = std::min(chunk_rows, batch);
+    cudaMemPool_t pool = nullptr;
+    cudaError_t e = workspace_pool(p->device, &pool);
+    if (e != cudaSuccess) return cuda_fail(e, "workspace pool");
+    double2 *ws = nullptr;
+    if ((e = cudaMallocFromPoolAsync(reinterpret_cast<void **>(&ws), chunk_rows * row_bytes, pool, st)) != cudaSuccess)
+        return cuda_fail(e, "workspace allocation");
+    for (uint64_t r0 = 0; r0 < batch && e == cudaSuccess; r0 += chunk_rows) {
+        const uint64_t rows = std::min(chunk_rows, batch - r0);
+        double2 *src = data + r0 * row_stride;
+        e = cudaMemcpy2DAsync(ws, row_bytes, src, pitch, row_bytes, rows, cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = launch_c64(p, inverse, ws, rows, st);
+        if (e == cudaSuccess) e = cudaMemcpy2DAsync(src, pitch, ws, row_bytes, row_bytes, rows, cudaMemcpyDeviceToDevice, st);
+    }
+    const cudaError_t e2 = cudaFreeAsync(ws, st);
+    if (e != cudaSuccess || e2 != cudaSuccess) return cuda_fail(e != cudaSuccess ? e : e2, "strided c64 transform");
+    return CFFT_OK;
+}
+
+cfft_status cfft_c64_fwd_strided(const cfft_plan *p, void *dev_buf, uint64_t row_stride, uint64_t batch, void *stream)
+{
+    return run_c64_strided(p, false, dev_buf, row_stride, batch, stream);
+}
+cfft_status cfft_c64_inv_strided(const cfft_plan *p, void *dev_buf, uint64_t row_stride, uint64_t batch, void *stream)
+{
+    return run_c64_strided(p, true, dev_buf, row_stride, batch, stream);
+}
+
 static cfft_status run_f128(const cfft_plan *p, bool inverse, double *re0, double *re1, double *im0, double *im1,
                             uint64_t batch, void *stream)
 {
@@ -761,6 +811,54 @@ cfft_status cfft_f128_inv(const cfft_plan *p, double *re0, double *re1, double *
                           void *stream)
 {
     return run_f128(p, true, re0, re1, im0, im1, batch, stream);
+}
+
+// fft128 with rows row_stride >= n doubles apart in each of the four planes: packed through the workspace like the
+// generic c64 path above (the fft128 kernels are FP64-bound, the two copies cost ~15 % at n = 2048)
+static cfft_status run_f128_strided(const cfft_plan *p, bool inverse, double *re0, double *re1, double *im0, double *im1,
+                                    uint64_t row_stride, uint64_t batch, void *stream)
+{
+    if (!p || p->kind != KIND_F128) return fail(CFFT_EINVAL, "not an fft128 plan");
+    if (row_stride == p->n || batch <= 1) return run_f128(p, inverse, re0, re1, im0, im1, batch, stream);
+    if (row_stride < p->n) return fail(CFFT_EINVAL, "row stride smaller than the transform size (rows would overlap)");
+    if (!re0 || !re1 || !im0 || !im1) return fail(CFFT_EINVAL, "null buffer");
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const uint64_t row_bytes = p->n * sizeof(double), pitch = row_stride * sizeof(double);
+    uint64_t chunk_rows = std::max<uint64_t>(1, (uint64_t{64} << 20) / row_bytes); // 4 planes x 64 MiB
+    chunk_rows = std::min(chunk_rows, batch);
+    cudaMemPool_t pool = nullptr;
+    cudaError_t e = workspace_pool(p->device, &pool);
+    if (e != cudaSuccess) return cuda_fail(e, "workspace pool");
+    double *ws = nullptr;
+    if ((e = cudaMallocFromPoolAsync(reinterpret_cast<void **>(&ws), 4 * chunk_rows * row_bytes, pool, st)) != cudaSuccess)
+        return cuda_fail(e, "workspace allocation");
+    double *planes[4] = {re0, re1, im0, im1};
+    for (uint64_t r0 = 0; r0 < batch && e == cudaSuccess; r0 += chunk_rows) {
+        const uint64_t rows = std::min(chunk_rows, batch - r0);
+        double *w[4];
+        for (int i = 0; i < 4 && e == cudaSuccess; i++) {
+            w[i] = ws + uint64_t(i) * chunk_rows * p->n;
+            e = cudaMemcpy2DAsync(w[i], row_bytes, planes[i] + r0 * row_stride, pitch, row_bytes, rows, cudaMemcpyDeviceToDevice, st);
+        }
+        if (e == cudaSuccess) e = launch_f128(p, inverse, w[0], w[1], w[2], w[3], rows, st);
+        for (int i = 0; i < 4 && e == cudaSuccess; i++)
+            e = cudaMemcpy2DAsync(planes[i] + r0 * row_stride, pitch, w[i], row_bytes, row_bytes, rows, cudaMemcpyDeviceToDevice, st);
+    }
+    const cudaError_t e2 = cudaFreeAsync(ws, st);
+    if (e != cudaSuccess || e2 != cudaSuccess) return cuda_fail(e != cudaSuccess ? e : e2, "strided fft128 transform");
+    return CFFT_OK;
+}
+cfft_status cfft_f128_fwd_strided(const cfft_plan *p, double *re0, double *re1, double *im0, double *im1, uint64_t row_stride,
+                                  uint64_t batch, void *stream)
+{
+    return run_f128_strided(p, false, re0, re1, im0, im1, row_stride, batch, stream);
+}
+cfft_status cfft_f128_inv_strided(const cfft_plan *p, double *re0, double *re1, double *im0, double *im1, uint64_t row_stride,
+                                  uint64_t batch, void *stream)
+{
+    return run_f128_strided(p, true, re0, re1, im0, im1, row_stride, batch, stream);
 }
 
 cfft_status cfft_f128_binary_op(int device, int op, const double *a_hi, const double *a_lo, const double *b_hi,

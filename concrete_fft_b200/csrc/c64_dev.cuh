@@ -101,6 +101,7 @@ template <bool PIN, bool POUT> struct BatchIo {
     const c64 *twist;
     uint64_t row_in, row_out, prow_in, prow_out;
     uint32_t n, flags;
+    uint32_t ahead; // plain c64 input only: rows ahead whose lines a kernel may request into L2 (0 = never)
     __device__ __forceinline__ RowIo<PIN, POUT> row(uint64_t r) const
     {
         RowIo<PIN, POUT> io;
@@ -128,6 +129,7 @@ inline BatchIo<false, false> plain_batch(const c64 *in, c64 *out, uint64_t row_i
     b.prow_in = b.prow_out = 0;
     b.n = 0;
     b.flags = 0;
+    b.ahead = 0;
     return b;
 }
 typedef RowIo<false, false> PlainRow;

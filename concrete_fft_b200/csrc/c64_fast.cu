@@ -142,7 +142,7 @@ cudaError_t launch_cluster(bool inverse, c64 *data, uint64_t batch, const FastTa
 }
 
 template <int N, int R1, int R2, bool STD = false>
-cudaError_t launch_cfg(bool inverse, c64 *data, uint64_t batch, const FastTables &tb, cudaStream_t stream)
+cudaError_t launch_cfg(bool inverse, c64 *data, uint64_t batch, const FastTables &tb, cudaStream_t stream, uint64_t row_stride = N)
 {
     using Cfg = FastCfg<N>;
     const size_t smem = size_t(Cfg::ROWS) * N * sizeof(c64);
@@ -160,7 +160,16 @@ cudaError_t launch_cfg(bool inverse, c64 *data, uint64_t batch, const FastTables
             configured_device = dev;
         }
     }
-    const BatchIo<false, false> bio = plain_batch(data, data, N, N);
+    BatchIo<false, false> bio = plain_batch(data, data, row_stride, row_stride);
+    // L2 prefetch of the successor CTA's rows (c64_fast_kernels.cuh): CFFT_B200_FAST_PREFETCH = waves ahead (0 = off)
+    static const int env_pf = [] { const char *e = getenv("CFFT_B200_FAST_PREFETCH"); return e ? atoi(e) : -1; }();
+    const int waves = env_pf >= 0 ? env_pf : (N >= 8192 && !STD ? 1 : 0);
+    if (waves > 0 && N >= 512) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        bio.ahead = uint32_t(sms) * uint32_t(Cfg::MINB * Cfg::ROWS * waves);
+    }
     if (inverse) inv_k<<<unsigned(ctas), Cfg::NT, smem, stream>>>(bio, batch, tb);
     else fwd_k<<<unsigned(ctas), Cfg::NT, smem, stream>>>(bio, batch, tb);
     count_launch();
@@ -447,6 +456,37 @@ cudaError_t launch_c64_fwd_mul_inv(const cfft_plan *plan, const double2 *a, uint
     }
     const cudaError_t e2 = cudaFreeAsync(ws, stream);
     return e != cudaSuccess ? e : e2;
+}
+
+// rows row_stride >= n elements apart, for the plans served by ONE fused kernel (fast_variant 1 and 5): the kernel's row
+// accessor takes the stride, nothing else changes
+bool fast_b256_strided_available(const cfft_plan *plan)
+{
+    return (plan->fast_variant == 1 || plan->fast_variant == 5) && plan->n >= 256 && plan->n <= 8192;
+}
+cudaError_t launch_c64_fast_b256_strided(const cfft_plan *plan, bool inverse, double2 *data, uint64_t row_stride, uint64_t batch,
+                                         cudaStream_t stream)
+{
+    if (batch == 0) return cudaSuccess;
+    if (!fast_b256_strided_available(plan) || row_stride < plan->n) return cudaErrorInvalidValue;
+    const FastTables tb = fast_tables(plan, inverse ? 1 : 0);
+    if (plan->fast_variant == 5) {
+        switch (plan->n) {
+        case 2048: return launch_cfg<2048, 8, 1, true>(inverse, data, batch, tb, stream, row_stride);
+        case 4096: return launch_cfg<4096, 8, 2, true>(inverse, data, batch, tb, stream, row_stride);
+        case 8192: return launch_cfg<8192, 8, 4, true>(inverse, data, batch, tb, stream, row_stride);
+        default: return cudaErrorInvalidValue;
+        }
+    }
+    switch (plan->n) {
+    case 256: return launch_cfg<256, 1, 1>(inverse, data, batch, tb, stream, row_stride);
+    case 512: return launch_cfg<512, 2, 1>(inverse, data, batch, tb, stream, row_stride);
+    case 1024: return launch_cfg<1024, 4, 1>(inverse, data, batch, tb, stream, row_stride);
+    case 2048: return launch_cfg<2048, 8, 1>(inverse, data, batch, tb, stream, row_stride);
+    case 4096: return launch_cfg<4096, 8, 2>(inverse, data, batch, tb, stream, row_stride);
+    case 8192: return launch_cfg<8192, 8, 4>(inverse, data, batch, tb, stream, row_stride);
+    default: return cudaErrorInvalidValue;
+    }
 }
 
 cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *data, uint64_t batch, cudaStream_t stream)

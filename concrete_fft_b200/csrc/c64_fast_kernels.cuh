@@ -13,6 +13,8 @@ namespace cfft {
 namespace fastk {
 using namespace dev;
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // One unordered level of span NCUR on the 16 register values of a thread: B = 16/R butterflies,
 // butterfly j covers positions base_j + m*k.  Twiddles planar: tw[(k-1)*m + p].
 // G_IN / G_OUT: the level reads / writes the row in global memory through the accessor `io` (c64_dev.cuh: plain c64 or a
@@ -199,12 +201,24 @@ c64_fast_b256_kernel(BatchIo<PIN, POUT> bio, uint64_t batch, FastTables tb)
     };
 
     constexpr bool FUSED = (R1 == 8 && R2 == 2); // both levels in registers, see level_8x2
+    // Large transforms leave one or two CTAs per SM, so a CTA's first loads wait for HBM with little else to run: once
+    // its own loads are done it asks L2 for the row the CTA that takes its place will start with (`ahead` rows on = one
+    // wave of resident CTAs), N / 8 lines of 128 bytes = two requests per thread.
+    auto prefetch_successor = [&] {
+        if (!PIN && bio.ahead && grow + bio.ahead < batch) {
+            const c64 *nx = bio.in + (grow + bio.ahead) * bio.row_in;
+#pragma unroll
+            for (int i = 0; i < 2; i++) prefetch_l2(nx + (t + Cfg::TPR * i) * 8);
+        }
+    };
     if (FWD) {
         if (FUSED) {
             if (active) level_8x2_io<N, Cfg::TPR, true>(io, s, tb.top1, tb.top2, t, v);
+            prefetch_successor();
             __syncthreads();
         } else if (R1 > 1) {
             if (active) level_io<R1, N, Cfg::TPR, true, true, false>(io, nullptr, s, tb.top1, t, v);
+            prefetch_successor();
             __syncthreads();
         }
         if (R2 > 1 && !FUSED) {
@@ -238,6 +252,7 @@ c64_fast_b256_kernel(BatchIo<PIN, POUT> bio, uint64_t batch, FastTables tb)
             if (R1 > 1) base256_io<false, true, false>(io, blk * 256, nullptr, s + blk * 256, s + blk * 256, tb.base, lane16, v);
             else base256_io<false, true, true>(io, blk * 256, nullptr, s + blk * 256, nullptr, tb.base, lane16, v);
         }
+        if (R1 > 1) prefetch_successor();
         if (FUSED) {
             __syncthreads();
             if (active) level_8x2_io<N, Cfg::TPR, false>(io, s, tb.top1, tb.top2, t, v);
@@ -289,8 +304,6 @@ template <int N, bool MULTI> struct FusedMulCfg {
     static constexpr int NT = FastCfg<N>::NT;
     static constexpr int MINB = !MULTI ? FastCfg<N>::MINB : (NT <= 128 ? 3 : 1);
 };
-
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // PIN: the terms a[r][k] are integer polynomials (2N coefficients each); POUT: so is out[r] (c64_dev.cuh, RowIo) -- the
 // whole negacyclic product step of a caller in one kernel, integers in, integers out.

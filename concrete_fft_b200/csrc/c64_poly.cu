@@ -31,6 +31,7 @@ BatchIo<true, false> poly_in_batch(const long long *pin, uint64_t prow_in, c64 *
     b.prow_out = 0;
     b.n = n;
     b.flags = flags;
+    b.ahead = 0;
     return b;
 }
 BatchIo<false, true> poly_out_batch(const c64 *in, uint64_t row_in, long long *pout, uint64_t prow_out, const c64 *twist, uint32_t n, uint32_t flags)
@@ -47,6 +48,7 @@ BatchIo<false, true> poly_out_batch(const c64 *in, uint64_t row_in, long long *p
     b.prow_out = prow_out;
     b.n = n;
     b.flags = flags;
+    b.ahead = 0;
     return b;
 }
 

@@ -255,7 +255,7 @@ template <int NT> F128_DEV void pass_barrier(uint32_t n, int d0_a, int d0_b, uin
 template <bool FWD, int NT, int MINB = 512 / NT>
 __global__ void __launch_bounds__(NT, MINB)
 f128_tile_kernel(Planes data, uint64_t total, uint32_t tile, uint32_t n, uint32_t logn, PassList passes,
-                 const Tw4 *__restrict__ tw, bool vec)
+                 const Tw4 *__restrict__ tw, bool vec, uint32_t ahead)
 {
     constexpr int SMAX = MINB == 3 ? 2 : 3; // three CTAs per SM leave 80 registers: two-stage groups only
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -274,6 +274,18 @@ f128_tile_kernel(Planes data, uint64_t total, uint32_t tile, uint32_t n, uint32_
         return;
     }
     dispatch_pass<FWD, true, false, NT, SMAX>(passes.s[0], g, sre, sim, valid, tile, row_off, n, logn, passes.d0[0], tw, vec);
+    // With one or two CTAs per SM the first pass waits for HBM with nothing else to run (FP64-bound kernel, 20 % of a
+    // 4096-element tile's time).  Ask L2 for the tile that the CTA taking this one's place will load (`ahead` tiles on =
+    // one wave of resident CTAs) while this tile computes; its first pass then finds the data in L2.
+    if (ahead) {
+        const uint64_t nstart = start + uint64_t(ahead) * tile;
+        if (nstart < total) {
+            const uint32_t nvalid = (total - nstart < tile) ? uint32_t(total - nstart) : tile;
+            for (uint32_t i = threadIdx.x * 16u; i < nvalid; i += NT * 16u) // one 128-byte line per plane and step
+#pragma unroll
+                for (int pl = 0; pl < 4; pl++) asm volatile("prefetch.global.L2 [%0];" ::"l"(data.p[pl] + nstart + i));
+        }
+    }
     int prev_d0 = passes.d0[0];
 #pragma unroll
     for (int pi = 1; pi < kMaxPasses - 1; pi++) {
@@ -476,6 +488,16 @@ cudaError_t launch_f128(const cfft_plan *plan, bool inverse, double *re0, double
                        reinterpret_cast<uintptr_t>(im1)) & 15) == 0;
     const unsigned tiles = unsigned((total + tile - 1) / tile);
     cudaError_t e;
+    // L2 prefetch distance of the tile kernel = one wave of resident CTAs (SMs x CTAs per SM by shared memory);
+    // CFFT_B200_F128_PREFETCH=0 turns it off, =k sets the distance in waves
+    static const int env_pf = [] { const char *e = getenv("CFFT_B200_F128_PREFETCH"); return e ? atoi(e) : 1; }();
+    uint32_t ahead = 0;
+    if (env_pf > 0 && tile >= 1024) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, plan->device);
+        const uint32_t per_sm = tile > 2048 ? 1u : (smax == 2 ? 3u : 2u);
+        ahead = uint32_t(sms) * per_sm * uint32_t(env_pf);
+    }
 
     if (!inverse) {
         for (int i = 0; i < gcount; i++)
@@ -483,13 +505,13 @@ cudaError_t launch_f128(const cfft_plan *plan, bool inverse, double *re0, double
         // 8 elements per thread and pass: a 4096-element tile gets 512 threads (16 warps per SM)
         if (tile > 2048) {
             if ((e = configure_tile_kernel<true, 512>()) != cudaSuccess) return e;
-            f128_tile_kernel<true, 512><<<tiles, 512, smem, stream>>>(data, total, tile, n, logn, passes, tw, vec);
+            f128_tile_kernel<true, 512><<<tiles, 512, smem, stream>>>(data, total, tile, n, logn, passes, tw, vec, ahead);
         } else if (smax == 2) {
             if ((e = configure_tile_kernel<true, 256, 3>()) != cudaSuccess) return e;
-            f128_tile_kernel<true, 256, 3><<<tiles, 256, smem, stream>>>(data, total, tile, n, logn, passes, tw, vec);
+            f128_tile_kernel<true, 256, 3><<<tiles, 256, smem, stream>>>(data, total, tile, n, logn, passes, tw, vec, ahead);
         } else {
             if ((e = configure_tile_kernel<true, 256>()) != cudaSuccess) return e;
-            f128_tile_kernel<true, 256><<<tiles, 256, smem, stream>>>(data, total, tile, n, logn, passes, tw, vec);
+            f128_tile_kernel<true, 256><<<tiles, 256, smem, stream>>>(data, total, tile, n, logn, passes, tw, vec, ahead);
         }
         count_launch();
         return cudaGetLastError();
@@ -503,13 +525,13 @@ cudaError_t launch_f128(const cfft_plan *plan, bool inverse, double *re0, double
     }
     if (tile > 2048) {
         if ((e = configure_tile_kernel<false, 512>()) != cudaSuccess) return e;
-        f128_tile_kernel<false, 512><<<tiles, 512, smem, stream>>>(data, total, tile, n, logn, rev, tw, vec);
+        f128_tile_kernel<false, 512><<<tiles, 512, smem, stream>>>(data, total, tile, n, logn, rev, tw, vec, ahead);
     } else if (smax == 2) {
         if ((e = configure_tile_kernel<false, 256, 3>()) != cudaSuccess) return e;
-        f128_tile_kernel<false, 256, 3><<<tiles, 256, smem, stream>>>(data, total, tile, n, logn, rev, tw, vec);
+        f128_tile_kernel<false, 256, 3><<<tiles, 256, smem, stream>>>(data, total, tile, n, logn, rev, tw, vec, ahead);
     } else {
         if ((e = configure_tile_kernel<false, 256>()) != cudaSuccess) return e;
-        f128_tile_kernel<false, 256><<<tiles, 256, smem, stream>>>(data, total, tile, n, logn, rev, tw, vec);
+        f128_tile_kernel<false, 256><<<tiles, 256, smem, stream>>>(data, total, tile, n, logn, rev, tw, vec, ahead);
     }
     count_launch();
     if ((e = cudaGetLastError()) != cudaSuccess) return e;

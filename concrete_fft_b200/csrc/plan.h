@@ -107,6 +107,9 @@ cudaError_t launch_c64_regs_spec(bool inverse, uint64_t n, int radix, bool dit, 
 // kernels (c64_fast.cu)
 bool fast_b256_supported(uint64_t n, int base_algo, uint64_t base_n);
 cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *data, uint64_t batch, cudaStream_t st);
+bool fast_b256_strided_available(const cfft_plan *plan);
+cudaError_t launch_c64_fast_b256_strided(const cfft_plan *plan, bool inverse, double2 *data, uint64_t row_stride, uint64_t batch,
+                                         cudaStream_t st);
 // fwd -> point-wise multiply-accumulate over k terms -> inv (c64_fast.cu): one fused kernel for (Dif16, 256) plans
 // with n <= 4096, the same arithmetic composed from the plan's kernels otherwise
 bool fused_mul_kernel_available(const cfft_plan *plan);

@@ -75,6 +75,30 @@ class Plan:
             fn = N.lib.cfft_f128_inv if inverse else N.lib.cfft_f128_fwd
             N.check(fn(self._h, *ptrs, batch, current_stream_ptr(dev)))
 
+    def _run_strided(self, planes, inverse):
+        """Four CUDA float64 VIEWS [batch, n] with unit inner stride and one common row stride >= n (cfft_f128_*_strided)."""
+        import torch
+
+        n = self.fft_size()
+        for p in planes:
+            if not (isinstance(p, torch.Tensor) and p.is_cuda and p.dtype == torch.float64):
+                raise TypeError("planes must be CUDA float64 tensors")
+            if p.dim() != 2 or p.shape != planes[0].shape or p.shape[1] != n or p.stride(1) != 1 or p.stride(0) != planes[0].stride(0) \
+                    or (p.shape[0] > 1 and p.stride(0) < n):
+                raise N.PanicError("assertion failed: planes have shape [batch, fft_size], unit inner stride, one row stride >= fft_size")
+            if p.device.index != self.device():
+                raise ValueError("planes must live on the plan's device cuda:%d" % self.device())
+        batch = int(planes[0].shape[0])
+        stride = int(planes[0].stride(0)) if batch > 1 else n
+        fn = N.lib.cfft_f128_inv_strided if inverse else N.lib.cfft_f128_fwd_strided
+        N.check(fn(self._h, *[p.data_ptr() for p in planes], stride, batch, current_stream_ptr(self.device())))
+
+    def fwd_strided(self, buf_re0, buf_re1, buf_im0, buf_im1):
+        self._run_strided((buf_re0, buf_re1, buf_im0, buf_im1), False)
+
+    def inv_strided(self, buf_re0, buf_re1, buf_im0, buf_im1):
+        self._run_strided((buf_re0, buf_re1, buf_im0, buf_im1), True)
+
     def fwd(self, buf_re0, buf_re1, buf_im0, buf_im1):
         """src/fft128/mod.rs:1905-1928: standard order in, bit-reversed order out."""
         self._run((buf_re0, buf_re1, buf_im0, buf_im1), False)

@@ -123,6 +123,30 @@ class _PlanBase:
         """In-place unnormalised inverse transform."""
         self._c64(buf, True)
 
+    def _c64_strided(self, view, inverse):
+        """Rows of a 2-D CUDA tensor VIEW [batch, n] with unit inner stride and row stride >= n (cfft_c64_*_strided): the
+        polynomials of a larger record, e.g. x[:, j] of a contiguous [batch, k, n] tensor, transformed where they are."""
+        import torch
+
+        n = self.fft_size()
+        if not (isinstance(view, torch.Tensor) and view.is_cuda and view.dtype == torch.complex128):
+            raise TypeError("buf must be a CUDA complex128 tensor")
+        if view.dim() != 2 or view.shape[1] != n or view.stride(1) != 1 or (view.shape[0] > 1 and view.stride(0) < n):
+            raise N.PanicError("assertion failed: buf has shape [batch, fft_size], unit inner stride, row stride >= fft_size")
+        if view.device.index != self.device():
+            raise ValueError("buffer is on cuda:%d but the plan lives on cuda:%d" % (view.device.index, self.device()))
+        batch = int(view.shape[0])
+        stride = int(view.stride(0)) if batch > 1 else n
+        fn = N.lib.cfft_c64_inv_strided if inverse else N.lib.cfft_c64_fwd_strided
+        N.check(fn(self._h, view.data_ptr(), stride, batch, current_stream_ptr(self.device())))
+
+    def fwd_strided(self, view):
+        """Plan::fwd on every row of a strided [batch, n] view, in place; elements between the rows are not touched."""
+        self._c64_strided(view, False)
+
+    def inv_strided(self, view):
+        self._c64_strided(view, True)
+
     def fwd_inv_host(self, buf):
         """fwd then inv on the device between one upload and one download (bench `e2e` step)."""
         n = self.fft_size()

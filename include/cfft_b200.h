@@ -127,6 +127,14 @@ uint64_t cfft_plan_tuning_report(const cfft_plan *plan, char *buf, uint64_t buf_
 cfft_status cfft_c64_fwd(const cfft_plan *plan, void *dev_buf, uint64_t batch, void *stream);
 cfft_status cfft_c64_inv(const cfft_plan *plan, void *dev_buf, uint64_t batch, void *stream);
 
+/* The same with rows `row_stride` >= n c64 apart (row r starts at dev_buf + r * row_stride): the stride_elems of
+ * SURVEY.md section 8b, for callers whose polynomials sit inside larger records (Plan::fwd on buf[r * stride ..][..n]
+ * for every r).  Elements between the rows are never touched.  row_stride < n: CFFT_EINVAL.  Plans with a single
+ * fused kernel (n = 256 .. 8192, base (Dif16, 256), and the ordered extension 2^11 .. 2^13) read and write the
+ * strided rows directly; other plans go through a packed workspace (same bits, two extra passes over the data). */
+cfft_status cfft_c64_fwd_strided(const cfft_plan *plan, void *dev_buf, uint64_t row_stride, uint64_t batch, void *stream);
+cfft_status cfft_c64_inv_strided(const cfft_plan *plan, void *dev_buf, uint64_t row_stride, uint64_t batch, void *stream);
+
 /* Same on HOST memory, synchronous: H2D, transform, D2H through an internal pinned, chunked,
  * double-buffered pipeline.  This is the literal drop-in for Plan::fwd(&mut [c64], stack)
  * (batch = 1) and the entry bench.py times as `e2e`.  `len` = number of c64 in host_buf and
@@ -172,6 +180,11 @@ cfft_status cfft_f128_fwd(const cfft_plan *plan, double *re0, double *re1, doubl
                           double *im1, uint64_t batch, void *stream);
 cfft_status cfft_f128_inv(const cfft_plan *plan, double *re0, double *re1, double *im0,
                           double *im1, uint64_t batch, void *stream);
+/* rows row_stride >= n doubles apart in each plane (packed through a workspace; see cfft_c64_fwd_strided) */
+cfft_status cfft_f128_fwd_strided(const cfft_plan *plan, double *re0, double *re1, double *im0, double *im1,
+                                  uint64_t row_stride, uint64_t batch, void *stream);
+cfft_status cfft_f128_inv_strided(const cfft_plan *plan, double *re0, double *re1, double *im0, double *im1,
+                                  uint64_t row_stride, uint64_t batch, void *stream);
 /* host-memory versions; `len` = doubles per array, must equal batch * n */
 cfft_status cfft_f128_fwd_host(const cfft_plan *plan, double *re0, double *re1, double *im0,
                                double *im1, uint64_t len, uint64_t batch);

@@ -29,6 +29,10 @@ extern "C" {
     pub fn cfft_plan_tuning_report(plan: *const cfft_plan, buf: *mut c_char, buf_len: u64) -> u64;
     pub fn cfft_c64_fwd(plan: *const cfft_plan, dev_buf: *mut c_void, batch: u64, stream: *mut c_void) -> cfft_status;
     pub fn cfft_c64_inv(plan: *const cfft_plan, dev_buf: *mut c_void, batch: u64, stream: *mut c_void) -> cfft_status;
+    pub fn cfft_c64_fwd_strided(plan: *const cfft_plan, dev_buf: *mut c_void, row_stride: u64, batch: u64, stream: *mut c_void) -> cfft_status;
+    pub fn cfft_c64_inv_strided(plan: *const cfft_plan, dev_buf: *mut c_void, row_stride: u64, batch: u64, stream: *mut c_void) -> cfft_status;
+    pub fn cfft_f128_fwd_strided(plan: *const cfft_plan, re0: *mut f64, re1: *mut f64, im0: *mut f64, im1: *mut f64, row_stride: u64, batch: u64, stream: *mut c_void) -> cfft_status;
+    pub fn cfft_f128_inv_strided(plan: *const cfft_plan, re0: *mut f64, re1: *mut f64, im0: *mut f64, im1: *mut f64, row_stride: u64, batch: u64, stream: *mut c_void) -> cfft_status;
     pub fn cfft_c64_fwd_host(plan: *const cfft_plan, host_buf: *mut c_void, len: u64, batch: u64) -> cfft_status;
     pub fn cfft_c64_inv_host(plan: *const cfft_plan, host_buf: *mut c_void, len: u64, batch: u64) -> cfft_status;
     pub fn cfft_c64_fwd_inv_host(plan: *const cfft_plan, host_buf: *mut c_void, len: u64, batch: u64) -> cfft_status;

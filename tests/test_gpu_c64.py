@@ -1032,3 +1032,42 @@ def test_alignment_rules(C, torch):
     dev = torch.zeros(2 * n * 2 + 2, dtype=torch.float64, device="cuda")
     st = C._native.lib.cfft_c64_fwd(plan._h, dev.data_ptr() + 8, 2, None)
     assert st == C._native.EINVAL
+
+
+def test_strided_rows_bit_exact(C, torch):
+    """cfft_c64_fwd_strided / _inv_strided (SURVEY.md 8b stride_elems): rows row_stride >= n apart, transformed where they are --
+    x[:, j] of a [batch, k, n] record -- bit-identical to the packed call, neighbours untouched; fused-kernel plans take the
+    stride in the kernel, other plans (generic register kernel, n = 2^14 passes, ordered) go through the packed workspace."""
+    rng = np.random.default_rng(515)
+    A = C.ordered.FftAlgo
+    U = C.unordered
+    plans = [(U.Plan(2048, U.Method.UserProvided(A.Dif16, 256)), O.UnorderedPlan(2048, O.DIF16, 256)),
+             (U.Plan(256, U.Method.UserProvided(A.Dif16, 256)), O.UnorderedPlan(256, O.DIF16, 256)),
+             (U.Plan(8192, U.Method.UserProvided(A.Dif16, 256)), O.UnorderedPlan(8192, O.DIF16, 256)),
+             (U.Plan(2048, U.Method.UserProvided(A.Dif4, 32)), O.UnorderedPlan(2048, O.DIF4, 32)),
+             (U.Plan(16384, U.Method.UserProvided(A.Dif16, 256)), O.UnorderedPlan(16384, O.DIF16, 256)),
+             (C.ordered.Plan(512, C.ordered.Method.UserProvided(A.Dif8)), O.OrderedPlan(512, O.DIF8))]
+    for plan, ref in plans:
+        n = plan.fft_size()
+        for batch, k, j in [(5, 3, 1), (1, 2, 1), (4, 1, 0)]:
+            x = rand_c(rng, batch, k, n)
+            d = torch.from_numpy(x.copy()).cuda()
+            plan.fwd_strided(d[:, j])
+            torch.cuda.synchronize()
+            got = d.cpu().numpy()
+            want = x.copy()
+            want[:, j] = ref.fwd(np.ascontiguousarray(x[:, j]))
+            assert bits_equal(got, want), (plan.kernel_name(), n, batch, k, j)
+            plan.inv_strided(d[:, j])
+            torch.cuda.synchronize()
+            want[:, j] = ref.inv(np.ascontiguousarray(want[:, j]))
+            assert bits_equal(d.cpu().numpy(), want), (plan.kernel_name(), n, batch, k, j)
+    p = plans[0][0]
+    d = torch.zeros((4, 2, 2048), dtype=torch.complex128, device="cuda")
+    with pytest.raises(C.PanicError):
+        p.fwd_strided(d[:, :, ::2][:, 0])  # inner stride 2
+    with pytest.raises(C.PanicError):
+        p.fwd_strided(d.reshape(8, 2048)[:, :1024])  # wrong row length
+    # the C entry itself rejects overlapping rows
+    import ctypes
+    assert C._native.lib.cfft_c64_fwd_strided(p._h, d.data_ptr(), 1024, 2, None) == C._native.EINVAL
