@@ -44,6 +44,9 @@ _SIGNATURES = {
     "cfft_f128_plan_create": (ctypes.c_int32, [_pp, _int, _u64]),
     "cfft_plan_destroy": (None, [_vp]),
     "cfft_plan_clone": (ctypes.c_int32, [_vp, _pp]),
+    "cfft_plan_clone_to_device": (ctypes.c_int32, [_vp, _int, _pp]),
+    "cfft_c64_host_multi": (ctypes.c_int32, [_pp, _int, _int, _vp, _u64, _u64]),
+    "cfft_f128_host_multi": (ctypes.c_int32, [_pp, _int, _int, _vp, _vp, _vp, _vp, _u64, _u64]),
     "cfft_plan_fft_size": (_u64, [_vp]),
     "cfft_plan_algo": (ctypes.c_int32, [_vp, ctypes.POINTER(_int), ctypes.POINTER(_u64)]),
     "cfft_plan_scratch_req": (ctypes.c_int32, [_vp, ctypes.POINTER(_u64), ctypes.POINTER(_u64)]),

@@ -532,14 +532,17 @@ void cfft_plan_destroy(cfft_plan *p)
     delete p;
 }
 
-cfft_status cfft_plan_clone(const cfft_plan *p, cfft_plan **out)
+cfft_status cfft_plan_clone(const cfft_plan *p, cfft_plan **out) { return cfft_plan_clone_to_device(p, p ? p->device : 0, out); }
+
+// a replica of the plan -- same transform, same Fourier-domain order, same tuned kernel variant -- with its tables on `device`
+cfft_status cfft_plan_clone_to_device(const cfft_plan *p, int device, cfft_plan **out)
 {
     if (!p || !out) return fail(CFFT_EINVAL, "null argument");
     cfft_status st;
     switch (p->kind) {
-    case KIND_ORDERED: st = cfft_ordered_plan_create(out, p->device, p->n, CFFT_METHOD_USER, p->algo, p->allow_large); break;
-    case KIND_UNORDERED: st = cfft_unordered_plan_create(out, p->device, p->n, CFFT_METHOD_USER, p->algo, p->base_n); break;
-    default: st = cfft_f128_plan_create(out, p->device, p->n); break;
+    case KIND_ORDERED: st = cfft_ordered_plan_create(out, device, p->n, CFFT_METHOD_USER, p->algo, p->allow_large); break;
+    case KIND_UNORDERED: st = cfft_unordered_plan_create(out, device, p->n, CFFT_METHOD_USER, p->algo, p->base_n); break;
+    default: st = cfft_f128_plan_create(out, device, p->n); break;
     }
     if (st == CFFT_OK) { // keep the source plan's tuned variant
         (*out)->method = p->method;

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/cfft_b200.h"
@@ -423,6 +424,77 @@ cfft_status cfft_f128_fwd_inv_host(const cfft_plan *p, double *re0, double *re1,
                                    uint64_t batch)
 {
     return f128_host(p, re0, re1, im0, im1, len, batch, 2);
+}
+
+// ---- one host call, several GPUs (north_star item 5 inside the library) ---------------------------------------------
+// `plans` are replicas of ONE plan on the devices that should share the work (cfft_plan_clone_to_device; two replicas may
+// sit on the same device).  The batch is cut into nplans contiguous row ranges and every range runs through its replica's
+// own chunked H2D / kernels / D2H pipeline on a host thread of its own: no collective, no peer traffic -- polynomials are
+// independent (Plan::fwd is one polynomial per call).  What limits it is the host side of PCIe, not the GPUs.
+static bool same_transform(const cfft_plan *a, const cfft_plan *b)
+{
+    return a->kind == b->kind && a->n == b->n && (a->kind == KIND_F128 || (a->algo == b->algo && a->base_n == b->base_n && a->allow_large == b->allow_large));
+}
+
+static cfft_status host_multi(const cfft_plan *const *plans, int nplans, void *const *planes, int nplanes, size_t row_bytes, uint64_t batch, int op)
+{
+    if (nplans == 1) {
+        std::string err;
+        cfft_status st = run_pipeline(plans[0], planes, nplanes, row_bytes, batch, op, err);
+        return st == CFFT_OK ? st : set_last_error(st, err);
+    }
+    std::vector<std::thread> workers;
+    std::vector<cfft_status> status(size_t(nplans), CFFT_OK);
+    std::vector<std::string> errs{size_t(nplans)};
+    const uint64_t base = batch / uint64_t(nplans), rem = batch % uint64_t(nplans);
+    uint64_t row0 = 0;
+    for (int i = 0; i < nplans; i++) {
+        const uint64_t rows = base + (uint64_t(i) < rem ? 1 : 0);
+        if (rows == 0) continue;
+        workers.emplace_back([=, &status, &errs] {
+            void *shifted[4] = {nullptr, nullptr, nullptr, nullptr};
+            for (int pl = 0; pl < nplanes; pl++) shifted[pl] = static_cast<char *>(planes[pl]) + row0 * row_bytes;
+            status[size_t(i)] = run_pipeline(plans[i], shifted, nplanes, row_bytes, rows, op, errs[size_t(i)]);
+        });
+        row0 += rows;
+    }
+    for (std::thread &w : workers) w.join();
+    for (int i = 0; i < nplans; i++)
+        if (status[size_t(i)] != CFFT_OK) return set_last_error(status[size_t(i)], "replica " + std::to_string(i) + " (cuda:" + std::to_string(plans[i]->device) + "): " + errs[size_t(i)]);
+    return CFFT_OK;
+}
+
+static cfft_status check_replicas(const cfft_plan *const *plans, int nplans, bool f128)
+{
+    if (!plans || nplans < 1 || nplans > 64) return set_last_error(CFFT_EINVAL, "need 1 .. 64 plan replicas");
+    for (int i = 0; i < nplans; i++) {
+        if (!plans[i] || (plans[i]->kind == KIND_F128) != f128) return set_last_error(CFFT_EINVAL, f128 ? "not an fft128 plan" : "not a c64 plan");
+        if (!same_transform(plans[0], plans[i])) return set_last_error(CFFT_EINVAL, "replicas must describe the same transform (kind, n, base algorithm, base size)");
+    }
+    return CFFT_OK;
+}
+
+cfft_status cfft_c64_host_multi(const cfft_plan *const *plans, int nplans, int op, void *host_buf, uint64_t len, uint64_t batch)
+{
+    cfft_status st = check_replicas(plans, nplans, false);
+    if (st != CFFT_OK) return st;
+    if (op < 0 || op > 2) return set_last_error(CFFT_EINVAL, "op: 0 fwd, 1 inv, 2 fwd then inv");
+    if (len != batch * plans[0]->n) return set_last_error(CFFT_ELENGTH, "buffer length != batch * fft size (src/unordered.rs:827)");
+    if (!host_buf && len) return set_last_error(CFFT_EINVAL, "null buffer");
+    void *planes[1] = {host_buf};
+    return host_multi(plans, nplans, planes, 1, size_t(plans[0]->n) * sizeof(cplx), batch, op);
+}
+
+cfft_status cfft_f128_host_multi(const cfft_plan *const *plans, int nplans, int op, double *re0, double *re1, double *im0, double *im1,
+                                 uint64_t len, uint64_t batch)
+{
+    cfft_status st = check_replicas(plans, nplans, true);
+    if (st != CFFT_OK) return st;
+    if (op < 0 || op > 2) return set_last_error(CFFT_EINVAL, "op: 0 fwd, 1 inv, 2 fwd then inv");
+    if (len != batch * plans[0]->n) return set_last_error(CFFT_ELENGTH, "buffer length != batch * fft size (src/fft128/mod.rs:1912-1915)");
+    if (len && (!re0 || !re1 || !im0 || !im1)) return set_last_error(CFFT_EINVAL, "null buffer");
+    void *planes[4] = {re0, re1, im0, im1};
+    return host_multi(plans, nplans, planes, 4, size_t(plans[0]->n) * sizeof(double), batch, op);
 }
 
 cfft_status cfft_c64_poly_mul_host(const cfft_plan *p, const int64_t *a_host, uint64_t k_terms, const void *b_dev, uint64_t b_row_stride,

@@ -33,3 +33,67 @@ def job_throughput(units_per_rank, seconds_per_rank, dist=None, device=None):
     u = torch.tensor([float(units_per_rank)], dtype=torch.float64, device=device)
     dist.all_reduce(u, op=dist.ReduceOp.SUM)
     return float(u.item()) / max_over_ranks(seconds_per_rank, dist, device)
+
+
+class MultiGpu:
+    """One plan, several GPUs, ONE process: host-memory calls whose batch the library itself cuts into contiguous row ranges, one
+    per replica of the plan (cfft_plan_clone_to_device + cfft_c64_host_multi / cfft_f128_host_multi).  `devices`: CUDA
+    device indices (default: all visible; an index may repeat).  Same bits as the plan's own host entry points."""
+
+    def __init__(self, plan, devices=None):
+        import ctypes
+
+        from . import _native as N
+
+        if devices is None:
+            import torch
+
+            devices = list(range(torch.cuda.device_count()))
+        if not devices:
+            raise ValueError("no devices")
+        self._N, self._plan, self._replicas = N, plan, []
+        for d in devices:
+            h = ctypes.c_void_p()
+            N.check(N.lib.cfft_plan_clone_to_device(plan._h, int(d), ctypes.byref(h)))
+            self._replicas.append(h)
+        self._arr = (ctypes.c_void_p * len(self._replicas))(*[h.value for h in self._replicas])
+        self.devices = [int(d) for d in devices]
+
+    def __del__(self):
+        for h in getattr(self, "_replicas", []):
+            self._N.lib.cfft_plan_destroy(h)
+        self._replicas = []
+
+    def _is_f128(self):
+        return self._N.lib.cfft_plan_kind(self._plan._h) == 2
+
+    def _c64(self, buf, op):
+        import numpy as np
+
+        n = self._plan.fft_size()
+        if not isinstance(buf, np.ndarray) or buf.dtype != np.complex128 or not buf.flags["C_CONTIGUOUS"] or not buf.flags["WRITEABLE"]:
+            raise TypeError("buf must be a writeable C-contiguous numpy complex128 array (host memory)")
+        if buf.size == 0 or buf.size % n:
+            raise self._N.PanicError("assertion failed: buf.len() == batch * fft_size")
+        self._N.check(self._N.lib.cfft_c64_host_multi(self._arr, len(self._replicas), op, buf.ctypes.data, buf.size, buf.size // n))
+
+    def _f128(self, planes, op):
+        import numpy as np
+
+        n = self._plan.fft_size()
+        for p in planes:
+            if not isinstance(p, np.ndarray) or p.dtype != np.float64 or not p.flags["C_CONTIGUOUS"] or p.size != planes[0].size:
+                raise TypeError("planes must be four C-contiguous numpy float64 arrays of one size (host memory)")
+        if planes[0].size == 0 or planes[0].size % n:
+            raise self._N.PanicError("assertion failed: buf.len() == batch * fft_size")
+        self._N.check(self._N.lib.cfft_f128_host_multi(self._arr, len(self._replicas), op, *[p.ctypes.data for p in planes], planes[0].size,
+                                                       planes[0].size // n))
+
+    def fwd(self, *bufs):
+        self._f128(bufs, 0) if self._is_f128() else self._c64(bufs[0], 0)
+
+    def inv(self, *bufs):
+        self._f128(bufs, 1) if self._is_f128() else self._c64(bufs[0], 1)
+
+    def fwd_inv(self, *bufs):
+        self._f128(bufs, 2) if self._is_f128() else self._c64(bufs[0], 2)

@@ -79,6 +79,9 @@ void cfft_plan_destroy(cfft_plan *plan);
 
 /* Clone for the three Plan types (#[derive(Clone)], src/unordered.rs:495). */
 cfft_status cfft_plan_clone(const cfft_plan *plan, cfft_plan **out);
+/* The same with the replica's tables on another GPU of the box: same transform, same Fourier-domain order, same tuned
+ * kernel variant.  Replicas are what cfft_c64_host_multi / cfft_f128_host_multi shard one host call over. */
+cfft_status cfft_plan_clone_to_device(const cfft_plan *plan, int device, cfft_plan **out);
 
 /* ---- plan queries ----------------------------------------------------------------- */
 
@@ -145,6 +148,12 @@ cfft_status cfft_c64_inv_host(const cfft_plan *plan, void *host_buf, uint64_t le
  * BASELINE.json "fwd+inv" step); result = n * input. */
 cfft_status cfft_c64_fwd_inv_host(const cfft_plan *plan, void *host_buf, uint64_t len, uint64_t batch);
 
+/* One host call sharded over several GPUs (north_star item 5 inside the library): `plans` = nplans replicas of one plan
+ * (cfft_plan_clone_to_device), the batch is cut into nplans contiguous row ranges, each range runs through its
+ * replica's own H2D / kernels / D2H pipeline on its own host thread; no collective, no peer traffic.  op: 0 fwd, 1 inv,
+ * 2 fwd then inv.  Same results, bit for bit, as the single-GPU entry points. */
+cfft_status cfft_c64_host_multi(const cfft_plan *const *plans, int nplans, int op, void *host_buf, uint64_t len, uint64_t batch);
+
 /* unordered::Plan::fwd_monomial(degree, buf), src/unordered.rs:844-900: writes the permuted
  * forward transform of X^degree.  degree < n (CFFT_EINVAL otherwise). */
 cfft_status cfft_unordered_fwd_monomial(const cfft_plan *plan, uint64_t degree, void *dev_buf,
@@ -185,6 +194,9 @@ cfft_status cfft_f128_fwd_strided(const cfft_plan *plan, double *re0, double *re
                                   uint64_t row_stride, uint64_t batch, void *stream);
 cfft_status cfft_f128_inv_strided(const cfft_plan *plan, double *re0, double *re1, double *im0, double *im1,
                                   uint64_t row_stride, uint64_t batch, void *stream);
+/* fft128 counterpart of cfft_c64_host_multi */
+cfft_status cfft_f128_host_multi(const cfft_plan *const *plans, int nplans, int op, double *re0, double *re1, double *im0,
+                                 double *im1, uint64_t len, uint64_t batch);
 /* host-memory versions; `len` = doubles per array, must equal batch * n */
 cfft_status cfft_f128_fwd_host(const cfft_plan *plan, double *re0, double *re1, double *im0,
                                double *im1, uint64_t len, uint64_t batch);

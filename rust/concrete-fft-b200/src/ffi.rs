@@ -29,6 +29,9 @@ extern "C" {
     pub fn cfft_plan_tuning_report(plan: *const cfft_plan, buf: *mut c_char, buf_len: u64) -> u64;
     pub fn cfft_c64_fwd(plan: *const cfft_plan, dev_buf: *mut c_void, batch: u64, stream: *mut c_void) -> cfft_status;
     pub fn cfft_c64_inv(plan: *const cfft_plan, dev_buf: *mut c_void, batch: u64, stream: *mut c_void) -> cfft_status;
+    pub fn cfft_plan_clone_to_device(plan: *const cfft_plan, device: c_int, out: *mut *mut cfft_plan) -> cfft_status;
+    pub fn cfft_c64_host_multi(plans: *const *const cfft_plan, nplans: c_int, op: c_int, host_buf: *mut c_void, len: u64, batch: u64) -> cfft_status;
+    pub fn cfft_f128_host_multi(plans: *const *const cfft_plan, nplans: c_int, op: c_int, re0: *mut f64, re1: *mut f64, im0: *mut f64, im1: *mut f64, len: u64, batch: u64) -> cfft_status;
     pub fn cfft_c64_fwd_strided(plan: *const cfft_plan, dev_buf: *mut c_void, row_stride: u64, batch: u64, stream: *mut c_void) -> cfft_status;
     pub fn cfft_c64_inv_strided(plan: *const cfft_plan, dev_buf: *mut c_void, row_stride: u64, batch: u64, stream: *mut c_void) -> cfft_status;
     pub fn cfft_f128_fwd_strided(plan: *const cfft_plan, re0: *mut f64, re1: *mut f64, im0: *mut f64, im1: *mut f64, row_stride: u64, batch: u64, stream: *mut c_void) -> cfft_status;

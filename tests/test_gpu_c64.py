@@ -1071,3 +1071,35 @@ def test_strided_rows_bit_exact(C, torch):
     # the C entry itself rejects overlapping rows
     import ctypes
     assert C._native.lib.cfft_c64_fwd_strided(p._h, d.data_ptr(), 1024, 2, None) == C._native.EINVAL
+
+
+def test_host_call_sharded_over_replicas(C, torch):
+    """cfft_c64_host_multi: ONE host call whose batch the library cuts over replicas of the plan (north_star item 5 inside the
+    library).  Two replicas on cuda:0 always; cuda:0 + cuda:1 when the box has them.  Bit-identical to the oracle."""
+    from concrete_fft_b200.sharding import MultiGpu
+
+    rng = np.random.default_rng(808)
+    A = C.ordered.FftAlgo
+    plan = C.unordered.Plan(2048, C.unordered.Method.UserProvided(A.Dif16, 256))
+    ref = O.UnorderedPlan(2048, O.DIF16, 256)
+    device_sets = [[0, 0], [0, 0, 0]] + ([[0, 1]] if torch.cuda.device_count() >= 2 else [])
+    for devices in device_sets:
+        mg = MultiGpu(plan, devices)
+        for batch in (1, 5, 1031):  # fewer rows than replicas, a ragged split, a multi-chunk split
+            x = rand_c(rng, batch, 2048)
+            h = x.copy()
+            mg.fwd(h)
+            want = ref.fwd(x, threads=8)
+            assert bits_equal(h, want), (devices, batch)
+            mg.inv(h)
+            assert bits_equal(h, ref.inv(want, threads=8)), (devices, batch)
+            h = x.copy()
+            mg.fwd_inv(h)
+            assert bits_equal(h, ref.inv(want, threads=8)), (devices, batch)
+    with pytest.raises(C.PanicError):
+        MultiGpu(plan, [0, 0]).fwd(np.zeros(100, np.complex128))
+    other = C.unordered.Plan(2048, C.unordered.Method.UserProvided(A.Dif4, 32))
+    import ctypes
+    arr = (ctypes.c_void_p * 2)(plan._h.value if hasattr(plan._h, "value") else plan._h, other._h.value if hasattr(other._h, "value") else other._h)
+    buf = np.zeros(2 * 2048, np.complex128)
+    assert C._native.lib.cfft_c64_host_multi(arr, 2, 0, buf.ctypes.data, buf.size, 2) == C._native.EINVAL  # different transforms

@@ -403,3 +403,23 @@ def test_strided_planes_bit_exact(C, torch):
         for w, o in zip(want, back):
             w[:, j] = o
         assert bits_equal([d.cpu().numpy() for d in dev], want), (n, batch, k, j)
+
+
+def test_host_call_sharded_over_replicas(C, torch):
+    """cfft_f128_host_multi: one host call, the batch cut over replicas of the plan; bit-identical to the oracle."""
+    from concrete_fft_b200.sharding import MultiGpu
+
+    rng = np.random.default_rng(909)
+    n = 1024
+    plan = C.fft128.Plan(n)
+    ref = O.F128Plan(n)
+    for devices in [[0, 0]] + ([[0, 1]] if torch.cuda.device_count() >= 2 else []):
+        mg = MultiGpu(plan, devices)
+        for batch in (1, 7):
+            planes = planes_random(rng, batch, n)
+            h = [p.copy() for p in planes]
+            mg.fwd(*h)
+            want = ref.fwd(*planes, variant=O.F128_FMA)
+            assert bits_equal(h, want), (devices, batch)
+            mg.inv(*h)
+            assert bits_equal(h, ref.inv(*want, variant=O.F128_FMA)), (devices, batch)
