@@ -124,6 +124,7 @@ struct ColParams {
     uint32_t tiles_per_chunk;  // stride / CW
     uint32_t tiles_per_row;    // n / (CW RG)
     const c64 *tw[3];          // planar twiddles of the group's levels, outermost first
+    uint32_t ahead;            // L2 prefetch distance in tiles (one wave of resident CTAs), 0 = off
 };
 
 // Tile width CW: 16 columns (256 B segments) except for RG = 256, where 8 columns (128 B = one full line)
@@ -159,6 +160,14 @@ c64_column_kernel(const c64 *__restrict__ src, c64 *__restrict__ dst, ColParams 
     c64 v[16];
     const uint32_t st = prm.stride;
 
+    // the tile the CTA taking this one's place will start with: RG rows of CW * 16 bytes, requested into L2 now
+    if (prm.ahead && tile + prm.ahead < prm.total_tiles) {
+        const uint64_t t2 = tile + prm.ahead, row2 = t2 / prm.tiles_per_row;
+        const uint32_t tt2 = uint32_t(t2 - row2 * prm.tiles_per_row), chunk2 = tt2 / prm.tiles_per_chunk;
+        const c64 *g2 = src + row2 * prm.n + size_t(chunk2) * prm.span0 + (tt2 - chunk2 * prm.tiles_per_chunk) * CW;
+        constexpr int LPR = CW / 8; // 128-byte lines per tile row
+        for (int i = t; i < RG * LPR; i += Cfg::TPT) asm volatile("prefetch.global.L2 [%0];" ::"l"(g2 + size_t(i / LPR) * st + (i % LPR) * 8));
+    }
     column_tile<RA, RB, RC, CW, FWD>(g, go, s, prm.tw, st, col0, t, active, v);
 }
 
@@ -171,6 +180,8 @@ cudaError_t launch_group(bool inverse, const c64 *src, c64 *dst, ColParams prm, 
     prm.tiles_per_row = prm.n / (CW * RG);
     prm.total_tiles = batch * prm.tiles_per_row;
     const size_t smem = (RB == 1) ? 0 : size_t(Cfg::NT) * 16 * sizeof(c64);
+    static const int env_pf = [] { const char *e = getenv("CFFT_B200_COLUMN_PREFETCH"); return e ? atoi(e) : 1; }();
+    prm.ahead = env_pf > 0 ? uint32_t(148 * Cfg::MINB * Cfg::TPC * env_pf) : 0u;
     auto fk = c64_column_kernel<RA, RB, RC, CW, true>;
     auto ik = c64_column_kernel<RA, RB, RC, CW, false>;
     if (smem > 48 * 1024) {
@@ -209,6 +220,7 @@ struct TwoPassParams {
     const c64 *tw[3];   // planar twiddles of the column group's levels, outermost first
     const c64 *tw_base; // planar half of init_wt(16, 256)
     uint32_t *sync;     // [0] queue head; [1 + j] finished first-phase items of transform j
+    uint32_t prefetch;  // L2 prefetch of the first-phase item one wave ahead (CFFT_B200_TWOPASS_PREFETCH, default on)
 };
 
 __device__ unsigned int g_twopass_timeouts = 0; // second-phase items that gave up waiting for their first phase
@@ -258,6 +270,25 @@ c64_twopass_kernel(TwoPassParams prm)
         const uint32_t step = q / W, r = q - step * W;
         const bool first = r < F_ITEMS;
         const bool valid = first ? step < prm.batch : step >= prm.lag;
+        if (prm.prefetch) {
+            // The item one wave of CTAs further down the queue will be picked up by SOME CTA about one item time from now.
+            // If it is a first-phase item its data still sits in HBM: ask L2 for it now (second-phase items read what the
+            // first phase has just written, i.e. L2 already).  A hint only: nothing depends on who ends up with the item.
+            const uint32_t q2 = q + gridDim.x, step2 = q2 / W, r2 = q2 - step2 * W;
+            if (r2 < uint32_t(F_ITEMS) && step2 < prm.batch) {
+                const c64 *row2 = prm.data + size_t(step2) * prm.n;
+                if (FWD) { // column item: TPC tiles of RG rows x CW columns, rows 256 elements apart
+                    constexpr int LPR = CW / 8, LINES = Cfg::TPC * RG * LPR; // 128-byte lines per row / per item
+                    for (int i = threadIdx.x; i < LINES; i += NT) {
+                        const int tile = i / (RG * LPR), rem = i - tile * (RG * LPR), rr = rem / LPR, l = rem - rr * LPR;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(row2 + (r2 * Cfg::TPC + tile) * CW + size_t(rr) * 256 + l * 8));
+                    }
+                } else { // rows item: ROWS_PER_ITEM * 256 contiguous elements
+                    for (int i = threadIdx.x; i < ROWS_PER_ITEM * 32; i += NT)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(row2 + size_t(r2) * ROWS_PER_ITEM * 256 + i * 8));
+                }
+            }
+        }
         if (valid) {
             const uint32_t j = first ? step : step - prm.lag;
             const uint32_t sub = first ? r : r - F_ITEMS;
@@ -319,6 +350,8 @@ cudaError_t launch_twopass(bool inverse, const TwoPassParams &prm_in, int device
         configured_device = device;
     }
     TwoPassParams prm = prm_in;
+    static const int env_pf = [] { const char *e = getenv("CFFT_B200_TWOPASS_PREFETCH"); return e ? atoi(e) : 1; }();
+    prm.prefetch = (env_pf > 0 && !inverse) ? 1u : 0u; // measured: forward +1 .. +3 %, inverse -1 .. -3 % (profiles/r2e_prefetch_ab.txt)
     if (prm.lag == 0) prm.lag = uint32_t((3 * resident / 2 + W - 1) / W); // ~1.5 waves of items between the phases
     if (prm.lag > prm.batch) prm.lag = prm.batch;
     if (uint64_t(prm.batch) + prm.lag > (0xFFFFFFFFull / W)) return cudaErrorInvalidValue;
@@ -354,6 +387,7 @@ cudaError_t launch_c64_column_group(bool inverse, const double2 *src, double2 *d
     prm.stride = span0 / rg;
     prm.tiles_per_chunk = prm.tiles_per_row = 0; // filled in per tile width by launch_group
     prm.total_tiles = 0;
+    prm.ahead = 0;
     for (int i = 0; i < 3; i++) prm.tw[i] = tw[i];
     const int key = ra * 100 + rb * 10 + rc;
     // two radix-8 levels: one thread per column with tensor memory between the levels (c64_tmem.cu), bit-identical.
@@ -362,9 +396,12 @@ cudaError_t launch_c64_column_group(bool inverse, const double2 *src, double2 *d
     static const bool use_tmem = [] { const char *e = getenv("CFFT_B200_TMEM_COLUMNS"); return e && atoi(e) != 0; }();
     if (key == 881 && use_tmem && tmem_column88_supported(n, span0))
         return launch_c64_tmem_column88(inverse, src, dst, batch, n, span0, tw[0], tw[1], stream);
-    // groups of two or three levels: the persistent kernel of c64_colpipe.cu (CFFT_B200_COLPIPE=0: the one-shot tiles
-    // below; CFFT_B200_COLPIPE_MIN_BATCH: smallest batch per launch that takes it; same bits either way)
-    static const bool use_pipe = [] { const char *e = getenv("CFFT_B200_COLPIPE"); return !e || atoi(e) != 0; }();
+    // groups of two or three levels: optionally the persistent kernel of c64_colpipe.cu (CFFT_B200_COLPIPE_MIN_BATCH:
+    // smallest batch per launch that takes it; same bits either way)
+    // measured on the B200 (profiles/r2c_variants*.txt): 3-8 % SLOWER than the one-shot tiles in every schedule (244 registers
+    // -> eight warps per SM; persistent grids sized for the whole machine also serialise the multi-stream chunked
+    // schedule), so it is opt-in: CFFT_B200_COLPIPE=1
+    static const bool use_pipe = [] { const char *e = getenv("CFFT_B200_COLPIPE"); return e && atoi(e) != 0; }();
     static const long pipe_min_batch = [] { const char *e = getenv("CFFT_B200_COLPIPE_MIN_BATCH"); return e ? atol(e) : 1; }();
     if (use_pipe && colpipe_supported(radices) && long(batch) >= pipe_min_batch) {
         int dev = 0;
@@ -410,6 +447,7 @@ cudaError_t launch_c64_twopass(bool inverse, double2 *data, uint64_t batch, uint
     for (int i = 0; i < 3; i++) prm.tw[i] = tw[i];
     prm.tw_base = tw_base;
     prm.sync = nullptr;
+    prm.prefetch = 0;
     const int key = radices[0] * 100 + radices[1] * 10 + radices[2];
     if (n == 16384 && key == 881) return launch_twopass<8, 8, 1>(inverse, prm, device, stream);
     if (n == 32768 && key == 882) return launch_twopass<8, 8, 2>(inverse, prm, device, stream);

@@ -59,6 +59,8 @@ c64_cluster_kernel(c64 *__restrict__ data, FastTables tb)
     c64 *g = data + size_t(blockIdx.x / CSZ) * N;
     c64 v[16];
     const int blk = t / 16, lane16 = t % 16;
+    // (An L2 prefetch of the successor cluster's transform, the trick that gives the single-CTA kernel +23 % at this size,
+    // changes nothing here -- profiles/r2d_prefetch_bulkstore_twsplit_ab.txt: two CTAs per SM already overlap their loads.)
 
     if (FWD) {
         cluster.sync(); // every CTA of the cluster is resident before anyone writes remote shared memory
@@ -163,7 +165,11 @@ cudaError_t launch_cfg(bool inverse, c64 *data, uint64_t batch, const FastTables
     BatchIo<false, false> bio = plain_batch(data, data, row_stride, row_stride);
     // L2 prefetch of the successor CTA's rows (c64_fast_kernels.cuh): CFFT_B200_FAST_PREFETCH = waves ahead (0 = off)
     static const int env_pf = [] { const char *e = getenv("CFFT_B200_FAST_PREFETCH"); return e ? atoi(e) : -1; }();
-    const int waves = env_pf >= 0 ? env_pf : (N >= 8192 && !STD ? 1 : 0);
+    // measured (profiles/r2c_fast_prefetch.txt): n = 8192 3.74 / 3.78 -> 4.61 / 4.57 TB/s, n = 4096 fwd 5.31 -> 6.15 (inv 6.11 -> 5.99:
+    // left off), n = 2048 6.66 / 6.84 -> 6.90 / 6.88
+    // standard-order variant (profiles/r2e_prefetch_ab.txt): n = 8192 3.04 / 3.61 -> 3.57 / 3.67, n = 4096 inv 5.27 -> 5.62 (fwd 5.34 -> 5.24: off)
+    const bool on = N >= 2048 && (N != 4096 || (STD ? inverse : !inverse));
+    const int waves = env_pf >= 0 ? env_pf : (on ? 1 : 0);
     if (waves > 0 && N >= 512) {
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
@@ -199,25 +205,35 @@ cudaError_t launch_fused_mul(const c64 *a, const c64 *b, c64 *out, uint64_t batc
     }
     static const int env_flags = [] { const char *e = getenv("CFFT_B200_FUSED_MUL_FLAGS"); return e ? atoi(e) : 3; }();
     uint32_t flags = uint32_t(env_flags) & 3;
+    // bits 8..: L2 prefetch distance in rows = one wave of resident CTAs (c64_fast_kernels.cuh); CFFT_B200_FUSED_MUL_PREFETCH=0: off
+    static const int env_pf = [] { const char *e = getenv("CFFT_B200_FUSED_MUL_PREFETCH"); return e ? atoi(e) : 1; }();
+    auto ahead_bits = [&](int minb) -> uint32_t {
+        if (env_pf <= 0 || N < 2048) return 0u;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        return uint32_t(sms * minb * Cfg::ROWS * env_pf) << 8;
+    };
+    const uint32_t pf1 = ahead_bits(FusedMulCfg<N, false>::MINB), pfm = ahead_bits(FusedMulCfg<N, ALLOW_MULTI>::MINB);
     if (chain) {
         // cfft_c64_fwd_mul_add: ONE term per row (rows kterms * N apart), Fourier-domain result stored (bit 4) on top of
         // what `out` holds (bit 3) -- no inverse
-        k1<<<unsigned(ctas), Cfg::NT, smem, stream>>>(plain_batch(a, nullptr, N, 0), b, plain_batch(nullptr, out, 0, N), batch, kterms, b_row_stride, tf, ti, (flags & 1) | chain);
+        k1<<<unsigned(ctas), Cfg::NT, smem, stream>>>(plain_batch(a, nullptr, N, 0), b, plain_batch(nullptr, out, 0, N), batch, kterms, b_row_stride, tf, ti, (flags & 1) | chain | pf1);
         count_launch();
         return cudaGetLastError();
     }
     if (!ALLOW_MULTI && kterms > 1) {
         // one launch per term: out holds the Fourier-domain partial sum between launches, the last launch inverts it
         for (uint32_t k = 0; k < kterms; k++) {
-            const uint32_t f = (flags & 1) | (k > 0 ? 8u : 0u) | (k + 1 < kterms ? 16u : 0u);
+            const uint32_t f = (flags & 1) | (k > 0 ? 8u : 0u) | (k + 1 < kterms ? 16u : 0u) | pf1;
             k1<<<unsigned(ctas), Cfg::NT, smem, stream>>>(plain_batch(a + uint64_t(k) * N, nullptr, N, 0), b + uint64_t(k) * N, plain_batch(nullptr, out, 0, N), batch, kterms, b_row_stride, tf, ti, f);
             count_launch();
         }
         return cudaGetLastError();
     }
     const BatchIo<false, false> ain = plain_batch(a, nullptr, N, 0), oout = plain_batch(nullptr, out, 0, N);
-    if (kterms == 1 && !(env_flags & 4)) k1<<<unsigned(ctas), Cfg::NT, smem, stream>>>(ain, b, oout, batch, kterms, b_row_stride, tf, ti, flags);
-    else km<<<unsigned(ctas), Cfg::NT, smem, stream>>>(ain, b, oout, batch, kterms, b_row_stride, tf, ti, flags);
+    if (kterms == 1 && !(env_flags & 4)) k1<<<unsigned(ctas), Cfg::NT, smem, stream>>>(ain, b, oout, batch, kterms, b_row_stride, tf, ti, flags | pf1);
+    else km<<<unsigned(ctas), Cfg::NT, smem, stream>>>(ain, b, oout, batch, kterms, b_row_stride, tf, ti, flags | pfm);
     count_launch();
     return cudaGetLastError();
 }
@@ -282,10 +298,99 @@ c64_rows256_std_kernel(const c64 *__restrict__ src, c64 *__restrict__ dst, uint3
     }
 }
 
+// TW = 16, round 2: the same pass with the un-permutation folded into the base FFT's OWN exchange instead of a second trip
+// through shared memory.  The 256-point FFT is radix-16 (pass 1, x[p + 16k]) -> 16 x 16 transpose -> radix-16 (pass 2,
+// y[j + 16k']), and nothing says the two passes of a row must run on the same half-warp.  Forward: pass 1 runs with
+// half-warp = row d, lane = p (row-side loads coalesced); pass 2 runs with half-warp = j, lane = row d, so the sixteen
+// lanes of a half-warp finish with X[hi = j + 16k''] of sixteen CONSECUTIVE lo and store 256-byte runs of standard order
+// straight from registers.  Inverse: the mirror image (standard-order gathers with lanes on lo, pass 2 on rows).  The
+// transpose between the passes now crosses rows, so it is one block barrier instead of a half-warp one; shared memory sees
+// each element once in and once out (LSU passes per element 7.9 -> 5.9).  Layout: element (row d, p, k)
+// at d * 257 + 16 p + (k ^ p): lanes varying p (pass 1) or d (pass 2) both fall into eight different 16-byte bank groups.
+template <bool FWD>
+__global__ void __launch_bounds__(256, 2)
+c64_rows256_std16_kernel(const c64 *__restrict__ src, c64 *__restrict__ dst, uint32_t n, uint32_t logm, const c64 *__restrict__ tw_base)
+{
+    constexpr int TW = 16, PITCH = 257;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c64 *s = reinterpret_cast<c64 *>(smem_raw);
+    const uint32_t m = 1u << logm;
+    const uint32_t tiles_per_row = m / TW;
+    const uint32_t b = blockIdx.x / tiles_per_row;
+    const uint32_t lo0 = (blockIdx.x - b * tiles_per_row) * TW;
+    const int hw = threadIdx.x >> 4, lane = threadIdx.x & 15;
+    const size_t row_base = size_t(b) * n;
+    c64 v[16];
+    if (FWD) {
+        {   // pass 1: half-warp = row d, lane = p                                   src/dif16.rs:449-623
+            const int d = hw, p = lane;
+            const c64 *g = src + row_base + size_t(__brev(lo0 + uint32_t(d)) >> (32 - logm)) * 256; // the row that holds lo = lo0 + d
+#pragma unroll
+            for (int k = 0; k < 16; k++) v[k] = ld_stream(g + p + 16 * k);
+            bf16<true>(v);
+#pragma unroll
+            for (int k = 1; k < 16; k++) v[k] = cmul(ld_tw(tw_base + p + 16 * k), v[k]);
+#pragma unroll
+            for (int k = 0; k < 16; k++) s[d * PITCH + 16 * p + (k ^ p)] = v[k];
+        }
+        __syncthreads();
+        {   // pass 2: half-warp = j, lane = row d                                   src/dif16.rs:649-827
+            const int j = hw, d = lane;
+#pragma unroll
+            for (int k = 0; k < 16; k++) v[k] = s[d * PITCH + 16 * k + (j ^ k)];
+            bf16<true>(v);
+            c64 *o = dst + row_base + lo0 + d;
+#pragma unroll
+            for (int k = 0; k < 16; k++) st_stream(o + size_t(j + 16 * k) * m, v[k]); // X[hi = j + 16k] at hi * M + lo
+        }
+    } else {
+        {   // pass 1 on standard-order input: half-warp = p, lane = row d (gathers of 256-byte runs M c64 apart)
+            const int p = hw, d = lane;
+            const c64 *g = src + row_base + lo0 + d;
+#pragma unroll
+            for (int k = 0; k < 16; k++) v[k] = ld_stream(g + size_t(p + 16 * k) * m);
+            bf16<false>(v);
+#pragma unroll
+            for (int k = 1; k < 16; k++) v[k] = cmul(ld_tw(tw_base + p + 16 * k), v[k]);
+#pragma unroll
+            for (int k = 0; k < 16; k++) s[d * PITCH + 16 * p + (k ^ p)] = v[k];
+        }
+        __syncthreads();
+        {   // pass 2: half-warp = row d, lane = j, rows written back in the unordered layout
+            const int d = hw, j = lane;
+#pragma unroll
+            for (int k = 0; k < 16; k++) v[k] = s[d * PITCH + 16 * k + (j ^ k)];
+            bf16<false>(v);
+            c64 *o = dst + row_base + size_t(__brev(lo0 + uint32_t(d)) >> (32 - logm)) * 256 + j;
+#pragma unroll
+            for (int k = 0; k < 16; k++) st_stream(o + 16 * k, v[k]);
+        }
+    }
+}
+
 template <int TW>
 cudaError_t launch_rows_std(bool inverse, const c64 *src, c64 *dst, uint64_t batch, uint32_t n, const c64 *tw_base,
                             cudaStream_t stream)
 {
+    // TW = 16: the one-exchange kernel above unless CFFT_B200_ROWS_STD_TWO_EXCHANGES=1 (the round-1 kernel, kept for the A/B and as
+    // a second implementation the tests compare bit for bit)
+    static const bool old_kernel = [] { const char *e = getenv("CFFT_B200_ROWS_STD_TWO_EXCHANGES"); return e && atoi(e) != 0; }();
+    if (TW == 16 && !old_kernel) {
+        const uint32_t m16 = n / 256;
+        uint32_t lg = 0;
+        while ((1u << lg) < m16) lg++;
+        const size_t smem16 = size_t(16) * 257 * sizeof(c64);
+        auto fk16 = c64_rows256_std16_kernel<true>;
+        auto ik16 = c64_rows256_std16_kernel<false>;
+        cudaError_t e = allow_smem(fk16, smem16);
+        if (e == cudaSuccess) e = allow_smem(ik16, smem16);
+        if (e != cudaSuccess) return e;
+        const uint64_t ctas16 = batch * (m16 / 16);
+        if (inverse) ik16<<<unsigned(ctas16), 256, smem16, stream>>>(src, dst, n, lg, tw_base);
+        else fk16<<<unsigned(ctas16), 256, smem16, stream>>>(src, dst, n, lg, tw_base);
+        count_launch();
+        return cudaGetLastError();
+    }
     const uint32_t m = n / 256;
     uint32_t logm = 0;
     while ((1u << logm) < m) logm++;

@@ -350,11 +350,20 @@ c64_fwd_mul_inv_kernel(BatchIo<PIN, false> ain, const c64 *__restrict__ b, Batch
         if (MULTI && k > 0 && R1 > 1) __syncthreads(); // the previous term's base FFTs have consumed the tile
         if (FUSED) {
             level_8x2_io<N, Cfg::TPR, true>(io, s, tf.top1, tf.top2, t, v);
-            __syncthreads();
         } else if (R1 > 1) {
             level_io<R1, N, Cfg::TPR, true, true, false>(io, nullptr, s, tf.top1, t, v);
-            __syncthreads();
         }
+        // own loads of the row's first term are done: ask L2 for the first term (and, in a chained launch, the partial sum)
+        // of the row the CTA taking this one's place will start with -- flags >> 8 rows on, one wave of resident CTAs
+        if (R1 > 1 && k == 0 && !PIN && (flags >> 8) && grow + (flags >> 8) < batch) {
+            const uint64_t r2 = grow + (flags >> 8);
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                prefetch_l2(ain.in + r2 * kterms * ain.row_in + (t + Cfg::TPR * i) * 8);
+                if (!POUT && (flags & 8)) prefetch_l2(oout.out + r2 * oout.row_out + (t + Cfg::TPR * i) * 8);
+            }
+        }
+        if (R1 > 1) __syncthreads();
         if (R2 > 1 && !FUSED) {
             level<R2, N2, Cfg::TPR, true, false, false>(s, s, tf.top2, t, v);
             __syncthreads();

@@ -492,7 +492,7 @@ cudaError_t launch_f128(const cfft_plan *plan, bool inverse, double *re0, double
     // CFFT_B200_F128_PREFETCH=0 turns it off, =k sets the distance in waves
     static const int env_pf = [] { const char *e = getenv("CFFT_B200_F128_PREFETCH"); return e ? atoi(e) : 1; }();
     uint32_t ahead = 0;
-    if (env_pf > 0 && tile >= 1024) {
+    if (env_pf > 0 && tile > 2048) { // measured (profiles/r2c_f128_prefetch.txt): +2 % at n = 4096 and n = 2^15, nothing (or -1 %) with two CTAs per SM
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, plan->device);
         const uint32_t per_sm = tile > 2048 ? 1u : (smax == 2 ? 3u : 2u);

@@ -405,6 +405,62 @@ pub mod fft128 {
     }
 }
 
+/// One host call, several GPUs: replicas of a plan on the devices that share the work; `fwd_batch` / `inv_batch` cut the
+/// batch into contiguous row ranges, one per replica, each on its own host thread and copy pipeline inside the library
+/// (`cfft_c64_host_multi` / `cfft_f128_host_multi`).  No collective: polynomials are independent.
+pub mod multi_gpu {
+    use crate::{c64, ffi};
+
+    pub struct Replicas {
+        h: Vec<*mut ffi::cfft_plan>,
+        n: usize,
+    }
+    unsafe impl Send for Replicas {}
+    unsafe impl Sync for Replicas {}
+
+    impl Replicas {
+        /// `plan`: `Plan::as_raw()` of any plan type; `devices`: CUDA device indices (an index may repeat).
+        /// # Safety
+        /// `plan` must be a live plan handle.
+        pub unsafe fn new(plan: *const ffi::cfft_plan, devices: &[i32]) -> Self {
+            assert!(!devices.is_empty());
+            let mut h = Vec::with_capacity(devices.len());
+            for &d in devices {
+                let mut out = core::ptr::null_mut();
+                ffi::check(ffi::cfft_plan_clone_to_device(plan, d, &mut out));
+                h.push(out);
+            }
+            Self { h, n: ffi::cfft_plan_fft_size(plan) as usize }
+        }
+        fn raw(&self) -> Vec<*const ffi::cfft_plan> {
+            self.h.iter().map(|p| *p as *const ffi::cfft_plan).collect()
+        }
+        /// `Plan::fwd` on every `fft_size` chunk of `buf` (op 0), `inv` (1) or `fwd` then `inv` (2).
+        pub fn c64(&self, op: i32, buf: &mut [c64]) {
+            assert_eq!(buf.len() % self.n, 0);
+            let r = self.raw();
+            ffi::check(unsafe { ffi::cfft_c64_host_multi(r.as_ptr(), r.len() as i32, op, buf.as_mut_ptr().cast(), buf.len() as u64, (buf.len() / self.n) as u64) });
+        }
+        pub fn f128(&self, op: i32, re0: &mut [f64], re1: &mut [f64], im0: &mut [f64], im1: &mut [f64]) {
+            assert_eq!(re0.len() % self.n, 0);
+            assert_eq!(re0.len(), re1.len());
+            assert_eq!(re0.len(), im0.len());
+            assert_eq!(re0.len(), im1.len());
+            let r = self.raw();
+            ffi::check(unsafe {
+                ffi::cfft_f128_host_multi(r.as_ptr(), r.len() as i32, op, re0.as_mut_ptr(), re1.as_mut_ptr(), im0.as_mut_ptr(), im1.as_mut_ptr(), re0.len() as u64, (re0.len() / self.n) as u64)
+            });
+        }
+    }
+    impl Drop for Replicas {
+        fn drop(&mut self) {
+            for p in self.h.drain(..) {
+                unsafe { ffi::cfft_plan_destroy(p) };
+            }
+        }
+    }
+}
+
 /// Device-pointer entry points (stream ordered, no host copies) for callers that keep their
 /// polynomials on the GPU.
 pub mod device {
@@ -421,6 +477,29 @@ pub mod device {
     /// See [`c64_fwd`].
     pub unsafe fn c64_inv(plan: *const ffi::cfft_plan, dev_buf: *mut c_void, batch: u64, stream: *mut c_void) {
         ffi::check(ffi::cfft_c64_inv(plan, dev_buf, batch, stream));
+    }
+    /// `fwd` on `batch` rows that start `row_stride >= n` c64 apart (polynomials inside larger records, transformed where
+    /// they are; elements between the rows are not touched).
+    /// # Safety
+    /// `dev_buf` addresses `(batch - 1) * row_stride + n` c64 on the plan's device.
+    pub unsafe fn c64_fwd_strided(plan: *const ffi::cfft_plan, dev_buf: *mut c_void, row_stride: u64, batch: u64, stream: *mut c_void) {
+        ffi::check(ffi::cfft_c64_fwd_strided(plan, dev_buf, row_stride, batch, stream));
+    }
+    /// # Safety
+    /// See [`c64_fwd_strided`].
+    pub unsafe fn c64_inv_strided(plan: *const ffi::cfft_plan, dev_buf: *mut c_void, row_stride: u64, batch: u64, stream: *mut c_void) {
+        ffi::check(ffi::cfft_c64_inv_strided(plan, dev_buf, row_stride, batch, stream));
+    }
+    /// fft128 `fwd` / `inv` on rows `row_stride >= n` doubles apart in each of the four planes.
+    /// # Safety
+    /// Every plane addresses `(batch - 1) * row_stride + n` doubles on the plan's device.
+    pub unsafe fn f128_fwd_strided(plan: *const ffi::cfft_plan, p: [*mut f64; 4], row_stride: u64, batch: u64, stream: *mut c_void) {
+        ffi::check(ffi::cfft_f128_fwd_strided(plan, p[0], p[1], p[2], p[3], row_stride, batch, stream));
+    }
+    /// # Safety
+    /// See [`f128_fwd_strided`].
+    pub unsafe fn f128_inv_strided(plan: *const ffi::cfft_plan, p: [*mut f64; 4], row_stride: u64, batch: u64, stream: *mut c_void) {
+        ffi::check(ffi::cfft_f128_inv_strided(plan, p[0], p[1], p[2], p[3], row_stride, batch, stream));
     }
     /// `lhs[i] *= rhs[i]` on `len` device c64 (the Fourier-domain step between `fwd` and `inv`; the bits of
     /// `num_complex`'s `*`).

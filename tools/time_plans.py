@@ -25,11 +25,16 @@ def timeit(fn, reps=10):
 
 
 for spec in sys.argv[1:]:
-    n, algo, base_n = spec.split(":")
-    n, base_n = int(n), int(base_n)
+    n, algo, base_n = spec.split(":")  # base_n "ord": the ordered (standard order) plan of that algorithm
+    n = int(n)
     batch = int(os.environ.get("CMP_BATCH", 0)) or (1 << 31) // (16 * n)
     data = torch.view_as_complex(torch.rand(batch, n, 2, dtype=torch.float64, device="cuda")).contiguous()
-    plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(A[algo], base_n))
+    if base_n == "ord":
+        plan = C.ordered.Plan(n, C.ordered.Method.UserProvided(A[algo]), allow_large=n > 1024)
+        base_n = n
+    else:
+        base_n = int(base_n)
+        plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(A[algo], base_n))
     for _ in range(3):
         plan.fwd(data); plan.inv(data); data.mul_(1.0 / n)
     f = timeit(lambda: plan.fwd(data)); data.mul_(float(n) ** -10)

@@ -48,11 +48,11 @@ template <int M> __device__ __forceinline__ void map_rc(int t, int k, int &row, 
     else row = 16 * q + k;                                // contiguous
 }
 
-template <int E> __global__ void __launch_bounds__(128, 4) lsu_tiles(double2 *data, int tiles_per_row)
+template <int E> __global__ void __launch_bounds__(128, 4) lsu_tiles(double2 *data, int tiles_per_row, int tiles)
 {
     __shared__ double2 s[RG * CW];
     const int t = threadIdx.x;
-    const size_t tile = blockIdx.x;
+    const size_t tile = blockIdx.x % unsigned(tiles); // the grid sweeps the buffer several times (L2-resident case)
     const size_t j = tile / tiles_per_row, c0 = (tile % tiles_per_row) * CW;
     double2 *g = data + j * (size_t(RG) * ROWSTRIDE) + c0;
     double2 v[16];
@@ -139,7 +139,7 @@ __device__ __forceinline__ int swz(int row, int col) { return row * CW + (col ^ 
 // WARPCOL: every level's 16 x 16 elements of a half-warp are one COLUMN (rows of one column), so warps never exchange
 // with each other and the barrier is __syncwarp
 template <int NLEV, int S, bool WARPCOL>
-__global__ void __launch_bounds__(160, 1) tma_tiles(const __grid_constant__ CUtensorMap map, int tiles_total, int tiles_per_row)
+__global__ void __launch_bounds__(160, 1) tma_tiles(const __grid_constant__ CUtensorMap map, int tiles_total, int tiles_per_row, int tiles)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ uint64_t full[S], done[S];
@@ -161,14 +161,14 @@ __global__ void __launch_bounds__(160, 1) tma_tiles(const __grid_constant__ CUte
                 const int s = it % S;
                 if (it >= S) { // tile it - S has been processed in place: write it back, then the buffer is free again
                     mbar_wait(&done[s], ((it / S) - 1) & 1);
-                    const int tile = first + (it - S) * step;
+                    const int tile = (first + (it - S) * step) % tiles;
                     const int j = tile / tiles_per_row, c0 = (tile % tiles_per_row) * CW;
                     tma_store_2d(&map, c0 * 2, j * RG, bufs + size_t(s) * RG * CW);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 }
                 if (it < mine) {
-                    const int tile = first + it * step;
+                    const int tile = (first + it * step) % tiles;
                     const int j = tile / tiles_per_row, c0 = (tile % tiles_per_row) * CW;
                     mbar_expect_tx(&full[s], TILE_BYTES);
                     tma_load_2d(bufs + size_t(s) * RG * CW, &map, c0 * 2, j * RG, &full[s]);
@@ -215,6 +215,55 @@ __global__ void __launch_bounds__(160, 1) tma_tiles(const __grid_constant__ CUte
     }
 }
 
+// ---- C: contiguous tiles (the shape of the N = 2048 kernel, the 256-point rows pass and the generic register kernel): a CTA of
+// 128 threads owns 2048 contiguous c64; LDG.128 in, E exchanges through shared memory, then out either by STG.128 (which
+// ncu shows costing TWO data-pipe wavefronts per 128 bytes, l1tex__data_pipe_lsu_wavefronts_mem_lgds) or by STS.128 into the
+// tile + one cp.async.bulk (TMA, 1-D) per warp of 8 KiB, which leaves the LSU data pipe out of the store.
+template <int E, bool BULK> __global__ void __launch_bounds__(128, 4) contig_tiles(double2 *data, int tiles)
+{
+    __shared__ __align__(128) double2 s[2048];
+    const int t = threadIdx.x, w = t >> 5, l = t & 31;
+    double2 *g = data + size_t(blockIdx.x % unsigned(tiles)) * 2048;
+    double2 v[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = ldg_stream(g + t + 128 * k);
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        double2 *blk = s + 256 * (t >> 4); // the 16 x 16 transpose of base256 (c64_dev.cuh): XOR swizzle, conflict-free
+        const int l16 = t & 15;
+#pragma unroll
+        for (int k = 0; k < 16; k++) blk[16 * l16 + (k ^ l16)] = v[k];
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 16; k++) v[k] = blk[16 * k + (l16 ^ k)];
+        __syncwarp();
+    }
+    if (!BULK) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) stg_stream(g + t + 128 * k, v[k]);
+    } else {
+        // warp w stores its own 512 contiguous elements (8 KiB): natural order, lanes on consecutive c64
+#pragma unroll
+        for (int k = 0; k < 16; k++) s[512 * w + l + 32 * k] = v[k];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (l == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 8192;" ::"l"(g + 512 * w), "r"(smem_u32(s + 512 * w)) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    }
+}
+
+template <int E, bool BULK> static void run_contig(const char *name, double2 *d, size_t bytes, int reps, int sweeps)
+{
+    const int tiles = int(bytes / TILE_BYTES);
+    const float ms = time_ms(reps, [&] { contig_tiles<E, BULK><<<tiles * sweeps, 128>>>(d, tiles); });
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    printf("%-44s                   %8.3f ms  %7.0f GB/s (read + write)\n", name, ms, 2.0 * bytes * sweeps / ms / 1e6);
+}
+
 typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                 const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
@@ -237,7 +286,7 @@ static float time_ms(int reps, const std::function<void()> &fn)
     return ms / reps;
 }
 
-template <int NLEV, int S, bool WARPCOL> static void run_tma(const char *name, const CUtensorMap &map, size_t bytes, int sms, int ctas_per_sm, int reps)
+template <int NLEV, int S, bool WARPCOL> static void run_tma(const char *name, const CUtensorMap &map, size_t bytes, int sms, int ctas_per_sm, int reps, int sweeps)
 {
     const int tiles = int(bytes / TILE_BYTES), tiles_per_row = ROWSTRIDE / CW;
     const size_t smem = size_t(S) * TILE_BYTES + 1024;
@@ -250,19 +299,19 @@ template <int NLEV, int S, bool WARPCOL> static void run_tma(const char *name, c
         return;
     }
     const int grid = sms * ctas_per_sm;
-    const float ms = time_ms(reps, [&] { k<<<grid, 160, smem>>>(map, tiles, tiles_per_row); });
+    const float ms = time_ms(reps, [&] { k<<<grid, 160, smem>>>(map, tiles * sweeps, tiles_per_row, tiles); });
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
-    printf("%-44s S=%d x %d CTA/SM  %8.3f ms  %7.0f GB/s (read + write)\n", name, S, ctas_per_sm, ms, 2.0 * bytes / ms / 1e6);
+    printf("%-44s S=%d x %d CTA/SM  %8.3f ms  %7.0f GB/s (read + write)\n", name, S, ctas_per_sm, ms, 2.0 * bytes * sweeps / ms / 1e6);
 }
 
-template <int E> static void run_lsu(const char *name, double2 *d, size_t bytes, int reps)
+template <int E> static void run_lsu(const char *name, double2 *d, size_t bytes, int reps, int sweeps)
 {
     const int tiles = int(bytes / TILE_BYTES), tiles_per_row = ROWSTRIDE / CW;
-    const float ms = time_ms(reps, [&] { lsu_tiles<E><<<tiles, 128>>>(d, tiles_per_row); });
+    const float ms = time_ms(reps, [&] { lsu_tiles<E><<<tiles * sweeps, 128>>>(d, tiles_per_row, tiles); });
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
-    printf("%-44s                   %8.3f ms  %7.0f GB/s (read + write)\n", name, ms, 2.0 * bytes / ms / 1e6);
+    printf("%-44s                   %8.3f ms  %7.0f GB/s (read + write)\n", name, ms, 2.0 * bytes * sweeps / ms / 1e6);
 }
 
 int main()
@@ -294,20 +343,28 @@ int main()
             printf("cuTensorMapEncodeTiled failed: %d\n", int(r));
             return 1;
         }
-        const int reps = mib <= 64 ? 200 : 10;
+        const int reps = 10, sweeps = mib <= 64 ? 64 : 1; // L2-resident: 64 sweeps per launch so that launch overhead vanishes
         printf("---- buffer %zu MiB (%s), tiles of %d rows x %d c64, row stride %d c64 ----\n", mib, mib <= 64 ? "L2-resident" : "HBM", RG, CW, ROWSTRIDE);
-        run_lsu<0>("LSU: LDG -> STG", d, bytes, reps);
-        run_lsu<1>("LSU: LDG, 1 exchange, STG", d, bytes, reps);
-        run_lsu<2>("LSU: LDG, 2 exchanges, STG", d, bytes, reps);
-        run_tma<1, 3, false>("TMA: 1 in-place level", map, bytes, sms, 1, reps);
-        run_tma<1, 3, false>("TMA: 1 in-place level", map, bytes, sms, 2, reps);
-        run_tma<1, 2, false>("TMA: 1 in-place level", map, bytes, sms, 3, reps);
-        run_tma<2, 3, false>("TMA: 2 in-place levels, block barrier", map, bytes, sms, 2, reps);
-        run_tma<3, 3, false>("TMA: 3 in-place levels, block barrier", map, bytes, sms, 2, reps);
-        run_tma<3, 2, false>("TMA: 3 in-place levels, block barrier", map, bytes, sms, 3, reps);
-        run_tma<3, 3, true>("TMA: 3 in-place levels, half-warp columns", map, bytes, sms, 2, reps);
-        run_tma<3, 2, true>("TMA: 3 in-place levels, half-warp columns", map, bytes, sms, 3, reps);
-        run_tma<3, 6, true>("TMA: 3 in-place levels, half-warp columns", map, bytes, sms, 1, reps);
+        run_lsu<0>("LSU: LDG -> STG", d, bytes, reps, sweeps);
+        run_lsu<1>("LSU: LDG, 1 exchange, STG", d, bytes, reps, sweeps);
+        run_lsu<2>("LSU: LDG, 2 exchanges, STG", d, bytes, reps, sweeps);
+        run_tma<1, 3, false>("TMA: 1 in-place level", map, bytes, sms, 1, reps, sweeps);
+        run_tma<1, 3, false>("TMA: 1 in-place level", map, bytes, sms, 2, reps, sweeps);
+        run_tma<1, 2, false>("TMA: 1 in-place level", map, bytes, sms, 3, reps, sweeps);
+        run_tma<2, 3, false>("TMA: 2 in-place levels, block barrier", map, bytes, sms, 2, reps, sweeps);
+        run_tma<3, 3, false>("TMA: 3 in-place levels, block barrier", map, bytes, sms, 2, reps, sweeps);
+        run_tma<3, 2, false>("TMA: 3 in-place levels, block barrier", map, bytes, sms, 3, reps, sweeps);
+        run_tma<3, 3, true>("TMA: 3 in-place levels, half-warp columns", map, bytes, sms, 2, reps, sweeps);
+        run_tma<3, 2, true>("TMA: 3 in-place levels, half-warp columns", map, bytes, sms, 3, reps, sweeps);
+        run_tma<3, 6, true>("TMA: 3 in-place levels, half-warp columns", map, bytes, sms, 1, reps, sweeps);
+        run_contig<0, false>("contig: LDG -> STG", d, bytes, reps, sweeps);
+        run_contig<0, true>("contig: LDG -> STS + bulk store", d, bytes, reps, sweeps);
+        run_contig<1, false>("contig: LDG, 1 exchange, STG", d, bytes, reps, sweeps);
+        run_contig<1, true>("contig: LDG, 1 exchange, STS + bulk store", d, bytes, reps, sweeps);
+        run_contig<2, false>("contig: LDG, 2 exchanges, STG", d, bytes, reps, sweeps);
+        run_contig<2, true>("contig: LDG, 2 exchanges, STS + bulk store", d, bytes, reps, sweeps);
+        run_contig<3, false>("contig: LDG, 3 exchanges, STG", d, bytes, reps, sweeps);
+        run_contig<3, true>("contig: LDG, 3 exchanges, STS + bulk store", d, bytes, reps, sweeps);
         CK(cudaFree(d));
     }
     return 0;
