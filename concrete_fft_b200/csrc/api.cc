@@ -189,8 +189,8 @@ const char *variant_name(const cfft_plan *p)
     case 8: return "fast-b256-persistent-2pass";
     case 9: return "fast-b256-column+fused-rows";
     default:
-        if (p->exact_regs && p->kind == KIND_UNORDERED && !getenv("CFFT_B200_REGS_NO_SPEC") &&
-            regs_spec_supported(p->n, algo_radix(p->algo), algo_is_dit(p->algo), p->base_n))
+        if (p->exact_regs && (p->kind == KIND_UNORDERED || !p->allow_large) && !getenv("CFFT_B200_REGS_NO_SPEC") &&
+            regs_spec_supported(p->n, algo_radix(p->algo), algo_is_dit(p->algo), p->kind == KIND_ORDERED ? p->n : p->base_n))
             return "exact-regs-spec"; // compile-time schedule (c64_regs.cu)
         return p->exact_regs ? "exact-regs" : "exact-tile";
     }
@@ -601,11 +601,16 @@ cfft_status cfft_plan_autotune(cfft_plan *p, uint64_t batch_hint)
             for (uint32_t t : {1024u, 2048u, 4096u})
                 if (t >= p->n) cands.push_back({std::string(fam) + "/" + std::to_string(t), p->kind == KIND_F128 ? p->fast_variant : 0, t});
         if (p->kind != KIND_F128 && p->n > 2048) cands.push_back({"exact-tile/4096", 0, 0});
+        if (p->kind == KIND_F128 && p->n >= 4096) { // one CTA per SM on 4096-element tiles, or one more HBM pass and two CTAs per SM
+            cands.push_back({std::string(fam) + "/4096", p->fast_variant, 4096u});
+            cands.push_back({std::string(fam) + "/2048+hbm-pass", p->fast_variant, 2048u});
+        }
         if (p->kind == KIND_F128 && p->n <= 2048) // two-stage groups in 80 registers: three CTAs per SM
             cands.push_back({std::string(fam) + "/2048/3-per-SM", p->fast_variant, 2048u, 0, 1, 2});
     } else if (p->fast_variant == 3 || p->fast_variant == 5) {
         if (p->n <= 8192) cands.push_back({"ordered-b256-regs-std", 5, 0});
         cands.push_back({"ordered-b256-column+rows-std", 3, 0});
+        cands.push_back({"ordered-b256-column+rows-std/L2-8MBx4", 3, 0, 8, 4}); // out of place: chunk + workspace share L2
         cands.push_back({"ordered-b256-column+rows-std/L2-16MBx4", 3, 0, 16, 4});
         cands.push_back({"ordered-b256-column+rows-std/L2-32MBx2", 3, 0, 32, 2});
     } else if (p->fast_variant == 1 || p->fast_variant == 2 || p->fast_variant == 4 || p->fast_variant == 8 || p->fast_variant == 9) {

@@ -372,10 +372,12 @@ template <int TW>
 cudaError_t launch_rows_std(bool inverse, const c64 *src, c64 *dst, uint64_t batch, uint32_t n, const c64 *tw_base,
                             cudaStream_t stream)
 {
-    // TW = 16: the one-exchange kernel above unless CFFT_B200_ROWS_STD_TWO_EXCHANGES=1 (the round-1 kernel, kept for the A/B and as
-    // a second implementation the tests compare bit for bit)
-    static const bool old_kernel = [] { const char *e = getenv("CFFT_B200_ROWS_STD_TWO_EXCHANGES"); return e && atoi(e) != 0; }();
-    if (TW == 16 && !old_kernel) {
+    // TW = 16: the one-exchange kernel above with CFFT_B200_ROWS_STD_ONE_EXCHANGE=1.  Measured (profiles/r2f_ordered_rows_ab.txt): no
+    // faster than the two-exchange kernel below (n = 2^16 whole batch 2.89 / 3.02 vs 2.96 / 2.99 TB/s, chunked 3.02 / 3.28 vs
+    // 2.98 / 3.30) -- this pass is bound by its 256-byte scatter / gather, M c64 apart, not by the LSU pipe -- so the
+    // round-1 kernel stays the default and this one a second implementation the tests compare bit for bit.
+    static const bool one_exchange = [] { const char *e = getenv("CFFT_B200_ROWS_STD_ONE_EXCHANGE"); return e && atoi(e) != 0; }();
+    if (TW == 16 && one_exchange) {
         const uint32_t m16 = n / 256;
         uint32_t lg = 0;
         while ((1u << lg) < m16) lg++;

@@ -322,10 +322,10 @@ cudaError_t launch_c64_exact(const cfft_plan *plan, bool inverse, double2 *data,
         if (!(full.st[i].kind == ST_TOP && full.st[i].span > tile)) in_tile.st[in_tile.count++] = full.st[i];
 
     cudaError_t e;
-    if (regs && plan->kind == KIND_UNORDERED && n <= kTileMax && !getenv("CFFT_B200_REGS_NO_SPEC")) {
+    if (regs && (plan->kind == KIND_UNORDERED || !plan->allow_large) && n <= kTileMax && !getenv("CFFT_B200_REGS_NO_SPEC")) {
         // plans with a compile-time schedule (c64_regs.cu): same stages, same tables, index arithmetic folded away
         bool taken = false;
-        e = launch_c64_regs_spec(inverse, n, algo_radix(plan->algo), algo_is_dit(plan->algo), plan->base_n, full, data, total, tw,
+        e = launch_c64_regs_spec(inverse, n, algo_radix(plan->algo), algo_is_dit(plan->algo), plan->kind == KIND_ORDERED ? n : plan->base_n, full, data, total, tw,
                                  plan->d_top_tw[inverse ? 1 : 0], stream, &taken);
         if (e != cudaSuccess || taken) return e;
     }

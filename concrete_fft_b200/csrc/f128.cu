@@ -385,6 +385,19 @@ f128_global_pass(Planes data, uint64_t total, uint32_t n, uint32_t logn, int d0,
             const uint64_t i = base + uint64_t(e) * u;
             z[e] = {{data.p[0][i], data.p[1][i]}, {data.p[2][i], data.p[3][i]}};
         }
+        // this thread's NEXT group: its 4 x G lines are requested into L2 while the current group's ~G/2 * S * 94 FP64
+        // instructions run (lanes hold consecutive elements, so one lane in sixteen covers a 128-byte line)
+        if ((threadIdx.x & 15) == 0) {
+            const uint64_t g2 = g + uint64_t(gridDim.x) * kThreads;
+            if (g2 < groups) {
+                const uint64_t hi2 = g2 / u;
+                const uint64_t base2 = hi2 * (uint64_t(G) * u) + (g2 - hi2 * u);
+#pragma unroll
+                for (int e = 0; e < G; e++)
+#pragma unroll
+                    for (int pl = 0; pl < 4; pl++) asm volatile("prefetch.global.L2 [%0];" ::"l"(data.p[pl] + base2 + uint64_t(e) * u));
+            }
+        }
         run_group<S, FWD>(z, tw, uint32_t(base & (n - 1)), logn, d0);
 #pragma unroll
         for (int e = 0; e < G; e++) {
@@ -442,11 +455,14 @@ cudaError_t launch_f128(const cfft_plan *plan, bool inverse, double *re0, double
     // costs, so it keeps both busy), the rest on sub-blocks of n >> D0 elements in the tile kernel.
     uint32_t tile;
     int D0 = 0; // stages d < D0 run as HBM passes
-    static const uint32_t tile_max = [] {
+    static const uint32_t env_tile_max = [] {
         const char *e = getenv("CFFT_B200_F128_TILEMAX");
         const long v = e ? atol(e) : 0;
-        return (v == 2048 || v == 4096) ? uint32_t(v) : kF128TileMax;
+        return (v == 2048 || v == 4096) ? uint32_t(v) : 0u;
     }();
+    // n >= 4096: 4096-element tiles (one CTA per SM) or 2048-element tiles after one more HBM pass (two CTAs per SM); the
+    // autotuner times both (plan->tile_elems == 2048 selects the latter)
+    const uint32_t tile_max = env_tile_max ? env_tile_max : ((n >= 4096 && plan->tile_elems == 2048) ? 2048u : kF128TileMax);
     if (n > tile_max) {
         const int over = int(logn - ilog2(tile_max));
         D0 = 3 * ((over + 2) / 3);

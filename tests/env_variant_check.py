@@ -44,7 +44,7 @@ for n in (4096, 16384, 65536):
         d = torch.from_numpy(x.copy()).cuda()
         plan.fwd(d)
         torch.cuda.synchronize()
-        want = ref.fwd(x, threads=8)[:, pi]
+        want = np.ascontiguousarray(ref.fwd(x, threads=8)[:, pi])
         assert np.array_equal(d.cpu().numpy().view(np.uint64), want.view(np.uint64)), ("ordered fwd", n, batch, plan.kernel_name())
         plan.inv(d)
         torch.cuda.synchronize()

@@ -663,7 +663,7 @@ def test_ord16_register_kernel_bit_exact(C, torch, n):
     po = C.ordered.Plan(n, C.ordered.Method.UserProvided(A.Dif16))
     pu = C.unordered.Plan(n, C.unordered.Method.UserProvided(A.Dif16, n))
     assert po.kernel_name() == "ord16-regs" and pu.kernel_name() == "ord16-regs"
-    assert C.ordered.Plan(n, C.ordered.Method.UserProvided(A.Dit16)).kernel_name() == "exact-regs"
+    assert C.ordered.Plan(n, C.ordered.Method.UserProvided(A.Dit16)).kernel_name() == ("exact-regs-spec" if n == 1024 else "exact-regs")
     assert np.array_equal(pu.permutation(), np.arange(n))
     ref = O.OrderedPlan(n, O.DIF16)
     uref = O.UnorderedPlan(n, O.DIF16, n)
@@ -746,6 +746,30 @@ def test_compile_time_schedule_kernels_bit_exact(C, torch, n, algo, base_n):
         os.environ["CFFT_B200_REGS_NO_SPEC"] = "1"
         try:
             assert bits_equal(dev_run(torch, plan.fwd, x), y) and bits_equal(dev_run(torch, plan.inv, y), back)
+        finally:
+            del os.environ["CFFT_B200_REGS_NO_SPEC"]
+
+
+@pytest.mark.parametrize("n,algo", [(1024, O.DIF8), (1024, O.DIT8), (1024, O.DIT16), (512, O.DIF8), (512, O.DIT8), (1024, O.DIF4)])
+def test_compile_time_schedule_ordered_plans_bit_exact(C, torch, n, algo):
+    """The same for whole-transform plans: ordered::Plan with a radix-4 / 8 algorithm or Dit16 (Dif16 has its own kernels), and
+    the unordered plan with base_n == n, whose output order is the natural one."""
+    rng = np.random.default_rng(4200 + n + algo)
+    A = C.ordered.FftAlgo
+    po = C.ordered.Plan(n, C.ordered.Method.UserProvided(A(algo)))
+    pu = C.unordered.Plan(n, C.unordered.Method.UserProvided(A(algo), n))
+    assert po.kernel_name() == "exact-regs-spec" and pu.kernel_name() == "exact-regs-spec"
+    ref = O.OrderedPlan(n, algo)
+    for batch in (1, 3, 129):
+        x = rand_c(rng, batch, n)
+        y = dev_run(torch, po.fwd, x)
+        want = ref.fwd(x)
+        assert bits_equal(y, want) and bits_equal(dev_run(torch, pu.fwd, x), want), (n, algo, batch)
+        back = dev_run(torch, po.inv, y)
+        assert bits_equal(back, ref.inv(want)), (n, algo, batch)
+        os.environ["CFFT_B200_REGS_NO_SPEC"] = "1"
+        try:
+            assert bits_equal(dev_run(torch, po.fwd, x), y) and bits_equal(dev_run(torch, po.inv, y), back)
         finally:
             del os.environ["CFFT_B200_REGS_NO_SPEC"]
 
