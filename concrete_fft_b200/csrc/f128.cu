@@ -460,9 +460,11 @@ cudaError_t launch_f128(const cfft_plan *plan, bool inverse, double *re0, double
         const long v = e ? atol(e) : 0;
         return (v == 2048 || v == 4096) ? uint32_t(v) : 0u;
     }();
-    // n >= 4096: 4096-element tiles (one CTA per SM) or 2048-element tiles after one more HBM pass (two CTAs per SM); the
-    // autotuner times both (plan->tile_elems == 2048 selects the latter)
-    const uint32_t tile_max = env_tile_max ? env_tile_max : ((n >= 4096 && plan->tile_elems == 2048) ? 2048u : kF128TileMax);
+    // n >= 4096: 2048-element tiles after one more HBM pass (two CTAs per SM) by default, 4096-element tiles (one CTA per SM)
+    // when plan->tile_elems == 4096 (the autotuner times both).  Measured with the prefetching HBM pass
+    // (profiles/r2g_f128.txt, T FP64 instr/s fwd / inv): n = 4096 13.2 / 13.5 vs 12.4 / 12.9, n = 2^15 13.0 / 13.2 vs 12.3 / 12.7,
+    // n = 2^18 12.9 / 12.8 vs 12.3 / 12.5 (n = 8192 and 2^16 end up with 2048-element tiles either way).
+    const uint32_t tile_max = env_tile_max ? env_tile_max : ((n >= 4096 && plan->tile_elems == 4096) ? kF128TileMax : 2048u);
     if (n > tile_max) {
         const int over = int(logn - ilog2(tile_max));
         D0 = 3 * ((over + 2) / 3);

@@ -84,4 +84,41 @@ h = rng.random((7, 1024)) + 0j
 p.fwd(h)
 torch.cuda.synchronize()
 run_fused_mul()
+# round-2 additions: compile-time schedules, batches longer than one wave of resident CTAs (the L2 prefetch distance), strided
+# rows, polynomial entry points, replicas, the fft128 HBM pass with its prefetch
+for n, algo, base in [(2048, A.Dif16, 1024), (2048, A.Dif8, 512), (2048, A.Dif4, 32), (1024, A.Dif8, 512), (4096, A.Dif16, 1024)]:
+    run_c64(C.unordered.Plan(n, C.unordered.Method.UserProvided(algo, base)), n, 7)
+for n, algo in [(1024, A.Dif8), (512, A.Dit8), (1024, A.Dit16)]:
+    run_c64(C.ordered.Plan(n, C.ordered.Method.UserProvided(algo)), n, 9)
+for n, batch in [(2048, 700), (4096, 350), (8192, 170)]:
+    run_c64(C.unordered.Plan(n, C.unordered.Method.UserProvided(A.Dif16, 256)), n, batch)
+    run_c64(C.ordered.Plan(n, C.ordered.Method.UserProvided(A.Dif16), allow_large=True), n, batch)
+run_c64(C.unordered.Plan(16384, C.unordered.Method.UserProvided(A.Dif16, 256)), 16384, 80)
+plan = C.unordered.Plan(2048, C.unordered.Method.UserProvided(A.Dif16, 256))
+rec = torch.from_numpy(rng.random((6, 3, 2048)) + 1j * rng.random((6, 3, 2048))).cuda()
+plan.fwd_strided(rec[:, 1])
+plan.inv_strided(rec[:, 1])
+gen = C.unordered.Plan(2048, C.unordered.Method.UserProvided(A.Dif4, 32))
+gen.fwd_strided(rec[:, 2])
+a = torch.from_numpy(rng.random((700, 4, 2048)) + 1j * rng.random((700, 4, 2048))).cuda()
+b = torch.from_numpy(rng.random((4, 2048)) + 1j * rng.random((4, 2048))).cuda()
+plan.fwd_mul_inv(a, b)
+big = C.unordered.Plan(8192, C.unordered.Method.UserProvided(A.Dif16, 256))
+a8 = torch.from_numpy(rng.random((170, 2, 8192)) + 1j * rng.random((170, 2, 8192))).cuda()
+big.fwd_mul_inv(a8, torch.from_numpy(rng.random((2, 8192)) + 1j * rng.random((2, 8192))).cuda())
+poly = torch.from_numpy(rng.integers(-1000, 1000, size=(5, 2, 4096))).cuda()
+key = plan.fwd_poly(torch.from_numpy(rng.integers(-8, 8, size=(2, 4096))).cuda())
+out = plan.poly_mul(poly, key)
+plan.inv_poly(plan.fwd_poly(out))
+from concrete_fft_b200.sharding import MultiGpu
+
+h = rng.random((9, 2048)) + 0j
+MultiGpu(plan, [0, 0]).fwd_inv(h)
+p128 = C.fft128.Plan(8192)
+planes = [torch.rand(310, 8192, dtype=torch.float64, device="cuda") for _ in range(4)]
+p128.fwd(*planes)
+p128.inv(*planes)
+rec128 = [torch.rand(4, 2, 1024, dtype=torch.float64, device="cuda") for _ in range(4)]
+C.fft128.Plan(1024).fwd_strided(*[r[:, 1] for r in rec128])
+torch.cuda.synchronize()
 print("sanitize_small done, launches =", C.launch_count())
