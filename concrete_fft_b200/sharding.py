@@ -60,8 +60,10 @@ class MultiGpu:
         self.devices = [int(d) for d in devices]
 
     def __del__(self):
-        for h in getattr(self, "_replicas", []):
-            self._N.lib.cfft_plan_destroy(h)
+        lib = getattr(getattr(self, "_N", None), "lib", None)  # None while the interpreter shuts down
+        if lib is not None:
+            for h in getattr(self, "_replicas", []):
+                lib.cfft_plan_destroy(h)
         self._replicas = []
 
     def _is_f128(self):

@@ -14,6 +14,7 @@ SETTINGS = [
     {"CFFT_B200_FAST_PREFETCH": "2", "CFFT_B200_COLUMN_PREFETCH": "2"},
     {"CFFT_B200_FAST_PREFETCH": "1", "CFFT_B200_FUSED_MUL_PREFETCH": "0"},
     {"CFFT_B200_COLPIPE": "1"},
+    {"CFFT_B200_TMEM_COLUMNS": "1"},
     {"CFFT_B200_ROWS_STD_ONE_EXCHANGE": "1"},
     {},
 ]
