@@ -125,6 +125,41 @@ int main(void)
     CHECK(memcmp(o1, o2, 16 * n) == 0);                                             /* bit-identical */
     CHECK(cfft_c64_fwd(p, (char *)d_a + 8, 1, NULL) == CFFT_EINVAL);                /* 16-byte alignment of device buffers */
 
+    /* ---- device::c64_fwd_strided / c64_inv_strided: rows inside larger records; multi_gpu::Replicas ---- */
+    {
+        void *d_rec = NULL;
+        double *rec = malloc(16 * 3 * 2 * n), *got = malloc(16 * 3 * 2 * n), *row = malloc(16 * n);
+        for (uint64_t i = 0; i < 2 * 3 * 2 * n; i++) rec[i] = frand(&seed);
+        CHECK(cudaMalloc(&d_rec, 16 * 3 * 2 * n) == 0 && cudaMemcpy(d_rec, rec, 16 * 3 * 2 * n, 1) == 0);
+        /* three records of two polynomials each: transform the SECOND polynomial of every record where it is */
+        CHECK(cfft_c64_fwd_strided(p, (char *)d_rec + 16 * n, 2 * n, 3, NULL) == CFFT_OK);
+        CHECK(cudaMemcpy(got, d_rec, 16 * 3 * 2 * n, 2) == 0);
+        for (int r = 0; r < 3; r++) {
+            memcpy(row, rec + (size_t)(2 * r + 1) * 2 * n, 16 * n);
+            CHECK(cfft_c64_fwd_host(p, row, n, 1) == CFFT_OK);
+            CHECK(memcmp(row, got + (size_t)(2 * r + 1) * 2 * n, 16 * n) == 0);                         /* same bits as the packed call */
+            CHECK(memcmp(rec + (size_t)(2 * r) * 2 * n, got + (size_t)(2 * r) * 2 * n, 16 * n) == 0);   /* neighbours untouched */
+        }
+        CHECK(cfft_c64_inv_strided(p, (char *)d_rec + 16 * n, 2 * n, 3, NULL) == CFFT_OK);
+        CHECK(cfft_c64_fwd_strided(p, d_rec, n / 2, 3, NULL) == CFFT_EINVAL);                           /* rows would overlap */
+        /* Replicas::new(plan.as_raw(), &[0, 0]) and Replicas::c64(2, buf): one host call over two replicas */
+        cfft_plan *rep[2] = {NULL, NULL};
+        const cfft_plan *crep[2];
+        CHECK(cfft_plan_clone_to_device(p, 0, &rep[0]) == CFFT_OK && cfft_plan_clone_to_device(p, 0, &rep[1]) == CFFT_OK);
+        CHECK(cfft_plan_clone_to_device(p, 9999, &q) == CFFT_EINVAL);
+        crep[0] = rep[0];
+        crep[1] = rep[1];
+        memcpy(got, rec, 16 * 3 * 2 * n);
+        CHECK(cfft_c64_host_multi(crep, 2, 2, got, 6 * n, 6) == CFFT_OK);                               /* fwd then inv of six rows */
+        for (uint64_t i = 0; i < 2 * 6 * n; i++) CHECK(fabs(got[i] / (double)n - rec[i]) < 1e-11);
+        CHECK(cfft_c64_host_multi(crep, 2, 0, got, 6 * n - 1, 6) == CFFT_ELENGTH);
+        CHECK(cfft_c64_host_multi(crep, 0, 0, got, 6 * n, 6) == CFFT_EINVAL);
+        cfft_plan_destroy(rep[0]);
+        cfft_plan_destroy(rep[1]);
+        cudaFree(d_rec);
+        free(rec); free(got); free(row);
+    }
+
     /* ---- the polynomial host entry: integers in host memory, operand resident on the device ---- */
     int64_t *pa = malloc(sizeof(int64_t) * 2 * n), *pb = malloc(sizeof(int64_t) * 2 * n), *pc = malloc(sizeof(int64_t) * 2 * n);
     void *d_pb = NULL;

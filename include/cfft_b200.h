@@ -103,7 +103,8 @@ int cfft_plan_device(const cfft_plan *plan);
 
 /* Which kernel family serves this plan: "fast-b256-regs", "fast-b256-cluster", "fast-b256-column+rows",
  * "fast-b256-column+fused-rows", "fast-b256-persistent-2pass", "ordered-b256-regs-std",
- * "ordered-b256-column+rows-std", "ord16-regs", "exact-regs", "exact-tile", "f128-radix8-tile", with
+ * "ordered-b256-column+rows-std", "ord16-regs", "exact-regs-spec" (stage schedule built at compile time), "exact-regs",
+ * "exact-tile", "f128-radix8-tile", with
  * "/L2-chunked" appended when the passes run chunk by chunk. */
 const char *cfft_plan_kernel_name(const cfft_plan *plan);
 

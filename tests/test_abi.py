@@ -75,6 +75,20 @@ def test_fused_product_entry_points_reject_bad_plans_before_cuda(C):
     assert lib.cfft_plan_has_fused_mul_kernel(None) == 0
 
 
+def test_strided_and_replica_entry_points_reject_bad_arguments_before_cuda(C):
+    """cfft_*_strided / cfft_*_host_multi / cfft_plan_clone_to_device: null plans and empty replica lists are CFFT_EINVAL
+    without any CUDA call."""
+    lib, N = C._native.lib, C._native
+    assert lib.cfft_c64_fwd_strided(None, None, 4096, 2, None) == N.EINVAL
+    assert lib.cfft_c64_inv_strided(None, None, 4096, 2, None) == N.EINVAL
+    assert lib.cfft_f128_fwd_strided(None, None, None, None, None, 4096, 2, None) == N.EINVAL
+    assert lib.cfft_f128_inv_strided(None, None, None, None, None, 4096, 2, None) == N.EINVAL
+    assert lib.cfft_c64_host_multi(None, 0, 0, None, 0, 0) == N.EINVAL
+    assert b"replicas" in lib.cfft_last_error()
+    assert lib.cfft_f128_host_multi(None, 2, 0, None, None, None, None, 0, 0) == N.EINVAL
+    assert lib.cfft_plan_clone_to_device(None, 0, None) == N.EINVAL
+
+
 def test_no_cpu_fallback(C):
     import torch
 
