@@ -364,7 +364,7 @@ def run_reference(args):
         extra["poly_mul"]["value"] = extra["poly_mul"]["cpu_baseline"]["value"]
         extra["cpu_n1024_1thread"] = cpu_single_polynomial()
         line["extra"] = extra
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -757,7 +757,23 @@ def poly_leg(ctx, steps, e2e_steps, cpu_seconds):
     return line
 
 
+_JSON_OUT = sys.stdout
+
+
+def keep_stdout_for_the_json_line():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner on the first collective), so file
+    descriptor 1 is pointed at stderr for the rest of the run and the line goes to a private copy of the original stdout."""
+    global _JSON_OUT
+    try:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    except OSError:
+        _JSON_OUT = sys.stdout
+
+
 def main():
+    keep_stdout_for_the_json_line()
     args = parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -812,7 +828,7 @@ def main():
             line["fp64_probe"] = ctx.fp64_probe
         if extra:
             line["extra"] = extra
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if ctx.dist is not None:
         ctx.dist.destroy_process_group()
 
