@@ -81,6 +81,69 @@ __device__ __forceinline__ void col_level(const c64 *__restrict__ g, c64 *__rest
     }
 }
 
+// A radix-8 level whose blocks span SG rows followed by the radix-2 level below it (blocks of SG / 8 = 2 rows), fused in
+// registers like level_8x2 of c64_fast_kernels.cuh: thread (blk, col) runs BOTH radix-8 butterflies of its block and column
+// (prow = 0 and 1), and the radix-2 level pairs exactly output k of the one with output k of the other (rows
+// blk SG + 2 brev(k) + {0, 1}), so nothing is exchanged between the two levels and the group (8, 8, 2) of n = 2^15 needs ONE
+// trip through shared memory instead of two.  Same butterflies, same twiddles, same order of operations per butterfly
+// (src/unordered.rs:24-43, 98-219) => same bits.  Forward: shared memory in, global out; inverse: global in, shared out.
+template <int SG, int RG, int CW, bool FWD>
+__device__ __forceinline__ void col_level_8x2(const c64 *__restrict__ g, c64 *__restrict__ gout, c64 *__restrict__ s,
+                                              const c64 *__restrict__ tw8, const c64 *__restrict__ tw2, uint32_t stride, uint32_t col0,
+                                              int t, bool active, c64 (&v)[16])
+{
+    static_assert(SG == 16, "the radix-2 level below a radix-8 level of 16-row blocks works on 2-row blocks");
+    static_assert(RG * CW / 16 == (RG / SG) * CW, "one thread per (block, column)");
+    const int col = t & (CW - 1), blk = t / CW;
+    const int rbase = blk * SG;
+    const uint32_t m8 = 2u * stride;                   // MROW = SG / 8 = 2
+    const uint32_t pcol = col0 + uint32_t(col);        // radix-2 twiddle index (prow = 0); radix-8: prow * stride + pcol
+    if (FWD) {
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[j * 8 + k] = s[(rbase + j + 2 * k) * CW + col];
+        if (!active) return;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            c64 *x = &v[j * 8];
+            bf8<true>(x);
+#pragma unroll
+            for (int k = 1; k < 8; k++) x[k] = cmul(ld_tw(tw8 + size_t(k - 1) * m8 + uint32_t(j) * stride + pcol), x[k]);
+        }
+        const c64 w = ld_tw(tw2 + pcol);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const c64 a = v[k], b = v[8 + k];
+            c64 *o = gout + size_t(rbase + 2 * brev_c<8>(k)) * stride + col;
+            st_stream(o, cadd(a, b));                    // fwd_butterfly_x2
+            st_stream(o + stride, cmul(w, csub(a, b)));
+        }
+    } else {
+        if (active) {
+            const c64 w = ld_tw(tw2 + pcol);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const c64 *i = g + size_t(rbase + 2 * brev_c<8>(k)) * stride + col;
+                const c64 a = ld_stream(i), b = cmul(w, ld_stream(i + stride)); // inv_butterfly_x2
+                v[k] = cadd(a, b);
+                v[8 + k] = csub(a, b);
+            }
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                c64 *x = &v[j * 8];
+#pragma unroll
+                for (int k = 1; k < 8; k++) x[k] = cmul(ld_tw(tw8 + size_t(k - 1) * m8 + uint32_t(j) * stride + pcol), x[k]);
+                bf8<false>(x);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) s[(rbase + j + 2 * k) * CW + col] = v[j * 8 + k];
+    }
+}
+
 // all levels of one group on one tile (RG rows x 16 columns); every thread of the CTA must call it
 template <int RA, int RB, int RC, int CW, bool FWD>
 __device__ __forceinline__ void column_tile(const c64 *__restrict__ g, c64 *__restrict__ go, c64 *__restrict__ s,
@@ -89,6 +152,18 @@ __device__ __forceinline__ void column_tile(const c64 *__restrict__ g, c64 *__re
 {
     constexpr int RG = RA * RB * RC;
     constexpr int SG0 = RG, SG1 = RG / RA, SG2 = RG / (RA * RB);
+    if constexpr (RA == 8 && RB == 8 && RC == 2) { // n = 2^15: the last two levels fused in registers, one exchange
+        if (FWD) {
+            col_level<RA, SG0, RG, CW, true, true, false>(g, go, s, tw[0], st, col0, t, active, v);
+            __syncthreads();
+            col_level_8x2<SG1, RG, CW, true>(g, go, s, tw[1], tw[2], st, col0, t, active, v);
+        } else {
+            col_level_8x2<SG1, RG, CW, false>(g, go, s, tw[1], tw[2], st, col0, t, active, v);
+            __syncthreads();
+            col_level<RA, SG0, RG, CW, false, false, true>(g, go, s, tw[0], st, col0, t, active, v);
+        }
+        return;
+    }
     if (FWD) {
         col_level<RA, SG0, RG, CW, true, true, (RB == 1)>(g, go, s, tw[0], st, col0, t, active, v);
         if (RB > 1) {

@@ -16,8 +16,8 @@ import concrete_fft_b200 as C
 
 rng = np.random.default_rng(31337)
 A = C.ordered.FftAlgo
-for n in (256, 512, 1024, 2048, 4096, 8192, 16384):
-    variants = [None] + (["4"] if n in (8192, 16384) else [])
+for n in (256, 512, 1024, 2048, 4096, 8192, 16384, 32768):
+    variants = [None] + (["4"] if n in (8192, 16384) else []) + (["8"] if n == 32768 else [])
     for var in variants:
         if var:
             os.environ["CFFT_B200_FAST_VARIANT"] = var

@@ -593,7 +593,7 @@ def test_fast_large_n_column_passes_bit_exact(C, torch, logn):
     assert np.linalg.norm(y[0][pi] - f) / np.linalg.norm(f) <= 1e-13 * logn
 
 
-@pytest.mark.parametrize("logn", [11, 12, 13, 14, 16, 17, 19, 20])
+@pytest.mark.parametrize("logn", [11, 12, 13, 14, 15, 16, 17, 18, 19, 20])
 def test_ordered_above_reference_cap(C, torch, logn):
     """BASELINE configs[2]: standard-order transforms for n > 2^10.  The reference cannot build these
     (src/ordered.rs:244), so the oracle is the DFT definition: the unordered reference plan
