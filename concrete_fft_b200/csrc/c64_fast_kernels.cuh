@@ -169,10 +169,11 @@ template <int N> struct FastCfg {
 };
 
 // STD = true: standard-order ("ordered") in / out.  X_i sits in the unordered layout at chunk
-// c = bitrev_L(i mod M), offset i / M (M = N / 256 chunks, src/unordered.rs:1046-1051), so the kernel
-// adds one more shared-memory exchange: chunk c keeps offset hi at (hi ^ (lo & 7)), lo = bitrev_L(c),
-// which makes both the base FFT's 16-consecutive accesses and the transposing pass (lanes on
-// consecutive i, i.e. on consecutive lo first) conflict-free; HBM sees consecutive i only.
+// c = bitrev_L(i mod M), offset i / M (M = N / 256 chunks, src/unordered.rs:1046-1051).  Round 1 added one more
+// shared-memory exchange for the un-permutation; since round 2 it rides on the base FFT's own 16 x 16 transpose (the two
+// radix-16 passes of a chunk need not run on the same half-warp), so the standard-order kernel moves each element through
+// shared memory exactly as often as the unordered one and HBM still sees consecutive i only: n = 2048 6.10 -> 6.91 TB/s,
+// n = 8192 3.9 -> 4.1-4.4 (profiles/r2l_std_one_exchange_ab.txt).
 // PIN / POUT: the rows in global memory are integer polynomials on the input / output side (c64_dev.cuh, RowIo).
 template <int N, int R1, int R2, bool FWD, bool STD = false, bool PIN = false, bool POUT = false>
 __global__ void __launch_bounds__(FastCfg<N>::NT, FastCfg<N>::MINB)
@@ -195,11 +196,6 @@ c64_fast_b256_kernel(BatchIo<PIN, POUT> bio, uint64_t batch, FastTables tb)
 
     constexpr int M = N / 256, LOGM = (M == 8 ? 3 : (M == 16 ? 4 : 5));
     const int sw = STD ? int(__brev(unsigned(blk)) >> (32 - LOGM)) & 7 : 0; // (lo & 7) of this thread's chunk
-    auto std_pos = [](int i) { // shared-memory position of standard index i
-        const int lo = i & (M - 1), hi = i / M;
-        return int(__brev(unsigned(lo)) >> (32 - LOGM)) * 256 + (hi ^ (lo & 7));
-    };
-
     constexpr bool FUSED = (R1 == 8 && R2 == 2); // both levels in registers, see level_8x2
     // Large transforms leave one or two CTAs per SM, so a CTA's first loads wait for HBM with little else to run: once
     // its own loads are done it asks L2 for the row the CTA that takes its place will start with (`ahead` rows on = one
@@ -226,13 +222,32 @@ c64_fast_b256_kernel(BatchIo<PIN, POUT> bio, uint64_t batch, FastTables tb)
             __syncthreads();
         }
         if (STD) {
-            base256<true, false, false>(s + blk * 256, s + blk * 256, s + blk * 256, tb.base, lane16, v, 0, sw);
+            // The un-permutation folded into the base FFT's OWN transpose: pass 1 (radix 16 on x[p + 16k]) runs with half-warp =
+            // chunk, lane = p; pass 2 (radix 16 on y[j + 16k']) runs with lanes on W = min(M, 16) CONSECUTIVE lo, so that a lane
+            // group finishes with X[hi = j + 16k''] of consecutive standard indices i = hi M + lo and stores full lines straight
+            // from registers -- no natural-order write-back, no transposing read.  The transposed block of chunk c is XORed
+            // with (lo & 7) in its low three bits: lanes on consecutive p (write) and lanes on consecutive lo (read) both land in
+            // eight different 16-byte bank groups.
+            c64 *sb = s + blk * 256;
+            const unsigned hmask = 0xFFFFu << (threadIdx.x & 16);
+#pragma unroll
+            for (int k = 0; k < 16; k++) v[k] = sb[lane16 + 16 * k];
+            bf16<true>(v);
+#pragma unroll
+            for (int k = 1; k < 16; k++) v[k] = cmul(ld_tw(tb.base + lane16 + 16 * k), v[k]);
+            __syncwarp(hmask);
+#pragma unroll
+            for (int k = 0; k < 16; k++) sb[16 * lane16 + ((k ^ lane16) ^ sw)] = v[k];
             __syncthreads();
+            constexpr int W = M < 16 ? M : 16;
+            const int lo = (t % W) + W * (t / (16 * W)), j = (t / W) % 16;
+            const c64 *sc = s + int(__brev(unsigned(lo)) >> (32 - LOGM)) * 256;
+#pragma unroll
+            for (int k = 0; k < 16; k++) v[k] = sc[16 * k + ((j ^ k) ^ (lo & 7))];
+            bf16<true>(v);
             if (active) {
 #pragma unroll
-                for (int j = 0; j < 16; j++) v[j] = s[std_pos(t + Cfg::TPR * j)];
-#pragma unroll
-                for (int j = 0; j < 16; j++) io.st(t + Cfg::TPR * j, v[j]);
+                for (int k = 0; k < 16; k++) io.st((j + 16 * k) * M + lo, v[k]);
             }
         } else if (active) {
             if (R1 > 1) base256_io<true, false, true>(io, blk * 256, s + blk * 256, s + blk * 256, nullptr, tb.base, lane16, v);
@@ -240,14 +255,26 @@ c64_fast_b256_kernel(BatchIo<PIN, POUT> bio, uint64_t batch, FastTables tb)
         }
     } else {
         if (STD) {
-            if (active) {
+            // mirror image: pass 1 on standard-order input with lanes on consecutive lo, pass 2 on the thread's own chunk
+            constexpr int W = M < 16 ? M : 16;
+            const int lo = (t % W) + W * (t / (16 * W)), p = (t / W) % 16;
+            c64 *sc = s + int(__brev(unsigned(lo)) >> (32 - LOGM)) * 256;
 #pragma unroll
-                for (int j = 0; j < 16; j++) v[j] = io.ld(t + Cfg::TPR * j);
+            for (int k = 0; k < 16; k++) v[k] = io.ld((p + 16 * k) * M + lo);
+            bf16<false>(v);
 #pragma unroll
-                for (int j = 0; j < 16; j++) s[std_pos(t + Cfg::TPR * j)] = v[j];
-            }
+            for (int k = 1; k < 16; k++) v[k] = cmul(ld_tw(tb.base + p + 16 * k), v[k]);
+#pragma unroll
+            for (int k = 0; k < 16; k++) sc[16 * p + ((k ^ p) ^ (lo & 7))] = v[k];
             __syncthreads();
-            base256<false, false, false>(s + blk * 256, s + blk * 256, s + blk * 256, tb.base, lane16, v, sw, 0);
+            c64 *sb = s + blk * 256;
+            const unsigned hmask = 0xFFFFu << (threadIdx.x & 16);
+#pragma unroll
+            for (int k = 0; k < 16; k++) v[k] = sb[16 * k + ((lane16 ^ k) ^ sw)];
+            bf16<false>(v);
+            __syncwarp(hmask); // the half-warp has consumed the transposed block before it is overwritten in natural order
+#pragma unroll
+            for (int k = 0; k < 16; k++) sb[lane16 + 16 * k] = v[k];
         } else if (active) {
             if (R1 > 1) base256_io<false, true, false>(io, blk * 256, nullptr, s + blk * 256, s + blk * 256, tb.base, lane16, v);
             else base256_io<false, true, true>(io, blk * 256, nullptr, s + blk * 256, nullptr, tb.base, lane16, v);

@@ -35,11 +35,11 @@ for n in (256, 512, 1024, 2048, 4096, 8192, 16384, 32768):
             torch.cuda.synchronize()
             assert np.array_equal(d.cpu().numpy().view(np.uint64), ref.inv(want, threads=8).view(np.uint64)), ("inv", n, var, batch)
 # ordered (standard order) plans above the reference's cap: the DFT definition = the unordered reference plan un-permuted
-for n in (4096, 16384, 65536):
+for n in (2048, 4096, 8192, 16384, 65536):
     plan = C.ordered.Plan(n, C.ordered.Method.UserProvided(A.Dif16), allow_large=True)
     ref = O.UnorderedPlan(n, O.DIF16, 256)
     pi = O.permutation(n, 256)
-    for batch in (1, 5):
+    for batch in (1, 5) + ((300,) if n <= 8192 else ()):
         x = rng.random((batch, n)) + 1j * rng.random((batch, n))
         d = torch.from_numpy(x.copy()).cuda()
         plan.fwd(d)
