@@ -322,6 +322,7 @@ cudaError_t launch_regs_t(const StageProgram &prog, c64 *data, uint64_t total, u
 #define CFFT_SPEC_PLANS(X)                                                                                          \
     X(2048, 16, false, 1024) X(2048, 16, false, 512) X(2048, 8, false, 512) X(2048, 4, false, 32) X(2048, 16, true, 1024) \
     X(1024, 16, false, 512) X(1024, 8, false, 512) X(4096, 16, false, 1024) X(4096, 8, false, 512)                  \
+    X(2048, 8, true, 512) X(2048, 16, true, 512) X(1024, 16, true, 512) X(1024, 8, true, 512) X(4096, 16, true, 1024) X(4096, 8, true, 512) \
     /* whole-transform plans (ordered plans, and unordered plans with base_n == n): no levels, Stockham stages only */ \
     X(1024, 8, false, 1024) X(1024, 8, true, 1024) X(1024, 16, true, 1024) X(512, 8, false, 512) X(512, 8, true, 512) X(1024, 4, false, 1024)
 

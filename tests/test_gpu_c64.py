@@ -723,7 +723,8 @@ def test_generic_register_kernel_matches_tile_kernel_and_oracle(C, torch, algo):
 
 
 SPEC_PLANS = [(2048, O.DIF16, 1024), (2048, O.DIF16, 512), (2048, O.DIF8, 512), (2048, O.DIF4, 32), (2048, O.DIT16, 1024),
-              (1024, O.DIF16, 512), (1024, O.DIF8, 512), (4096, O.DIF16, 1024), (4096, O.DIF8, 512)]
+              (1024, O.DIF16, 512), (1024, O.DIF8, 512), (4096, O.DIF16, 1024), (4096, O.DIF8, 512),
+              (2048, O.DIT8, 512), (2048, O.DIT16, 512), (1024, O.DIT16, 512), (1024, O.DIT8, 512), (4096, O.DIT16, 1024), (4096, O.DIT8, 512)]
 
 
 @pytest.mark.parametrize("n,algo,base_n", SPEC_PLANS)
