@@ -85,6 +85,8 @@ _SIGNATURES = {
     "cfft_f128_fwd_mul_inv": (ctypes.c_int32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, ctypes.c_double, _u64, _vp]),
     "cfft_c64_fwd_mul_inv": (ctypes.c_int32, [_vp, _vp, _u64, _vp, _u64, _vp, _u64, _vp]),
     "cfft_c64_fwd_mul_add": (ctypes.c_int32, [_vp, _vp, _u64, _vp, _u64, _vp, _int, _u64, _vp]),
+    "cfft_c64_fwd_mul_inv_multi": (ctypes.c_int32, [_vp, _vp, _u64, _vp, _u64, _u64, _vp, _u64, _vp]),
+    "cfft_plan_has_fused_mul2_kernel": (_int, [_vp]),
     "cfft_plan_has_fused_mul_kernel": (_int, [_vp]),
     "cfft_status_string": (ctypes.c_char_p, [ctypes.c_int32]),
     "cfft_last_error": (ctypes.c_char_p, []),

@@ -1019,6 +1019,37 @@ cfft_status cfft_c64_fwd_mul_inv(const cfft_plan *p, const void *a_dev, uint64_t
     return CFFT_OK;
 }
 
+cfft_status cfft_c64_fwd_mul_inv_multi(const cfft_plan *p, const void *a_dev, uint64_t k_terms, const void *b_dev, uint64_t b_row_stride,
+                                       uint64_t n_out, void *out_dev, uint64_t batch, void *stream)
+{
+    if (!p || p->kind == KIND_F128) return fail(CFFT_EINVAL, "not a c64 plan");
+    if (k_terms == 0) return fail(CFFT_EINVAL, "k_terms must be >= 1");
+    if (n_out == 0 || n_out > 64) return fail(CFFT_EINVAL, "n_out must be 1 .. 64");
+    if (batch && (!a_dev || !b_dev || !out_dev)) return fail(CFFT_EINVAL, "null buffer");
+    if ((reinterpret_cast<uintptr_t>(a_dev) | reinterpret_cast<uintptr_t>(b_dev) | reinterpret_cast<uintptr_t>(out_dev)) & 15)
+        return fail(CFFT_EINVAL, "device buffers must be 16-byte aligned (128-bit accesses)");
+    if (b_row_stride != 0 && b_row_stride < k_terms * n_out * p->n) return fail(CFFT_EINVAL, "b_row_stride must be 0 (b shared by every row) or >= k_terms * n_out * n");
+    {   // out is written while a and b are still being read by other rows: no overlap at all (there is no in-place form)
+        const uint64_t row = p->n * sizeof(cplx);
+        const uint64_t a_bytes = batch * k_terms * row, out_bytes = batch * n_out * row;
+        const uint64_t b_bytes = batch == 0 ? 0 : (b_row_stride == 0 ? k_terms * n_out * row : ((batch - 1) * b_row_stride + k_terms * n_out * p->n) * sizeof(cplx));
+        if (n_out == 1 && out_dev == a_dev) {
+            if (k_terms != 1) return fail(CFFT_EINVAL, "out may alias a only when k_terms == 1 and n_out == 1");
+        } else if (ranges_overlap(out_dev, out_bytes, a_dev, a_bytes)) {
+            return fail(CFFT_EINVAL, "out overlaps a");
+        }
+        if (ranges_overlap(out_dev, out_bytes, b_dev, b_bytes)) return fail(CFFT_EINVAL, "out must not overlap b");
+    }
+    DeviceGuard guard(p->device);
+    if (!guard.ok) return fail(CFFT_ECUDA, "cudaSetDevice failed");
+    cudaError_t e = launch_c64_fwd_mul_inv_multi(p, static_cast<const double2 *>(a_dev), k_terms, static_cast<const double2 *>(b_dev), b_row_stride,
+                                                 n_out, static_cast<double2 *>(out_dev), batch, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "c64 fwd-mul-inv (several outputs) launch");
+    return CFFT_OK;
+}
+
+int cfft_plan_has_fused_mul2_kernel(const cfft_plan *p) { return (p && p->kind != KIND_F128 && fused_mul2_kernel_available(p)) ? 1 : 0; }
+
 cfft_status cfft_c64_fwd_mul_add(const cfft_plan *p, const void *a_dev, uint64_t a_row_stride, const void *b_dev,
                                  uint64_t b_row_stride, void *acc_dev, int accumulate, uint64_t batch, void *stream)
 {

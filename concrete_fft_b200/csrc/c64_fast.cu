@@ -596,6 +596,85 @@ cudaError_t launch_c64_fast_b256_strided(const cfft_plan *plan, bool inverse, do
     }
 }
 
+// ---- several outputs per row: out[r][o] = inv( sum_k fwd(a[r][k]) (.) b[r][k][o] ), o < n_out (the GLWE external product) ----
+template <int N, int R1, int R2>
+static cudaError_t launch_fused_mul2(const cfft_plan *plan, const c64 *a, const c64 *b, c64 *out, uint64_t batch, uint32_t kterms,
+                                     uint64_t b_row_stride, cudaStream_t stream)
+{
+    using Cfg = FastCfg<N>;
+    const size_t smem = size_t(Cfg::ROWS) * N * sizeof(c64);
+    auto k = c64_fwd_mul_inv2_kernel<N, R1, R2>;
+    cudaError_t e = allow_smem(k, smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint64_t ctas = (batch + Cfg::ROWS - 1) / Cfg::ROWS;
+    k<<<unsigned(ctas), Cfg::NT, smem, stream>>>(a, b, out, batch, kterms, b_row_stride, fast_tables(plan, 0), fast_tables(plan, 1),
+                                                 N >= 2048 ? uint32_t(sms * 2 * Cfg::ROWS) : 0u);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// one kernel for two outputs: the (Dif16, 256) plans of n = 512, 1024, 2048 (TFHE polynomial sizes 1024 .. 4096)
+bool fused_mul2_kernel_available(const cfft_plan *plan)
+{
+    return fused_mul_kernel_available(plan) && (plan->n == 512 || plan->n == 1024 || plan->n == 2048);
+}
+
+cudaError_t launch_c64_fwd_mul_inv_multi(const cfft_plan *plan, const double2 *a, uint64_t kterms, const double2 *b, uint64_t b_row_stride,
+                                         uint64_t n_out, double2 *out, uint64_t batch, cudaStream_t stream)
+{
+    if (batch == 0 || kterms == 0 || n_out == 0) return cudaSuccess;
+    if (n_out == 1) return launch_c64_fwd_mul_inv(plan, a, kterms, b, b_row_stride, out, batch, stream);
+    const uint64_t n = plan->n;
+    const bool force_composed = getenv("CFFT_B200_FUSED_MUL_COMPOSED") != nullptr; // testing hook, read per call
+    if (n_out == 2 && fused_mul2_kernel_available(plan) && !force_composed && kterms <= 0xFFFFFFFFull) {
+        switch (n) {
+        case 512: return launch_fused_mul2<512, 2, 1>(plan, a, b, out, batch, uint32_t(kterms), b_row_stride, stream);
+        case 1024: return launch_fused_mul2<1024, 4, 1>(plan, a, b, out, batch, uint32_t(kterms), b_row_stride, stream);
+        default: return launch_fused_mul2<2048, 8, 1>(plan, a, b, out, batch, uint32_t(kterms), b_row_stride, stream);
+        }
+    }
+    // every other case: one output at a time through the single-output call (the forward transforms are recomputed per
+    // output), with the operand rows of that output gathered into, and the results scattered from, the stream-ordered workspace
+    const uint64_t row_bytes = n * sizeof(c64);
+    const bool shared_b = b_row_stride == 0;
+    uint64_t chunk_rows = (uint64_t{128} << 20) / (row_bytes * (shared_b ? 1 : kterms + 1));
+    if (chunk_rows < 1) chunk_rows = 1;
+    if (chunk_rows > batch) chunk_rows = batch;
+    cudaMemPool_t pool = nullptr;
+    cudaError_t e = workspace_pool(plan->device, &pool);
+    if (e != cudaSuccess) return e;
+    c64 *ws_out = nullptr, *ws_b = nullptr;
+    if ((e = cudaMallocFromPoolAsync(reinterpret_cast<void **>(&ws_out), chunk_rows * row_bytes, pool, stream)) != cudaSuccess) return e;
+    e = cudaMallocFromPoolAsync(reinterpret_cast<void **>(&ws_b), (shared_b ? 1 : chunk_rows) * kterms * row_bytes, pool, stream);
+    if (e != cudaSuccess) {
+        cudaFreeAsync(ws_out, stream);
+        return e;
+    }
+    for (uint64_t o = 0; o < n_out && e == cudaSuccess; o++) {
+        if (shared_b) e = cudaMemcpy2DAsync(ws_b, row_bytes, b + o * n, n_out * row_bytes, row_bytes, kterms, cudaMemcpyDeviceToDevice, stream);
+        for (uint64_t r0 = 0; r0 < batch && e == cudaSuccess; r0 += chunk_rows) {
+            const uint64_t rows = batch - r0 < chunk_rows ? batch - r0 : chunk_rows;
+            if (!shared_b) {
+                if (b_row_stride == kterms * n_out * n) {
+                    e = cudaMemcpy2DAsync(ws_b, row_bytes, b + r0 * b_row_stride + o * n, n_out * row_bytes, row_bytes, rows * kterms, cudaMemcpyDeviceToDevice, stream);
+                } else {
+                    for (uint64_t r = 0; r < rows && e == cudaSuccess; r++)
+                        e = cudaMemcpy2DAsync(ws_b + r * kterms * n, row_bytes, b + (r0 + r) * b_row_stride + o * n, n_out * row_bytes, row_bytes, kterms,
+                                              cudaMemcpyDeviceToDevice, stream);
+                }
+            }
+            if (e == cudaSuccess) e = launch_c64_fwd_mul_inv(plan, a + r0 * kterms * n, kterms, ws_b, shared_b ? 0 : kterms * n, ws_out, rows, stream);
+            if (e == cudaSuccess)
+                e = cudaMemcpy2DAsync(out + (r0 * n_out + o) * n, n_out * row_bytes, ws_out, row_bytes, row_bytes, rows, cudaMemcpyDeviceToDevice, stream);
+        }
+    }
+    const cudaError_t e2 = cudaFreeAsync(ws_out, stream), e3 = cudaFreeAsync(ws_b, stream);
+    return e != cudaSuccess ? e : (e2 != cudaSuccess ? e2 : e3);
+}
+
 cudaError_t launch_c64_fast_b256(const cfft_plan *plan, bool inverse, double2 *data, uint64_t batch, cudaStream_t stream)
 {
     if (batch == 0) return cudaSuccess;

@@ -454,5 +454,99 @@ c64_fwd_mul_inv_kernel(BatchIo<PIN, false> ain, const c64 *__restrict__ b, Batch
     }
 }
 
+// ---- the same step with TWO outputs per row: out[r][o] = inv( sum_k fwd(a[r][k]) (.) b[r][k][o] ), o < 2 -------------------
+// The GLWE external product of a caller such as TFHE-rs (GLWE dimension 1): every decomposed term a[r][k] feeds BOTH output
+// polynomials, each against its own row of the Fourier-domain key.  With cfft_c64_fwd_mul_inv once per output the k forward
+// transforms run twice; here each runs once and its 16 coefficients per thread are multiplied into two running sums
+// (2 x 16 c64 registers), then the two inverse transforms go through the same shared-memory tile one after the other.
+// 2 k + 2 transforms per row instead of 2 k + 2 + 2 k.  Arithmetic per output exactly as c64_fwd_mul_inv_kernel (num_complex
+// product, terms added in order) => bit-identical to calling that kernel per output.
+template <int N, int R1, int R2>
+__global__ void __launch_bounds__(FastCfg<N>::NT, 2)
+c64_fwd_mul_inv2_kernel(const c64 *__restrict__ a, const c64 *__restrict__ b, c64 *__restrict__ out, uint64_t batch, uint32_t kterms,
+                        uint64_t b_row_stride, FastTables tf, FastTables ti, uint32_t ahead)
+{
+    static_assert(N == 256 * R1 * R2, "n = 256 * R1 * R2");
+    using Cfg = FastCfg<N>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int row = threadIdx.x / Cfg::TPR, t = threadIdx.x % Cfg::TPR;
+    const uint64_t grow = uint64_t(blockIdx.x) * Cfg::ROWS + row;
+    const bool active = grow < batch; // inactive rows compute on row 0's data and store nothing
+    const uint64_t r = active ? grow : 0;
+    const c64 *gb = b + r * b_row_stride; // [kterms][2][N]
+    c64 *s = reinterpret_cast<c64 *>(smem_raw) + row * N;
+    c64 v[16], acc0[16], acc1[16];
+    constexpr int N2 = N / R1;
+    constexpr bool FUSED = (R1 == 8 && R2 == 2);
+    const int blk = t / 16, lane16 = t % 16;
+    c64 *sb = s + blk * 256;
+
+    for (uint32_t k = 0; k < kterms; k++) {
+        const PlainRow io = plain_row(a + (r * kterms + k) * N, nullptr);
+        if (k + 1 < kterms) { // next term's input and both multiplier rows on their way to L2 while this term computes
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                prefetch_l2(io.in + N + (t + Cfg::TPR * i) * 8);
+                prefetch_l2(gb + uint64_t(k + 1) * 2 * N + (t + Cfg::TPR * i) * 8);
+                prefetch_l2(gb + uint64_t(k + 1) * 2 * N + N + (t + Cfg::TPR * i) * 8);
+            }
+        }
+        if (k > 0 && R1 > 1) __syncthreads(); // the previous term's base FFTs have consumed the tile
+        if (FUSED) {
+            level_8x2_io<N, Cfg::TPR, true>(io, s, tf.top1, tf.top2, t, v);
+        } else if (R1 > 1) {
+            level_io<R1, N, Cfg::TPR, true, true, false>(io, nullptr, s, tf.top1, t, v);
+        }
+        if (R1 > 1 && k == 0 && ahead && grow + ahead < batch) { // the row of the CTA that takes this one's place
+#pragma unroll
+            for (int i = 0; i < 2; i++) prefetch_l2(a + (grow + ahead) * kterms * N + (t + Cfg::TPR * i) * 8);
+        }
+        if (R1 > 1) __syncthreads();
+        if (R2 > 1 && !FUSED) {
+            level<R2, N2, Cfg::TPR, true, false, false>(s, s, tf.top2, t, v);
+            __syncthreads();
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = R1 > 1 ? sb[lane16 + 16 * j] : io.ld(blk * 256 + lane16 + 16 * j);
+        base256_core<true>(sb, tf.base, lane16, v);
+        const c64 *bk = gb + uint64_t(k) * 2 * N + blk * 256 + lane16;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const c64 p0 = cmul_nc(v[j], ld_stream(bk + 16 * j)), p1 = cmul_nc(v[j], ld_stream(bk + N + 16 * j));
+            acc0[j] = k == 0 ? p0 : cadd(acc0[j], p0);
+            acc1[j] = k == 0 ? p1 : cadd(acc1[j], p1);
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < 2; o++) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = o == 0 ? acc0[j] : acc1[j];
+        if (o == 1 && R1 > 1) __syncthreads(); // the first output's levels have consumed the tile
+        base256_core<false>(sb, ti.base, lane16, v);
+        const PlainRow io_out = plain_row(nullptr, out + (r * 2 + o) * N);
+        if (R1 == 1) {
+            if (active) {
+#pragma unroll
+                for (int j = 0; j < 16; j++) io_out.st(blk * 256 + lane16 + 16 * j, v[j]);
+            }
+            continue;
+        }
+        __syncwarp(0xFFFFu << (threadIdx.x & 16));
+#pragma unroll
+        for (int j = 0; j < 16; j++) sb[lane16 + 16 * j] = v[j];
+        if (FUSED) {
+            __syncthreads();
+            if (active) level_8x2_io<N, Cfg::TPR, false>(io_out, s, ti.top1, ti.top2, t, v);
+        } else {
+            if (R2 > 1) {
+                __syncthreads();
+                level<R2, N2, Cfg::TPR, false, false, false>(s, s, ti.top2, t, v);
+            }
+            __syncthreads();
+            if (active) level_io<R1, N, Cfg::TPR, false, false, true>(io_out, s, nullptr, ti.top1, t, v);
+        }
+    }
+}
+
 } // namespace fastk
 } // namespace cfft

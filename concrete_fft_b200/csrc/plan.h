@@ -115,6 +115,10 @@ cudaError_t launch_c64_fast_b256_strided(const cfft_plan *plan, bool inverse, do
 bool fused_mul_kernel_available(const cfft_plan *plan);
 cudaError_t launch_c64_fwd_mul_inv(const cfft_plan *plan, const double2 *a, uint64_t kterms, const double2 *b,
                                    uint64_t b_row_stride, double2 *out, uint64_t batch, cudaStream_t st);
+// the same with n_out outputs per row sharing the forward transforms (b: [k][n_out][n]); one kernel for n_out == 2, n = 512 .. 2048
+bool fused_mul2_kernel_available(const cfft_plan *plan);
+cudaError_t launch_c64_fwd_mul_inv_multi(const cfft_plan *plan, const double2 *a, uint64_t kterms, const double2 *b, uint64_t b_row_stride,
+                                         uint64_t n_out, double2 *out, uint64_t batch, cudaStream_t st);
 cudaError_t launch_c64_fwd_mul_add(const cfft_plan *plan, const double2 *a, uint64_t a_row_terms, const double2 *b,
                                    uint64_t b_row_stride, double2 *acc, bool accumulate, uint64_t batch, cudaStream_t st);
 // kernels (c64_poly.cu): integer polynomials (2n signed 64-bit coefficients per row) <-> the Fourier domain with the fold,

@@ -189,6 +189,36 @@ class _PlanBase:
                                            current_stream_ptr(dev)))
         return out
 
+    def fwd_mul_inv_multi(self, a, b, out=None):
+        """out[r, o] = inv(sum_k fwd(a[r, k]) * b[r, k, o])  (cfft_c64_fwd_mul_inv_multi): the GLWE external product -- every
+        forward transform feeds all n_out outputs.  `a` [batch, k, n]; `b` [k, n_out, n] shared by every row or [batch, k, n_out, n];
+        returns `out` [batch, n_out, n].  Bit-identical to fwd_mul_inv once per output."""
+        import torch
+
+        n = self.fft_size()
+        for name, t in (("a", a), ("b", b)):
+            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.complex128 and t.is_contiguous()):
+                raise TypeError("%s must be a contiguous CUDA complex128 tensor" % name)
+        if a.dim() != 3 or a.shape[2] != n or a.shape[1] < 1:
+            raise N.PanicError("assertion failed: a has shape [batch, k, fft_size]")
+        batch, k = int(a.shape[0]), int(a.shape[1])
+        if b.dim() == 3 and b.shape[0] == k and b.shape[2] == n:
+            n_out, stride = int(b.shape[1]), 0
+        elif b.dim() == 4 and tuple(b.shape[:2]) == (batch, k) and b.shape[3] == n:
+            n_out, stride = int(b.shape[2]), k * int(b.shape[2]) * n
+        else:
+            raise N.PanicError("assertion failed: b has shape [k, n_out, fft_size] or [batch, k, n_out, fft_size]")
+        if out is None:
+            out = torch.empty((batch, n_out, n), dtype=torch.complex128, device=a.device)
+        if not (isinstance(out, torch.Tensor) and out.is_cuda and out.dtype == torch.complex128 and out.is_contiguous()
+                and tuple(out.shape) == (batch, n_out, n)):
+            raise N.PanicError("assertion failed: out is a contiguous [batch, n_out, fft_size] complex128 CUDA tensor")
+        dev = a.device.index
+        if dev != self.device() or b.device.index != dev or out.device.index != dev:
+            raise ValueError("all buffers must live on the plan's device cuda:%d" % self.device())
+        N.check(N.lib.cfft_c64_fwd_mul_inv_multi(self._h, a.data_ptr(), k, b.data_ptr(), stride, n_out, out.data_ptr(), batch, current_stream_ptr(dev)))
+        return out
+
     def fwd_mul_add(self, a, b, acc, accumulate=True):
         """acc[r] (Fourier domain) <- [acc[r] +] fwd(a[r]) * b[r]  (cfft_c64_fwd_mul_add), no inverse.  `a`: [batch, n] CUDA
         complex128, possibly a strided view a3[:, j] of a contiguous [batch, k, n] tensor; `b`: [n] / [batch, n] (or such a

@@ -299,6 +299,18 @@ cfft_status cfft_c64_mul_add_assign(int device, void *acc_dev, const void *a_dev
  * kernels through a stream-ordered workspace.  Stream ordered on the plan's device. */
 cfft_status cfft_c64_fwd_mul_inv(const cfft_plan *plan, const void *a_dev, uint64_t k_terms, const void *b_dev,
                                  uint64_t b_row_stride, void *out_dev, uint64_t batch, void *stream);
+/* The same with n_out outputs per row that share the forward transforms -- the GLWE external product of a caller such as
+ * TFHE-rs, where every decomposed term feeds each of the glwe_dimension + 1 output polynomials against its own row of the
+ * Fourier-domain key:    out[r][o] = inv( sum_{k < k_terms} fwd(a[r][k]) (.) b[r][k][o] ),   o < n_out.
+ *   a [batch][k_terms][n];  b [k_terms][n_out][n] (b_row_stride == 0: shared by every row) or per row at
+ *   b + r * b_row_stride (>= k_terms * n_out * n);  out [batch][n_out][n], overlapping neither a nor b.
+ * Defined as -- and bit-identical to -- cfft_c64_fwd_mul_inv once per output.  n_out == 2 on (Dif16, 256) plans of
+ * n = 512 / 1024 / 2048 (polynomial sizes 1024 .. 4096) runs as ONE kernel in which every forward transform runs once
+ * (2 k + 2 transforms per row instead of 4 k + 2; cfft_plan_has_fused_mul2_kernel tells); everything else runs output by
+ * output through the stream-ordered workspace. */
+cfft_status cfft_c64_fwd_mul_inv_multi(const cfft_plan *plan, const void *a_dev, uint64_t k_terms, const void *b_dev,
+                                       uint64_t b_row_stride, uint64_t n_out, void *out_dev, uint64_t batch, void *stream);
+int cfft_plan_has_fused_mul2_kernel(const cfft_plan *plan);
 /* acc[r] <- fwd(a[r]) (.) b[r]  (accumulate == 0)   or   acc[r] <- acc[r] + fwd(a[r]) (.) b[r]  (accumulate != 0), r < batch:
  * the forward transform and the element-wise multiply[-accumulate] into a FOURIER-DOMAIN accumulator (this plan's order)
  * in one call, without the inverse -- for loops that produce their terms one at a time or feed several accumulators

@@ -55,6 +55,8 @@ extern "C" {
     pub fn cfft_c64_mul_add_assign(device: c_int, acc_dev: *mut c_void, a_dev: *const c_void, b_dev: *const c_void, len: u64, stream: *mut c_void) -> cfft_status;
     pub fn cfft_f128_fwd_mul_inv(plan: *const cfft_plan, l_re0: *mut f64, l_re1: *mut f64, l_im0: *mut f64, l_im1: *mut f64, r_re0: *const f64, r_re1: *const f64, r_im0: *const f64, r_im1: *const f64, rhs_row_stride: u64, factor: f64, batch: u64, stream: *mut c_void) -> cfft_status;
     pub fn cfft_c64_fwd_mul_inv(plan: *const cfft_plan, a_dev: *const c_void, k_terms: u64, b_dev: *const c_void, b_row_stride: u64, out_dev: *mut c_void, batch: u64, stream: *mut c_void) -> cfft_status;
+    pub fn cfft_c64_fwd_mul_inv_multi(plan: *const cfft_plan, a_dev: *const c_void, k_terms: u64, b_dev: *const c_void, b_row_stride: u64, n_out: u64, out_dev: *mut c_void, batch: u64, stream: *mut c_void) -> cfft_status;
+    pub fn cfft_plan_has_fused_mul2_kernel(plan: *const cfft_plan) -> c_int;
     pub fn cfft_c64_fwd_mul_add(plan: *const cfft_plan, a_dev: *const c_void, a_row_stride: u64, b_dev: *const c_void, b_row_stride: u64, acc_dev: *mut c_void, accumulate: c_int, batch: u64, stream: *mut c_void) -> cfft_status;
     pub fn cfft_plan_has_fused_mul_kernel(plan: *const cfft_plan) -> c_int;
     pub fn cfft_f128_cplx_mul_scale(device: c_int, l_re0: *mut f64, l_re1: *mut f64, l_im0: *mut f64, l_im1: *mut f64, r_re0: *const f64, r_re1: *const f64, r_im0: *const f64, r_im1: *const f64, factor: f64, len: u64, stream: *mut c_void) -> cfft_status;

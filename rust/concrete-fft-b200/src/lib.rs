@@ -501,6 +501,15 @@ pub mod device {
     pub unsafe fn f128_inv_strided(plan: *const ffi::cfft_plan, p: [*mut f64; 4], row_stride: u64, batch: u64, stream: *mut c_void) {
         ffi::check(ffi::cfft_f128_inv_strided(plan, p[0], p[1], p[2], p[3], row_stride, batch, stream));
     }
+    /// `out[r][o] = inv(sum_k fwd(a[r][k]) * b[r][k][o])`, `o < n_out`: the GLWE external product, every forward transform feeding
+    /// all outputs (one kernel for `n_out == 2`, `n` = 512 / 1024 / 2048); bit-identical to [`c64_fwd_mul_inv`] once per output.
+    /// # Safety
+    /// `a`: `batch * k_terms * n` c64, `b`: `k_terms * n_out * n` (shared, `b_row_stride == 0`) or `batch` rows `b_row_stride` apart,
+    /// `out`: `batch * n_out * n` c64 overlapping neither, all on the plan's device.
+    #[allow(clippy::too_many_arguments)]
+    pub unsafe fn c64_fwd_mul_inv_multi(plan: *const ffi::cfft_plan, a: *const c_void, k_terms: u64, b: *const c_void, b_row_stride: u64, n_out: u64, out: *mut c_void, batch: u64, stream: *mut c_void) {
+        ffi::check(ffi::cfft_c64_fwd_mul_inv_multi(plan, a, k_terms, b, b_row_stride, n_out, out, batch, stream));
+    }
     /// `lhs[i] *= rhs[i]` on `len` device c64 (the Fourier-domain step between `fwd` and `inv`; the bits of
     /// `num_complex`'s `*`).
     /// # Safety

@@ -1128,3 +1128,49 @@ def test_host_call_sharded_over_replicas(C, torch):
     arr = (ctypes.c_void_p * 2)(plan._h.value if hasattr(plan._h, "value") else plan._h, other._h.value if hasattr(other._h, "value") else other._h)
     buf = np.zeros(2 * 2048, np.complex128)
     assert C._native.lib.cfft_c64_host_multi(arr, 2, 0, buf.ctypes.data, buf.size, 2) == C._native.EINVAL  # different transforms
+
+
+@pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096])
+def test_fwd_mul_inv_several_outputs_bit_exact(C, torch, n):
+    """cfft_c64_fwd_mul_inv_multi (the GLWE external product: every forward transform feeds all outputs): bit-identical to
+    cfft_c64_fwd_mul_inv once per output and to the oracle composition; one kernel for two outputs at n = 512 .. 2048, the
+    output-by-output path elsewhere, b shared by the batch or per row, ragged tiles, the composed path."""
+    rng = np.random.default_rng(7700 + n)
+    A = C.ordered.FftAlgo
+    plan = C.unordered.Plan(n, C.unordered.Method.UserProvided(A.Dif16, 256))
+    ref = O.UnorderedPlan(n, O.DIF16, 256)
+    assert C._native.lib.cfft_plan_has_fused_mul2_kernel(plan._h) == (1 if n in (512, 1024, 2048) else 0)
+    for batch, k, n_out, per_row in [(5, 3, 2, False), (1, 1, 2, False), (700 if n <= 1024 else 310, 2, 2, False), (4, 2, 2, True), (3, 2, 3, False)]:
+        a = rand_c(rng, batch, k, n) - (0.5 + 0.5j)
+        b = (rand_c(rng, batch, k, n_out, n) if per_row else rand_c(rng, k, n_out, n)) - (0.5 + 0.5j)
+        da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+        got = plan.fwd_mul_inv_multi(da, db)
+        torch.cuda.synchronize()
+        for o in range(n_out):
+            bo = torch.from_numpy(np.ascontiguousarray(b[:, :, o] if per_row else b[:, o])).cuda()
+            single = plan.fwd_mul_inv(da, bo)
+            torch.cuda.synchronize()
+            assert bits_equal(got[:, o].cpu().numpy(), single.cpu().numpy()), (n, batch, k, n_out, per_row, o)
+        if batch <= 5:  # the oracle composition, row by row
+            for r in range(batch):
+                for o in range(n_out):
+                    acc = None
+                    for i in range(k):
+                        acc = O.c64_pointwise(ref.fwd(a[r, i]), (b[r, i, o] if per_row else b[i, o]), acc)
+                    assert bits_equal(got[r, o].cpu().numpy(), ref.inv(acc)), (n, r, o)
+    os.environ["CFFT_B200_FUSED_MUL_COMPOSED"] = "1"
+    try:
+        a = rand_c(rng, 3, 2, n)
+        b = rand_c(rng, 2, 2, n)
+        da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+        composed = plan.fwd_mul_inv_multi(da, db)
+        torch.cuda.synchronize()
+    finally:
+        del os.environ["CFFT_B200_FUSED_MUL_COMPOSED"]
+    fused = plan.fwd_mul_inv_multi(da, db)
+    torch.cuda.synchronize()
+    assert bits_equal(composed.cpu().numpy(), fused.cpu().numpy())
+    with pytest.raises(C.PanicError):
+        plan.fwd_mul_inv_multi(da, torch.zeros((3, 2, n), dtype=torch.complex128, device="cuda"))  # k mismatch
+    lib = C._native.lib
+    assert lib.cfft_c64_fwd_mul_inv_multi(plan._h, da.data_ptr(), 2, db.data_ptr(), 0, 2, da.data_ptr(), 3, None) == C._native.EINVAL  # out overlaps a
