@@ -106,6 +106,10 @@ plan.fwd_mul_inv(a, b)
 big = C.unordered.Plan(8192, C.unordered.Method.UserProvided(A.Dif16, 256))
 a8 = torch.from_numpy(rng.random((170, 2, 8192)) + 1j * rng.random((170, 2, 8192))).cuda()
 big.fwd_mul_inv(a8, torch.from_numpy(rng.random((2, 8192)) + 1j * rng.random((2, 8192))).cuda())
+for n2, rows in [(512, 9), (1024, 5), (2048, 310), (4096, 3)]:  # two outputs per row: one kernel (512 .. 2048), output by output (4096)
+    p2 = C.unordered.Plan(n2, C.unordered.Method.UserProvided(A.Dif16, 256))
+    a2 = torch.from_numpy(rng.random((rows, 3, n2)) + 1j * rng.random((rows, 3, n2))).cuda()
+    p2.fwd_mul_inv_multi(a2, torch.from_numpy(rng.random((3, 2, n2)) + 1j * rng.random((3, 2, n2))).cuda())
 poly = torch.from_numpy(rng.integers(-1000, 1000, size=(5, 2, 4096))).cuda()
 key = plan.fwd_poly(torch.from_numpy(rng.integers(-8, 8, size=(2, 4096))).cuda())
 out = plan.poly_mul(poly, key)
