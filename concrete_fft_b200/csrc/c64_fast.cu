@@ -168,7 +168,8 @@ cudaError_t launch_cfg(bool inverse, c64 *data, uint64_t batch, const FastTables
     // measured (profiles/r2c_fast_prefetch.txt): n = 8192 3.74 / 3.78 -> 4.61 / 4.57 TB/s, n = 4096 fwd 5.31 -> 6.15 (inv 6.11 -> 5.99:
     // left off), n = 2048 6.66 / 6.84 -> 6.90 / 6.88
     // standard-order variant (profiles/r2l_std_one_exchange_ab.txt): on in both directions at every size (n = 4096 fwd 5.24 -> 5.87)
-    const bool on = N >= 2048 && (STD || N != 4096 || !inverse);
+    // n = 1024: fwd 6.51 -> 6.84 TB/s (profiles/r2o_small_n_prefetch.txt); n <= 512: no effect, left off
+    const bool on = N >= 1024 && (STD || N != 4096 || !inverse);
     const int waves = env_pf >= 0 ? env_pf : (on ? 1 : 0);
     if (waves > 0 && N >= 512) {
         int dev = 0, sms = 148;
